@@ -1,0 +1,480 @@
+// conv_tc.cu — 3x3 (dilated, stride-1, zero-padded) convolution as an implicit GEMM on the
+// Blackwell 5th-gen tensor cores: TMA-im2col -> shared memory -> tcgen05.mma -> TMEM -> epilogue.
+//
+// Replaces the cuDNN calls behind nn.Conv2d in the reference ConvLayer
+// (/root/reference/models/unet.py:188) and the aux-path bottleneck conv
+// (/root/reference/models/aux_path_memory.py:24): forward, data gradient and weight gradient.
+//
+//   forward / dgrad :  D[pixel, co] = sum_{tap, ci} X[pixel + off(tap), ci] * Wp[tap, co, ci]
+//       M = 128 output pixels (a {bw x bh x bn} box of the NHWC tensor), N = BLOCK_N channels,
+//       K = 9 taps x (C0 + C1) input channels walked in BK-channel slices. The A slice of one tap is
+//       ONE TMA box of the activation tensor shifted by (dx*dil, dy*dil): out-of-bounds rows/cols are
+//       zero-filled by the TMA unit, which is exactly the conv's zero padding. The channel concat
+//       of the decoder (torch.cat((up, skip), 1), unet.py:151) is never materialised: the K loop
+//       walks two tensor maps. dgrad is the same kernel on spatially flipped, transposed weights
+//       and can scatter its N tiles to two destination tensors (the two concat sources).
+//   wgrad :  dW[tap, co, ci] = sum_pixel dY[pixel, co] * X[pixel + off(tap), ci]
+//       M = 128 output channels, N = BLOCK_N input channels, K = pixels; both operands are the
+//       same NHWC TMA boxes, consumed as MN-major UMMA operands. Split-K over pixel ranges with
+//       fp32 red.global accumulation.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
+// (one lane), warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include "pp_common.cuh"
+
+namespace pp {
+
+static constexpr int kTcThreads = 192;
+static constexpr int kMaxStages = 8;
+
+struct ConvTcParams {
+  int N, H, W;
+  int dil;
+  int bw, bh, bn;              // pixel box (bw*bh*bn == 128)
+  int tiles_w, tiles_h;        // tiles per row / column (tiles_n = gridDim.x / (tiles_w*tiles_h))
+  int kc0, kc1;                // K slices per tap in source 0 / source 1
+  int ctot;                    // C0 + C1
+  int c0;                      // channels of source 0 (K offset of source 1 inside a tap)
+  int stages;
+  __nv_bfloat16* out0;         // destination of GEMM columns [0, outc0)
+  __nv_bfloat16* out1;         // destination of GEMM columns [outc0, outc0+outc1)
+  int outc0, outc1;
+  int acc0, acc1;              // 1: out += result (read-modify-write)
+  const float* bias;           // [outc0 + outc1] or null
+};
+
+template <int BLOCK_N, int BK>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+  constexpr int A_BYTES = 128 * BK * 2;
+  constexpr int B_BYTES = BLOCK_N * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t SWZ = (BK == 64) ? SWZ_128B : SWZ_64B;
+  constexpr uint32_t SBO = 8 * BK * 2;  // 8 rows of one swizzle atom
+  constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int m_tile = blockIdx.x;
+  const int n_tile = blockIdx.y;
+  const int tw = m_tile % p.tiles_w;
+  const int th = (m_tile / p.tiles_w) % p.tiles_h;
+  const int tn = m_tile / (p.tiles_w * p.tiles_h);
+  const int x0 = tw * p.bw, y0 = th * p.bh, n0 = tn * p.bn;
+  const int num_k = 9 * (p.kc0 + p.kc1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.kc1 > 0) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int oy = (tap / 3 - 1) * p.dil, ox = (tap % 3 - 1) * p.dil;
+        for (int kc = 0; kc < p.kc0 + p.kc1; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          int kofs;
+          if (kc < p.kc0) {
+            tma_load_4d(sa, &tmA0, &full_bar[stage], kc * BK, x0 + ox, y0 + oy, n0);
+            kofs = kc * BK;
+          } else {
+            tma_load_4d(sa, &tmA1, &full_bar[stage], (kc - p.kc0) * BK, x0 + ox, y0 + oy, n0);
+            kofs = p.c0 + (kc - p.kc0) * BK;
+          }
+          tma_load_3d(sb, &tmB, &full_bar[stage], kofs, n_tile * BLOCK_N, tap);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < num_k; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = make_smem_desc(sa + k * 32, 16, SBO, SWZ);
+          const uint64_t db = make_smem_desc(sb + k * 32, 16, SBO, SWZ);
+          umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> (+bias, +old) -> bf16 NHWC =====
+    const int q = warp & 3;          // TMEM lane quarter accessible to this warp
+    const int r = q * 32 + lane;     // tile row == pixel index inside the box
+    const int lx = r % p.bw, ly = (r / p.bw) % p.bh, ln = r / (p.bw * p.bh);
+    const int px = x0 + lx, py = y0 + ly, pn = n0 + ln;
+    const bool valid = (px < p.W) && (py < p.H) && (pn < p.N);
+    const long long pix = (static_cast<long long>(pn) * p.H + py) * p.W + px;
+
+    const int col0 = n_tile * BLOCK_N;  // first GEMM column of this CTA
+    __nv_bfloat16* dst;
+    int dstc, acc, ch0;
+    if (col0 < p.outc0) { dst = p.out0; dstc = p.outc0; acc = p.acc0; ch0 = col0; }
+    else                { dst = p.out1; dstc = p.outc1; acc = p.acc1; ch0 = col0 - p.outc0; }
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c), v);
+      tmem_wait_ld();
+      if (valid) {
+        __nv_bfloat16* o = dst + pix * dstc + ch0 + c;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += __ldg(p.bias + col0 + c + g * 8 + j);
+          }
+          Vec8<__nv_bfloat16> pk;
+          if (acc) {
+            float old[8];
+            pk.load(o + g * 8);
+            pk.get(old);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += old[j];
+          }
+          pk.set(f);
+          pk.store(o + g * 8);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncwarp();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// wgrad
+// ----------------------------------------------------------------------------------------------
+struct WgradTcParams {
+  int N, H, W, dil;
+  int bw, bh, bn;            // pixel box of one K block (bw*bh*bn == 64)
+  int tiles_w, tiles_h, tiles_total;
+  int Cout, C0, C1;
+  int ci_tiles0, ci_tiles1;  // N tiles per source
+  int kb_per_split;
+  int stages;
+  float* dw;                 // [9][Cout][C0+C1] fp32, pre-zeroed, accumulated with red.global
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX0,
+                        const __grid_constant__ CUtensorMap tmX1, const WgradTcParams p) {
+  constexpr int PIXK = 64;                    // pixels (GEMM K) per pipeline stage
+  constexpr int BOX_BYTES = PIXK * 128;       // one {64 ch x 64 px} box, 128-byte rows
+  constexpr int A_BYTES = 2 * BOX_BYTES;      // M = 128 output channels = 2 boxes
+  constexpr int NB = BLOCK_N / 64;            // boxes on the N side
+  constexpr int B_BYTES = NB * BOX_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = BLOCK_N;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int ci_tiles = p.ci_tiles0 + p.ci_tiles1;
+  const int co_tile = blockIdx.x / ci_tiles;
+  const int ci_tile = blockIdx.x % ci_tiles;
+  const int tap = blockIdx.y;
+  const int split = blockIdx.z;
+  const bool src1 = ci_tile >= p.ci_tiles0;
+  const int ci0 = (src1 ? ci_tile - p.ci_tiles0 : ci_tile) * BLOCK_N;  // channel offset inside the source
+  const int co0 = co_tile * 128;
+  const int kb_begin = split * p.kb_per_split;
+  const int kb_end = min(kb_begin + p.kb_per_split, p.tiles_total);
+  const int num_k = kb_end - kb_begin;
+  const int oy = (tap / 3 - 1) * p.dil, ox = (tap % 3 - 1) * p.dil;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(src1 ? &tmX1 : &tmX0);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_k > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const CUtensorMap* tmX = src1 ? &tmX1 : &tmX0;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          const int tw = kb % p.tiles_w;
+          const int th = (kb / p.tiles_w) % p.tiles_h;
+          const int tn = kb / (p.tiles_w * p.tiles_h);
+          const int x0 = tw * p.bw, y0 = th * p.bh, n0 = tn * p.bn;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_4d(sa, &tmDY, &full_bar[stage], co0, x0, y0, n0);
+          tma_load_4d(sa + BOX_BYTES, &tmDY, &full_bar[stage], co0 + 64, x0, y0, n0);
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+            tma_load_4d(sb + b * BOX_BYTES, tmX, &full_bar[stage], ci0 + b * 64, x0 + ox, y0 + oy, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);  // both operands MN-major
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < num_k; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < PIXK / 16; ++k) {
+            // 16 pixels (K) = 16 rows of 128 B; MN chunks of 64 channels are BOX_BYTES apart (LBO);
+            // groups of 8 K rows are 1024 B apart (SBO).
+            const uint64_t da = make_smem_desc(sa + k * 2048, BOX_BYTES, 1024, SWZ_128B);
+            const uint64_t db = make_smem_desc(sb + k * 2048, BOX_BYTES, 1024, SWZ_128B);
+            umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tmem_full_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int co = co0 + q * 32 + lane;
+      const int csrc = src1 ? p.C1 : p.C0;
+      const int ctot = p.C0 + p.C1;
+      const int cbase = (src1 ? p.C0 : 0) + ci0;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c), v);
+        tmem_wait_ld();
+        if (co < p.Cout) {
+          float* o = p.dw + (static_cast<long long>(tap) * p.Cout + co) * ctot + cbase + c;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (ci0 + c + j < csrc) atomicAdd(o + j, __uint_as_float(v[j]));
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncwarp();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Host launchers
+// ----------------------------------------------------------------------------------------------
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+static void pixel_box(int W, int H, int pixels, int* bw, int* bh, int* bn) {
+  *bw = pow2_ceil(W) < pixels ? pow2_ceil(W) : pixels;
+  const int rest = pixels / *bw;
+  *bh = pow2_ceil(H) < rest ? pow2_ceil(H) : rest;
+  *bn = rest / *bh;
+}
+static int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
+
+template <int BLOCK_N, int BK>
+static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, ConvTcParams p,
+                          int m_tiles, int n_tiles, cudaStream_t stream) {
+  constexpr int STAGE_BYTES = 128 * BK * 2 + BLOCK_N * BK * 2;
+  int stages = (200 * 1024) / STAGE_BYTES;
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.stages = stages;
+  const int smem = stages * STAGE_BYTES + 1024 + 256;
+  static bool attr_set = false;  // benign race: idempotent
+  if (!attr_set) {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<BLOCK_N, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024 + 1024 + 256));
+    attr_set = true;
+  }
+  conv3x3_tc_kernel<BLOCK_N, BK><<<dim3(m_tiles, n_tiles), kTcThreads, smem, stream>>>(a0, a1, b, p);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// x0:[N,H,W,C0] x1:[N,H,W,C1] (or null), wpack:[9][outc0+outc1][C0+C1] bf16.
+int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
+               int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil,
+               cudaStream_t stream) {
+  const int cout = outc0 + outc1;
+  const int ctot = C0 + C1;
+  PP_REQUIRE(N > 0 && H > 0 && W > 0 && dil >= 1, "conv3x3_tc: bad shape N=%d H=%d W=%d dil=%d", N, H, W, dil);
+  PP_REQUIRE(C0 % 32 == 0 && C1 % 32 == 0 && C0 > 0, "conv3x3_tc: input channels must be multiples of 32 (C0=%d C1=%d)",
+             C0, C1);
+  PP_REQUIRE((x1 == nullptr) == (C1 == 0), "conv3x3_tc: x1/C1 mismatch");
+  PP_REQUIRE((out1 == nullptr) == (outc1 == 0), "conv3x3_tc: out1/outc1 mismatch");
+  const int bk = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
+  int g = gcd_int(outc0, outc1 == 0 ? outc0 : outc1);
+  int block_n = 256;
+  while (block_n > 32 && g % block_n != 0) block_n >>= 1;
+  PP_REQUIRE(g % block_n == 0, "conv3x3_tc: output channels must be multiples of 32 (outc0=%d outc1=%d)", outc0, outc1);
+
+  ConvTcParams p{};
+  p.N = N; p.H = H; p.W = W; p.dil = dil;
+  pixel_box(W, H, 128, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = ceil_div(W, p.bw);
+  p.tiles_h = ceil_div(H, p.bh);
+  const int tiles_n = ceil_div(N, p.bn);
+  const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+  // keep at least ~2 waves of CTAs when the problem allows it
+  while (block_n > 64 && static_cast<long long>(m_tiles) * (cout / block_n) < 2LL * sm_count()) block_n >>= 1;
+  p.kc0 = C0 / bk; p.kc1 = C1 / bk; p.ctot = ctot; p.c0 = C0;
+  p.out0 = static_cast<__nv_bfloat16*>(out0); p.out1 = static_cast<__nv_bfloat16*>(out1);
+  p.outc0 = outc0; p.outc1 = outc1; p.acc0 = acc0; p.acc1 = acc1; p.bias = bias;
+
+  CUtensorMap a0, a1, b;
+  int rc = encode_tmap_nhwc(&a0, x0, N, H, W, C0, bk, p.bw, p.bh, p.bn, bk == 64);
+  if (rc) return rc;
+  if (C1 > 0) rc = encode_tmap_nhwc(&a1, x1, N, H, W, C1, bk, p.bw, p.bh, p.bn, bk == 64);
+  else a1 = a0;
+  if (rc) return rc;
+  rc = encode_tmap_weights(&b, wpack, 9, cout, ctot, bk, block_n, bk == 64);
+  if (rc) return rc;
+
+  const int n_tiles = cout / block_n;
+#define PP_CONV_CASE(BN_, BK_) \
+  if (block_n == BN_ && bk == BK_) return launch_conv_tc<BN_, BK_>(a0, a1, b, p, m_tiles, n_tiles, stream);
+  PP_CONV_CASE(256, 64) PP_CONV_CASE(128, 64) PP_CONV_CASE(64, 64) PP_CONV_CASE(32, 64)
+  PP_CONV_CASE(256, 32) PP_CONV_CASE(128, 32) PP_CONV_CASE(64, 32) PP_CONV_CASE(32, 32)
+#undef PP_CONV_CASE
+  set_error("conv3x3_tc: no kernel for block_n=%d bk=%d", block_n, bk);
+  return PP_ERR_INVALID;
+}
+
+template <int BLOCK_N>
+static int launch_wgrad_tc(const CUtensorMap& dy, const CUtensorMap& x0, const CUtensorMap& x1, WgradTcParams p,
+                           dim3 grid, cudaStream_t stream) {
+  constexpr int STAGE_BYTES = (2 + BLOCK_N / 64) * 64 * 128;
+  int stages = (200 * 1024) / STAGE_BYTES;
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.stages = stages;
+  const int smem = stages * STAGE_BYTES + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024 + 1024 + 256));
+    attr_set = true;
+  }
+  conv3x3_wgrad_tc_kernel<BLOCK_N><<<grid, kTcThreads, smem, stream>>>(dy, x0, x1, p);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// dy:[N,H,W,Cout] bf16, x0/x1 as in forward; dw:[9][Cout][C0+C1] fp32, MUST be zeroed by the caller.
+int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw, int N,
+                     int H, int W, int dil, cudaStream_t stream) {
+  PP_REQUIRE(N > 0 && H > 0 && W > 0 && dil >= 1, "conv3x3_wgrad_tc: bad shape");
+  PP_REQUIRE(Cout % 8 == 0 && C0 % 8 == 0 && C1 % 8 == 0 && C0 > 0, "conv3x3_wgrad_tc: channels must be multiples of 8");
+  PP_REQUIRE((x1 == nullptr) == (C1 == 0), "conv3x3_wgrad_tc: x1/C1 mismatch");
+  WgradTcParams p{};
+  p.N = N; p.H = H; p.W = W; p.dil = dil;
+  pixel_box(W, H, 64, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = ceil_div(W, p.bw);
+  p.tiles_h = ceil_div(H, p.bh);
+  p.tiles_total = p.tiles_w * p.tiles_h * ceil_div(N, p.bn);
+  p.Cout = Cout; p.C0 = C0; p.C1 = C1; p.dw = dw;
+  const int cmax = C0 > C1 ? C0 : C1;
+  const int block_n = cmax <= 64 ? 64 : (cmax <= 128 ? 128 : 256);
+  p.ci_tiles0 = ceil_div(C0, block_n);
+  p.ci_tiles1 = C1 > 0 ? ceil_div(C1, block_n) : 0;
+  const int co_tiles = ceil_div(Cout, 128);
+  const int base_ctas = co_tiles * (p.ci_tiles0 + p.ci_tiles1) * 9;
+  int splits = ceil_div(3 * sm_count(), base_ctas);
+  if (splits > p.tiles_total) splits = p.tiles_total;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = ceil_div(p.tiles_total, splits);
+  splits = ceil_div(p.tiles_total, p.kb_per_split);
+
+  CUtensorMap tdy, tx0, tx1;
+  int rc = encode_tmap_nhwc(&tdy, dy, N, H, W, Cout, 64, p.bw, p.bh, p.bn, true);
+  if (rc) return rc;
+  rc = encode_tmap_nhwc(&tx0, x0, N, H, W, C0, 64, p.bw, p.bh, p.bn, true);
+  if (rc) return rc;
+  if (C1 > 0) rc = encode_tmap_nhwc(&tx1, x1, N, H, W, C1, 64, p.bw, p.bh, p.bn, true);
+  else tx1 = tx0;
+  if (rc) return rc;
+  dim3 grid(co_tiles * (p.ci_tiles0 + p.ci_tiles1), 9, splits);
+  if (block_n == 64) return launch_wgrad_tc<64>(tdy, tx0, tx1, p, grid, stream);
+  if (block_n == 128) return launch_wgrad_tc<128>(tdy, tx0, tx1, p, grid, stream);
+  return launch_wgrad_tc<256>(tdy, tx0, tx1, p, grid, stream);
+}
+
+}  // namespace pp
