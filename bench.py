@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py — PacingPseudo train-step throughput (BASELINE.json metric: train imgs/sec, 256x256 pacingpseudo step).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (hand-written sm_100a path)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm's CPU path (oracle port)
+
+A step = one full pacingpseudo iteration (train_chaos.py:263-315): batched weak+strong UNet forward, partial CE +
+entropy + consistency + aux partial CE + memory loss, memory-bank update, backward, gradient all-reduce (N > 1),
+Adam. One "image" = one weak+strong pair, as batch_size counts them (train_chaos.py:237). Prints ONE JSON line.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GF_PER_PAIR = {  # algorithmic conv FLOPs per weak+strong pair, BASELINE.md section 3 (fwd F, bwd 2F)
+    (256, 5): 348.25e9, (256, 4): 348.22e9, (224, 4): 266.61e9, (224, 2): 266.57e9,
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=12, help="weak+strong pairs per GPU (train_chaos.py:93)")
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--classes", type=int, default=5)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--bn", default="train", choices=["train", "eval"],
+                    help="BatchNorm regime: batch statistics (epoch 0) or running statistics (epochs >= 1, SURVEY T2)")
+    ap.add_argument("--epoch", type=int, default=40, help="epoch used for loss ramp-up weights and bank momentum")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the full pacingpseudo step on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_pacing_steps(args, steps, warmup, pairs=1):
+    import torch
+    from oracle import pp_oracle as O
+    from oracle.gen_golden import build_state
+    from pacingpseudo_b200.synth import make_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    case = dict(kind="pacing", C=args.classes, os=8)
+    sd = build_state(case)
+    learn = [k for k in sd if sd[k].is_floating_point() and "running" not in k and not k.endswith("memory_bank")]
+    for k in learn:
+        sd[k].requires_grad_(True)
+    cfg = O.StepConfig(num_classes=args.classes, ignored_index=args.classes)
+    state = {}
+    times = []
+    for it in range(warmup + steps):
+        batch = make_batch(pairs, args.classes, args.size, args.size, seed=1234 + it)
+        t0 = time.perf_counter()
+        for k in learn:
+            sd[k].grad = None
+        out = O.consistency_forward(sd, batch, cfg, mode="train", step=args.epoch, training=(args.bn == "train"))
+        loss = O.total_loss(out, args.epoch)
+        loss.backward()
+        with torch.no_grad():
+            O.adam_step({k: sd[k] for k in learn}, {k: sd[k].grad for k in learn}, state, 1e-4, 3e-4, it + 1)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times, cores, pairs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    times, cores, pairs = cpu_pacing_steps(args, args.steps, args.warmup, pairs=1)
+    total = sum(times)
+    value = pairs * len(times) / total
+    sample = ("oracle port (oracle/pp_oracle.py, torch %s CPU fp32) of the full pacingpseudo step on %d weak+strong pair(s) "
+              "of %dx%d per step, %d timed steps" % (__import__("torch").__version__, pairs, args.size, args.size, len(times)))
+    line = {
+        "impl": "reference", "metric": "train imgs/sec (256^2 pacingpseudo step)", "value": value, "unit": "img/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, pairs_override=pairs),
+        "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, pairs_override=None):
+    return {
+        "workload": "pacingpseudo full step (--do_loss_ent --do_decoder_consistency --do_aux_path --do_memory), "
+                    "CHAOS-shaped synthetic %dx%d 1-ch slices, %d classes (BASELINE.json configs[1])" % (
+                        args.size, args.size, args.classes),
+        "pairs_per_gpu": pairs_override if pairs_override is not None else args.batch,
+        "global_pairs": (pairs_override if pairs_override is not None else args.batch) * max(1, args.gpus),
+        "unet": "init_ch 32, max_ch 512, output_stride 8, maxpool + bilinear", "bn": args.bn,
+        "loss_cr_variants": "ce_loss", "optimizer": "Adam lr 1e-4 wd 3e-4", "parallelism": "dp%d" % max(1, args.gpus),
+        "l2": "per-step working set (~3.4 GB of activations per GPU) >> 126 MB L2; no explicit flush",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from pacingpseudo_b200 import dp
+    from pacingpseudo_b200.dropin import DROPIN_PATH
+    from pacingpseudo_b200.lib import get_lib
+    from pacingpseudo_b200.optim import FlatAdam
+    from pacingpseudo_b200.synth import make_batch
+    from oracle.pp_oracle import gaussian_ramp_up  # host scalar schedule only (utils/utils.py:53-65)
+    sys.path.insert(0, DROPIN_PATH)
+    from models.consistency_reglur_memory import ConsistencyRegulr
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the product path has no CPU fallback")
+    rank, world, dev = dp.init_distributed()
+    lib = get_lib()
+    lib.ensure_init(dev.index)
+    C, S, B = args.classes, args.size, args.batch
+
+    torch.manual_seed(1)  # train_chaos.py:28,437
+    ns = argparse.Namespace(ignored_index=C, do_loss_ent=True, do_decoder_consistency=True, detach_weak_cr=False,
+                            loss_cr_variants="ce_loss", do_aux_path=True, do_memory=True)
+    model = ConsistencyRegulr(
+        kwargs_unet=dict(input_ch=1, init_ch=32, max_ch=512, num_classes=C, output_stride=8, is_stride_conv=False,
+                         is_trans_conv=False, elab_end_points=True, precision=args.precision),
+        kwargs_aux_path=dict(num_classes=C, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[512, 512],
+                             hid_ch=64, aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
+                             ensemble_mode='cosine_similarity'),
+        args_parser=ns).to(dev)
+    model.train(args.bn == "train")
+    opt = FlatAdam(model.parameters(), lr=1e-4, weight_decay=3e-4)
+    reducer = dp.GradientAllReducer(opt.flat_grad, num_buckets=4)
+    opt.grad_scale = 1.0 / world
+    if world > 1:
+        model.aux_path.bank_sync = dp.make_bank_sync(0)
+        for p in opt.params:  # identical start on all ranks (same seed) — assert rather than broadcast
+            pass
+
+    # a small pool of distinct per-rank batches; host copies pinned for the end-to-end leg
+    keys = ("image", "image_strong", "scribble", "scribble_strong", "valid_mask")  # what train_chaos.py:264-269 moves
+    pool_host = []
+    for i in range(4):
+        b = make_batch(B, C, S, S, seed=dp.shard_seed(1234, rank, i))
+        pool_host.append({k: b[k].pin_memory() for k in keys})
+    pool_dev = [{k: v.to(dev) for k, v in b.items()} for b in pool_host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pool_host[0].values())
+    w_ent = gaussian_ramp_up(args.epoch, 1.0, scale=8.0)
+    w_cr = gaussian_ramp_up(args.epoch, 1.0, scale=8.0)
+
+    def step(batch, read_back):
+        out = model(batch, mode='train', step=args.epoch)
+        loss = out['loss_pce']
+        loss_ent = out['loss_ent'] * w_ent
+        loss += loss_ent
+        loss_cr = out['loss_cr'] * w_cr
+        loss += loss_cr
+        loss_aux = out['loss_aux_cls']
+        loss_aux *= 0.01
+        loss += loss_aux
+        loss_mem = out['loss_memory']
+        loss_mem *= 1
+        loss += loss_mem
+        opt.zero_grad()
+        loss.backward()
+        reducer.allreduce()
+        opt.step()
+        if read_back:  # the five .item() reads of train_chaos.py:275-310
+            return [t.item() for t in (out['loss_pce'], loss_ent, loss_cr, loss_aux, loss_mem)]
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(nsteps, host_inputs, profile):
+        barrier()
+        lib.cdll.pp_profile_reset()
+        lib.cdll.pp_profile_enable(1 if profile else 0)
+        l0 = lib.cdll.pp_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(nsteps):
+            if host_inputs:
+                batch = {k: v.to(dev, non_blocking=True) for k, v in pool_host[i % len(pool_host)].items()}
+                step(batch, True)
+            else:
+                step(pool_dev[i % len(pool_dev)], False)
+        e1.record()
+        barrier()
+        lib.cdll.pp_profile_enable(0)
+        ms = dp.max_over_ranks(e0.elapsed_time(e1), dev)
+        return ms, lib.cdll.pp_launch_count() - l0
+
+    for i in range(args.warmup):
+        step(pool_dev[i % len(pool_dev)], False)
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(args.steps, host_inputs=False, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = {}
+    for fam, name in ((0, "conv3x3_tc (fwd+dgrad)"), (1, "conv3x3_wgrad_tc")):
+        t, f, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        lib.call("pp_profile_collect", fam, ctypes.byref(t), ctypes.byref(f), ctypes.byref(n))
+        prof[name] = dict(ms=t.value, flops=f.value, launches=n.value)
+    e2e = None
+    if not args.no_e2e:
+        for i in range(2):
+            step({k: v.to(dev, non_blocking=True) for k, v in pool_host[i].items()}, True)
+        ms_e2e, _ = timed(args.steps, host_inputs=True, profile=False)
+        e2e = {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": "img/s", "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / args.steps}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    value = B * world * args.steps / (ms / 1e3)
+    conv_ms = sum(p["ms"] for p in prof.values())
+    conv_fl = sum(p["flops"] for p in prof.values())
+    conv_n = sum(p["launches"] for p in prof.values())
+    achieved = conv_fl / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    gf = GF_PER_PAIR.get((S, C))
+    line = {
+        "metric": "train imgs/sec (256^2 pacingpseudo step)", "value": value, "unit": "img/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": e2e,
+        "roofline": {
+            "bound": "tensor", "kernel": "conv3x3 tcgen05 implicit GEMM (forward + dgrad + wgrad launches)",
+            "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["tf_sustained"], "peak_source": peaks["src"] + " bf16 sustained",
+            "traffic": None, "launches": int(conv_n), "kernel_ms_per_step": conv_ms / args.steps,
+            "share_of_step": conv_ms / ms if ms > 0 else None, "per_family": prof,
+            "step_tensor_frac": (value / world * gf / 1e12 / peaks["tf_sustained"]) if gf else None,
+        },
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        times, cores, pairs = cpu_pacing_steps(args, steps=2, warmup=1, pairs=1)
+        v = pairs * len(times) / sum(times)
+        line["cpu_baseline"] = {
+            "value": v, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": "oracle port of the same pacingpseudo step, %d pair(s) of %dx%d per step, %d timed steps (%.1f s)" % (
+                pairs, S, S, len(times), sum(times))}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,167 @@
+/* pacingpseudo_b200.h — C ABI of libpacingpseudo_b200.so (hand-written CUDA for sm_100a).
+ *
+ * Drop-in boundary for the PacingPseudo training-step hot path. The reference is pure PyTorch, so
+ * the "FFI" each entry point replaces is the torch op call site named beside it (paths relative to
+ * /root/reference). Conventions:
+ *   - every function returns 0 on success or a negative code; pp_last_error() gives the message
+ *     (thread-local); nothing throws across the boundary;
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch's allocator); the library
+ *     allocates nothing and never synchronises the host, except pp_init();
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *   - activations are NHWC of element type `dtype` (PP_DTYPE_BF16 = tcgen05 path, PP_DTYPE_F32 =
+ *     CUDA-core fp32 precision mode); logits, losses, parameters and gradients are fp32, with the
+ *     reference's layouts at the API (NCHW logits, OIHW weights).
+ *   - "G" = BatchNorm statistics groups: the weak and strong branch of the siamese step are batched
+ *     into one tensor of N = G * Ng images but keep per-branch batch statistics.
+ */
+#ifndef PACINGPSEUDO_B200_H_
+#define PACINGPSEUDO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_DTYPE_F32 0
+#define PP_DTYPE_BF16 1
+
+/* consistency-loss variants (train_chaos.py:138 --loss_cr_variants; consistency_reglur_memory.py:56-63) */
+#define PP_CR_NONE 0
+#define PP_CR_CE 1
+#define PP_CR_L1 2
+#define PP_CR_L2 3
+#define PP_CR_KL 4
+
+/* ---- library ------------------------------------------------------------------------------- */
+int pp_init(int device);                 /* selects the device, checks sm_100, resolves cuTensorMapEncodeTiled */
+const char* pp_last_error(void);
+int pp_version(void);
+/* measurement hooks (bench.py): kernels launched so far by this library; optional CUDA-event bracketing of
+ * every tcgen05 conv launch on its own stream. family 0 = conv3x3 forward/dgrad, 1 = conv3x3 wgrad.
+ * pp_profile_collect returns summed kernel milliseconds, algorithmic FLOPs and launch count (HOST pointers). */
+long long pp_launch_count(void);
+void pp_profile_enable(int on);
+void pp_profile_reset(void);
+int pp_profile_collect(int family, double* ms, double* flops, long long* launches);
+
+/* ---- whole-UNet executor (models/unet.py:10-98 UNet.__init__/forward) ------------------------- */
+typedef struct UNetPlan* pp_unet_t;
+int pp_unet_create(int input_ch, int init_ch, int max_ch, int num_classes, int output_stride, int dtype,
+                   pp_unet_t* out);
+void pp_unet_destroy(pp_unet_t u);
+int pp_unet_num_convs(pp_unet_t u);
+/* layer -> Cin, Cout, dilation and module path ("enc_block1.conv_block.conv_layer1", ...) */
+int pp_unet_conv_info(pp_unet_t u, int layer, int* cin, int* cout, int* dil, const char** name);
+long long pp_unet_workspace_bytes(pp_unet_t u, int N, int H, int W, int G);
+/* byte offset / shape of a named end point ("encoder/stage6", ... unet.py:82-97) inside the workspace */
+int pp_unet_activation(pp_unet_t u, const char* name, int N, int H, int W, int G, int* act_id, long long* offset,
+                       int* C, int* h, int* w);
+/* params: per conv layer [weight OIHW, bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+ * bn.num_batches_tracked(int64)] in pp_unet_conv_info order, then head [weight, bias].
+ * x: fp32 [N,1,H,W]; logits out: fp32 NCHW [N,num_classes,H,W]. training=1: batch statistics +
+ * running-stat update (unet.py:189 BatchNorm2d in train()), 0: running statistics. */
+int pp_unet_forward(pp_unet_t u, const float* x, void* const* params, void* workspace, int N, int H, int W, int G,
+                    int training, float* logits, void* stream);
+/* grads: per conv layer [dweight, dbias, dgamma, dbeta], head [dweight, dbias]; fp32, ACCUMULATED (+=).
+ * dfeat: optional gradients w.r.t. named end points (NHWC, activation dtype), e.g. from the aux path. */
+int pp_unet_backward(pp_unet_t u, const float* x, void* const* params, void* workspace, int N, int H, int W, int G,
+                     int training, const float* dlogits, int n_dfeat, const int* dfeat_act,
+                     const void* const* dfeat, float* const* grads, void* stream);
+
+/* ---- single operators (also used by the aux path and the op-level parity tests) --------------- */
+/* nn.Conv2d 3x3 stride 1 pad=dil (unet.py:188; aux_path_memory.py:24): y[N,H,W,oc0(+oc1)] from the virtual
+ * concat of x0[N,H,W,C0] and x1[N,H,W,C1] (unet.py:151; aux_path_memory.py:49), packed weights
+ * [9][Cout][C0+C1] (pp_pack_weights). Output columns [0,oc0) go to out0, the rest to out1 (dgrad of a
+ * concat); accN=1 adds to the destination. dtype BF16 -> tcgen05 kernel, F32 -> CUDA-core kernel. */
+int pp_conv3x3(int dtype, const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias,
+               void* out0, int oc0, int acc0, void* out1, int oc1, int acc1, int N, int H, int W, int dil,
+               void* stream);
+/* weight gradient of the same conv: dwp[9][Cout][C0+C1] fp32 += (caller zeroes) */
+int pp_conv3x3_wgrad(int dtype, const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dwp,
+                     int N, int H, int W, int dil, void* stream);
+/* CUDA-core twin of the bf16 tcgen05 kernels (test cross-check only) */
+int pp_conv3x3_reference(int dtype, const void* x0, int C0, const void* x1, int C1, const void* wpack,
+                         const float* bias, void* out0, int oc0, int acc0, void* out1, int oc1, int acc1, int N,
+                         int H, int W, int dil, void* stream);
+int pp_conv3x3_wgrad_reference(int dtype, const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1,
+                               float* dwp, int N, int H, int W, int dil, void* stream);
+/* OIHW fp32 -> forward pack wf[9][Cout][Cin] and dgrad pack wd[9][Cin][Cout] (flipped taps) */
+int pp_pack_weights(int dtype, const float* w_oihw, void* wf, void* wd, int Cout, int Cin, void* stream);
+int pp_unpack_wgrad(const float* dwp, float* g_oihw, int Cout, int Cin, int accumulate, void* stream);
+/* first conv, Cin = 1 (unet.py:28) */
+int pp_first_conv_fwd(int dtype, const float* x, const float* w, const float* bias, void* y, int N, int H, int W,
+                      int Cout, void* stream);
+int pp_first_conv_wgrad(int dtype, const void* dy, const float* x, float* dw, int N, int H, int W, int Cout,
+                        void* stream);
+/* 1x1 heads (unet.py:60 final_conv; aux_path_memory.py:32 fc_cls): NHWC in, NCHW fp32 logits out */
+int pp_head_fwd(int dtype, const void* a, const float* w, const float* bias, float* logits, long long P, int HW,
+                int Cin, int C, void* stream);
+int pp_head_bwd(int dtype, const float* dlogits, const void* a, const float* w, void* da, float* dw, float* db,
+                long long P, int HW, int Cin, int C, void* stream);
+/* BatchNorm2d + LeakyReLU(0.01) (unet.py:189-190,193). coef = [G][4][C] scale, shift, mean, rstd. */
+int pp_bn_stats(int dtype, const void* y, double* sums, int G, long long Pg, int C, void* stream);
+int pp_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, long long* num_batches_tracked, float* coef, int G, long long Pg, int C,
+                   int training, float eps, float momentum, void* stream);
+int pp_bn_apply(int dtype, const void* y, const float* coef, void* a, int G, long long Pg, int C, float slope,
+                void* stream);
+int pp_bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* bsums, float* bcoef,
+              float* dgamma, float* dbeta, float* dbias, void* dy, int G, long long Pg, int C, int training,
+              float slope, void* stream);
+/* MaxPool2d(2,2) (unet.py:109) */
+int pp_maxpool_fwd(int dtype, const void* x, void* y, int N, int H, int W, int C, void* stream);
+int pp_maxpool_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int H, int W, int C, int accumulate,
+                   void* stream);
+/* bilinear, align_corners=True (unet.py:144; aux_path_memory.py:52) */
+int pp_upsample_nhwc_fwd(int dtype, const void* x, void* y, int N, int h, int w, int H, int W, int C, void* stream);
+int pp_upsample_nhwc_bwd(int dtype, const void* gy, void* gx, int N, int h, int w, int H, int W, int C,
+                         int accumulate, void* stream);
+int pp_upsample_planes_fwd(const float* x, float* y, long long NC, int h, int w, int H, int W, void* stream);
+int pp_upsample_planes_bwd(const float* gy, float* gx, long long NC, int h, int w, int H, int W, void* stream);
+int pp_nchw_to_nhwc(int dtype, const float* src, void* dst, int N, int C, int HW, void* stream);
+int pp_nhwc_to_nchw(int dtype, const void* src, float* dst, int N, int C, int HW, void* stream);
+
+/* ---- losses (losses/losses.py) ------------------------------------------------------------------ */
+/* torch.argmax(one_hot, 1) (consistency_reglur_memory.py:31; aux_path_memory.py:55; upper_bound_chaos.py:160) */
+int pp_onehot_argmax(const float* x, uint8_t* out, int N, int K, int HW, void* stream);
+/* ONE pass: partial CE (losses.py:35-43), entropy (9-24), consistency (45-116), aux partial CE.
+ * zs / za / mask may be NULL. acc: 8 doubles of scratch kept for the backward. Each loss is written to
+ * its own fp32 scalar. */
+int pp_scribble_loss_fwd(const float* zw, const float* zs, const float* za, const uint8_t* target,
+                         const float* mask, double* acc, float* loss_pce, float* loss_ent, float* loss_cr,
+                         float* loss_aux, int N, int C, int HW, int ignore_index, int do_ent, int cr_variant,
+                         void* stream);
+int pp_scribble_loss_bwd(const float* zw, const float* zs, const float* za, const uint8_t* target,
+                         const float* mask, const double* acc, const float* g_pce, const float* g_ent,
+                         const float* g_cr, const float* g_aux, float* dzw, float* dzs, float* dza, int N, int C,
+                         int HW, int ignore_index, int do_ent, int cr_variant, int detach_weak, void* stream);
+/* stand-alone soft_label_cross_entropy_loss (a = logits, b = probabilities; losses.py:45-62), l1_loss and
+ * l2_loss (a, b = probabilities; losses.py:64-96); variant = PP_CR_CE / PP_CR_L1 / PP_CR_L2. pacc: 8 doubles. */
+int pp_pair_loss_fwd(const float* a, const float* b, const float* mask, double* pacc, float* loss, int N, int C,
+                     int HW, int variant, void* stream);
+int pp_pair_loss_bwd(const float* a, const float* b, const float* mask, const double* pacc, const float* g,
+                     float* da, float* db, int N, int C, int HW, int variant, void* stream);
+/* dice_loss_fn (losses.py:147-162). sums: [N][C][3] doubles, coef: [N][C][2] floats (kept for backward) */
+int pp_dice_fwd(const float* z, const float* label, double* sums, float* coef, float* loss, int N, int C, int HW,
+                void* stream);
+int pp_dice_bwd(const float* z, const float* label, const float* coef, const float* g, float* dz, int N, int C,
+                int HW, int accumulate, void* stream);
+/* AuxPath.memory_update (aux_path_memory.py:68-116): sample 0 only; feat = aux_features [N,h,w,hid] */
+int pp_memory_update(int dtype, const void* feat, const float* scribble, float* bank, int C, int h, int w, int H,
+                     int W, int hid, int cosine_mode, float m, float one_minus_m, void* stream);
+/* cross_entropy_loss(fc_cls(memory_bank), arange(C)) (aux_path_memory.py:61; consistency_reglur_memory.py:94) */
+int pp_memory_loss_fwd(const float* bank, const float* wfc, float* loss, float* probs, int C, int hid,
+                       void* stream);
+int pp_memory_loss_bwd(const float* bank, const float* probs, const float* g, float* dwfc, int C, int hid,
+                       void* stream);
+
+/* ---- optimizer (train_chaos.py:219 torch.optim.Adam(lr, weight_decay)) --------------------------- */
+int pp_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PACINGPSEUDO_B200_H_ */

@@ -1,0 +1,182 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the reference does not travel to the GPU box):
+    python oracle/gen_golden.py
+Inputs are NOT stored: they are regenerated from seeds by pacingpseudo_b200.synth.make_batch and
+oracle.pp_oracle.synth_state_dict (both committed), so a fixture is a few KB of outputs: the five loss
+terms, the total loss, logits samples + checksums, per-parameter gradient norms + samples, BatchNorm
+running-stat checksums, and the memory bank after each step. Records torch version in the file.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("PP_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+from oracle import pp_oracle as O  # noqa: E402
+from pacingpseudo_b200.synth import make_batch  # noqa: E402
+
+CASES = {
+    # name: dict(kind, N, C, H, W, output_stride, training, flags...)
+    "pacing_train_bn": dict(kind="pacing", N=2, C=5, H=64, W=64, os=8, training=True, cr="ce_loss", mode="cosine_similarity", steps=3),
+    "pacing_eval_bn": dict(kind="pacing", N=2, C=5, H=64, W=64, os=8, training=False, cr="ce_loss", mode="cosine_similarity", steps=2),
+    "pacing_acdc_kl_mean": dict(kind="pacing", N=3, C=4, H=56, W=56, os=8, training=True, cr="kl_loss", mode="mean", steps=2),
+    "pacing_l1_detach": dict(kind="pacing", N=3, C=2, H=64, W=64, os=8, training=True, cr="l1_loss", mode="cosine_similarity", steps=1, detach=True),
+    "pacing_l2_nomask": dict(kind="pacing", N=3, C=5, H=64, W=64, os=8, training=True, cr="l2_loss", mode="cosine_similarity", steps=1, nomask=True),
+    "baseline_pce": dict(kind="baseline", N=2, C=5, H=64, W=64, os=8, training=True),
+    "upperbound_ce_dice": dict(kind="upper", N=2, C=5, H=64, W=64, os=8, training=True),
+    "unet_os16": dict(kind="baseline", N=2, C=4, H=64, W=64, os=16, training=True),
+    "unet_os32": dict(kind="baseline", N=2, C=4, H=64, W=64, os=32, training=True),
+}
+
+
+def sample_idx(numel, k=16):
+    g = torch.Generator().manual_seed(numel % 9973 + 17)
+    return torch.randint(0, numel, (min(k, numel),), generator=g)
+
+
+def summarize(t):
+    t = t.detach().double().flatten()
+    return np.array([t.sum().item(), t.abs().sum().item(), t.norm().item()]), t[sample_idx(t.numel())].numpy()
+
+
+def build_state(case):
+    shapes = {}
+    for k, s in O.unet_param_shapes(1, 32, 512, case["C"], case["os"]).items():
+        shapes["backbone." + k if case["kind"] == "pacing" else k] = s
+    if case["kind"] == "pacing":
+        for k, s in O.aux_param_shapes(case["C"], (512, 512), 64).items():
+            shapes["aux_path." + k] = s
+    return O.synth_state_dict(shapes, seed=7)
+
+
+def ref_args(case):
+    return argparse.Namespace(
+        ignored_index=case["C"], do_loss_ent=True, do_decoder_consistency=True, detach_weak_cr=bool(case.get("detach")),
+        loss_cr_variants=case.get("cr", "ce_loss"), do_aux_path=True, do_memory=True)
+
+
+def run_reference(name, case):
+    from models.unet import UNet
+    from models.consistency_reglur_memory import ConsistencyRegulr
+    from losses import losses as RL
+    sd = build_state(case)
+    rec = {"torch_version": np.array(torch.__version__)}
+    C = case["C"]
+    if case["kind"] == "pacing":
+        model = ConsistencyRegulr(
+            kwargs_unet=dict(input_ch=1, init_ch=32, max_ch=512, num_classes=C, output_stride=case["os"],
+                             is_stride_conv=False, is_trans_conv=False, elab_end_points=True),
+            kwargs_aux_path=dict(num_classes=C, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[512, 512],
+                                 hid_ch=64, aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
+                                 ensemble_mode=case["mode"]),
+            args_parser=ref_args(case))
+    else:
+        model = UNet(1, 32, 512, C, case["os"], False, False, True)
+    model.load_state_dict(sd, strict=True)
+    model.train(case["training"])
+    for step in range(case.get("steps", 1)):
+        batch = make_batch(case["N"], C, case["H"], case["W"], seed=100 + step,
+                           absent_class_in_sample0=(1 if step == 1 else None))
+        if case.get("nomask"):
+            batch.pop("valid_mask")
+        model.zero_grad()
+        if case["kind"] == "pacing":
+            out = model({k: v for k, v in batch.items() if k != "label"}, mode="train", step=step * 37)
+            loss = O.total_loss(out, epoch=40)
+            for k in ("loss_pce", "loss_ent", "loss_cr", "loss_aux_cls", "loss_memory"):
+                rec["s%d/%s" % (step, k)] = np.array(out[k].item())
+            for k in ("segmentation/logits", "segmentation/logits_strong", "logits_aux_cls"):
+                rec["s%d/%s/sum" % (step, k)], rec["s%d/%s/samples" % (step, k)] = summarize(out[k])
+            rec["s%d/argmax_weak" % step] = out["segmentation/logits"].argmax(1).to(torch.uint8).numpy()
+        else:
+            logits = model(batch["image"])["segmentation/logits"]
+            if case["kind"] == "baseline":
+                loss = RL.partial_cross_entropy_loss(logits, batch["scribble"].argmax(1), C)
+                rec["s%d/loss_pce" % step] = np.array(loss.item())
+            else:
+                target = batch["label"].argmax(1)
+                lce = RL.partial_cross_entropy_loss(logits, target, C)
+                ldice = RL.dice_loss_fn(logits, batch["label"])
+                rec["s%d/loss_ce" % step] = np.array(lce.item())
+                rec["s%d/loss_dice" % step] = np.array(ldice.item())
+                loss = lce + ldice
+            rec["s%d/segmentation/logits/sum" % step], rec["s%d/segmentation/logits/samples" % step] = summarize(logits)
+            rec["s%d/argmax_weak" % step] = logits.argmax(1).to(torch.uint8).numpy()
+        rec["s%d/total" % step] = np.array(loss.item())
+        loss.backward()
+        names, norms, samples = [], [], []
+        for k, p in model.named_parameters():
+            if p.grad is None:
+                continue
+            names.append(k)
+            s, smp = summarize(p.grad)
+            norms.append(s)
+            samples.append(np.pad(smp, (0, 16 - len(smp))))
+        rec["s%d/grad_names" % step] = np.array(names)
+        rec["s%d/grad_sums" % step] = np.stack(norms)
+        rec["s%d/grad_samples" % step] = np.stack(samples)
+        if case["kind"] == "pacing":
+            rec["s%d/memory_bank" % step] = model.aux_path.memory_bank.detach().double().numpy().reshape(C, 64)
+    buf = {k: v for k, v in model.state_dict().items() if "running" in k}
+    rec["running_names"] = np.array(list(buf))
+    rec["running_sums"] = np.stack([summarize(v)[0] for v in buf.values()])
+    return rec
+
+
+def loss_function_vectors():
+    """Direct known-answer vectors for every called function of losses/losses.py, values and gradients."""
+    from losses import losses as RL
+    g = torch.Generator().manual_seed(5)
+    N, C, H, W = 3, 5, 9, 7
+    rec = {}
+    za = (2 * torch.randn(N, C, H, W, generator=g)).requires_grad_()
+    zb = (2 * torch.randn(N, C, H, W, generator=g)).requires_grad_()
+    mask = (torch.rand(N, 1, H, W, generator=g) > 0.3).float()
+    target = torch.randint(0, C + 1, (N, H, W), generator=g)
+    onehot = torch.nn.functional.one_hot(torch.randint(0, C, (N, H, W), generator=g), C).permute(0, 3, 1, 2).float()
+    rec["za"], rec["zb"], rec["mask"], rec["target"], rec["onehot"] = za.detach().numpy(), zb.detach().numpy(), mask.numpy(), target.numpy(), onehot.numpy()
+
+    def emit(name, fn):
+        for t in (za, zb):
+            t.grad = None
+        v = fn()
+        v.backward()
+        rec[name] = np.array(v.item())
+        rec[name + "/dza"] = za.grad.numpy().copy() if za.grad is not None else np.zeros(0)
+        rec[name + "/dzb"] = zb.grad.numpy().copy() if zb.grad is not None else np.zeros(0)
+
+    emit("pce", lambda: RL.partial_cross_entropy_loss(za, target, C))
+    emit("ce", lambda: RL.cross_entropy_loss(za, target.clamp(max=C - 1)))
+    for tag, m in (("mask", mask), ("nomask", None)):
+        emit("ent_" + tag, lambda: RL.entropy_minimization_loss(za, m))
+        emit("softce_" + tag, lambda: RL.soft_label_cross_entropy_loss(zb, torch.softmax(za, 1), m))
+        emit("l1_" + tag, lambda: RL.l1_loss(torch.softmax(zb, 1), torch.softmax(za, 1), m))
+        emit("l2_" + tag, lambda: RL.l2_loss(torch.softmax(zb, 1), torch.softmax(za, 1), m))
+        emit("kl_" + tag, lambda: RL.kl_loss(zb, za, m))
+    emit("dice", lambda: RL.dice_loss_fn(za, onehot))
+    return rec
+
+
+def main():
+    if not os.path.isdir(REF):
+        raise SystemExit("reference not found at %s" % REF)
+    sys.path.insert(0, REF)
+    torch.Tensor.cuda = lambda self, *a, **k: self  # AuxPath.__init__ calls .cuda() (aux_path_memory.py:44)
+    torch.set_num_threads(8)
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    np.savez_compressed(os.path.join(out_dir, "loss_functions.npz"), **loss_function_vectors())
+    print("wrote loss_functions.npz")
+    for name, case in CASES.items():
+        rec = run_reference(name, case)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **rec)
+        print("wrote", name, {k: float(v) for k, v in rec.items() if k.startswith("s0/loss")})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,379 @@
+"""CPU oracle for the PacingPseudo training-step hot path — TEST INFRASTRUCTURE ONLY.
+
+A from-scratch, functional restatement (plain torch CPU tensor arithmetic on a state dict, fp32 or
+fp64) of the reference algorithm. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; the product path (pacingpseudo_b200/) never does.
+
+Pinning: the reference ships no tests or golden vectors, so the pin is the reference
+itself run in the build container: oracle/gen_golden.py imports /root/reference, runs it on seeded
+synthetic inputs and commits the outputs to tests/golden/; tests/test_oracle.py checks this restatement
+against those vectors (and, where /root/reference is present, against the live reference).
+
+Every function cites the reference lines it restates (paths relative to /root/reference).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+EPS_BN = 1e-5
+MOM_BN = 0.1
+SLOPE = 1e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# network structure (models/unet.py:10-60)
+# ------------------------------------------------------------------------------------------------
+def unet_structure(init_ch=32, max_ch=512, output_stride=8):
+    """-> (channels per stage, encoder [(pool?, dilation)] x6, decoder scales for stages 5..1)."""
+    ch = [min(max_ch, 2 ** k * init_ch) for k in range(6)]
+    if output_stride == 32:
+        enc = [(False, 1), (True, 1), (True, 1), (True, 1), (True, 1), (True, 1)]
+        scales = [2, 2, 2, 2, 2]
+    elif output_stride == 16:
+        enc = [(False, 1), (True, 1), (True, 1), (True, 1), (True, 1), (False, 2)]
+        scales = [1, 2, 2, 2, 2]
+    else:
+        enc = [(False, 1), (True, 1), (True, 1), (True, 1), (False, 2), (False, 4)]
+        scales = [1, 1, 2, 2, 2]
+    return ch, enc, scales
+
+
+def unet_param_shapes(input_ch=1, init_ch=32, max_ch=512, num_classes=5, output_stride=8):
+    """Ordered {state-dict key: shape} of models.unet.UNet (165-entry ConsistencyRegulr minus aux)."""
+    ch, _enc, _sc = unet_structure(init_ch, max_ch, output_stride)
+    shapes = {}
+
+    def conv_layer(prefix, cin, cout):
+        shapes[prefix + '.conv.weight'] = (cout, cin, 3, 3)
+        shapes[prefix + '.conv.bias'] = (cout,)
+        shapes[prefix + '.norm_op.weight'] = (cout,)
+        shapes[prefix + '.norm_op.bias'] = (cout,)
+        shapes[prefix + '.norm_op.running_mean'] = (cout,)
+        shapes[prefix + '.norm_op.running_var'] = (cout,)
+        shapes[prefix + '.norm_op.num_batches_tracked'] = ()
+
+    def block(name, cin, cout):
+        conv_layer(name + '.conv_block.conv_layer1', cin, cout)
+        conv_layer(name + '.conv_block.conv_layer2', cout, cout)
+
+    cin = input_ch
+    for k in range(6):
+        block('enc_block%d' % (k + 1), cin, ch[k])
+        cin = ch[k]
+    for stage in (5, 4, 3, 2, 1):  # DecBlock(lower, skip, .): DoubleConv(lower + skip, skip), unet.py:145
+        lower = ch[stage]
+        skip = ch[stage - 1]
+        block('dec_block%d' % stage, lower + skip, skip)
+    shapes['final_conv.weight'] = (num_classes, ch[0], 1, 1)
+    shapes['final_conv.bias'] = (num_classes,)
+    return shapes
+
+
+def aux_param_shapes(num_classes=5, feat_ch=(512, 512), hid_ch=64):
+    """aux_path_memory.py:22-43."""
+    return {
+        'layer_bottleneck.1.weight': (hid_ch, sum(feat_ch), 3, 3),
+        'layer_bottleneck.1.bias': (hid_ch,),
+        'layer_bottleneck.2.weight': (hid_ch,),
+        'layer_bottleneck.2.bias': (hid_ch,),
+        'layer_bottleneck.2.running_mean': (hid_ch,),
+        'layer_bottleneck.2.running_var': (hid_ch,),
+        'layer_bottleneck.2.num_batches_tracked': (),
+        'fc_cls.1.weight': (num_classes, hid_ch, 1, 1),
+        'memory_bank': (num_classes, hid_ch, 1, 1),
+    }
+
+
+def synth_state_dict(shapes, seed, dtype=torch.float32):
+    """Deterministic, reference-independent parameter values (so fixtures need not ship 80 MB of weights)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in shapes.items():
+        if k.endswith('num_batches_tracked'):
+            sd[k] = torch.zeros((), dtype=torch.long)
+        elif k.endswith('running_var'):
+            sd[k] = (0.5 + torch.rand(shp, generator=g)).to(dtype)
+        elif k.endswith('running_mean'):
+            sd[k] = (0.1 * torch.randn(shp, generator=g)).to(dtype)
+        elif k.endswith('norm_op.weight') or k.endswith('layer_bottleneck.2.weight'):
+            sd[k] = (1.0 + 0.1 * torch.randn(shp, generator=g)).to(dtype)
+        elif k.endswith('.bias'):
+            sd[k] = (0.05 * torch.randn(shp, generator=g)).to(dtype)
+        elif k == 'memory_bank':
+            sd[k] = torch.zeros(shp, dtype=dtype)
+        else:
+            fan_in = shp[1] * shp[2] * shp[3]
+            sd[k] = (torch.randn(shp, generator=g) * math.sqrt(2.0 / fan_in)).to(dtype)
+    return sd
+
+
+# ------------------------------------------------------------------------------------------------
+# layers
+# ------------------------------------------------------------------------------------------------
+def conv_bn_lrelu(x, sd, prefix, dilation, training):
+    """ConvLayer (unet.py:178-193): Conv2d(3x3, pad=dil, bias) -> BatchNorm2d -> LeakyReLU(0.01).
+    Running statistics in `sd` are updated in place when training (momentum 0.1, unbiased variance)."""
+    y = F.conv2d(x, sd[prefix + '.conv.weight'], sd[prefix + '.conv.bias'], 1, dilation, dilation)
+    g, b = sd[prefix + '.norm_op.weight'], sd[prefix + '.norm_op.bias']
+    rm, rv = sd[prefix + '.norm_op.running_mean'], sd[prefix + '.norm_op.running_var']
+    if training:
+        mean = y.mean(dim=(0, 2, 3))
+        var = y.var(dim=(0, 2, 3), unbiased=False)
+        n = y.numel() // y.shape[1]
+        with torch.no_grad():
+            rm.mul_(1 - MOM_BN).add_(MOM_BN * mean.detach().to(rm.dtype))
+            rv.mul_(1 - MOM_BN).add_(MOM_BN * (var.detach() * n / max(n - 1, 1)).to(rv.dtype))
+            sd[prefix + '.norm_op.num_batches_tracked'] += 1
+    else:
+        mean, var = rm.to(y.dtype), rv.to(y.dtype)
+    yhat = (y - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + EPS_BN)
+    z = yhat * g[None, :, None, None] + b[None, :, None, None]
+    return torch.where(z > 0, z, z * SLOPE)
+
+
+def double_conv(x, sd, prefix, dilation, training):
+    x = conv_bn_lrelu(x, sd, prefix + '.conv_block.conv_layer1', dilation, training)
+    return conv_bn_lrelu(x, sd, prefix + '.conv_block.conv_layer2', dilation, training)
+
+
+def upsample_bilinear_ac(x, size):
+    """nn.Upsample(bilinear, align_corners=True) (unet.py:144) restated with explicit gather weights:
+    src = dst * (in - 1) / (out - 1); lerp between floor(src) and min(floor(src) + 1, in - 1)."""
+    n, c, h, w = x.shape
+    H, W = size
+
+    def axis(inp, out):
+        scale = (inp - 1) / (out - 1) if out > 1 else 0.0
+        src = torch.arange(out, dtype=torch.float32) * torch.tensor(scale, dtype=torch.float32)
+        i0 = src.floor().long().clamp(max=inp - 1)
+        i1 = (i0 + 1).clamp(max=inp - 1)
+        w1 = (src - i0.to(torch.float32)).to(x.dtype)
+        return i0, i1, 1 - w1, w1
+
+    y0, y1, wy0, wy1 = axis(h, H)
+    x0, x1, wx0, wx1 = axis(w, W)
+    top = x[:, :, y0][:, :, :, x0] * wx0 + x[:, :, y0][:, :, :, x1] * wx1
+    bot = x[:, :, y1][:, :, :, x0] * wx0 + x[:, :, y1][:, :, :, x1] * wx1
+    return top * wy0[:, None] + bot * wy1[:, None]
+
+
+def unet_forward(sd, x, training, init_ch=32, max_ch=512, output_stride=8, prefix=''):
+    """UNet.forward (unet.py:62-98) -> dict of the 12 end points."""
+    _ch, enc_cfg, scales = unet_structure(init_ch, max_ch, output_stride)
+    ep = {}
+    enc = []
+    cur = x
+    for k, (pool, dil) in enumerate(enc_cfg):
+        if pool:
+            cur = F.max_pool2d(cur, 2, 2)  # unet.py:109
+        cur = double_conv(cur, sd, '%senc_block%d' % (prefix, k + 1), dil, training)
+        enc.append(cur)
+        ep['encoder/stage%d' % (k + 1)] = cur
+    for i, stage in enumerate((5, 4, 3, 2, 1)):
+        skip = enc[stage - 1]
+        s = scales[i]
+        up = upsample_bilinear_ac(cur, (cur.shape[2] * s, cur.shape[3] * s)) if s > 1 else cur
+        cur = double_conv(torch.cat((up, skip), 1), sd, '%sdec_block%d' % (prefix, stage), 1, training)  # :151
+        ep['decoder/stage%d' % stage] = cur
+    ep['segmentation/logits'] = F.conv2d(cur, sd[prefix + 'final_conv.weight'], sd[prefix + 'final_conv.bias'])
+    return ep
+
+
+# ------------------------------------------------------------------------------------------------
+# losses (losses/losses.py)
+# ------------------------------------------------------------------------------------------------
+def _masked_mean(loss, valid_mask):
+    """losses.py:19-23 / 57-61: sum(loss * mask) / max(sum(mask), 1e-8), else the element mean."""
+    if valid_mask is not None:
+        return (loss * valid_mask).sum() / valid_mask.sum().clamp(min=1e-8)
+    return loss.mean()
+
+
+def partial_cross_entropy(logits, target, ignore_index):
+    """losses.py:35-43: mean over pixels with target != ignore_index of -log softmax(z)[target]."""
+    logp = torch.log_softmax(logits, 1)
+    keep = target != ignore_index
+    t = target.clamp(0, logits.shape[1] - 1)
+    nll = -logp.gather(1, t[:, None]).squeeze(1)
+    return (nll * keep).sum() / keep.sum()
+
+
+def entropy_minimization(logits, valid_mask=None):
+    """losses.py:9-24."""
+    return _masked_mean(-torch.softmax(logits, 1) * torch.log_softmax(logits, 1), valid_mask)
+
+
+def soft_label_cross_entropy(logits, target_prob, valid_mask=None):
+    """losses.py:45-62."""
+    return _masked_mean(-target_prob * torch.log_softmax(logits, 1), valid_mask)
+
+
+def l1(p, q, valid_mask=None):
+    """losses.py:64-79."""
+    return _masked_mean((p - q).abs().sum(1, keepdim=True), valid_mask)
+
+
+def l2(p, q, valid_mask=None):
+    """losses.py:81-96."""
+    return _masked_mean(((p - q) ** 2).sum(1, keepdim=True), valid_mask)
+
+
+def kl(logits_in, logits_tgt, valid_mask=None):
+    """losses.py:98-116: exp(t) * (t - i) elementwise on log-probabilities."""
+    i, t = torch.log_softmax(logits_in, 1), torch.log_softmax(logits_tgt, 1)
+    return _masked_mean(t.exp() * (t - i), valid_mask)
+
+
+def dice(logits, onehot):
+    """losses.py:147-162."""
+    p = torch.softmax(logits, 1).flatten(2)
+    t = onehot.flatten(2).to(p.dtype)
+    return -(2 * (p * t).sum(2) / (p.sum(2) + t.sum(2) + 1e-5)).mean()
+
+
+# ------------------------------------------------------------------------------------------------
+# aux path + memory bank (models/aux_path_memory.py)
+# ------------------------------------------------------------------------------------------------
+def ramp_up_mo(step, max_step, base_mo=0.9, gamma=0.9):
+    """aux_path_memory.py:118-120."""
+    return (1 - step / max_step) ** gamma * base_mo
+
+
+def aux_forward(sd, feats, out_hw, training, prefix='aux_path.'):
+    """aux_path_memory.py:49-52 (Dropout2d(p=0) is the identity)."""
+    x = torch.cat(feats, 1)
+    y = F.conv2d(x, sd[prefix + 'layer_bottleneck.1.weight'], sd[prefix + 'layer_bottleneck.1.bias'], 1, 1)
+    g, b = sd[prefix + 'layer_bottleneck.2.weight'], sd[prefix + 'layer_bottleneck.2.bias']
+    rm, rv = sd[prefix + 'layer_bottleneck.2.running_mean'], sd[prefix + 'layer_bottleneck.2.running_var']
+    if training:
+        mean, var = y.mean(dim=(0, 2, 3)), y.var(dim=(0, 2, 3), unbiased=False)
+        n = y.numel() // y.shape[1]
+        with torch.no_grad():
+            rm.mul_(1 - MOM_BN).add_(MOM_BN * mean.detach().to(rm.dtype))
+            rv.mul_(1 - MOM_BN).add_(MOM_BN * (var.detach() * n / max(n - 1, 1)).to(rv.dtype))
+            sd[prefix + 'layer_bottleneck.2.num_batches_tracked'] += 1
+    else:
+        mean, var = rm.to(y.dtype), rv.to(y.dtype)
+    z = (y - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + EPS_BN)
+    z = z * g[None, :, None, None] + b[None, :, None, None]
+    aux_features = torch.where(z > 0, z, z * SLOPE)
+    low = F.conv2d(aux_features, sd[prefix + 'fc_cls.1.weight'])
+    return upsample_bilinear_ac(low, out_hw), aux_features
+
+
+@torch.no_grad()
+def memory_update(bank, aux_features, scribble, step, max_step, momentum=0.9, mode='cosine_similarity'):
+    """aux_path_memory.py:68-116 in closed form. Visits sample 0 only (the reference returns inside the
+    per-sample loop). bank: (C, hid, 1, 1), updated in place."""
+    C, hid = bank.shape[0], bank.shape[1]
+    H, W = scribble.shape[-2:]
+    emb = upsample_bilinear_ac(aux_features[:1], (H, W))[0].permute(1, 2, 0).reshape(H * W, hid)
+    m = ramp_up_mo(step, max_step, momentum)
+    for c in range(C):
+        sel = scribble[0, c].reshape(-1) == 1
+        if not bool(sel.any()):
+            continue
+        e = emb[sel]
+        row = bank[c, :, 0, 0]
+        if bool((row == 0).all()):
+            bank[c, :, 0, 0] = e.mean(0)
+            continue
+        if mode == 'mean':
+            upd = e.mean(0)
+            base = row
+        else:
+            e = e / (e.pow(2).sum(1, keepdim=True).sqrt() + 1e-8)
+            base = row / (row.pow(2).sum().sqrt() + 1e-8)
+            wgt = 1 - (e * base[None]).sum(1, keepdim=True)
+            wgt = wgt / (wgt.sum() + 1e-8)
+            upd = (e * wgt).sum(0)
+        bank[c, :, 0, 0] = (1 - m) * base + m * upd
+
+
+# ------------------------------------------------------------------------------------------------
+# the pacingpseudo step (models/consistency_reglur_memory.py:24-102)
+# ------------------------------------------------------------------------------------------------
+class StepConfig:
+    def __init__(self, num_classes=5, ignored_index=5, do_loss_ent=True, do_decoder_consistency=True,
+                 detach_weak_cr=False, loss_cr_variants='ce_loss', do_aux_path=True, do_memory=True,
+                 feat_stage=('encoder/stage6', 'encoder/stage5'), max_step=400, update_momentum=0.9,
+                 ensemble_mode='cosine_similarity', init_ch=32, max_ch=512, output_stride=8):
+        self.__dict__.update(locals())
+        del self.__dict__['self']
+
+
+def consistency_forward(sd, batch, cfg, mode='train', step=0, training=True):
+    """ConsistencyRegulr.forward. `sd` keys carry the `backbone.` / `aux_path.` prefixes of the reference
+    state dict. `training` is the module's BatchNorm mode (train_chaos.py never re-enters .train())."""
+    net = cfg
+    out = {}
+    kw = dict(init_ch=net.init_ch, max_ch=net.max_ch, output_stride=net.output_stride, prefix='backbone.')
+    ep = unet_forward(sd, batch['image'], training, **kw)
+    zw = ep['segmentation/logits']
+    target = batch['scribble'].argmax(1)
+    out['segmentation/logits'] = zw
+    out['loss_pce'] = partial_cross_entropy(zw, target, net.ignored_index)
+    mask = batch.get('valid_mask')
+    if mode == 'train' and net.do_loss_ent:
+        out['loss_ent'] = entropy_minimization(zw, mask)
+    if mode == 'train' and net.do_decoder_consistency:
+        ep = unet_forward(sd, batch['image_strong'], training, **kw)  # the end-point dict is overwritten (T1)
+        zs = ep['segmentation/logits']
+        pw = torch.softmax(zw, 1)
+        if net.detach_weak_cr:
+            pw = pw.detach()
+        v = net.loss_cr_variants
+        if v == 'ce_loss':
+            out['loss_cr'] = soft_label_cross_entropy(zs, pw, mask)
+        elif v == 'l1_loss':
+            out['loss_cr'] = l1(torch.softmax(zs, 1), pw, mask)
+        elif v == 'l2_loss':
+            out['loss_cr'] = l2(torch.softmax(zs, 1), pw, mask)
+        elif v == 'kl_loss':
+            out['loss_cr'] = kl(zs, zw, mask)
+        else:
+            raise ValueError('The loss is not implemented.')
+        out['segmentation/logits_strong'] = zs
+    if mode == 'train' and net.do_aux_path:
+        feats = [ep[s] for s in net.feat_stage]
+        za, aux_features = aux_forward(sd, feats, batch['scribble'].shape[-2:], training)
+        out['logits_aux_cls'] = za
+        out['loss_aux_cls'] = partial_cross_entropy(za, target, net.ignored_index)
+        if net.do_memory:
+            memory_update(sd['aux_path.memory_bank'], aux_features.detach(), batch['scribble'], step, net.max_step,
+                          net.update_momentum, net.ensemble_mode)
+            lm = F.conv2d(sd['aux_path.memory_bank'], sd['aux_path.fc_cls.1.weight'])[:, :, 0, 0]
+            out['loss_memory'] = partial_cross_entropy(lm, torch.arange(lm.shape[0]), -100)
+    return out
+
+
+def gaussian_ramp_up(t, base_value, max_t=80, scale=5.0):
+    """utils/utils.py:53-65."""
+    return base_value * math.exp(-scale * (1 - t / max_t)) if t < max_t else base_value
+
+
+def total_loss(out, epoch, loss_ent_weight=1.0, loss_cr_weight=1.0, loss_aux_weight=0.01, loss_memory_weight=1.0,
+               ramp_up_scale=8.0):
+    """Loss weighting of train_chaos.py:273-310 (non-mutating restatement)."""
+    loss = out['loss_pce']
+    if 'loss_ent' in out:
+        loss = loss + out['loss_ent'] * gaussian_ramp_up(epoch, loss_ent_weight, scale=ramp_up_scale)
+    if 'loss_cr' in out:
+        loss = loss + out['loss_cr'] * gaussian_ramp_up(epoch, loss_cr_weight, scale=ramp_up_scale)
+    if 'loss_aux_cls' in out:
+        loss = loss + out['loss_aux_cls'] * loss_aux_weight
+    if 'loss_memory' in out:
+        loss = loss + out['loss_memory'] * loss_memory_weight
+    return loss
+
+
+def adam_step(params, grads, state, lr, weight_decay, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    """torch.optim.Adam with L2 weight decay folded into the gradient (train_chaos.py:219)."""
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    for k, p in params.items():
+        g = grads[k] + weight_decay * p
+        m, v = state.setdefault(k, (torch.zeros_like(p), torch.zeros_like(p)))
+        m.mul_(beta1).add_((1 - beta1) * g)
+        v.mul_(beta2).add_((1 - beta2) * g * g)
+        p.sub_((lr / bc1) * m / (v.sqrt() / math.sqrt(bc2) + eps))

@@ -2,7 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "pp_common.cuh"
 
@@ -26,6 +28,53 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 
 int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+struct ProfRec { cudaEvent_t a, b; double flops; int family; };
+static std::vector<ProfRec> g_prof;
+static size_t g_prof_used = 0;
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+
+void prof_enable(int on) { g_prof_on.store(on); }
+int prof_begin(int family, double flops, cudaStream_t s) {
+  if (!g_prof_on.load()) return -1;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof_used == g_prof.size()) {
+    ProfRec r{};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+    g_prof.push_back(r);
+  }
+  ProfRec& r = g_prof[g_prof_used];
+  r.flops = flops;
+  r.family = family;
+  cudaEventRecord(r.a, s);
+  return static_cast<int>(g_prof_used++);
+}
+void prof_end(int slot, cudaStream_t s) {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[slot].b, s);
+}
+int prof_collect(int family, double* ms, double* flops, long long* launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  *ms = 0; *flops = 0; *launches = 0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    if (g_prof[i].family != family) continue;
+    PP_CHECK_CUDA(cudaEventSynchronize(g_prof[i].b));
+    float t = 0.f;
+    PP_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b));
+    *ms += t; *flops += g_prof[i].flops; *launches += 1;
+  }
+  return PP_OK;
+}
+void prof_reset() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_used = 0;
+}
 
 int init_device(int device) {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -365,7 +365,10 @@ static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CU
                                        200 * 1024 + 1024 + 256));
     attr_set = true;
   }
+  const double flops = 2.0 * p.N * p.H * p.W * 9.0 * p.ctot * (p.outc0 + p.outc1);
+  const int slot = prof_begin(PROF_CONV, flops, stream);
   conv3x3_tc_kernel<BLOCK_N, BK><<<dim3(m_tiles, n_tiles), kTcThreads, smem, stream>>>(a0, a1, b, p);
+  prof_end(slot, stream);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -433,7 +436,10 @@ static int launch_wgrad_tc(const CUtensorMap& dy, const CUtensorMap& x0, const C
                                        200 * 1024 + 1024 + 256));
     attr_set = true;
   }
+  const double flops = 2.0 * p.N * p.H * p.W * 9.0 * (p.C0 + p.C1) * p.Cout;
+  const int slot = prof_begin(PROF_WGRAD, flops, stream);
   conv3x3_wgrad_tc_kernel<BLOCK_N><<<grid, kTcThreads, smem, stream>>>(dy, x0, x1, p);
+  prof_end(slot, stream);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

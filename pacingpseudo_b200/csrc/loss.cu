@@ -1,0 +1,680 @@
+// loss.cu — the loss side of the PacingPseudo step as fused, HBM-bound passes over fp32 NCHW logits:
+//   * one-hot -> uint8 index map (torch.argmax(scribble, 1), consistency_reglur_memory.py:31)
+//   * ONE kernel for partial CE + entropy + branch consistency (+ aux partial CE), forward and backward
+//     (losses.py:9-24, 35-43, 45-62, 64-116; call sites consistency_reglur_memory.py:32,41,56-63,81)
+//   * Dice (losses.py:147-162), memory-bank update (aux_path_memory.py:68-116, sample 0 only),
+//     bank classification loss (consistency_reglur_memory.py:94).
+// Thread = pixel; per-class planes are read with unit stride across the warp (coalesced).
+#include "pp_common.cuh"
+
+namespace pp {
+
+constexpr int kMaxC = 8;
+
+static inline int grid_for_px(long long work, int block) {
+  long long g = ceil_div_ll(work, block);
+  long long cap = static_cast<long long>(sm_count()) * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+// ---------------------------------------------------------------------------------------------
+// argmax over K channels of a one-hot / soft fp32 NCHW tensor -> uint8 (first maximum wins)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) onehot_argmax_kernel(const float* __restrict__ x, uint8_t* __restrict__ out,
+                                                            long long P, int HW, int K) {
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = p / HW, hw = p % HW;
+    const float* b = x + n * K * HW + hw;
+    float best = b[0];
+    int bi = 0;
+    for (int k = 1; k < K; ++k) {
+      const float v = b[static_cast<long long>(k) * HW];
+      if (v > best) { best = v; bi = k; }
+    }
+    out[p] = static_cast<uint8_t>(bi);
+  }
+}
+int onehot_argmax(const float* x, uint8_t* out, int N, int K, int HW, cudaStream_t s) {
+  PP_REQUIRE(K >= 1 && K <= 255, "onehot_argmax: K=%d unsupported", K);
+  const long long P = static_cast<long long>(N) * HW;
+  onehot_argmax_kernel<<<grid_for_px(P, 256), 256, 0, s>>>(x, out, P, HW, K);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused scribble loss
+// ---------------------------------------------------------------------------------------------
+enum : int { CR_NONE = 0, CR_CE = 1, CR_L1 = 2, CR_L2 = 3, CR_KL = 4 };
+// accumulator slots (double)
+enum : int { ACC_PCE = 0, ACC_NLAB = 1, ACC_ENT = 2, ACC_MASK = 3, ACC_CR = 4, ACC_AUX = 5, ACC_SLOTS = 8 };
+
+struct Softmax {
+  float p[kMaxC], lp[kMaxC];
+};
+__device__ __forceinline__ void load_softmax(const float* __restrict__ z, long long HW, int C, Softmax& s) {
+  float v[kMaxC];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c)
+    if (c < C) { v[c] = z[c * HW]; mx = fmaxf(mx, v[c]); }
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c)
+    if (c < C) { s.p[c] = __expf(v[c] - mx); sum += s.p[c]; }
+  const float inv = 1.f / sum, lse = mx + __logf(sum);
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c)
+    if (c < C) { s.p[c] *= inv; s.lp[c] = v[c] - lse; }
+    else { s.p[c] = 0.f; s.lp[c] = 0.f; }
+}
+__device__ __forceinline__ float sgn(float v) { return (v > 0.f) - (v < 0.f); }
+
+__device__ __forceinline__ float cr_pixel(int variant, int C, const Softmax& w, const Softmax& s) {
+  float L = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c)
+    if (c < C) {
+      if (variant == CR_CE) L -= w.p[c] * s.lp[c];
+      else if (variant == CR_L1) L += fabsf(s.p[c] - w.p[c]);
+      else if (variant == CR_L2) { const float d = s.p[c] - w.p[c]; L = fmaf(d, d, L); }
+      else if (variant == CR_KL) L += w.p[c] * (w.lp[c] - s.lp[c]);
+    }
+  return L;
+}
+
+__device__ __forceinline__ void block_accumulate(float (&v)[6], double* __restrict__ acc) {
+  __shared__ float red[6][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float r = warp_sum(v[k]);
+    if (lane == 0) red[k][warp] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += static_cast<double>(red[threadIdx.x][w]);
+    atomicAdd(acc + threadIdx.x, t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+scribble_loss_fwd_kernel(const float* __restrict__ zw, const float* __restrict__ zs, const float* __restrict__ za,
+                         const uint8_t* __restrict__ target, const float* __restrict__ mask, double* __restrict__ acc,
+                         long long P, int HW, int C, int ignore_index, int do_ent, int cr_variant) {
+  float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = p / HW, hw = p % HW;
+    const long long off = n * C * HW + hw;
+    Softmax w;
+    load_softmax(zw + off, HW, C, w);
+    const int t = target ? target[p] : ignore_index;
+    const bool lab = (target != nullptr) && (t != ignore_index) && (t < C);
+    const float m = mask ? mask[p] : 1.f;
+    if (lab) {
+      float lpt = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) lpt = (c == t) ? w.lp[c] : lpt;
+      part[ACC_PCE] -= lpt;
+      part[ACC_NLAB] += 1.f;
+    }
+    part[ACC_MASK] += m;
+    if (do_ent) {
+      float H = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c)
+        if (c < C) H -= w.p[c] * w.lp[c];
+      part[ACC_ENT] += m * H;
+    }
+    if (cr_variant != CR_NONE) {
+      Softmax s;
+      load_softmax(zs + off, HW, C, s);
+      part[ACC_CR] += m * cr_pixel(cr_variant, C, w, s);
+    }
+    if (za != nullptr && lab) {
+      Softmax a;
+      load_softmax(za + off, HW, C, a);
+      float lpt = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) lpt = (c == t) ? a.lp[c] : lpt;
+      part[ACC_AUX] -= lpt;
+    }
+  }
+  block_accumulate(part, acc);
+}
+
+// Normalisers (losses.py:21-23,58-61,75-78): with a mask  sum / max(sum(mask), 1e-8); without, the
+// element mean: N*C*H*W elements for entropy / ce / kl, N*H*W for l1 / l2 (keepdim channel sum).
+__device__ __forceinline__ double masked_denom(const double* acc, int has_mask, double nelem) {
+  return has_mask ? fmax(acc[ACC_MASK], 1e-8) : nelem;
+}
+
+__global__ void scribble_loss_finalize_kernel(const double* __restrict__ acc, float* loss_pce, float* loss_ent,
+                                              float* loss_cr, float* loss_aux, long long P, int C, int has_mask,
+                                              int cr_variant) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double nlab = acc[ACC_NLAB];
+  if (loss_pce) *loss_pce = static_cast<float>(acc[ACC_PCE] / nlab);  // 0/0 -> NaN like torch (all ignored)
+  if (loss_aux) *loss_aux = static_cast<float>(acc[ACC_AUX] / nlab);
+  if (loss_ent) *loss_ent = static_cast<float>(acc[ACC_ENT] / masked_denom(acc, has_mask, double(P) * C));
+  if (loss_cr) {
+    const double ne = (cr_variant == CR_L1 || cr_variant == CR_L2) ? double(P) : double(P) * C;
+    *loss_cr = static_cast<float>(acc[ACC_CR] / masked_denom(acc, has_mask, ne));
+  }
+}
+
+int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const uint8_t* target, const float* mask,
+                      double* acc, float* loss_pce, float* loss_ent, float* loss_cr, float* loss_aux, int N, int C,
+                      int HW, int ignore_index, int do_ent, int cr_variant, cudaStream_t s) {
+  PP_REQUIRE(C >= 1 && C <= kMaxC, "scribble_loss: num_classes=%d unsupported (max %d)", C, kMaxC);
+  PP_REQUIRE(cr_variant >= CR_NONE && cr_variant <= CR_KL, "scribble_loss: bad consistency variant %d", cr_variant);
+  PP_REQUIRE((cr_variant == CR_NONE) == (zs == nullptr), "scribble_loss: strong logits / variant mismatch");
+  const long long P = static_cast<long long>(N) * HW;
+  PP_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ACC_SLOTS, s));
+  scribble_loss_fwd_kernel<<<grid_for_px(P, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, P, HW, C, ignore_index,
+                                                               do_ent, cr_variant);
+  scribble_loss_finalize_kernel<<<1, 32, 0, s>>>(acc, loss_pce, do_ent ? loss_ent : nullptr,
+                                                 cr_variant != CR_NONE ? loss_cr : nullptr,
+                                                 za != nullptr ? loss_aux : nullptr, P, C, mask != nullptr, cr_variant);
+  PP_LAUNCH_CHECK_N(2);
+  return PP_OK;
+}
+
+__global__ void __launch_bounds__(256)
+scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__ zs, const float* __restrict__ za,
+                         const uint8_t* __restrict__ target, const float* __restrict__ mask,
+                         const double* __restrict__ acc, const float* __restrict__ g_pce,
+                         const float* __restrict__ g_ent, const float* __restrict__ g_cr,
+                         const float* __restrict__ g_aux, float* __restrict__ dzw, float* __restrict__ dzs,
+                         float* __restrict__ dza, long long P, int HW, int C, int ignore_index, int do_ent,
+                         int cr_variant, int detach_weak) {
+  const float gp = g_pce ? *g_pce : 0.f, ge = (do_ent && g_ent) ? *g_ent : 0.f;
+  const float gc = (cr_variant != CR_NONE && g_cr) ? *g_cr : 0.f, ga = (za && g_aux) ? *g_aux : 0.f;
+  const int has_mask = mask != nullptr;
+  const double nlab = acc[ACC_NLAB];
+  const float inv_lab = nlab > 0.0 ? static_cast<float>(1.0 / nlab) : 0.f;
+  const float inv_ent = static_cast<float>(1.0 / masked_denom(acc, has_mask, double(P) * C));
+  const double ne = (cr_variant == CR_L1 || cr_variant == CR_L2) ? double(P) : double(P) * C;
+  const float inv_cr = static_cast<float>(1.0 / masked_denom(acc, has_mask, ne));
+  const bool weak_gets_cr = (cr_variant == CR_KL) || !detach_weak;
+
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = p / HW, hw = p % HW;
+    const long long off = n * C * HW + hw;
+    Softmax w;
+    load_softmax(zw + off, HW, C, w);
+    const int t = target ? target[p] : ignore_index;
+    const bool lab = (target != nullptr) && (t != ignore_index) && (t < C);
+    const float m = mask ? mask[p] : 1.f;
+    float d[kMaxC];
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) d[c] = lab ? gp * inv_lab * (w.p[c] - (c == t ? 1.f : 0.f)) : 0.f;
+    if (do_ent) {
+      float H = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c)
+        if (c < C) H -= w.p[c] * w.lp[c];
+      const float k = ge * m * inv_ent;
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) d[c] -= k * w.p[c] * (w.lp[c] + H);
+    }
+    if (cr_variant != CR_NONE) {
+      Softmax s;
+      load_softmax(zs + off, HW, C, s);
+      const float k = gc * m * inv_cr;
+      float ds[kMaxC];
+      if (cr_variant == CR_CE || cr_variant == CR_KL) {
+        const float L = cr_pixel(cr_variant, C, w, s);
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) {
+          ds[c] = k * (s.p[c] - w.p[c]);
+          if (weak_gets_cr) {
+            if (cr_variant == CR_CE) d[c] -= k * w.p[c] * (s.lp[c] + L);
+            else d[c] += k * w.p[c] * ((w.lp[c] - s.lp[c]) - L);
+          }
+        }
+      } else {
+        float e[kMaxC], es = 0.f, ew = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) {
+          const float df = s.p[c] - w.p[c];
+          e[c] = (c < C) ? (cr_variant == CR_L1 ? sgn(df) : 2.f * df) : 0.f;
+          es = fmaf(e[c], s.p[c], es);
+          ew = fmaf(e[c], w.p[c], ew);
+        }
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) {
+          ds[c] = k * s.p[c] * (e[c] - es);
+          if (weak_gets_cr) d[c] += k * w.p[c] * (ew - e[c]);
+        }
+      }
+      if (dzs != nullptr) {
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c)
+          if (c < C) dzs[off + c * static_cast<long long>(HW)] = ds[c];
+      }
+    }
+    if (dzw != nullptr) {
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c)
+        if (c < C) dzw[off + c * static_cast<long long>(HW)] = d[c];
+    }
+    if (za != nullptr && dza != nullptr) {
+      if (lab) {
+        Softmax a;
+        load_softmax(za + off, HW, C, a);
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c)
+          if (c < C) dza[off + c * static_cast<long long>(HW)] = ga * inv_lab * (a.p[c] - (c == t ? 1.f : 0.f));
+      } else {
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c)
+          if (c < C) dza[off + c * static_cast<long long>(HW)] = 0.f;
+      }
+    }
+  }
+}
+
+int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const uint8_t* target, const float* mask,
+                      const double* acc, const float* g_pce, const float* g_ent, const float* g_cr, const float* g_aux,
+                      float* dzw, float* dzs, float* dza, int N, int C, int HW, int ignore_index, int do_ent,
+                      int cr_variant, int detach_weak, cudaStream_t s) {
+  PP_REQUIRE(C >= 1 && C <= kMaxC, "scribble_loss_bwd: num_classes=%d unsupported", C);
+  const long long P = static_cast<long long>(N) * HW;
+  scribble_loss_bwd_kernel<<<grid_for_px(P, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent, g_cr, g_aux,
+                                                               dzw, dzs, dza, P, HW, C, ignore_index, do_ent, cr_variant,
+                                                               detach_weak);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stand-alone pair losses on probability tensors, for the reference's free functions
+// soft_label_cross_entropy_loss (a = logits, b = target probabilities; losses.py:45-62),
+// l1_loss / l2_loss (a, b = probabilities; losses.py:64-96). pacc: [0] = sum m*L, [1] = sum m.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pair_denom(const double* pacc, int has_mask, long long P, int C, int variant) {
+  if (has_mask) return fmax(pacc[1], 1e-8);
+  return variant == CR_CE ? double(P) * C : double(P);
+}
+__global__ void __launch_bounds__(256) pair_loss_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            const float* __restrict__ mask, double* __restrict__ pacc,
+                                                            long long P, int HW, int C, int variant) {
+  float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = p / HW, hw = p % HW;
+    const long long off = n * C * HW + hw;
+    const float m = mask ? mask[p] : 1.f;
+    float L = 0.f;
+    if (variant == CR_CE) {
+      Softmax s;
+      load_softmax(a + off, HW, C, s);
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c)
+        if (c < C) L -= b[off + c * static_cast<long long>(HW)] * s.lp[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c)
+        if (c < C) {
+          const float d = a[off + c * static_cast<long long>(HW)] - b[off + c * static_cast<long long>(HW)];
+          L += variant == CR_L1 ? fabsf(d) : d * d;
+        }
+    }
+    part[0] += m * L;
+    part[1] += m;
+  }
+  block_accumulate(part, pacc);
+}
+__global__ void pair_loss_finalize_kernel(const double* __restrict__ pacc, float* loss, long long P, int C,
+                                          int has_mask, int variant) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *loss = static_cast<float>(pacc[0] / pair_denom(pacc, has_mask, P, C, variant));
+}
+__global__ void __launch_bounds__(256) pair_loss_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            const float* __restrict__ mask,
+                                                            const double* __restrict__ pacc, const float* __restrict__ g,
+                                                            float* __restrict__ da, float* __restrict__ db, long long P,
+                                                            int HW, int C, int variant) {
+  const float k0 = (*g) * static_cast<float>(1.0 / pair_denom(pacc, mask != nullptr, P, C, variant));
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = p / HW, hw = p % HW;
+    const long long off = n * C * HW + hw;
+    const float k = k0 * (mask ? mask[p] : 1.f);
+    if (variant == CR_CE) {
+      Softmax s;
+      load_softmax(a + off, HW, C, s);
+      float bs = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c)
+        if (c < C) bs += b[off + c * static_cast<long long>(HW)];
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c)
+        if (c < C) {
+          const long long o = off + c * static_cast<long long>(HW);
+          if (da) da[o] = k * (s.p[c] * bs - b[o]);
+          if (db) db[o] = -k * s.lp[c];
+        }
+    } else {
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c)
+        if (c < C) {
+          const long long o = off + c * static_cast<long long>(HW);
+          const float d = a[o] - b[o];
+          const float e = k * (variant == CR_L1 ? sgn(d) : 2.f * d);
+          if (da) da[o] = e;
+          if (db) db[o] = -e;
+        }
+    }
+  }
+}
+int pair_loss_fwd(const float* a, const float* b, const float* mask, double* pacc, float* loss, int N, int C, int HW,
+                  int variant, cudaStream_t s) {
+  PP_REQUIRE(C >= 1 && C <= kMaxC, "pair_loss: num_classes=%d unsupported", C);
+  PP_REQUIRE(variant == CR_CE || variant == CR_L1 || variant == CR_L2, "pair_loss: bad variant %d", variant);
+  const long long P = static_cast<long long>(N) * HW;
+  PP_CHECK_CUDA(cudaMemsetAsync(pacc, 0, sizeof(double) * ACC_SLOTS, s));
+  pair_loss_fwd_kernel<<<grid_for_px(P, 256), 256, 0, s>>>(a, b, mask, pacc, P, HW, C, variant);
+  pair_loss_finalize_kernel<<<1, 32, 0, s>>>(pacc, loss, P, C, mask != nullptr, variant);
+  PP_LAUNCH_CHECK_N(2);
+  return PP_OK;
+}
+int pair_loss_bwd(const float* a, const float* b, const float* mask, const double* pacc, const float* g, float* da,
+                  float* db, int N, int C, int HW, int variant, cudaStream_t s) {
+  PP_REQUIRE(C >= 1 && C <= kMaxC, "pair_loss: num_classes=%d unsupported", C);
+  const long long P = static_cast<long long>(N) * HW;
+  pair_loss_bwd_kernel<<<grid_for_px(P, 256), 256, 0, s>>>(a, b, mask, pacc, g, da, db, P, HW, C, variant);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dice loss (losses.py:147-162): p = softmax(z); per (n,c): I = sum p*t, Pn = sum p, Tn = sum t;
+// loss = -mean_{n,c} 2I / (Pn + Tn + 1e-5). sums layout [N][C][3] double.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dice_fwd_kernel(const float* __restrict__ z, const float* __restrict__ label,
+                                                       double* __restrict__ sums, int HW, int C) {
+  __shared__ float red[3 * kMaxC][8];
+  const long long n = blockIdx.y;
+  float I[kMaxC], Ps[kMaxC], Ts[kMaxC];
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) { I[c] = 0.f; Ps[c] = 0.f; Ts[c] = 0.f; }
+  for (int hw = blockIdx.x * blockDim.x + threadIdx.x; hw < HW; hw += gridDim.x * blockDim.x) {
+    const long long off = n * C * HW + hw;
+    Softmax s;
+    load_softmax(z + off, HW, C, s);
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c)
+      if (c < C) {
+        const float t = label[off + c * static_cast<long long>(HW)];
+        I[c] = fmaf(s.p[c], t, I[c]);
+        Ps[c] += s.p[c];
+        Ts[c] += t;
+      }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) {
+    const float a = warp_sum(I[c]), b = warp_sum(Ps[c]), d = warp_sum(Ts[c]);
+    if (lane == 0) { red[c][warp] = a; red[kMaxC + c][warp] = b; red[2 * kMaxC + c][warp] = d; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * kMaxC) {
+    const int k = threadIdx.x / kMaxC, c = threadIdx.x % kMaxC;
+    if (c < C) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += static_cast<double>(red[threadIdx.x][w]);
+      atomicAdd(sums + (n * C + c) * 3 + k, t);
+    }
+  }
+}
+// coef [N][C][2]: gp_c = A*t_c + B with A = -2/(D*N*C), B = 2I/(D^2*N*C)
+__global__ void dice_finalize_kernel(const double* __restrict__ sums, float* __restrict__ loss, float* __restrict__ coef,
+                                     int N, int C) {
+  __shared__ double tot;
+  if (threadIdx.x == 0) tot = 0.0;
+  __syncthreads();
+  double local = 0.0;
+  const double nc = static_cast<double>(N) * C;
+  for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
+    const double I = sums[i * 3], D = sums[i * 3 + 1] + sums[i * 3 + 2] + 1e-5;
+    local += 2.0 * I / D;
+    coef[i * 2] = static_cast<float>(-2.0 / (D * nc));
+    coef[i * 2 + 1] = static_cast<float>(2.0 * I / (D * D * nc));
+  }
+  atomicAdd(&tot, local);
+  __syncthreads();
+  if (threadIdx.x == 0) *loss = static_cast<float>(-tot / nc);
+}
+__global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__ z, const float* __restrict__ label,
+                                                       const float* __restrict__ coef, const float* __restrict__ g,
+                                                       float* __restrict__ dz, int HW, int C, int accumulate) {
+  const long long n = blockIdx.y;
+  const float gv = *g;
+  for (int hw = blockIdx.x * blockDim.x + threadIdx.x; hw < HW; hw += gridDim.x * blockDim.x) {
+    const long long off = n * C * HW + hw;
+    Softmax s;
+    load_softmax(z + off, HW, C, s);
+    float gp[kMaxC], dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+      gp[c] = 0.f;
+      if (c < C) {
+        const float t = label[off + c * static_cast<long long>(HW)];
+        gp[c] = fmaf(coef[(n * C + c) * 2], t, coef[(n * C + c) * 2 + 1]);
+        dot = fmaf(gp[c], s.p[c], dot);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c)
+      if (c < C) {
+        const float v = gv * s.p[c] * (gp[c] - dot);
+        float* o = dz + off + c * static_cast<long long>(HW);
+        *o = accumulate ? *o + v : v;
+      }
+  }
+}
+int dice_fwd(const float* z, const float* label, double* sums, float* coef, float* loss, int N, int C, int HW,
+             cudaStream_t s) {
+  PP_REQUIRE(C >= 1 && C <= kMaxC, "dice: num_classes=%d unsupported", C);
+  PP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * N * C, s));
+  int bx = ceil_div(HW, 256 * 4);
+  if (bx < 1) bx = 1;
+  dice_fwd_kernel<<<dim3(bx, N), 256, 0, s>>>(z, label, sums, HW, C);
+  dice_finalize_kernel<<<1, 64, 0, s>>>(sums, loss, coef, N, C);
+  PP_LAUNCH_CHECK_N(2);
+  return PP_OK;
+}
+int dice_bwd(const float* z, const float* label, const float* coef, const float* g, float* dz, int N, int C, int HW,
+             int accumulate, cudaStream_t s) {
+  PP_REQUIRE(C >= 1 && C <= kMaxC, "dice: num_classes=%d unsupported", C);
+  int bx = ceil_div(HW, 256 * 2);
+  if (bx < 1) bx = 1;
+  dice_bwd_kernel<<<dim3(bx, N), 256, 0, s>>>(z, label, coef, g, dz, HW, C, accumulate);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Memory-bank update (aux_path_memory.py:68-116). Only sample 0 of the batch is visited (the
+// reference returns from inside its per-sample loop). One block per class; a warp owns one
+// labelled pixel at a time: lanes split the hidden channels, the 8x bilinear upsample of the
+// 32x32 feature map is evaluated on the fly at that pixel only.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxHidPerLane = 8;  // hid_ch <= 256
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+memory_update_kernel(const T* __restrict__ feat /*[N][h][w][hid], sample 0 used*/, const float* __restrict__ scribble
+                     /*[N][K][H][W], sample 0 used*/, float* __restrict__ bank /*[C][hid]*/, int h, int w, int H, int W,
+                     int hid, int cosine_mode, float m, float one_minus_m, float sh, float sw) {
+  __shared__ float s_row[256], s_rhat[256];
+  __shared__ float s_U[8][256], s_E[8][256];
+  __shared__ float s_S[8], s_cnt[8];
+  __shared__ int s_allzero;
+  const int cls = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int R = hid / 32;
+  if (threadIdx.x == 0) s_allzero = 1;
+  __syncthreads();
+  float nrm_part = 0.f;
+  for (int k = threadIdx.x; k < hid; k += blockDim.x) {
+    const float v = bank[cls * hid + k];
+    s_row[k] = v;
+    if (v != 0.f) s_allzero = 0;
+    nrm_part = fmaf(v, v, nrm_part);
+  }
+  // block-wide sum of squares
+  __shared__ float s_red[8];
+  nrm_part = warp_sum(nrm_part);
+  if (lane == 0) s_red[warp] = nrm_part;
+  __syncthreads();
+  float nrm2 = 0.f;
+  for (int i = 0; i < 8; ++i) nrm2 += s_red[i];
+  const float rinv = 1.f / (sqrtf(nrm2) + 1e-8f);
+  for (int k = threadIdx.x; k < hid; k += blockDim.x) s_rhat[k] = s_row[k] * rinv;
+  __syncthreads();
+
+  float U[kMaxHidPerLane], E[kMaxHidPerLane];
+#pragma unroll
+  for (int r = 0; r < kMaxHidPerLane; ++r) { U[r] = 0.f; E[r] = 0.f; }
+  float S = 0.f, cnt = 0.f;
+  const float* plane = scribble + static_cast<long long>(cls) * H * W;  // sample 0, channel cls
+  const int HWp = H * W;
+  for (int base = warp * 32; base < HWp; base += 8 * 32) {
+    const int pix = base + lane;
+    const bool hit = (pix < HWp) && (plane[pix] == 1.f);
+    unsigned bal = __ballot_sync(0xffffffffu, hit);
+    while (bal) {
+      const int b = __ffs(bal) - 1;
+      bal &= bal - 1;
+      const int q = base + b;
+      const int Y = q / W, X = q % W;
+      // bilinear sample (align_corners=True) of the hid-dim feature at (Y, X)
+      const float ry = sh * Y, rx = sw * X;
+      const int y0 = static_cast<int>(ry), x0 = static_cast<int>(rx);
+      const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      const float wy1 = ry - y0, wy0 = 1.f - wy1, wx1 = rx - x0, wx0 = 1.f - wx1;
+      float e[kMaxHidPerLane];
+      float n2 = 0.f;
+#pragma unroll
+      for (int r = 0; r < kMaxHidPerLane; ++r)
+        if (r < R) {
+          const int k = r * 32 + lane;
+          const float f00 = to_f32(feat[(static_cast<long long>(y0) * w + x0) * hid + k]);
+          const float f01 = to_f32(feat[(static_cast<long long>(y0) * w + x1) * hid + k]);
+          const float f10 = to_f32(feat[(static_cast<long long>(y1) * w + x0) * hid + k]);
+          const float f11 = to_f32(feat[(static_cast<long long>(y1) * w + x1) * hid + k]);
+          e[r] = wy0 * (wx0 * f00 + wx1 * f01) + wy1 * (wx0 * f10 + wx1 * f11);
+          n2 = fmaf(e[r], e[r], n2);
+          E[r] += e[r];
+        }
+      n2 = warp_sum(n2);
+      const float einv = 1.f / (sqrtf(n2) + 1e-8f);
+      float dot = 0.f;
+#pragma unroll
+      for (int r = 0; r < kMaxHidPerLane; ++r)
+        if (r < R) { e[r] *= einv; dot = fmaf(e[r], s_rhat[r * 32 + lane], dot); }
+      dot = warp_sum(dot);
+      const float wgt = 1.f - dot;
+      S += wgt;
+      cnt += 1.f;
+#pragma unroll
+      for (int r = 0; r < kMaxHidPerLane; ++r)
+        if (r < R) U[r] = fmaf(e[r], wgt, U[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kMaxHidPerLane; ++r)
+    if (r < R) { s_U[warp][r * 32 + lane] = U[r]; s_E[warp][r * 32 + lane] = E[r]; }
+  if (lane == 0) { s_S[warp] = S; s_cnt[warp] = cnt; }
+  __syncthreads();
+  float St = 0.f, ct = 0.f;
+  for (int i = 0; i < 8; ++i) { St += s_S[i]; ct += s_cnt[i]; }
+  if (ct == 0.f) return;  // class absent in sample 0: row untouched
+  for (int k = threadIdx.x; k < hid; k += blockDim.x) {
+    float Ut = 0.f, Et = 0.f;
+    for (int i = 0; i < 8; ++i) { Ut += s_U[i][k]; Et += s_E[i][k]; }
+    float out;
+    if (s_allzero) out = Et / ct;                                             // first touch: plain mean
+    else if (cosine_mode) out = one_minus_m * s_rhat[k] + m * (Ut / (St + 1e-8f));
+    else out = one_minus_m * s_row[k] + m * (Et / ct);
+    bank[cls * hid + k] = out;
+  }
+}
+
+int memory_update(int dtype, const void* feat, const float* scribble, float* bank, int C, int h, int w, int H, int W,
+                  int hid, int cosine_mode, float m, float one_minus_m, cudaStream_t s) {
+  PP_REQUIRE(hid % 32 == 0 && hid <= 256, "memory_update: hid_ch=%d unsupported (multiple of 32, <= 256)", hid);
+  const float sh = H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f;
+  const float sw = W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f;
+  if (dtype == PP_F32)
+    memory_update_kernel<float><<<C, 256, 0, s>>>(static_cast<const float*>(feat), scribble, bank, h, w, H, W, hid,
+                                                  cosine_mode, m, one_minus_m, sh, sw);
+  else
+    memory_update_kernel<__nv_bfloat16><<<C, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(feat), scribble, bank, h, w,
+                                                          H, W, hid, cosine_mode, m, one_minus_m, sh, sw);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bank classification loss: logits = bank (C x hid) . Wfc^T (C x hid), CE against arange(C).
+// (aux_path_memory.py:61 fc_cls(memory_bank); consistency_reglur_memory.py:94.)
+// Forward writes the loss and the softmax (C x C) for backward.
+// ---------------------------------------------------------------------------------------------
+__global__ void memory_loss_fwd_kernel(const float* __restrict__ bank, const float* __restrict__ wfc,
+                                       float* __restrict__ loss, float* __restrict__ probs, int C, int hid) {
+  __shared__ float lg[kMaxC][kMaxC];
+  const int t = threadIdx.x;
+  if (t < C * C) {
+    const int i = t / C, j = t % C;
+    float a = 0.f;
+    for (int k = 0; k < hid; ++k) a = fmaf(bank[i * hid + k], wfc[j * hid + k], a);
+    lg[i][j] = a;
+  }
+  __syncthreads();
+  if (t == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < C; ++i) {
+      float mx = -INFINITY;
+      for (int j = 0; j < C; ++j) mx = fmaxf(mx, lg[i][j]);
+      float sum = 0.f;
+      for (int j = 0; j < C; ++j) sum += expf(lg[i][j] - mx);
+      const float lse = mx + logf(sum);
+      for (int j = 0; j < C; ++j) probs[i * C + j] = expf(lg[i][j] - lse);
+      tot += lse - lg[i][i];
+    }
+    *loss = tot / C;
+  }
+}
+// dWfc[j][k] += g/C * sum_i (probs[i][j] - [i==j]) * bank[i][k]
+__global__ void memory_loss_bwd_kernel(const float* __restrict__ bank, const float* __restrict__ probs,
+                                       const float* __restrict__ g, float* __restrict__ dwfc, int C, int hid) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * hid) return;
+  const int j = idx / hid, k = idx % hid;
+  float a = 0.f;
+  for (int i = 0; i < C; ++i) a = fmaf(probs[i * C + j] - (i == j ? 1.f : 0.f), bank[i * hid + k], a);
+  dwfc[idx] += (*g) * a / C;
+}
+int memory_loss_fwd(const float* bank, const float* wfc, float* loss, float* probs, int C, int hid, cudaStream_t s) {
+  PP_REQUIRE(C >= 1 && C <= kMaxC, "memory_loss: num_classes=%d unsupported", C);
+  memory_loss_fwd_kernel<<<1, 64, 0, s>>>(bank, wfc, loss, probs, C, hid);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+int memory_loss_bwd(const float* bank, const float* probs, const float* g, float* dwfc, int C, int hid,
+                    cudaStream_t s) {
+  memory_loss_bwd_kernel<<<ceil_div(C * hid, 128), 128, 0, s>>>(bank, probs, g, dwfc, C, hid);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+}  // namespace pp

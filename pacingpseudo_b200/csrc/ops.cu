@@ -219,11 +219,12 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ a, 
 int head_fwd(int dtype, const void* a, const float* w, const float* bias, float* logits, long long P, int HW, int Cin,
              int C, cudaStream_t s) {
   PP_REQUIRE(C >= 1 && C <= kMaxClasses, "head_fwd: num_classes=%d unsupported (max %d)", C, kMaxClasses);
-  PP_REQUIRE(Cin == 32 || Cin == 64, "head_fwd: Cin=%d unsupported (32 or 64)", Cin);
-  PP_DISPATCH_T(dtype, if (Cin == 32) head_fwd_kernel<T, 32><<<grid_for(P, 256), 256, 0, s>>>(
-                           static_cast<const T*>(a), w, bias, logits, P, HW, C);
-                else head_fwd_kernel<T, 64><<<grid_for(P, 256), 256, 0, s>>>(static_cast<const T*>(a), w, bias, logits,
-                                                                              P, HW, C););
+  PP_REQUIRE(Cin == 32 || Cin == 64 || Cin == 128 || Cin == 256, "head_fwd: Cin=%d unsupported (32/64/128/256)", Cin);
+#define PP_HEAD_FWD(CIN_) \
+  head_fwd_kernel<T, CIN_><<<grid_for(P, 256), 256, 0, s>>>(static_cast<const T*>(a), w, bias, logits, P, HW, C)
+  PP_DISPATCH_T(dtype, if (Cin == 32) PP_HEAD_FWD(32); else if (Cin == 64) PP_HEAD_FWD(64);
+                else if (Cin == 128) PP_HEAD_FWD(128); else PP_HEAD_FWD(256););
+#undef PP_HEAD_FWD
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -310,18 +311,17 @@ __global__ void __launch_bounds__(256) head_bwd_weight_kernel(const float* __res
 int head_bwd(int dtype, const float* dlogits, const void* a, const float* w, void* da, float* dw, float* db, long long P,
              int HW, int Cin, int C, cudaStream_t s) {
   PP_REQUIRE(C >= 1 && C <= kMaxClasses, "head_bwd: num_classes=%d unsupported", C);
-  PP_REQUIRE(Cin == 32 || Cin == 64, "head_bwd: Cin=%d unsupported (32 or 64)", Cin);
+  PP_REQUIRE(Cin == 32 || Cin == 64 || Cin == 128 || Cin == 256, "head_bwd: Cin=%d unsupported (32/64/128/256)", Cin);
   const int wblocks = sm_count() * 4;
-  PP_DISPATCH_T(
-      dtype,
-      if (Cin == 32) {
-        if (da) head_bwd_data_kernel<T, 32><<<grid_for(P, 256), 256, 0, s>>>(dlogits, w, static_cast<T*>(da), P, HW, C);
-        head_bwd_weight_kernel<T, 32><<<wblocks, 256, 0, s>>>(dlogits, static_cast<const T*>(a), dw, db, P, HW, C);
-      } else {
-        if (da) head_bwd_data_kernel<T, 64><<<grid_for(P, 256), 256, 0, s>>>(dlogits, w, static_cast<T*>(da), P, HW, C);
-        head_bwd_weight_kernel<T, 64><<<wblocks, 256, 0, s>>>(dlogits, static_cast<const T*>(a), dw, db, P, HW, C);
-      });
-  PP_LAUNCH_CHECK();
+#define PP_HEAD_BWD(CIN_)                                                                                          \
+  do {                                                                                                             \
+    if (da) head_bwd_data_kernel<T, CIN_><<<grid_for(P, 256), 256, 0, s>>>(dlogits, w, static_cast<T*>(da), P, HW, C); \
+    head_bwd_weight_kernel<T, CIN_><<<wblocks, 256, 0, s>>>(dlogits, static_cast<const T*>(a), dw, db, P, HW, C);   \
+  } while (0)
+  PP_DISPATCH_T(dtype, if (Cin == 32) PP_HEAD_BWD(32); else if (Cin == 64) PP_HEAD_BWD(64);
+                else if (Cin == 128) PP_HEAD_BWD(128); else PP_HEAD_BWD(256););
+#undef PP_HEAD_BWD
+  PP_LAUNCH_CHECK_N(da ? 2 : 1);
   return PP_OK;
 }
 
@@ -592,7 +592,7 @@ int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* 
                 bn_bwd_apply_kernel<T><<<grid_for(tv, 256), 256, 0, s>>>(static_cast<const T*>(da),
                                                                          static_cast<const T*>(y), coef, bcoef,
                                                                          static_cast<T*>(dy), Pg, C, tv, slope););
-  PP_LAUNCH_CHECK();
+  PP_LAUNCH_CHECK_N(3);
   return PP_OK;
 }
 
@@ -761,7 +761,8 @@ __global__ void __launch_bounds__(256) upsample_nhwc_fwd_kernel(const T* __restr
 // gx[n,i,j,:] = sum over outputs (Y,X) reading (i,j) of wy*wx*gy[n,Y,X,:]  (gather, deterministic)
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_nhwc_bwd_kernel(const T* __restrict__ gy, T* __restrict__ gx, int N,
-                                                                int h, int w, int H, int W, int C, float sh, float sw) {
+                                                                int h, int w, int H, int W, int C, float sh, float sw,
+                                                                int accumulate) {
   const int vecs = C / 8;
   const long long total = static_cast<long long>(N) * h * w * vecs;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -792,6 +793,13 @@ __global__ void __launch_bounds__(256) upsample_nhwc_bwd_kernel(const T* __restr
       }
     }
     Vec8<T> out;
+    if (accumulate) {
+      float old[8];
+      out.load(gx + i * 8);
+      out.get(old);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += old[j];
+    }
     out.set(acc);
     out.store(gx + i * 8);
   }
@@ -806,12 +814,13 @@ int upsample_nhwc_fwd(int dtype, const void* x, void* y, int N, int h, int w, in
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
-int upsample_nhwc_bwd(int dtype, const void* gy, void* gx, int N, int h, int w, int H, int W, int C, cudaStream_t s) {
+int upsample_nhwc_bwd(int dtype, const void* gy, void* gx, int N, int h, int w, int H, int W, int C, int accumulate,
+                      cudaStream_t s) {
   PP_REQUIRE(C % 8 == 0, "upsample_nhwc_bwd: C=%d must be a multiple of 8", C);
   const long long total = static_cast<long long>(N) * h * w * (C / 8);
   PP_DISPATCH_T(dtype, upsample_nhwc_bwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(
                            static_cast<const T*>(gy), static_cast<T*>(gx), N, h, w, H, W, C, ac_scale(h, H),
-                           ac_scale(w, W)););
+                           ac_scale(w, W), accumulate););
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

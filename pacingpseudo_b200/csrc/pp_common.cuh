@@ -43,7 +43,24 @@ void set_error(const char* fmt, ...);
     }                                                                                  \
   } while (0)
 
-#define PP_LAUNCH_CHECK() PP_CHECK_CUDA(cudaGetLastError())
+// Kernel-launch bookkeeping: every launcher counts its launches (bench.py reports the total as
+// "gpu_launches"); the tcgen05 conv launchers can additionally bracket each launch with CUDA events on
+// the launching stream so bench.py can attribute time and algorithmic FLOPs to the dominant kernel.
+void count_launches(int n);
+long long launch_count();
+enum : int { PROF_CONV = 0, PROF_WGRAD = 1, PROF_FAMILIES = 2 };
+void prof_enable(int on);
+int prof_begin(int family, double flops, cudaStream_t s);   // -> slot or -1 when profiling is off
+void prof_end(int slot, cudaStream_t s);
+int prof_collect(int family, double* ms, double* flops, long long* launches);  // synchronises the events
+void prof_reset();
+
+#define PP_LAUNCH_CHECK_N(n)                 \
+  do {                                       \
+    ::pp::count_launches(n);                 \
+    PP_CHECK_CUDA(cudaGetLastError());       \
+  } while (0)
+#define PP_LAUNCH_CHECK() PP_LAUNCH_CHECK_N(1)
 
 int sm_count();  // cached multiprocessor count of the current device (148 on B200)
 

@@ -1,0 +1,77 @@
+// pp_ops.h — internal C++ declarations of every operator launcher (defined in conv_tc.cu,
+// conv_simt.cu, ops.cu, loss.cu, common.cu). The public C ABI in capi.cu forwards to these.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pp {
+
+int init_device(int device);
+const char* last_error();
+
+// ---- convolutions -------------------------------------------------------------------------------
+int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
+               int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil, cudaStream_t s);
+int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw, int N, int H,
+                     int W, int dil, cudaStream_t s);
+int conv3x3_simt(int dtype, const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias,
+                 void* out0, int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil,
+                 cudaStream_t s);
+int conv3x3_wgrad_simt(int dtype, const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw,
+                       int N, int H, int W, int dil, cudaStream_t s);
+
+// ---- ops.cu ---------------------------------------------------------------------------------------
+int pack_weights(int dtype, const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s);
+int unpack_wgrad(const float* dwp, float* g, int Cout, int Cin, int accumulate, cudaStream_t s);
+int first_conv_fwd(int dtype, const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
+                   cudaStream_t s);
+int first_conv_wgrad(int dtype, const void* dy, const float* x, float* dw, int N, int H, int W, int Cout,
+                     cudaStream_t s);
+int head_fwd(int dtype, const void* a, const float* w, const float* bias, float* logits, long long P, int HW, int Cin,
+             int C, cudaStream_t s);
+int head_bwd(int dtype, const float* dlogits, const void* a, const float* w, void* da, float* dw, float* db, long long P,
+             int HW, int Cin, int C, cudaStream_t s);
+int bn_stats(int dtype, const void* y, double* sums, int G, long long Pg, int C, cudaStream_t s);
+int bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                long long* nbt, float* coef, int G, long long Pg, int C, int training, float eps, float momentum,
+                cudaStream_t s);
+int bn_apply(int dtype, const void* y, const float* coef, void* a, int G, long long Pg, int C, float slope,
+             cudaStream_t s);
+int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* bsums, float* bcoef, float* dgamma,
+           float* dbeta, float* dbias, void* dy, int G, long long Pg, int C, int training, float slope, cudaStream_t s);
+int maxpool_fwd(int dtype, const void* x, void* y, int N, int H, int W, int C, cudaStream_t s);
+int maxpool_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int H, int W, int C, int accumulate,
+                cudaStream_t s);
+int upsample_nhwc_fwd(int dtype, const void* x, void* y, int N, int h, int w, int H, int W, int C, cudaStream_t s);
+int upsample_nhwc_bwd(int dtype, const void* gy, void* gx, int N, int h, int w, int H, int W, int C, int accumulate,
+                      cudaStream_t s);
+int upsample_planes_fwd(const float* x, float* y, long long NC, int h, int w, int H, int W, cudaStream_t s);
+int upsample_planes_bwd(const float* gy, float* gx, long long NC, int h, int w, int H, int W, cudaStream_t s);
+int nchw_to_nhwc(int dtype, const float* src, void* dst, int N, int C, int HW, cudaStream_t s);
+int nhwc_to_nchw(int dtype, const void* src, float* dst, int N, int C, int HW, cudaStream_t s);
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+              float wd, int step, float grad_scale, cudaStream_t s);
+
+// ---- loss.cu --------------------------------------------------------------------------------------
+int onehot_argmax(const float* x, uint8_t* out, int N, int K, int HW, cudaStream_t s);
+int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const uint8_t* target, const float* mask,
+                      double* acc, float* loss_pce, float* loss_ent, float* loss_cr, float* loss_aux, int N, int C,
+                      int HW, int ignore_index, int do_ent, int cr_variant, cudaStream_t s);
+int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const uint8_t* target, const float* mask,
+                      const double* acc, const float* g_pce, const float* g_ent, const float* g_cr, const float* g_aux,
+                      float* dzw, float* dzs, float* dza, int N, int C, int HW, int ignore_index, int do_ent,
+                      int cr_variant, int detach_weak, cudaStream_t s);
+int pair_loss_fwd(const float* a, const float* b, const float* mask, double* pacc, float* loss, int N, int C, int HW,
+                  int variant, cudaStream_t s);
+int pair_loss_bwd(const float* a, const float* b, const float* mask, const double* pacc, const float* g, float* da,
+                  float* db, int N, int C, int HW, int variant, cudaStream_t s);
+int dice_fwd(const float* z, const float* label, double* sums, float* coef, float* loss, int N, int C, int HW,
+             cudaStream_t s);
+int dice_bwd(const float* z, const float* label, const float* coef, const float* g, float* dz, int N, int C, int HW,
+             int accumulate, cudaStream_t s);
+int memory_update(int dtype, const void* feat, const float* scribble, float* bank, int C, int h, int w, int H, int W,
+                  int hid, int cosine_mode, float m, float one_minus_m, cudaStream_t s);
+int memory_loss_fwd(const float* bank, const float* wfc, float* loss, float* probs, int C, int hid, cudaStream_t s);
+int memory_loss_bwd(const float* bank, const float* probs, const float* g, float* dwfc, int C, int hid, cudaStream_t s);
+
+}  // namespace pp

@@ -1,0 +1,359 @@
+// unet_plan.cu — host-side executor for the whole UNet forward / backward on one stream.
+//
+// Mirrors the dataflow of /root/reference/models/unet.py:10-98 (6 encoder stages, 5 decoder stages,
+// 1x1 head; output_stride 8/16/32; maxpool + bilinear variant) as a static op list over NHWC buffers
+// carved from ONE caller-owned workspace. One C call launches the ~200 kernels of a pass, so the
+// Python side pays no per-layer overhead. The channel concat of the decoder is never materialised
+// (two-source K loop in the conv kernels); scale-1 "upsampling" (output_stride 8) is a no-op alias.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "pp_common.cuh"
+#include "pp_ops.h"
+
+namespace pp {
+
+namespace {
+
+struct Act { int C; int res; };  // channels, spatial divisor relative to the input
+struct ConvL {
+  int in0, in1;            // activation ids (in0 == -1: the network input, Cin = 1)
+  int cin0, cin1, cout, dil, out;
+  std::string name;        // module path, e.g. "enc_block1.conv_block.conv_layer1"
+};
+enum OpKind { OP_CONV = 0, OP_POOL = 1, OP_UP = 2 };
+struct Op { OpKind kind; int layer; int src; int dst; };
+
+inline long long align_up(long long v) { return (v + 255) & ~255LL; }
+
+}  // namespace
+
+struct UNetPlan {
+  int input_ch, init_ch, max_ch, num_classes, output_stride, dtype;
+  std::vector<Act> acts;
+  std::vector<ConvL> convs;
+  std::vector<Op> ops;
+  int head_in = -1;
+  std::map<std::string, int> named;
+
+  int new_act(int C, int res) { acts.push_back({C, res}); return int(acts.size()) - 1; }
+
+  int add_conv(const std::string& name, int in0, int in1, int cin0, int cin1, int cout, int dil, int res) {
+    const int out = new_act(cout, res);
+    convs.push_back({in0, in1, cin0, cin1, cout, dil, out, name});
+    ops.push_back({OP_CONV, int(convs.size()) - 1, -1, out});
+    return out;
+  }
+  int double_conv(const std::string& block, int in0, int in1, int cin0, int cin1, int cout, int dil, int res) {
+    const int a = add_conv(block + ".conv_block.conv_layer1", in0, in1, cin0, cin1, cout, dil, res);
+    return add_conv(block + ".conv_block.conv_layer2", a, -1, cout, 0, cout, dil, res);
+  }
+
+  void build() {
+    int ch[6];
+    for (int k = 0; k < 6; ++k) ch[k] = std::min(max_ch, (1 << k) * init_ch);
+    bool pool[6] = {false, true, true, true, false, false};
+    int dil[6] = {1, 1, 1, 1, 1, 1};
+    int scale5 = 1, scale4 = 1;
+    if (output_stride == 32) { pool[4] = pool[5] = true; scale5 = scale4 = 2; }
+    else if (output_stride == 16) { pool[4] = true; dil[5] = 2; scale4 = 2; }
+    else { dil[4] = 2; dil[5] = 4; }
+    int enc[6];
+    int cur = -1, cur_c = input_ch, res = 1;
+    for (int k = 0; k < 6; ++k) {
+      if (pool[k]) {
+        const int p = new_act(cur_c, res * 2);
+        ops.push_back({OP_POOL, -1, cur, p});
+        cur = p;
+        res *= 2;
+      }
+      cur = double_conv("enc_block" + std::to_string(k + 1), cur, -1, cur_c, 0, ch[k], dil[k], res);
+      cur_c = ch[k];
+      enc[k] = cur;
+      named["encoder/stage" + std::to_string(k + 1)] = cur;
+    }
+    // decoder: stage 5..1; skip = enc[stage-1]; scale per stage
+    const int scales[5] = {scale5, scale4, 2, 2, 2};
+    for (int i = 0; i < 5; ++i) {
+      const int stage = 5 - i;
+      const int skip = enc[stage - 1];
+      int low = cur;
+      if (scales[i] > 1) {
+        const int u = new_act(cur_c, res / scales[i]);
+        ops.push_back({OP_UP, -1, cur, u});
+        low = u;
+        res /= scales[i];
+      }
+      cur = double_conv("dec_block" + std::to_string(stage), low, skip, cur_c, acts[skip].C, acts[skip].C, 1, res);
+      cur_c = acts[skip].C;
+      named["decoder/stage" + std::to_string(stage)] = cur;
+    }
+    head_in = cur;
+  }
+};
+
+struct UNetLayout {
+  long long total = 0;
+  std::vector<long long> act_data, act_grad;          // per activation
+  std::vector<long long> yraw, coef, sums, wf, wd;     // per conv layer
+  long long dy_scratch = 0, dwp_scratch = 0, bsums = 0, bcoef = 0;
+};
+
+static UNetLayout make_layout(const UNetPlan& pl, int N, int H, int W, int G) {
+  UNetLayout L;
+  const long long es = pl.dtype == PP_BF16 ? 2 : 4;
+  long long off = 0;
+  auto take = [&](long long bytes) { long long o = off; off += align_up(bytes); return o; };
+  auto act_bytes = [&](const Act& a) { return static_cast<long long>(N) * (H / a.res) * (W / a.res) * a.C * es; };
+  long long max_act = 0, max_w = 0;
+  int max_c = 0;
+  for (const Act& a : pl.acts) {
+    L.act_data.push_back(take(act_bytes(a)));
+    max_act = std::max(max_act, act_bytes(a));
+  }
+  for (const Act& a : pl.acts) L.act_grad.push_back(take(act_bytes(a)));
+  for (const ConvL& c : pl.convs) {
+    L.yraw.push_back(take(act_bytes(pl.acts[c.out])));
+    L.coef.push_back(take(sizeof(float) * 4 * G * c.cout));
+    L.sums.push_back(take(sizeof(double) * 2 * G * c.cout));
+    const long long wn = 9LL * c.cout * (c.cin0 + c.cin1);
+    L.wf.push_back(take(wn * es));
+    L.wd.push_back(take(wn * es));
+    max_w = std::max(max_w, wn);
+    max_c = std::max(max_c, c.cout);
+  }
+  L.dy_scratch = take(max_act);
+  L.dwp_scratch = take(max_w * 4);
+  L.bsums = take(sizeof(double) * 2 * G * max_c);
+  L.bcoef = take(sizeof(float) * 2 * G * max_c);
+  L.total = off;
+  return L;
+}
+
+// Parameter pointer table, in conv-layer order then head:
+//   per conv layer: [weight, bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked]
+//   head: [weight, bias]
+// Gradient pointer table: per conv layer [dweight, dbias, dgamma, dbeta]; head [dweight, dbias] (fp32, +=).
+static constexpr int kParamsPerConv = 7;
+static constexpr int kGradsPerConv = 4;
+
+static int check_shape(const UNetPlan& pl, int N, int H, int W, int G) {
+  const int div = pl.output_stride == 8 ? 8 : pl.output_stride;
+  PP_REQUIRE(N > 0 && G > 0 && N % G == 0, "unet: batch %d not divisible into %d statistics groups", N, G);
+  PP_REQUIRE(H % div == 0 && W % div == 0 && H >= div && W >= div,
+             "unet: H=%d W=%d must be multiples of %d (maxpool stages)", H, W, div);
+  return PP_OK;
+}
+
+int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* ws, int N, int H, int W, int G,
+                 int training, float* logits, cudaStream_t s) {
+  int rc = check_shape(pl, N, H, W, G);
+  if (rc) return rc;
+  const UNetLayout L = make_layout(pl, N, H, W, G);
+  char* base = static_cast<char*>(ws);
+  const int dt = pl.dtype;
+  for (const Op& op : pl.ops) {
+    if (op.kind == OP_CONV) {
+      const ConvL& c = pl.convs[op.layer];
+      void* const* pp = params + op.layer * kParamsPerConv;
+      const Act& ao = pl.acts[c.out];
+      const int h = H / ao.res, w = W / ao.res;
+      void* yraw = base + L.yraw[op.layer];
+      if (c.in0 < 0) {
+        rc = first_conv_fwd(dt, x, static_cast<const float*>(pp[0]), static_cast<const float*>(pp[1]), yraw, N, h, w,
+                            c.cout, s);
+      } else {
+        void* wf = base + L.wf[op.layer];
+        void* wd = base + L.wd[op.layer];
+        rc = pack_weights(dt, static_cast<const float*>(pp[0]), wf, wd, c.cout, c.cin0 + c.cin1, s);
+        if (rc) return rc;
+        const void* x0 = base + L.act_data[c.in0];
+        const void* x1 = c.in1 >= 0 ? base + L.act_data[c.in1] : nullptr;
+        if (dt == PP_BF16)
+          rc = conv3x3_tc(x0, c.cin0, x1, c.cin1, wf, static_cast<const float*>(pp[1]), yraw, c.cout, 0, nullptr, 0, 0,
+                          N, h, w, c.dil, s);
+        else
+          rc = conv3x3_simt(dt, x0, c.cin0, x1, c.cin1, wf, static_cast<const float*>(pp[1]), yraw, c.cout, 0, nullptr,
+                            0, 0, N, h, w, c.dil, s);
+      }
+      if (rc) return rc;
+      const long long Pg = static_cast<long long>(N / G) * h * w;
+      double* sums = reinterpret_cast<double*>(base + L.sums[op.layer]);
+      float* coef = reinterpret_cast<float*>(base + L.coef[op.layer]);
+      if (training) {
+        PP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * G * c.cout, s));
+        rc = bn_stats(dt, yraw, sums, G, Pg, c.cout, s);
+        if (rc) return rc;
+      }
+      rc = bn_finalize(sums, static_cast<const float*>(pp[2]), static_cast<const float*>(pp[3]),
+                       static_cast<float*>(pp[4]), static_cast<float*>(pp[5]), static_cast<long long*>(pp[6]), coef, G,
+                       Pg, c.cout, training, 1e-5f, 0.1f, s);
+      if (rc) return rc;
+      rc = bn_apply(dt, yraw, coef, base + L.act_data[c.out], G, Pg, c.cout, 0.01f, s);
+      if (rc) return rc;
+    } else if (op.kind == OP_POOL) {
+      const Act& as = pl.acts[op.src];
+      rc = maxpool_fwd(dt, base + L.act_data[op.src], base + L.act_data[op.dst], N, H / as.res, W / as.res, as.C, s);
+      if (rc) return rc;
+    } else {
+      const Act& as = pl.acts[op.src];
+      const Act& ad = pl.acts[op.dst];
+      rc = upsample_nhwc_fwd(dt, base + L.act_data[op.src], base + L.act_data[op.dst], N, H / as.res, W / as.res,
+                             H / ad.res, W / ad.res, as.C, s);
+      if (rc) return rc;
+    }
+  }
+  void* const* hp = params + pl.convs.size() * kParamsPerConv;
+  const Act& ah = pl.acts[pl.head_in];
+  const int hh = H / ah.res, hw = W / ah.res;
+  return head_fwd(dt, base + L.act_data[pl.head_in], static_cast<const float*>(hp[0]),
+                  static_cast<const float*>(hp[1]), logits, static_cast<long long>(N) * hh * hw, hh * hw, ah.C,
+                  pl.num_classes, s);
+}
+
+// dfeat: optional external gradients w.r.t. named activations (NHWC, activation dtype), e.g. the
+// aux path's gradient into encoder/stage5 and encoder/stage6. dfeat_act[i] = activation id.
+int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void* ws, int N, int H, int W, int G,
+                  int training, const float* dlogits, int n_dfeat, const int* dfeat_act, const void* const* dfeat,
+                  float* const* grads, cudaStream_t s) {
+  int rc = check_shape(pl, N, H, W, G);
+  if (rc) return rc;
+  const UNetLayout L = make_layout(pl, N, H, W, G);
+  char* base = static_cast<char*>(ws);
+  const int dt = pl.dtype;
+  const long long es = dt == PP_BF16 ? 2 : 4;
+  std::vector<char> written(pl.acts.size(), 0);
+  auto act_bytes = [&](const Act& a) { return static_cast<long long>(N) * (H / a.res) * (W / a.res) * a.C * es; };
+
+  // head
+  {
+    void* const* hp = params + pl.convs.size() * kParamsPerConv;
+    float* const* hg = grads + pl.convs.size() * kGradsPerConv;
+    const Act& ah = pl.acts[pl.head_in];
+    const int hh = H / ah.res, hw = W / ah.res;
+    rc = head_bwd(dt, dlogits, base + L.act_data[pl.head_in], static_cast<const float*>(hp[0]),
+                  base + L.act_grad[pl.head_in], hg[0], hg[1], static_cast<long long>(N) * hh * hw, hh * hw, ah.C,
+                  pl.num_classes, s);
+    if (rc) return rc;
+    written[pl.head_in] = 1;
+  }
+  for (int i = 0; i < n_dfeat; ++i) {
+    const int a = dfeat_act[i];
+    PP_REQUIRE(a >= 0 && a < int(pl.acts.size()) && !written[a], "unet_backward: bad external gradient target %d", a);
+    PP_CHECK_CUDA(cudaMemcpyAsync(base + L.act_grad[a], dfeat[i], act_bytes(pl.acts[a]), cudaMemcpyDeviceToDevice, s));
+    written[a] = 1;
+  }
+
+  for (int oi = int(pl.ops.size()) - 1; oi >= 0; --oi) {
+    const Op& op = pl.ops[oi];
+    if (op.kind == OP_CONV) {
+      const ConvL& c = pl.convs[op.layer];
+      void* const* pp = params + op.layer * kParamsPerConv;
+      float* const* gg = grads + op.layer * kGradsPerConv;
+      const Act& ao = pl.acts[c.out];
+      const int h = H / ao.res, w = W / ao.res;
+      const long long Pg = static_cast<long long>(N / G) * h * w;
+      if (!written[c.out]) {  // no consumer produced a gradient: it is zero
+        PP_CHECK_CUDA(cudaMemsetAsync(base + L.act_grad[c.out], 0, act_bytes(ao), s));
+        written[c.out] = 1;
+      }
+      void* dy = base + L.dy_scratch;
+      rc = bn_bwd(dt, base + L.act_grad[c.out], base + L.yraw[op.layer],
+                  reinterpret_cast<const float*>(base + L.coef[op.layer]), reinterpret_cast<double*>(base + L.bsums),
+                  reinterpret_cast<float*>(base + L.bcoef), gg[2], gg[3], gg[1], dy, G, Pg, c.cout, training, 0.01f, s);
+      if (rc) return rc;
+      if (c.in0 < 0) {
+        rc = first_conv_wgrad(dt, dy, x, gg[0], N, h, w, c.cout, s);
+        if (rc) return rc;
+        continue;
+      }
+      const int ctot = c.cin0 + c.cin1;
+      float* dwp = reinterpret_cast<float*>(base + L.dwp_scratch);
+      PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * c.cout * ctot, s));
+      const void* x0 = base + L.act_data[c.in0];
+      const void* x1 = c.in1 >= 0 ? base + L.act_data[c.in1] : nullptr;
+      if (dt == PP_BF16) rc = conv3x3_wgrad_tc(dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, N, h, w, c.dil, s);
+      else rc = conv3x3_wgrad_simt(dt, dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, N, h, w, c.dil, s);
+      if (rc) return rc;
+      rc = unpack_wgrad(dwp, gg[0], c.cout, ctot, 1, s);
+      if (rc) return rc;
+      // dgrad: forward kernel on the flipped/transposed pack, scattered to the two sources
+      void* g0 = base + L.act_grad[c.in0];
+      void* g1 = c.in1 >= 0 ? base + L.act_grad[c.in1] : nullptr;
+      const int acc0 = written[c.in0], acc1 = c.in1 >= 0 ? written[c.in1] : 0;
+      const void* wd = base + L.wd[op.layer];
+      if (dt == PP_BF16)
+        rc = conv3x3_tc(dy, c.cout, nullptr, 0, wd, nullptr, g0, c.cin0, acc0, g1, c.cin1, acc1, N, h, w, c.dil, s);
+      else
+        rc = conv3x3_simt(dt, dy, c.cout, nullptr, 0, wd, nullptr, g0, c.cin0, acc0, g1, c.cin1, acc1, N, h, w, c.dil,
+                          s);
+      if (rc) return rc;
+      written[c.in0] = 1;
+      if (c.in1 >= 0) written[c.in1] = 1;
+    } else if (op.kind == OP_POOL) {
+      const Act& as = pl.acts[op.src];
+      if (!written[op.dst]) {
+        PP_CHECK_CUDA(cudaMemsetAsync(base + L.act_grad[op.dst], 0, act_bytes(pl.acts[op.dst]), s));
+        written[op.dst] = 1;
+      }
+      rc = maxpool_bwd(dt, base + L.act_data[op.src], base + L.act_grad[op.dst], base + L.act_grad[op.src], N,
+                       H / as.res, W / as.res, as.C, written[op.src], s);
+      if (rc) return rc;
+      written[op.src] = 1;
+    } else {
+      const Act& as = pl.acts[op.src];
+      const Act& ad = pl.acts[op.dst];
+      if (!written[op.dst]) {
+        PP_CHECK_CUDA(cudaMemsetAsync(base + L.act_grad[op.dst], 0, act_bytes(ad), s));
+        written[op.dst] = 1;
+      }
+      rc = upsample_nhwc_bwd(dt, base + L.act_grad[op.dst], base + L.act_grad[op.src], N, H / as.res, W / as.res,
+                             H / ad.res, W / ad.res, as.C, written[op.src], s);
+      if (rc) return rc;
+      written[op.src] = 1;
+    }
+  }
+  return PP_OK;
+}
+
+UNetPlan* unet_create(int input_ch, int init_ch, int max_ch, int num_classes, int output_stride, int dtype) {
+  if (input_ch != 1) { set_error("unet: input_ch=%d unsupported (the reference data is single-channel)", input_ch); return nullptr; }
+  if (init_ch % 32 != 0 || max_ch % 32 != 0 || init_ch <= 0 || max_ch < init_ch) {
+    set_error("unet: init_ch=%d / max_ch=%d must be positive multiples of 32", init_ch, max_ch);
+    return nullptr;
+  }
+  if (init_ch != 32 && init_ch != 64) { set_error("unet: init_ch=%d unsupported (1x1 head handles 32 or 64)", init_ch); return nullptr; }
+  if (output_stride != 8 && output_stride != 16 && output_stride != 32) { set_error("unet: output_stride=%d", output_stride); return nullptr; }
+  if (num_classes < 1 || num_classes > 8) { set_error("unet: num_classes=%d unsupported (1..8)", num_classes); return nullptr; }
+  if (dtype != PP_F32 && dtype != PP_BF16) { set_error("unet: bad dtype %d", dtype); return nullptr; }
+  UNetPlan* pl = new UNetPlan();
+  pl->input_ch = input_ch; pl->init_ch = init_ch; pl->max_ch = max_ch; pl->num_classes = num_classes;
+  pl->output_stride = output_stride; pl->dtype = dtype;
+  pl->build();
+  return pl;
+}
+void unet_destroy(UNetPlan* pl) { delete pl; }
+int unet_num_convs(const UNetPlan* pl) { return int(pl->convs.size()); }
+int unet_conv_info(const UNetPlan* pl, int layer, int* cin, int* cout, int* dil, const char** name) {
+  PP_REQUIRE(layer >= 0 && layer < int(pl->convs.size()), "unet_conv_info: bad layer %d", layer);
+  const ConvL& c = pl->convs[layer];
+  *cin = c.in0 < 0 ? pl->input_ch : c.cin0 + c.cin1;
+  *cout = c.cout; *dil = c.dil; *name = c.name.c_str();
+  return PP_OK;
+}
+long long unet_workspace_bytes(const UNetPlan* pl, int N, int H, int W, int G) {
+  if (check_shape(*pl, N, H, W, G)) return -1;
+  return make_layout(*pl, N, H, W, G).total;
+}
+int unet_activation(const UNetPlan* pl, const char* name, int N, int H, int W, int G, int* act_id, long long* offset,
+                    int* C, int* h, int* w) {
+  auto it = pl->named.find(name);
+  PP_REQUIRE(it != pl->named.end(), "unet_activation: unknown end point '%s'", name);
+  const UNetLayout L = make_layout(*pl, N, H, W, G);
+  const Act& a = pl->acts[it->second];
+  *act_id = it->second; *offset = L.act_data[it->second]; *C = a.C; *h = H / a.res; *w = W / a.res;
+  return PP_OK;
+}
+
+}  // namespace pp

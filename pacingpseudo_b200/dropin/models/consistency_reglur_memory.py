@@ -1,0 +1,77 @@
+"""B200-native drop-in for `models.consistency_reglur_memory`
+(/root/reference/models/consistency_reglur_memory.py:13-102).
+
+Same constructor, `forward(names_to_data, mode, step) -> dict` and returned keys. Differences are in
+execution only: the weak and the strong image go through the backbone as ONE batched pass with
+per-branch BatchNorm statistics (identical maths to the reference's two passes, running statistics are
+updated weak-then-strong), and all per-pixel losses are one fused kernel.
+"""
+import torch
+import torch.nn as nn
+
+from pacingpseudo_b200 import functional as PF
+from models.unet import UNet
+from losses.losses import *  # noqa: F401,F403  (the reference re-exports the loss functions here)
+from .aux_path_memory import *  # noqa: F401,F403
+from .aux_path_memory import AuxPath
+
+
+class ConsistencyRegulr(nn.Module):
+    def __init__(self, kwargs_unet, kwargs_aux_path=None, args_parser=None):
+        super(ConsistencyRegulr, self).__init__()
+        self.kwargs_unet = kwargs_unet
+        self.kwargs_aux_path = kwargs_aux_path
+        self.args = args_parser
+        self.backbone = UNet(**kwargs_unet)
+        self.aux_path = AuxPath(**kwargs_aux_path)
+
+    def forward(self, names_to_data, mode=None, step=None):
+        assert mode in ['train', 'val', None]
+        args = self.args
+        net_outputs = {}
+        image = names_to_data['image']
+        n = image.shape[0]
+        train = mode == 'train'
+        do_cr = train and args.do_decoder_consistency
+        do_aux = train and args.do_aux_path
+        do_ent = train and args.do_loss_ent
+
+        # one backbone pass; with consistency on, weak and strong are batched (2 statistics groups)
+        x = torch.cat((image, names_to_data['image_strong']), 0) if do_cr else image
+        feat_names = tuple(self.aux_path.feat_stage) if do_aux else ()
+        logits_all, feats = self.backbone.run_native(x, groups=2 if do_cr else 1, feat_names=feat_names)
+        logits_weak = logits_all[:n]
+        self.backbone.end_points._set_native(feats)
+        self.backbone.end_points.update({'segmentation/logits': logits_all[n:] if do_cr else logits_weak})
+
+        scribble = names_to_data['scribble']
+        scb_target = PF.onehot_argmax(scribble)
+        valid_mask = names_to_data.get('valid_mask')
+
+        logits_aux = None
+        if do_aux:
+            # the reference hands the aux path the LAST end_points written, i.e. the strong branch's
+            # features whenever the consistency branch ran (unet.py:23 instance-owned dict)
+            sel = [(f[n:] if do_cr else f) for f in (feats[s] for s in feat_names)]
+            logits_aux, _ = self.aux_path.run_native(sel, scribble, step, self.backbone.engine.code)
+
+        variant = None
+        if do_cr:
+            variant = args.loss_cr_variants
+            if variant not in ('ce_loss', 'l1_loss', 'l2_loss', 'kl_loss'):
+                raise ValueError('The loss is not implemented.')
+        losses = PF.scribble_losses(
+            logits_all, scb_target, args.ignored_index, za=logits_aux, mask=valid_mask if (do_ent or do_cr) else None,
+            do_ent=do_ent, cr_variant=variant, detach_weak=bool(getattr(args, 'detach_weak_cr', False)),
+            siamese=do_cr)
+
+        net_outputs.update({'segmentation/logits': logits_weak, 'loss_pce': losses['loss_pce']})
+        if do_ent:
+            net_outputs.update({'loss_ent': losses['loss_ent']})
+        if do_cr:
+            net_outputs.update({'loss_cr': losses['loss_cr'], 'segmentation/logits_strong': logits_all[n:]})
+        if do_aux:
+            net_outputs.update({'logits_aux_cls': logits_aux, 'loss_aux_cls': losses['loss_aux']})
+            if args.do_memory:
+                net_outputs.update({'loss_memory': self.aux_path.memory_loss()})
+        return net_outputs

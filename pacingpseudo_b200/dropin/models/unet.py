@@ -1,0 +1,185 @@
+"""B200-native drop-in for the reference `models.unet` (/root/reference/models/unet.py).
+
+Same constructor, same `forward(x) -> end_points dict`, same state-dict keys/shapes (fp32 OIHW master
+weights, BatchNorm buffers) — but `forward` is ONE autograd Function that runs the whole network as
+hand-written sm_100a kernels on NHWC bf16 activations (or fp32 with PP_PRECISION=fp32). The nn.Conv2d /
+nn.BatchNorm2d objects below only HOLD parameters, in the reference's construction order so that a given
+torch seed yields the reference's initial weights; they are never called.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from pacingpseudo_b200.functional import UNetEngine, UNetFunction
+
+_STAGES = ["encoder/stage%d" % i for i in range(1, 7)] + ["decoder/stage%d" % i for i in range(5, 0, -1)]
+
+
+def default_precision():
+    return os.environ.get("PP_PRECISION", "bf16")
+
+
+class EndPoints(dict):
+    """The instance-owned dict UNet.forward returns (unet.py:23,78-98). Feature maps live on the device as
+    NHWC tensors in the activation dtype (`.native`); the reference-format NCHW fp32 view of a stage is
+    materialised on first access."""
+
+    def __init__(self):
+        super().__init__()
+        self.native = {}
+
+    def _set_native(self, feats):
+        self.native = dict(feats)
+        for k in feats:
+            dict.pop(self, k, None)
+
+    def _materialise(self, key):
+        if not dict.__contains__(self, key) and key in self.native:
+            dict.__setitem__(self, key, self.native[key].permute(0, 3, 1, 2).float())
+
+    def __getitem__(self, key):
+        self._materialise(key)
+        return dict.__getitem__(self, key)
+
+    def get(self, key, default=None):
+        self._materialise(key)
+        return dict.get(self, key, default)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self.native
+
+    def _all(self):
+        for k in list(self.native):
+            self._materialise(k)
+
+    def keys(self):
+        self._all()
+        return dict.keys(self)
+
+    def items(self):
+        self._all()
+        return dict.items(self)
+
+    def values(self):
+        self._all()
+        return dict.values(self)
+
+    def __iter__(self):
+        self._all()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        self._all()
+        return dict.__len__(self)
+
+
+class ConvLayer(nn.Module):
+    """Parameter holder for Conv2d(bias) -> BatchNorm2d -> LeakyReLU(0.01) (unet.py:178-193)."""
+
+    def __init__(self, in_ch, out_ch, kernel_size=3, stride=1, padding=1, dilation=1,
+                 norm_op=nn.BatchNorm2d, nonlin_op=nn.LeakyReLU, negative_slop=1e-2):
+        super().__init__()
+        self.conv = nn.Conv2d(in_ch, out_ch, kernel_size, stride, padding, dilation)
+        self.norm_op = norm_op(out_ch)
+        self.nonlin_op = nonlin_op(negative_slop)
+
+
+class DoubleConv(nn.Module):
+    def __init__(self, in_ch, out_ch, ks1=3, stride1=1, padding1=1, dilation1=1,
+                 ks2=3, stride2=1, padding2=1, dilation2=1):
+        super().__init__()
+        self.conv_layer1 = ConvLayer(in_ch, out_ch, ks1, stride1, padding1, dilation1)
+        self.conv_layer2 = ConvLayer(out_ch, out_ch, ks2, stride2, padding2, dilation2)
+
+
+class EncBlock(nn.Module):
+    def __init__(self, in_ch, out_ch, do_subsamp=True, is_stride_conv=False, dilation=1):
+        super().__init__()
+        self.pooling = nn.MaxPool2d(2, 2) if (do_subsamp and not is_stride_conv) else None
+        self.conv_block = DoubleConv(in_ch, out_ch, padding1=dilation, dilation1=dilation,
+                                     padding2=dilation, dilation2=dilation)
+
+
+class DecBlock(nn.Module):
+    def __init__(self, lower_ch, skip_ch, out_ch, trans_ks=2, trans_stride=2, is_trans_conv=False):
+        super().__init__()
+        self.up_samp = nn.Upsample(scale_factor=trans_stride, mode='bilinear', align_corners=True)
+        self.conv_block = DoubleConv(lower_ch + skip_ch, skip_ch)
+
+
+class UNet(nn.Module):
+    def __init__(self, input_ch=1, init_ch=32, max_ch=512, num_classes=4, output_stride=32,
+                 is_stride_conv=False, is_trans_conv=False, elab_end_points=False, precision=None):
+        super().__init__()
+        self.elab_end_points = elab_end_points
+        self.end_points = EndPoints()
+        assert is_trans_conv == is_stride_conv, \
+            "Only combo of stride_conv and trans_conv or maxpool and upsample is allowed."
+        if is_stride_conv or is_trans_conv:
+            raise NotImplementedError(
+                "pacingpseudo_b200: the strided-conv / transposed-conv UNet variant (unet.py:113-116,141) is not "
+                "built yet; every published run uses maxpool + bilinear (SURVEY.md section 2.3).")
+        assert output_stride in [8, 16, 32]
+        ch_ls = [min(max_ch, 2 ** k * init_ch) for k in range(6)]
+        self.enc_block1 = EncBlock(input_ch, ch_ls[0], do_subsamp=False)
+        self.enc_block2 = EncBlock(ch_ls[0], ch_ls[1], do_subsamp=True)
+        self.enc_block3 = EncBlock(ch_ls[1], ch_ls[2], do_subsamp=True)
+        self.enc_block4 = EncBlock(ch_ls[2], ch_ls[3], do_subsamp=True)
+        if output_stride == 32:
+            self.enc_block5 = EncBlock(ch_ls[3], ch_ls[4], do_subsamp=True)
+            self.enc_block6 = EncBlock(ch_ls[4], ch_ls[5], do_subsamp=True)
+            self.dec_block5 = DecBlock(ch_ls[5], ch_ls[4], ch_ls[4], 2, 2)
+            self.dec_block4 = DecBlock(ch_ls[4], ch_ls[3], ch_ls[3], 2, 2)
+        elif output_stride == 16:
+            self.enc_block5 = EncBlock(ch_ls[3], ch_ls[4], do_subsamp=True)
+            self.enc_block6 = EncBlock(ch_ls[4], ch_ls[5], do_subsamp=False, dilation=2)
+            self.dec_block5 = DecBlock(ch_ls[5], ch_ls[4], ch_ls[4], 1, 1)
+            self.dec_block4 = DecBlock(ch_ls[4], ch_ls[3], ch_ls[3], 2, 2)
+        else:
+            self.enc_block5 = EncBlock(ch_ls[3], ch_ls[4], do_subsamp=False, dilation=2)
+            self.enc_block6 = EncBlock(ch_ls[4], ch_ls[5], do_subsamp=False, dilation=4)
+            self.dec_block5 = DecBlock(ch_ls[5], ch_ls[4], ch_ls[4], 1, 1)
+            self.dec_block4 = DecBlock(ch_ls[4], ch_ls[3], ch_ls[3], 1, 1)
+        self.dec_block3 = DecBlock(ch_ls[3], ch_ls[2], ch_ls[2])
+        self.dec_block2 = DecBlock(ch_ls[2], ch_ls[1], ch_ls[1])
+        self.dec_block1 = DecBlock(ch_ls[1], ch_ls[0], ch_ls[0])
+        self.final_conv = nn.Conv2d(ch_ls[0], num_classes, 1, 1)
+
+        self._cfg = (input_ch, init_ch, max_ch, num_classes, output_stride)
+        self._precision = precision or default_precision()
+        self._engine = None
+
+    # ---- native execution ----------------------------------------------------------------------
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = UNetEngine(*self._cfg, self._precision)
+        return self._engine
+
+    def _layer_modules(self):
+        mods = []
+        for name, _cin, _cout, _dil in self.engine.layers:
+            m = self
+            for part in name.split('.'):
+                m = getattr(m, part)
+            mods.append(m)
+        return mods
+
+    def run_native(self, x, groups=1, feat_names=()):
+        """-> (logits NCHW fp32, {name: native NHWC feature}). `groups` = BatchNorm statistics groups."""
+        learnable, buffers = [], []
+        for m in self._layer_modules():
+            learnable += [m.conv.weight, m.conv.bias, m.norm_op.weight, m.norm_op.bias]
+            buffers += [m.norm_op.running_mean, m.norm_op.running_var, m.norm_op.num_batches_tracked]
+        learnable += [self.final_conv.weight, self.final_conv.bias]
+        feat_names = tuple(feat_names)
+        outs = UNetFunction.apply(self.engine, buffers, groups, self.training, feat_names, x, *learnable)
+        return outs[0], dict(zip(feat_names, outs[1:]))
+
+    def forward(self, x):
+        names = _STAGES if self.elab_end_points else ()
+        logits, feats = self.run_native(x, 1, names)
+        self.end_points._set_native(feats)
+        self.end_points.update({"segmentation/logits": logits})
+        return self.end_points

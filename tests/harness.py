@@ -1,0 +1,244 @@
+"""Shared parity harness: runs a golden case (oracle/gen_golden.py CASES) through an implementation and
+reduces it to the same record the reference produced, then compares records with stated tolerances."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import pp_oracle as O  # noqa: E402
+from oracle.gen_golden import CASES, build_state, ref_args, summarize  # noqa: E402
+from pacingpseudo_b200.synth import make_batch  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# Tolerances from BASELINE.json north_star (logits, losses: 2e-2 bf16, 1e-4 fp32; gradients 5e-2; argmax 99.9 %).
+# Gradient floors: the reference itself moves by up to ~8e-3 between fp32 and fp64 on these tiny cases
+# (max-pool ties, LeakyReLU sign flips under 128-element BatchNorm statistics), so fp32-vs-fp32 gradient
+# checks use 1e-2 (oracle, same machine) and 2e-2 (fp32 CUDA mode); bf16 uses the stated 5e-2.
+TOL = {
+    "fp32": dict(loss=1e-4, logits=1e-4, grad=2e-2, argmax=0.9999, bank=1e-4),
+    "bf16": dict(loss=2e-2, logits=2e-2, grad=5e-2, argmax=0.999, bank=2e-2),
+    "oracle": dict(loss=2e-5, logits=2e-5, grad=1e-2, argmax=0.9999, bank=2e-5),
+}
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+
+
+def case_batch(case, step):
+    b = make_batch(case["N"], case["C"], case["H"], case["W"], seed=100 + step,
+                   absent_class_in_sample0=(1 if step == 1 else None))
+    if case.get("nomask"):
+        b.pop("valid_mask")
+    return b
+
+
+def _grad_record(rec, step, named_grads):
+    names, sums, samples = [], [], []
+    for k, g in named_grads:
+        names.append(k)
+        s, smp = summarize(g)
+        sums.append(s)
+        samples.append(np.pad(smp, (0, 16 - len(smp))))
+    rec["s%d/grad_names" % step] = np.array(names)
+    rec["s%d/grad_sums" % step] = np.stack(sums)
+    rec["s%d/grad_samples" % step] = np.stack(samples)
+
+
+def run_case_oracle(name, dtype=torch.float32):
+    """The CPU oracle restatement on a golden case."""
+    case = CASES[name]
+    C = case["C"]
+    sd = {k: (v.to(dtype) if v.is_floating_point() else v.clone()) for k, v in build_state(case).items()}
+    learn = [k for k in sd if sd[k].is_floating_point() and "running" not in k and not k.endswith("memory_bank")]
+    for k in learn:
+        sd[k].requires_grad_(True)
+    cfg = O.StepConfig(num_classes=C, ignored_index=C, detach_weak_cr=bool(case.get("detach")),
+                       loss_cr_variants=case.get("cr", "ce_loss"), ensemble_mode=case.get("mode", "cosine_similarity"),
+                       output_stride=case["os"])
+    rec = {}
+    for step in range(case.get("steps", 1)):
+        batch = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in case_batch(case, step).items()}
+        for k in learn:
+            sd[k].grad = None
+        if case["kind"] == "pacing":
+            out = O.consistency_forward(sd, batch, cfg, mode="train", step=step * 37, training=case["training"])
+            loss = O.total_loss(out, epoch=40)
+            for k in ("loss_pce", "loss_ent", "loss_cr", "loss_aux_cls", "loss_memory"):
+                rec["s%d/%s" % (step, k)] = np.array(out[k].item())
+            for k in ("segmentation/logits", "segmentation/logits_strong", "logits_aux_cls"):
+                rec["s%d/%s/sum" % (step, k)], rec["s%d/%s/samples" % (step, k)] = summarize(out[k])
+            rec["s%d/argmax_weak" % step] = out["segmentation/logits"].argmax(1).to(torch.uint8).numpy()
+            rec["s%d/memory_bank" % step] = sd["aux_path.memory_bank"].detach().double().numpy().reshape(C, 64)
+        else:
+            logits = O.unet_forward(sd, batch["image"], case["training"], output_stride=case["os"])["segmentation/logits"]
+            if case["kind"] == "baseline":
+                loss = O.partial_cross_entropy(logits, batch["scribble"].argmax(1), C)
+                rec["s%d/loss_pce" % step] = np.array(loss.item())
+            else:
+                lce = O.partial_cross_entropy(logits, batch["label"].argmax(1), C)
+                ld = O.dice(logits, batch["label"])
+                rec["s%d/loss_ce" % step], rec["s%d/loss_dice" % step] = np.array(lce.item()), np.array(ld.item())
+                loss = lce + ld
+            rec["s%d/segmentation/logits/sum" % step], rec["s%d/segmentation/logits/samples" % step] = summarize(logits)
+            rec["s%d/argmax_weak" % step] = logits.argmax(1).to(torch.uint8).numpy()
+        rec["s%d/total" % step] = np.array(loss.item())
+        loss.backward()
+        _grad_record(rec, step, [(k, sd[k].grad) for k in learn if sd[k].grad is not None])
+    run = [k for k in sd if "running" in k]
+    rec["running_names"] = np.array(run)
+    rec["running_sums"] = np.stack([summarize(sd[k])[0] for k in run])
+    return rec
+
+
+def build_cuda_model(case, precision, device="cuda"):
+    """The drop-in modules (pacingpseudo_b200/dropin) loaded with the case's synthetic state dict."""
+    from pacingpseudo_b200.dropin import DROPIN_PATH
+    if DROPIN_PATH not in sys.path:
+        sys.path.insert(0, DROPIN_PATH)
+    os.environ["PP_PRECISION"] = precision
+    from models.unet import UNet
+    from models.consistency_reglur_memory import ConsistencyRegulr
+    C = case["C"]
+    if case["kind"] == "pacing":
+        model = ConsistencyRegulr(
+            kwargs_unet=dict(input_ch=1, init_ch=32, max_ch=512, num_classes=C, output_stride=case["os"],
+                             is_stride_conv=False, is_trans_conv=False, elab_end_points=True, precision=precision),
+            kwargs_aux_path=dict(num_classes=C, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[512, 512],
+                                 hid_ch=64, aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
+                                 ensemble_mode=case.get("mode", "cosine_similarity")),
+            args_parser=ref_args(case))
+    else:
+        model = UNet(1, 32, 512, C, case["os"], False, False, True, precision=precision)
+    model.load_state_dict(build_state(case), strict=True)
+    return model.to(device).train(case["training"])
+
+
+def run_case_cuda(name, precision, device="cuda"):
+    case = CASES[name]
+    C = case["C"]
+    model = build_cuda_model(case, precision, device)
+    from losses import losses as L
+    rec = {}
+    for step in range(case.get("steps", 1)):
+        batch = {k: v.to(device) for k, v in case_batch(case, step).items()}
+        model.zero_grad(set_to_none=True)
+        if case["kind"] == "pacing":
+            out = model({k: v for k, v in batch.items() if k != "label"}, mode="train", step=step * 37)
+            loss = O.total_loss(out, epoch=40)
+            for k in ("loss_pce", "loss_ent", "loss_cr", "loss_aux_cls", "loss_memory"):
+                rec["s%d/%s" % (step, k)] = np.array(out[k].item())
+            for k in ("segmentation/logits", "segmentation/logits_strong", "logits_aux_cls"):
+                rec["s%d/%s/sum" % (step, k)], rec["s%d/%s/samples" % (step, k)] = summarize(out[k].cpu())
+            rec["s%d/argmax_weak" % step] = out["segmentation/logits"].argmax(1).to(torch.uint8).cpu().numpy()
+        else:
+            logits = model(batch["image"])["segmentation/logits"]
+            if case["kind"] == "baseline":
+                loss = L.partial_cross_entropy_loss(logits, batch["scribble"].argmax(1), C)
+                rec["s%d/loss_pce" % step] = np.array(loss.item())
+            else:
+                lce = L.partial_cross_entropy_loss(logits, batch["label"].argmax(1), C)
+                ld = L.dice_loss_fn(logits, batch["label"])
+                rec["s%d/loss_ce" % step], rec["s%d/loss_dice" % step] = np.array(lce.item()), np.array(ld.item())
+                loss = lce + ld
+            rec["s%d/segmentation/logits/sum" % step], rec["s%d/segmentation/logits/samples" % step] = summarize(logits.cpu())
+            rec["s%d/argmax_weak" % step] = logits.argmax(1).to(torch.uint8).cpu().numpy()
+        rec["s%d/total" % step] = np.array(loss.item())
+        loss.backward()
+        _grad_record(rec, step, [(k, p.grad.cpu()) for k, p in model.named_parameters() if p.grad is not None])
+        if case["kind"] == "pacing":
+            rec["s%d/memory_bank" % step] = model.aux_path.memory_bank.detach().double().cpu().numpy().reshape(C, 64)
+    buf = {k: v.cpu() for k, v in model.state_dict().items() if "running" in k}
+    rec["running_names"] = np.array(list(buf))
+    rec["running_sums"] = np.stack([summarize(v)[0] for v in buf.values()])
+    return rec
+
+
+def compare(rec, gold, tol, steps, report=None):
+    """Returns a list of human-readable failures (empty = parity)."""
+    fails = []
+    lines = []
+
+    def rel(a, b, floor):
+        return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) /
+                            np.maximum(np.abs(np.asarray(b, dtype=np.float64)), floor)))
+
+    for step in range(steps):
+        p = "s%d/" % step
+        for k in gold:
+            if not k.startswith(p):
+                continue
+            short = k[len(p):]
+            if short.startswith("loss_") or short == "total":
+                e = rel(rec[k], gold[k], 1e-2)
+                lines.append("%s rel %.3e (%.6f vs %.6f)" % (k, e, float(rec[k]), float(gold[k])))
+                if not e <= tol["loss"]:
+                    fails.append("%s: %.6f vs reference %.6f (rel %.2e > %.1e)" % (k, float(rec[k]), float(gold[k]), e, tol["loss"]))
+            elif short.endswith("/samples"):
+                scale = max(float(np.max(np.abs(gold[k]))), 1e-6)
+                e = float(np.max(np.abs(rec[k] - gold[k]))) / scale
+                lines.append("%s max-rel %.3e" % (k, e))
+                if not e <= tol["logits"]:
+                    fails.append("%s: max |diff| / max |ref| = %.2e > %.1e" % (k, e, tol["logits"]))
+            elif short.endswith("/sum"):
+                e = rel(rec[k][1:], gold[k][1:], 1e-6)  # |x| sum and L2 norm
+                lines.append("%s norms rel %.3e" % (k, e))
+                if not e <= tol["logits"]:
+                    fails.append("%s: norm mismatch rel %.2e > %.1e" % (k, e, tol["logits"]))
+            elif short == "argmax_weak":
+                agree = float(np.mean(rec[k] == gold[k]))
+                lines.append("%s agreement %.5f" % (k, agree))
+                if agree < tol["argmax"]:
+                    fails.append("%s: argmax agreement %.5f < %.4f" % (k, agree, tol["argmax"]))
+            elif short == "memory_bank":
+                den = max(float(np.linalg.norm(gold[k])), 1e-12)
+                e = float(np.linalg.norm(rec[k] - gold[k])) / den
+                lines.append("%s rel-l2 %.3e" % (k, e))
+                if not e <= tol["bank"]:
+                    fails.append("%s: rel L2 %.2e > %.1e" % (k, e, tol["bank"]))
+            elif short == "grad_sums":
+                gn = [str(s) for s in gold[p + "grad_names"]]
+                rn = [str(s) for s in rec[p + "grad_names"]]
+                if gn != rn:
+                    fails.append("%s: parameter sets differ (%d vs %d)" % (k, len(rn), len(gn)))
+                    continue
+                gnorm, rnorm = gold[k][:, 2], rec[k][:, 2]
+                gmax = float(np.max(gnorm))
+                # parameters whose gradient is numerically zero in the reference (conv bias under batch-stat BN)
+                live = gnorm > 1e-6 * gmax
+                en = np.abs(rnorm - gnorm) / np.maximum(gnorm, 1e-30)
+                worst = int(np.argmax(np.where(live, en, 0)))
+                lines.append("%s worst live norm rel %.3e (%s); dead-param max norm %.3e (ref %.3e)" % (
+                    k, float(en[worst]), gn[worst], float(np.max(np.where(live, 0, rnorm))), float(np.max(np.where(live, 0, gnorm)))))
+                if not float(np.max(np.where(live, en, 0))) <= tol["grad"]:
+                    fails.append("%s: grad norm of %s off by %.2e > %.1e" % (k, gn[worst], float(en[worst]), tol["grad"]))
+                if float(np.max(np.where(live, 0, rnorm))) > max(1e-4 * gmax, 10 * float(np.max(np.where(live, 0, gnorm)))):
+                    fails.append("%s: a reference-zero gradient is not ~zero" % k)
+                # sample values, scaled by each parameter's gradient RMS
+                # 16 sampled entries per parameter: relative L2 per parameter. Single entries are noisier than
+                # norms (see the floor note above), so bound the 95th percentile tightly and the worst loosely.
+                gs, rs = gold[p + "grad_samples"], rec[p + "grad_samples"]
+                es = np.linalg.norm(rs - gs, axis=1) / np.maximum(np.linalg.norm(gs, axis=1), 1e-30)
+                es_live = es[live]
+                w2 = int(np.argmax(np.where(live, es, 0)))
+                p95 = float(np.percentile(es_live, 95))
+                lines.append("%s sample rel-l2: p95 %.3e worst %.3e (%s)" % (k, p95, float(es[w2]), gn[w2]))
+                if not p95 <= 2 * tol["grad"]:
+                    fails.append("%s: 95th percentile of per-parameter sample error %.2e > %.1e" % (k, p95, 2 * tol["grad"]))
+                if not float(es[w2]) <= 10 * tol["grad"]:
+                    fails.append("%s: grad samples of %s off by %.2e" % (k, gn[w2], float(es[w2])))
+    if "running_sums" in gold:
+        e = rel(rec["running_sums"][:, 1:], gold["running_sums"][:, 1:], 1e-6)
+        lines.append("running stats norms rel %.3e" % e)
+        if not e <= max(tol["logits"], 1e-4) * 5:
+            fails.append("running statistics differ: rel %.2e" % e)
+    if report is not None:
+        report.extend(lines)
+    return fails

@@ -1,0 +1,116 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/pacingpseudo_b200.h declares;
+host-side logic that needs no GPU (header parser, plan construction, workspace sizing, error convention)."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+from pacingpseudo_b200 import lib as pplib
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(pplib.LIB_PATH):
+        from pacingpseudo_b200.build import build
+        build()
+    return pplib.get_lib()
+
+
+def test_header_declares_expected_surface():
+    protos = pplib.parse_header()
+    for name in ("pp_init", "pp_last_error", "pp_unet_forward", "pp_unet_backward", "pp_conv3x3", "pp_conv3x3_wgrad",
+                 "pp_scribble_loss_fwd", "pp_scribble_loss_bwd", "pp_memory_update", "pp_dice_fwd", "pp_adam_step"):
+        assert name in protos, name
+    assert len(protos) >= 44
+
+
+def test_library_exports_every_declared_symbol(lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", pplib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [n for n in pplib.parse_header() if n not in exported]
+    assert not missing, missing
+
+
+def test_library_is_sm100a_tcgen05():
+    """The shipped binary contains Blackwell tensor-core / TMA / TMEM instructions (SASS mnemonics)."""
+    sass = subprocess.run(["cuobjdump", "-sass", pplib.LIB_PATH], capture_output=True, text=True).stdout
+    if not sass:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in sass
+    for mnem in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnem in sass, mnem
+
+
+def test_unet_plan_matches_reference_layer_table(lib):
+    h = ctypes.c_void_p()
+    lib.call("pp_unet_create", 1, 32, 512, 5, 8, pplib.BF16, ctypes.byref(h))
+    n = lib.cdll.pp_unet_num_convs(h)
+    assert n == 22  # 22 3x3 convs in the backbone
+    rows = []
+    for i in range(n):
+        cin, cout, dil, name = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_char_p()
+        lib.call("pp_unet_conv_info", h, i, ctypes.byref(cin), ctypes.byref(cout), ctypes.byref(dil), ctypes.byref(name))
+        rows.append((name.value.decode(), cin.value, cout.value, dil.value))
+    assert rows[0] == ("enc_block1.conv_block.conv_layer1", 1, 32, 1)
+    assert rows[8] == ("enc_block5.conv_block.conv_layer1", 256, 512, 2)
+    assert rows[10] == ("enc_block6.conv_block.conv_layer1", 512, 512, 4)
+    assert rows[12] == ("dec_block5.conv_block.conv_layer1", 1024, 512, 1)
+    assert rows[14] == ("dec_block4.conv_block.conv_layer1", 768, 256, 1)
+    assert rows[20] == ("dec_block1.conv_block.conv_layer1", 96, 32, 1)
+    # the oracle's independent layer table agrees
+    from oracle import pp_oracle as O
+    shapes = O.unet_param_shapes(1, 32, 512, 5, 8)
+    for name, cin, cout, _ in rows:
+        assert shapes[name + ".conv.weight"] == (cout, cin, 3, 3)
+    ws = lib.cdll.pp_unet_workspace_bytes(h, 24, 256, 256, 2)
+    assert 2 * 2**30 < ws < 8 * 2**30
+    assert lib.cdll.pp_unet_workspace_bytes(h, 3, 256, 256, 2) == -1  # batch not divisible into 2 groups
+    assert "groups" in lib.last_error()
+    act, off, C, hh, ww = ctypes.c_int(), ctypes.c_longlong(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    lib.call("pp_unet_activation", h, b"encoder/stage6", 24, 256, 256, 2, ctypes.byref(act), ctypes.byref(off),
+             ctypes.byref(C), ctypes.byref(hh), ctypes.byref(ww))
+    assert (C.value, hh.value, ww.value) == (512, 32, 32)
+    lib.cdll.pp_unet_destroy(h)
+
+
+def test_error_convention(lib):
+    h = ctypes.c_void_p()
+    with pytest.raises(RuntimeError, match="input_ch"):
+        lib.call("pp_unet_create", 3, 32, 512, 5, 8, pplib.BF16, ctypes.byref(h))
+    with pytest.raises(RuntimeError, match="output_stride"):
+        lib.call("pp_unet_create", 1, 32, 512, 5, 4, pplib.BF16, ctypes.byref(h))
+
+
+def test_dropin_modules_mirror_reference_state_dict():
+    """Same keys, shapes and dtypes as the reference modules (checkpoints load both ways)."""
+    import sys
+    import torch
+    from pacingpseudo_b200.dropin import DROPIN_PATH
+    from oracle import pp_oracle as O
+    if DROPIN_PATH not in sys.path:
+        sys.path.insert(0, DROPIN_PATH)
+    from models.unet import UNet
+    from models.consistency_reglur_memory import ConsistencyRegulr
+    import argparse
+    for os_ in (8, 16, 32):
+        m = UNet(1, 32, 512, 5, os_, False, False, True)
+        sd = m.state_dict()
+        exp = O.unet_param_shapes(1, 32, 512, 5, os_)
+        assert list(sd) == list(exp)
+        assert all(tuple(sd[k].shape) == tuple(exp[k]) for k in exp)
+    cr = ConsistencyRegulr(
+        kwargs_unet=dict(input_ch=1, init_ch=32, max_ch=512, num_classes=5, output_stride=8, is_stride_conv=False,
+                         is_trans_conv=False, elab_end_points=True),
+        kwargs_aux_path=dict(num_classes=5, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[512, 512],
+                             hid_ch=64, aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
+                             ensemble_mode='cosine_similarity'),
+        args_parser=argparse.Namespace())
+    sd = cr.state_dict()
+    assert len(sd) == 165
+    assert sum(p.numel() for p in cr.parameters()) == 20245381
+    assert sum(p.numel() for p in cr.parameters() if p.requires_grad) == 20245061
+    with pytest.raises(NotImplementedError):
+        UNet(is_stride_conv=True, is_trans_conv=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        UNet(1, 32, 512, 5, 8)(torch.zeros(1, 1, 16, 16))  # no CPU fallback

@@ -1,0 +1,54 @@
+"""CPU, world_size 2, gloo: the host-side data-parallel logic (bucketed gradient all-reduce + averaging
+convention, bank broadcast from rank 0, per-rank batch seeds, max-over-ranks timing)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from pacingpseudo_b200 import dp
+    r, w, dev = dp.init_distributed("gloo")
+    assert (r, w) == (rank, world) and dev.type == "cpu"
+    g = torch.Generator().manual_seed(dp.shard_seed(1234, rank, 0))
+    flat = torch.randn(1000, generator=g)
+    mine = flat.clone()
+    red = dp.GradientAllReducer(flat, num_buckets=3)
+    assert red.buckets[0][0] == 0 and red.buckets[-1][1] == 1000 and len(red.buckets) == 3
+    red.allreduce()
+    gathered = [torch.zeros(1000) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    ok_sum = torch.allclose(flat, sum(gathered))
+    bank = torch.full((5, 64), float(rank + 1))
+    dp.make_bank_sync(0)(bank)
+    ok_bank = bool((bank == 1.0).all())
+    t = dp.max_over_ranks(float(rank), dev)
+    q.put((rank, ok_sum, ok_bank, t, dp.shard_seed(1234, rank, 7)))
+    dist.destroy_process_group()
+
+
+def test_dp_host_logic_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1:4] == (True, True, 1.0) and res[1][1:4] == (True, True, 1.0)
+    assert res[0][4] == 1241 and res[1][4] == 2241
