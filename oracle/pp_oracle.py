@@ -109,12 +109,39 @@ def synth_state_dict(shapes, seed, dtype=torch.float32):
 
 
 # ------------------------------------------------------------------------------------------------
+# bf16 emulation: the CUDA path stores activations, activation gradients and 3x3-conv weights in bf16
+# (fp32 accumulation, fp32 BatchNorm statistics, fp32 heads / first conv / losses). With quant=True the
+# oracle rounds at exactly those storage points (straight-through forward, rounded gradient backward), so
+# a bf16 run can be checked TIGHTLY against "the reference algorithm under the same storage rounding";
+# the distance to the un-rounded reference is reported separately against the north-star tolerances.
+# ------------------------------------------------------------------------------------------------
+class _BF16Store(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().to(g.dtype)
+
+
+def _q(x, quant):
+    return _BF16Store.apply(x) if quant else x
+
+
+def _qw(w, quant):
+    return w.bfloat16().to(w.dtype) + (w - w.detach()) if quant else w
+
+
+# ------------------------------------------------------------------------------------------------
 # layers
 # ------------------------------------------------------------------------------------------------
-def conv_bn_lrelu(x, sd, prefix, dilation, training):
+def conv_bn_lrelu(x, sd, prefix, dilation, training, quant=False):
     """ConvLayer (unet.py:178-193): Conv2d(3x3, pad=dil, bias) -> BatchNorm2d -> LeakyReLU(0.01).
     Running statistics in `sd` are updated in place when training (momentum 0.1, unbiased variance)."""
-    y = F.conv2d(x, sd[prefix + '.conv.weight'], sd[prefix + '.conv.bias'], 1, dilation, dilation)
+    w = sd[prefix + '.conv.weight']
+    y = F.conv2d(x, _qw(w, quant and w.shape[1] > 1), sd[prefix + '.conv.bias'], 1, dilation, dilation)
+    y = _q(y, quant)
     g, b = sd[prefix + '.norm_op.weight'], sd[prefix + '.norm_op.bias']
     rm, rv = sd[prefix + '.norm_op.running_mean'], sd[prefix + '.norm_op.running_var']
     if training:
@@ -129,12 +156,12 @@ def conv_bn_lrelu(x, sd, prefix, dilation, training):
         mean, var = rm.to(y.dtype), rv.to(y.dtype)
     yhat = (y - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + EPS_BN)
     z = yhat * g[None, :, None, None] + b[None, :, None, None]
-    return torch.where(z > 0, z, z * SLOPE)
+    return _q(torch.where(z > 0, z, z * SLOPE), quant)
 
 
-def double_conv(x, sd, prefix, dilation, training):
-    x = conv_bn_lrelu(x, sd, prefix + '.conv_block.conv_layer1', dilation, training)
-    return conv_bn_lrelu(x, sd, prefix + '.conv_block.conv_layer2', dilation, training)
+def double_conv(x, sd, prefix, dilation, training, quant=False):
+    x = conv_bn_lrelu(x, sd, prefix + '.conv_block.conv_layer1', dilation, training, quant)
+    return conv_bn_lrelu(x, sd, prefix + '.conv_block.conv_layer2', dilation, training, quant)
 
 
 def upsample_bilinear_ac(x, size):
@@ -158,7 +185,7 @@ def upsample_bilinear_ac(x, size):
     return top * wy0[:, None] + bot * wy1[:, None]
 
 
-def unet_forward(sd, x, training, init_ch=32, max_ch=512, output_stride=8, prefix=''):
+def unet_forward(sd, x, training, init_ch=32, max_ch=512, output_stride=8, prefix='', quant=False):
     """UNet.forward (unet.py:62-98) -> dict of the 12 end points."""
     _ch, enc_cfg, scales = unet_structure(init_ch, max_ch, output_stride)
     ep = {}
@@ -167,14 +194,14 @@ def unet_forward(sd, x, training, init_ch=32, max_ch=512, output_stride=8, prefi
     for k, (pool, dil) in enumerate(enc_cfg):
         if pool:
             cur = F.max_pool2d(cur, 2, 2)  # unet.py:109
-        cur = double_conv(cur, sd, '%senc_block%d' % (prefix, k + 1), dil, training)
+        cur = double_conv(cur, sd, '%senc_block%d' % (prefix, k + 1), dil, training, quant)
         enc.append(cur)
         ep['encoder/stage%d' % (k + 1)] = cur
     for i, stage in enumerate((5, 4, 3, 2, 1)):
         skip = enc[stage - 1]
         s = scales[i]
-        up = upsample_bilinear_ac(cur, (cur.shape[2] * s, cur.shape[3] * s)) if s > 1 else cur
-        cur = double_conv(torch.cat((up, skip), 1), sd, '%sdec_block%d' % (prefix, stage), 1, training)  # :151
+        up = _q(upsample_bilinear_ac(cur, (cur.shape[2] * s, cur.shape[3] * s)), quant) if s > 1 else cur
+        cur = double_conv(torch.cat((up, skip), 1), sd, '%sdec_block%d' % (prefix, stage), 1, training, quant)  # :151
         ep['decoder/stage%d' % stage] = cur
     ep['segmentation/logits'] = F.conv2d(cur, sd[prefix + 'final_conv.weight'], sd[prefix + 'final_conv.bias'])
     return ep
@@ -240,10 +267,11 @@ def ramp_up_mo(step, max_step, base_mo=0.9, gamma=0.9):
     return (1 - step / max_step) ** gamma * base_mo
 
 
-def aux_forward(sd, feats, out_hw, training, prefix='aux_path.'):
+def aux_forward(sd, feats, out_hw, training, prefix='aux_path.', quant=False):
     """aux_path_memory.py:49-52 (Dropout2d(p=0) is the identity)."""
     x = torch.cat(feats, 1)
-    y = F.conv2d(x, sd[prefix + 'layer_bottleneck.1.weight'], sd[prefix + 'layer_bottleneck.1.bias'], 1, 1)
+    y = F.conv2d(x, _qw(sd[prefix + 'layer_bottleneck.1.weight'], quant), sd[prefix + 'layer_bottleneck.1.bias'], 1, 1)
+    y = _q(y, quant)
     g, b = sd[prefix + 'layer_bottleneck.2.weight'], sd[prefix + 'layer_bottleneck.2.bias']
     rm, rv = sd[prefix + 'layer_bottleneck.2.running_mean'], sd[prefix + 'layer_bottleneck.2.running_var']
     if training:
@@ -257,7 +285,7 @@ def aux_forward(sd, feats, out_hw, training, prefix='aux_path.'):
         mean, var = rm.to(y.dtype), rv.to(y.dtype)
     z = (y - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + EPS_BN)
     z = z * g[None, :, None, None] + b[None, :, None, None]
-    aux_features = torch.where(z > 0, z, z * SLOPE)
+    aux_features = _q(torch.where(z > 0, z, z * SLOPE), quant)
     low = F.conv2d(aux_features, sd[prefix + 'fc_cls.1.weight'])
     return upsample_bilinear_ac(low, out_hw), aux_features
 
@@ -298,7 +326,7 @@ class StepConfig:
     def __init__(self, num_classes=5, ignored_index=5, do_loss_ent=True, do_decoder_consistency=True,
                  detach_weak_cr=False, loss_cr_variants='ce_loss', do_aux_path=True, do_memory=True,
                  feat_stage=('encoder/stage6', 'encoder/stage5'), max_step=400, update_momentum=0.9,
-                 ensemble_mode='cosine_similarity', init_ch=32, max_ch=512, output_stride=8):
+                 ensemble_mode='cosine_similarity', init_ch=32, max_ch=512, output_stride=8, quant=False):
         self.__dict__.update(locals())
         del self.__dict__['self']
 
@@ -308,7 +336,8 @@ def consistency_forward(sd, batch, cfg, mode='train', step=0, training=True):
     state dict. `training` is the module's BatchNorm mode (train_chaos.py never re-enters .train())."""
     net = cfg
     out = {}
-    kw = dict(init_ch=net.init_ch, max_ch=net.max_ch, output_stride=net.output_stride, prefix='backbone.')
+    kw = dict(init_ch=net.init_ch, max_ch=net.max_ch, output_stride=net.output_stride, prefix='backbone.',
+              quant=net.quant)
     ep = unet_forward(sd, batch['image'], training, **kw)
     zw = ep['segmentation/logits']
     target = batch['scribble'].argmax(1)
@@ -337,7 +366,7 @@ def consistency_forward(sd, batch, cfg, mode='train', step=0, training=True):
         out['segmentation/logits_strong'] = zs
     if mode == 'train' and net.do_aux_path:
         feats = [ep[s] for s in net.feat_stage]
-        za, aux_features = aux_forward(sd, feats, batch['scribble'].shape[-2:], training)
+        za, aux_features = aux_forward(sd, feats, batch['scribble'].shape[-2:], training, quant=net.quant)
         out['logits_aux_cls'] = za
         out['loss_aux_cls'] = partial_cross_entropy(za, target, net.ignored_index)
         if net.do_memory:

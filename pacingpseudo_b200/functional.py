@@ -122,6 +122,7 @@ class UNetFunction(torch.autograd.Function):
             act_ids.append(act)
         ctx.engine, ctx.groups, ctx.training, ctx.act_ids = engine, groups, int(training), act_ids
         ctx.shape = (N, H, W)
+        ctx.set_materialize_grads(False)  # unused end points must arrive as None, not as zero tensors
         ctx.buffers = buffers
         ctx.save_for_backward(x, ws, *learnable)
         return (logits, *feats)

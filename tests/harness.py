@@ -21,9 +21,16 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 # Gradient floors: the reference itself moves by up to ~8e-3 between fp32 and fp64 on these tiny cases
 # (max-pool ties, LeakyReLU sign flips under 128-element BatchNorm statistics), so fp32-vs-fp32 gradient
 # checks use 1e-2 (oracle, same machine) and 2e-2 (fp32 CUDA mode); bf16 uses the stated 5e-2.
+# bf16: (a) "bf16_emul": against the oracle run with the SAME bf16 storage rounding (quant=True) — a tight check that
+# the kernels implement the reference algorithm; (b) "bf16": against the un-rounded fp32 reference at the north-star
+# tolerances, applied at BASELINE.json's full size (N=12, 256x256) where BatchNorm statistics are well conditioned;
+# (c) "bf16_small": against the fp32 golden vectors of the tiny cases (2-3 images, 8x8 bottleneck), where bf16
+# storage noise legitimately flips max-pool winners / LeakyReLU signs: losses and tensor norms only.
 TOL = {
     "fp32": dict(loss=1e-4, logits=1e-4, grad=2e-2, argmax=0.9999, bank=1e-4),
     "bf16": dict(loss=2e-2, logits=2e-2, grad=5e-2, argmax=0.999, bank=2e-2),
+    "bf16_emul": dict(loss=2e-3, logits=1.5e-2, grad=5e-2, argmax=0.99, bank=1e-2, running=2e-3),
+    "bf16_small": dict(loss=2e-2, logits=None, norms=2e-2, grad=None, argmax=None, bank=5e-2, running=2e-2),
     "oracle": dict(loss=2e-5, logits=2e-5, grad=1e-2, argmax=0.9999, bank=2e-5),
 }
 
@@ -52,8 +59,8 @@ def _grad_record(rec, step, named_grads):
     rec["s%d/grad_samples" % step] = np.stack(samples)
 
 
-def run_case_oracle(name, dtype=torch.float32):
-    """The CPU oracle restatement on a golden case."""
+def run_case_oracle(name, dtype=torch.float32, quant=False):
+    """The CPU oracle restatement on a golden case (quant=True: with the CUDA path's bf16 storage rounding)."""
     case = CASES[name]
     C = case["C"]
     sd = {k: (v.to(dtype) if v.is_floating_point() else v.clone()) for k, v in build_state(case).items()}
@@ -62,7 +69,7 @@ def run_case_oracle(name, dtype=torch.float32):
         sd[k].requires_grad_(True)
     cfg = O.StepConfig(num_classes=C, ignored_index=C, detach_weak_cr=bool(case.get("detach")),
                        loss_cr_variants=case.get("cr", "ce_loss"), ensemble_mode=case.get("mode", "cosine_similarity"),
-                       output_stride=case["os"])
+                       output_stride=case["os"], quant=quant)
     rec = {}
     for step in range(case.get("steps", 1)):
         batch = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in case_batch(case, step).items()}
@@ -78,7 +85,8 @@ def run_case_oracle(name, dtype=torch.float32):
             rec["s%d/argmax_weak" % step] = out["segmentation/logits"].argmax(1).to(torch.uint8).numpy()
             rec["s%d/memory_bank" % step] = sd["aux_path.memory_bank"].detach().double().numpy().reshape(C, 64)
         else:
-            logits = O.unet_forward(sd, batch["image"], case["training"], output_stride=case["os"])["segmentation/logits"]
+            logits = O.unet_forward(sd, batch["image"], case["training"], output_stride=case["os"],
+                                    quant=quant)["segmentation/logits"]
             if case["kind"] == "baseline":
                 loss = O.partial_cross_entropy(logits, batch["scribble"].argmax(1), C)
                 rec["s%d/loss_pce" % step] = np.array(loss.item())
@@ -182,6 +190,8 @@ def compare(rec, gold, tol, steps, report=None):
                 if not e <= tol["loss"]:
                     fails.append("%s: %.6f vs reference %.6f (rel %.2e > %.1e)" % (k, float(rec[k]), float(gold[k]), e, tol["loss"]))
             elif short.endswith("/samples"):
+                if tol.get("logits") is None:
+                    continue
                 scale = max(float(np.max(np.abs(gold[k]))), 1e-6)
                 e = float(np.max(np.abs(rec[k] - gold[k]))) / scale
                 lines.append("%s max-rel %.3e" % (k, e))
@@ -190,12 +200,13 @@ def compare(rec, gold, tol, steps, report=None):
             elif short.endswith("/sum"):
                 e = rel(rec[k][1:], gold[k][1:], 1e-6)  # |x| sum and L2 norm
                 lines.append("%s norms rel %.3e" % (k, e))
-                if not e <= tol["logits"]:
-                    fails.append("%s: norm mismatch rel %.2e > %.1e" % (k, e, tol["logits"]))
+                ntol = tol.get("norms", tol.get("logits"))
+                if not e <= ntol:
+                    fails.append("%s: norm mismatch rel %.2e > %.1e" % (k, e, ntol))
             elif short == "argmax_weak":
                 agree = float(np.mean(rec[k] == gold[k]))
                 lines.append("%s agreement %.5f" % (k, agree))
-                if agree < tol["argmax"]:
+                if tol.get("argmax") is not None and agree < tol["argmax"]:
                     fails.append("%s: argmax agreement %.5f < %.4f" % (k, agree, tol["argmax"]))
             elif short == "memory_bank":
                 den = max(float(np.linalg.norm(gold[k])), 1e-12)
@@ -204,6 +215,8 @@ def compare(rec, gold, tol, steps, report=None):
                 if not e <= tol["bank"]:
                     fails.append("%s: rel L2 %.2e > %.1e" % (k, e, tol["bank"]))
             elif short == "grad_sums":
+                if tol.get("grad") is None:
+                    continue
                 gn = [str(s) for s in gold[p + "grad_names"]]
                 rn = [str(s) for s in rec[p + "grad_names"]]
                 if gn != rn:
@@ -237,8 +250,9 @@ def compare(rec, gold, tol, steps, report=None):
     if "running_sums" in gold:
         e = rel(rec["running_sums"][:, 1:], gold["running_sums"][:, 1:], 1e-6)
         lines.append("running stats norms rel %.3e" % e)
-        if not e <= max(tol["logits"], 1e-4) * 5:
-            fails.append("running statistics differ: rel %.2e" % e)
+        rtol = tol.get("running", max(tol["logits"] or 0, 1e-4) * 5)
+        if not e <= rtol:
+            fails.append("running statistics differ: rel %.2e > %.1e" % (e, rtol))
     if report is not None:
         report.extend(lines)
     return fails
