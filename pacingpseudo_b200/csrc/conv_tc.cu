@@ -202,6 +202,7 @@ struct WgradTcParams {
   int tiles_w, tiles_h, tiles_total;
   int Cout, C0, C1;
   int ci_tiles0, ci_tiles1;  // N tiles per source
+  int ctot, cbase0, cbase1;  // row length of dw and the column offset of each source inside it
   int kb_per_split;
   int stages;
   float* dw;                 // [9][Cout][C0+C1] fp32, pre-zeroed, accumulated with red.global
@@ -308,8 +309,8 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_c
       const int q = warp & 3;
       const int co = co0 + q * 32 + lane;
       const int csrc = src1 ? p.C1 : p.C0;
-      const int ctot = p.C0 + p.C1;
-      const int cbase = (src1 ? p.C0 : 0) + ci0;
+      const int ctot = p.ctot;
+      const int cbase = (src1 ? p.cbase1 : p.cbase0) + ci0;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
 #pragma unroll 1
@@ -322,6 +323,157 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (ci0 + c + j < csrc) atomicAdd(o + j, __uint_as_float(v[j]));
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncwarp();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// wgrad for narrow layers (one source with 32 or 64 channels, Cout 32 or 64): the full-resolution
+// layers have millions of pixels (GEMM K) but a tiny 32x32..64x64 output per tap, so the generic kernel
+// above would re-stream dY for each of the 9 taps and pad M to 128. Here ONE CTA owns a pixel range and all
+// 9 taps: per K block it loads dY once and the 9 shifted X boxes, and packs taps into the MMA M dimension
+//     D_g[(tap - g0) * CI + ci, co] += sum_pixel X[pixel + off(tap), ci] * dY[pixel, co]
+// with 128 / CI taps per group g (CI = 32: tap groups {0-3, 4-7, 5-8}; CI = 64: {0-1, 2-3, 4-5, 6-7, 7-8};
+// the last group overlaps its predecessor and only its new tap is written back). The X boxes of consecutive
+// taps sit LBO bytes apart in shared memory, so one MN-major descriptor spans a whole group.
+// ----------------------------------------------------------------------------------------------
+struct WgradNarrowParams {
+  int N, H, W, dil;
+  int bw, bh, bn;            // pixel box of one K block (bw*bh*bn == pixk)
+  int tiles_w, tiles_h, tiles_total;
+  int Cout, Csrc, ctot, cbase;
+  int kb_per_cta, stages, pixk;
+  float* dw;
+};
+
+template <int CI, int NCOUT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3x3_wgrad_narrow_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                               const WgradNarrowParams p) {
+  constexpr int TPG = 128 / CI;                       // taps per MMA group
+  constexpr int NG = (9 + TPG - 1) / TPG;             // 3 (CI = 32) or 5 (CI = 64)
+  constexpr int ROW_A = CI * 2, ROW_B = (NCOUT < 64 ? NCOUT : 64) * 2;   // bytes per pixel row of a box
+  constexpr uint32_t SWZ_A = CI == 64 ? SWZ_128B : SWZ_64B;
+  constexpr uint32_t SWZ_B = NCOUT >= 64 ? SWZ_128B : SWZ_64B;
+  constexpr int NB_B = NCOUT > 64 ? NCOUT / 64 : 1;   // dY boxes
+  constexpr int TMEM_NEED = NG * NCOUT;
+  constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+  static_assert(TMEM_NEED <= 512, "accumulators do not fit TMEM");
+
+  const int xbox = p.pixk * ROW_A;                    // bytes of one X box
+  const int ybox = p.pixk * ROW_B;                    // bytes of one dY box
+  const int stage_bytes = 9 * xbox + NB_B * ybox;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kb_begin = blockIdx.x * p.kb_per_cta;
+  const int kb_end = min(kb_begin + p.kb_per_cta, p.tiles_total);
+  const int num_k = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_k > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          const int tw = kb % p.tiles_w;
+          const int th = (kb / p.tiles_w) % p.tiles_h;
+          const int tn = kb / (p.tiles_w * p.tiles_h);
+          const int x0 = tw * p.bw, y0 = th * p.bh, n0 = tn * p.bn;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sx = smem + stage * stage_bytes;
+          uint8_t* sy = sx + 9 * xbox;
+          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap)
+            tma_load_4d(sx + tap * xbox, &tmX, &full_bar[stage], 0, x0 + (tap % 3 - 1) * p.dil,
+                        y0 + (tap / 3 - 1) * p.dil, n0);
+#pragma unroll
+          for (int b = 0; b < NB_B; ++b) tma_load_4d(sy + b * ybox, &tmDY, &full_bar[stage], b * 64, x0, y0, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, NCOUT, 1, 1);  // both operands MN-major
+        const int ksteps = p.pixk / 16;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < num_k; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sx = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sy = sx + 9 * xbox;
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            const int g0 = (g == NG - 1) ? 9 - TPG : g * TPG;   // first tap of the group
+            for (int k = 0; k < ksteps; ++k) {
+              // K step = 16 pixel rows; MN chunks (one tap each) are xbox bytes apart; 8-row groups 8*ROW apart
+              const uint64_t da = make_smem_desc(sx + g0 * xbox + k * 16 * ROW_A, xbox, 8 * ROW_A, SWZ_A);
+              const uint64_t db = make_smem_desc(sy + k * 16 * ROW_B, ybox, 8 * ROW_B, SWZ_B);
+              umma_bf16(tmem_base + g * NCOUT, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tmem_full_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int r = q * 32 + lane;          // accumulator row = (tap - g0) * CI + ci
+      const int ci = r % CI;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < NG; ++g) {
+        const int g0 = (g == NG - 1) ? 9 - TPG : g * TPG;
+        const int tap = g0 + r / CI;
+        const int first_new = (g == NG - 1) ? (NG - 1) * TPG : g0;   // taps below were written by the previous group
+        const bool row_ok = (tap >= first_new) && (ci < p.Csrc);
+#pragma unroll 1
+        for (int c = 0; c < NCOUT; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(g * NCOUT + c), v);
+          tmem_wait_ld();
+          if (row_ok) {
+            float* o = p.dw + (static_cast<long long>(tap) * p.Cout + c) * p.ctot + p.cbase + ci;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c + j < p.Cout) atomicAdd(o + static_cast<long long>(j) * p.ctot, __uint_as_float(v[j]));
+          }
         }
       }
       tc_fence_before();
@@ -444,12 +596,57 @@ static int launch_wgrad_tc(const CUtensorMap& dy, const CUtensorMap& x0, const C
   return PP_OK;
 }
 
-// dy:[N,H,W,Cout] bf16, x0/x1 as in forward; dw:[9][Cout][C0+C1] fp32, MUST be zeroed by the caller.
-int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw, int N,
-                     int H, int W, int dil, cudaStream_t stream) {
-  PP_REQUIRE(N > 0 && H > 0 && W > 0 && dil >= 1, "conv3x3_wgrad_tc: bad shape");
-  PP_REQUIRE(Cout % 8 == 0 && C0 % 8 == 0 && C1 % 8 == 0 && C0 > 0, "conv3x3_wgrad_tc: channels must be multiples of 8");
-  PP_REQUIRE((x1 == nullptr) == (C1 == 0), "conv3x3_wgrad_tc: x1/C1 mismatch");
+template <int CI, int NCOUT>
+static int launch_wgrad_narrow(const void* dy, int Cout, const void* x, int Csrc, int ctot, int cbase, float* dw, int N,
+                               int H, int W, int dil, cudaStream_t stream) {
+  WgradNarrowParams p{};
+  p.N = N; p.H = H; p.W = W; p.dil = dil;
+  constexpr int ROW_A = CI * 2, ROW_B = (NCOUT < 64 ? NCOUT : 64) * 2, NB_B = NCOUT > 64 ? NCOUT / 64 : 1;
+  p.pixk = (64 * (9 * ROW_A + NB_B * ROW_B) <= 48 * 1024) ? 64 : 32;
+  pixel_box(W, H, p.pixk, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = ceil_div(W, p.bw);
+  p.tiles_h = ceil_div(H, p.bh);
+  p.tiles_total = p.tiles_w * p.tiles_h * ceil_div(N, p.bn);
+  p.Cout = Cout; p.Csrc = Csrc; p.ctot = ctot; p.cbase = cbase; p.dw = dw;
+  const int stage_bytes = p.pixk * (9 * ROW_A + NB_B * ROW_B);
+  p.stages = (200 * 1024) / stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  int ctas = sm_count() < p.tiles_total ? sm_count() : p.tiles_total;
+  p.kb_per_cta = ceil_div(p.tiles_total, ctas);
+  ctas = ceil_div(p.tiles_total, p.kb_per_cta);
+  CUtensorMap tx, tdy;
+  int rc = encode_tmap_nhwc(&tx, x, N, H, W, Csrc, CI, p.bw, p.bh, p.bn, CI == 64);
+  if (rc) return rc;
+  rc = encode_tmap_nhwc(&tdy, dy, N, H, W, Cout, NCOUT < 64 ? NCOUT : 64, p.bw, p.bh, p.bn, NCOUT >= 64);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_narrow_tc_kernel<CI, NCOUT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024 + 256));
+    attr_set = true;
+  }
+  const int smem = p.stages * stage_bytes + 1024 + 256;
+  const double flops = 2.0 * N * H * W * 9.0 * Csrc * Cout;
+  const int slot = prof_begin(PROF_WGRAD, flops, stream);
+  conv3x3_wgrad_narrow_tc_kernel<CI, NCOUT><<<ctas, kTcThreads, smem, stream>>>(tx, tdy, p);
+  prof_end(slot, stream);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+static bool narrow_ok(int Csrc, int Cout) { return (Csrc == 32 || Csrc == 64) && (Cout == 32 || Cout == 64); }
+
+static int wgrad_narrow(const void* dy, int Cout, const void* x, int Csrc, int ctot, int cbase, float* dw, int N, int H,
+                        int W, int dil, cudaStream_t stream) {
+  if (Csrc == 32 && Cout == 32) return launch_wgrad_narrow<32, 32>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, dil, stream);
+  if (Csrc == 32 && Cout == 64) return launch_wgrad_narrow<32, 64>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, dil, stream);
+  if (Csrc == 64 && Cout == 32) return launch_wgrad_narrow<64, 32>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, dil, stream);
+  return launch_wgrad_narrow<64, 64>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, dil, stream);
+}
+
+// generic kernel over the given sources; ctot / cbase place them inside the rows of dw
+static int wgrad_wide(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, int ctot, int cbase0,
+                      int cbase1, float* dw, int N, int H, int W, int dil, cudaStream_t stream) {
   WgradTcParams p{};
   p.N = N; p.H = H; p.W = W; p.dil = dil;
   pixel_box(W, H, 64, &p.bw, &p.bh, &p.bn);
@@ -457,13 +654,15 @@ int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const voi
   p.tiles_h = ceil_div(H, p.bh);
   p.tiles_total = p.tiles_w * p.tiles_h * ceil_div(N, p.bn);
   p.Cout = Cout; p.C0 = C0; p.C1 = C1; p.dw = dw;
+  p.ctot = ctot; p.cbase0 = cbase0; p.cbase1 = cbase1;
   const int cmax = C0 > C1 ? C0 : C1;
   const int block_n = cmax <= 64 ? 64 : (cmax <= 128 ? 128 : 256);
   p.ci_tiles0 = ceil_div(C0, block_n);
   p.ci_tiles1 = C1 > 0 ? ceil_div(C1, block_n) : 0;
   const int co_tiles = ceil_div(Cout, 128);
   const int base_ctas = co_tiles * (p.ci_tiles0 + p.ci_tiles1) * 9;
-  int splits = ceil_div(3 * sm_count(), base_ctas);
+  // split K so that the grid is at most ~2 full waves of one CTA per SM (fewer partial-tile reductions)
+  int splits = (2 * sm_count()) / base_ctas;
   if (splits > p.tiles_total) splits = p.tiles_total;
   if (splits < 1) splits = 1;
   p.kb_per_split = ceil_div(p.tiles_total, splits);
@@ -481,6 +680,26 @@ int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const voi
   if (block_n == 64) return launch_wgrad_tc<64>(tdy, tx0, tx1, p, grid, stream);
   if (block_n == 128) return launch_wgrad_tc<128>(tdy, tx0, tx1, p, grid, stream);
   return launch_wgrad_tc<256>(tdy, tx0, tx1, p, grid, stream);
+}
+
+// dy:[N,H,W,Cout] bf16, x0/x1 as in forward; dw:[9][Cout][C0+C1] fp32, MUST be zeroed by the caller.
+int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw, int N,
+                     int H, int W, int dil, cudaStream_t stream) {
+  PP_REQUIRE(N > 0 && H > 0 && W > 0 && dil >= 1, "conv3x3_wgrad_tc: bad shape");
+  PP_REQUIRE(Cout % 8 == 0 && C0 % 8 == 0 && C1 % 8 == 0 && C0 > 0, "conv3x3_wgrad_tc: channels must be multiples of 8");
+  PP_REQUIRE((x1 == nullptr) == (C1 == 0), "conv3x3_wgrad_tc: x1/C1 mismatch");
+  const int ctot = C0 + C1;
+  const bool n0 = narrow_ok(C0, Cout), n1 = C1 > 0 && narrow_ok(C1, Cout);
+  int rc = PP_OK;
+  if (n0) rc = wgrad_narrow(dy, Cout, x0, C0, ctot, 0, dw, N, H, W, dil, stream);
+  if (rc) return rc;
+  if (n1) rc = wgrad_narrow(dy, Cout, x1, C1, ctot, C0, dw, N, H, W, dil, stream);
+  if (rc) return rc;
+  if (!n0 && C1 > 0 && !n1) return wgrad_wide(dy, Cout, x0, C0, x1, C1, ctot, 0, C0, dw, N, H, W, dil, stream);
+  if (!n0) rc = wgrad_wide(dy, Cout, x0, C0, nullptr, 0, ctot, 0, 0, dw, N, H, W, dil, stream);
+  if (rc) return rc;
+  if (C1 > 0 && !n1 && n0) rc = wgrad_wide(dy, Cout, x1, C1, nullptr, 0, ctot, C0, 0, dw, N, H, W, dil, stream);
+  return rc;
 }
 
 }  // namespace pp

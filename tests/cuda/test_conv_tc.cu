@@ -37,6 +37,9 @@ static const Case kCases[] = {
     {2, 64, 64, 256, 128, 128, 0, 1, 0, "concat 256+128 64x64"},
     {12, 32, 32, 512, 0, 512, 0, 4, 0, "bottleneck dil4 full batch"},
     {3, 7, 5, 32, 0, 32, 0, 1, 0, "tiny odd 7x5"},
+    {2, 32, 32, 128, 64, 64, 0, 1, 0, "wgrad: wide source 0 + narrow source 1"},
+    {1, 128, 128, 64, 0, 64, 0, 1, 0, "narrow wgrad 64->64 128x128"},
+    {2, 64, 64, 32, 0, 64, 0, 2, 0, "narrow wgrad 32->64 dil2"},
 };
 
 static float bf16_round(float f) { return __bfloat162float(__float2bfloat16(f)); }
