@@ -78,6 +78,13 @@ int pp_unet_backward(pp_unet_t u, const float* x, void* const* params, void* wor
 int pp_conv3x3(int dtype, const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias,
                void* out0, int oc0, int acc0, void* out1, int oc1, int acc1, int N, int H, int W, int dil,
                void* stream);
+/* bf16 forward conv with the BatchNorm batch statistics fused into the epilogue (unet.py:188-189): besides y it
+ * accumulates sum / sum-of-squares of the ROUNDED output per statistics group into
+ * stats[pp_stat_replicas()][groups][Cout][2] doubles (caller zeroes; the replicas are summed when folding).
+ * A 128-pixel tile must not straddle two groups (error otherwise). */
+int pp_conv3x3_bn_stats(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* y,
+                        int Cout, double* stats, int groups, int N, int H, int W, int dil, void* stream);
+int pp_stat_replicas(void);
 /* weight gradient of the same conv: dwp[9][Cout][C0+C1] fp32 += (caller zeroes) */
 int pp_conv3x3_wgrad(int dtype, const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dwp,
                      int N, int H, int W, int dil, void* stream);

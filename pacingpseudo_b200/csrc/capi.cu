@@ -72,6 +72,11 @@ int pp_conv3x3(int dtype, const void* x0, int C0, const void* x1, int C1, const 
     return conv3x3_tc(x0, C0, x1, C1, wpack, bias, out0, oc0, acc0, out1, oc1, acc1, N, H, W, dil, ST(stream));
   return conv3x3_simt(dtype, x0, C0, x1, C1, wpack, bias, out0, oc0, acc0, out1, oc1, acc1, N, H, W, dil, ST(stream));
 }
+int pp_conv3x3_bn_stats(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* y,
+                        int Cout, double* stats, int groups, int N, int H, int W, int dil, void* stream) {
+  return conv3x3_tc(x0, C0, x1, C1, wpack, bias, y, Cout, 0, nullptr, 0, 0, N, H, W, dil, ST(stream), stats, groups);
+}
+int pp_stat_replicas(void) { return kStatReplicas; }
 int pp_conv3x3_wgrad(int dtype, const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dwp,
                      int N, int H, int W, int dil, void* stream) {
   if (dtype == PP_BF16) return conv3x3_wgrad_tc(dy, Cout, x0, C0, x1, C1, dwp, N, H, W, dil, ST(stream));

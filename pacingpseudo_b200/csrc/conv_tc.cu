@@ -41,10 +41,12 @@ struct ConvTcParams {
   int outc0, outc1;
   int acc0, acc1;              // 1: out += result (read-modify-write)
   const float* bias;           // [outc0 + outc1] or null
+  double* stats;               // optional [kStatReplicas][groups][cout][2] (sum, sum of squares) of the rounded output
+  int imgs_per_group, groups;  // images per BatchNorm statistics group / number of groups (stats != null)
 };
 
 template <int BLOCK_N, int BK>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, (BLOCK_N <= 96) ? 3 : 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
   constexpr int A_BYTES = 128 * BK * 2;
@@ -52,7 +54,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t SWZ = (BK == 64) ? SWZ_128B : SWZ_64B;
   constexpr uint32_t SBO = 8 * BK * 2;  // 8 rows of one swizzle atom
-  constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -60,6 +62,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 2);   // [4 warps][2][BLOCK_N] BatchNorm partial sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -147,46 +150,85 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const long long pix = (static_cast<long long>(pn) * p.H + py) * p.W + px;
 
     const int col0 = n_tile * BLOCK_N;  // first GEMM column of this CTA
-    __nv_bfloat16* dst;
-    int dstc, acc, ch0;
-    if (col0 < p.outc0) { dst = p.out0; dstc = p.outc0; acc = p.acc0; ch0 = col0; }
-    else                { dst = p.out1; dstc = p.outc1; acc = p.acc1; ch0 = col0 - p.outc0; }
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N; c += 32) {
+      // destination of this 32-column chunk (a CTA tile may straddle the two concat sources in dgrad)
+      const int col = col0 + c;
+      __nv_bfloat16* dst;
+      int dstc, acc, ch;
+      if (col < p.outc0) { dst = p.out0; dstc = p.outc0; acc = p.acc0; ch = col; }
+      else               { dst = p.out1; dstc = p.outc1; acc = p.acc1; ch = col - p.outc0; }
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c), v);
       tmem_wait_ld();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col + j);
+      }
       if (valid) {
-        __nv_bfloat16* o = dst + pix * dstc + ch0 + c;
+        __nv_bfloat16* o = dst + pix * dstc + ch;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += __ldg(p.bias + col0 + c + g * 8 + j);
-          }
           Vec8<__nv_bfloat16> pk;
+          float t[8];
           if (acc) {
-            float old[8];
             pk.load(o + g * 8);
-            pk.get(old);
+            pk.get(t);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += old[j];
+            for (int j = 0; j < 8; ++j) f[g * 8 + j] += t[j];
           }
-          pk.set(f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = f[g * 8 + j];
+          pk.set(t);
           pk.store(o + g * 8);
+          pk.get(t);   // statistics are taken of the bf16-ROUNDED values (what BatchNorm will read back)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[g * 8 + j] = t[j];
         }
+      }
+      if (p.stats != nullptr) {
+        // column sums over this warp's 32 rows: butterfly transpose-reduce, lane j ends with column j
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { s1[j] = valid ? f[j] : 0.f; s2[j] = s1[j] * s1[j]; }
+#pragma unroll
+        for (int w = 16; w >= 1; w >>= 1) {
+          const bool hi = (lane & w) != 0;
+#pragma unroll
+          for (int j = 0; j < w; ++j) {
+            const float a1 = hi ? s1[j] : s1[j + w], a2 = hi ? s2[j] : s2[j + w];
+            const float k1 = hi ? s1[j + w] : s1[j], k2 = hi ? s2[j + w] : s2[j];
+            s1[j] = k1 + __shfl_xor_sync(0xffffffffu, a1, w);
+            s2[j] = k2 + __shfl_xor_sync(0xffffffffu, a2, w);
+          }
+        }
+        s_stats[(q * 2 + 0) * BLOCK_N + c + lane] = s1[0];   // one slot per warp: summed in a fixed order below,
+        s_stats[(q * 2 + 1) * BLOCK_N + c + lane] = s2[0];   // so a forward pass is bit-reproducible
       }
     }
     tc_fence_before();
   }
   __syncwarp();
   __syncthreads();
+  if (p.stats != nullptr) {
+    // all rows of a tile belong to one statistics group (host guarantees bn | imgs_per_group or bn == 1)
+    const int grp = n0 / p.imgs_per_group;
+    const int cout = p.outc0 + p.outc1;
+    for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kTcThreads) {
+      const int st = i / BLOCK_N, cc = n_tile * BLOCK_N + i % BLOCK_N;
+      // kStatReplicas interleaved copies of the accumulator spread the same-address atomics of thousands of CTAs
+      const int j = i % BLOCK_N;
+      const double tot = (static_cast<double>(s_stats[(0 * 2 + st) * BLOCK_N + j]) + s_stats[(1 * 2 + st) * BLOCK_N + j]) +
+                         (static_cast<double>(s_stats[(2 * 2 + st) * BLOCK_N + j]) + s_stats[(3 * 2 + st) * BLOCK_N + j]);
+      atomicAdd(p.stats + ((static_cast<long long>(m_tile % kStatReplicas) * p.groups + grp) * cout + cc) * 2 + st, tot);
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -507,14 +549,17 @@ template <int BLOCK_N, int BK>
 static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, ConvTcParams p,
                           int m_tiles, int n_tiles, cudaStream_t stream) {
   constexpr int STAGE_BYTES = 128 * BK * 2 + BLOCK_N * BK * 2;
-  int stages = (200 * 1024) / STAGE_BYTES;
+  constexpr int TAIL = 1024 + 256 + 8 * BLOCK_N * 4;
+  // narrow tiles are latency-bound per CTA: keep the footprint small enough for 3 CTAs per SM
+  int stages = ((BLOCK_N <= 96 ? 70 : 200) * 1024) / STAGE_BYTES;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
   p.stages = stages;
-  const int smem = stages * STAGE_BYTES + 1024 + 256;
+  const int smem = stages * STAGE_BYTES + TAIL;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
     PP_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<BLOCK_N, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       200 * 1024 + 1024 + 256));
+                                       200 * 1024 + TAIL));
     attr_set = true;
   }
   const double flops = 2.0 * p.N * p.H * p.W * 9.0 * p.ctot * (p.outc0 + p.outc1);
@@ -528,7 +573,7 @@ static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CU
 // x0:[N,H,W,C0] x1:[N,H,W,C1] (or null), wpack:[9][outc0+outc1][C0+C1] bf16.
 int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
                int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil,
-               cudaStream_t stream) {
+               cudaStream_t stream, double* stats, int groups) {
   const int cout = outc0 + outc1;
   const int ctot = C0 + C1;
   PP_REQUIRE(N > 0 && H > 0 && W > 0 && dil >= 1, "conv3x3_tc: bad shape N=%d H=%d W=%d dil=%d", N, H, W, dil);
@@ -536,11 +581,15 @@ int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack
              C0, C1);
   PP_REQUIRE((x1 == nullptr) == (C1 == 0), "conv3x3_tc: x1/C1 mismatch");
   PP_REQUIRE((out1 == nullptr) == (outc1 == 0), "conv3x3_tc: out1/outc1 mismatch");
+  PP_REQUIRE(outc0 % 32 == 0 && outc1 % 32 == 0, "conv3x3_tc: output channels must be multiples of 32 (outc0=%d outc1=%d)",
+             outc0, outc1);
   const int bk = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
-  int g = gcd_int(outc0, outc1 == 0 ? outc0 : outc1);
-  int block_n = 256;
-  while (block_n > 32 && g % block_n != 0) block_n >>= 1;
-  PP_REQUIRE(g % block_n == 0, "conv3x3_tc: output channels must be multiples of 32 (outc0=%d outc1=%d)", outc0, outc1);
+  // N tile: the largest of {256,192,128,96,64,32} that divides the total output channels (a tile may straddle the two
+  // dgrad destinations: the epilogue picks the destination per 32-column chunk)
+  static const int kTiles[6] = {256, 192, 128, 96, 64, 32};
+  int block_n = 32;
+  for (int t = 0; t < 6; ++t)
+    if (cout % kTiles[t] == 0) { block_n = kTiles[t]; break; }
 
   ConvTcParams p{};
   p.N = N; p.H = H; p.W = W; p.dil = dil;
@@ -550,7 +599,15 @@ int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack
   const int tiles_n = ceil_div(N, p.bn);
   const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
   // keep at least ~2 waves of CTAs when the problem allows it
-  while (block_n > 64 && static_cast<long long>(m_tiles) * (cout / block_n) < 2LL * sm_count()) block_n >>= 1;
+  while (block_n > 64 && block_n % 64 == 0 && static_cast<long long>(m_tiles) * (cout / block_n) < 2LL * sm_count())
+    block_n >>= 1;
+  p.stats = stats;
+  p.imgs_per_group = groups > 0 ? N / groups : N;
+  p.groups = groups > 0 ? groups : 1;
+  if (stats != nullptr)
+    PP_REQUIRE(groups >= 1 && N % groups == 0 && (p.bn == 1 || p.imgs_per_group % p.bn == 0),
+               "conv3x3_tc: a pixel tile (%d images) would straddle BatchNorm statistics groups (%d images each)", p.bn,
+               p.imgs_per_group);
   p.kc0 = C0 / bk; p.kc1 = C1 / bk; p.ctot = ctot; p.c0 = C0;
   p.out0 = static_cast<__nv_bfloat16*>(out0); p.out1 = static_cast<__nv_bfloat16*>(out1);
   p.outc0 = outc0; p.outc1 = outc1; p.acc0 = acc0; p.acc1 = acc1; p.bias = bias;
@@ -567,8 +624,10 @@ int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack
   const int n_tiles = cout / block_n;
 #define PP_CONV_CASE(BN_, BK_) \
   if (block_n == BN_ && bk == BK_) return launch_conv_tc<BN_, BK_>(a0, a1, b, p, m_tiles, n_tiles, stream);
-  PP_CONV_CASE(256, 64) PP_CONV_CASE(128, 64) PP_CONV_CASE(64, 64) PP_CONV_CASE(32, 64)
-  PP_CONV_CASE(256, 32) PP_CONV_CASE(128, 32) PP_CONV_CASE(64, 32) PP_CONV_CASE(32, 32)
+  PP_CONV_CASE(256, 64) PP_CONV_CASE(192, 64) PP_CONV_CASE(128, 64) PP_CONV_CASE(96, 64) PP_CONV_CASE(64, 64)
+  PP_CONV_CASE(32, 64)
+  PP_CONV_CASE(256, 32) PP_CONV_CASE(192, 32) PP_CONV_CASE(128, 32) PP_CONV_CASE(96, 32) PP_CONV_CASE(64, 32)
+  PP_CONV_CASE(32, 32)
 #undef PP_CONV_CASE
   set_error("conv3x3_tc: no kernel for block_n=%d bk=%d", block_n, bk);
   return PP_ERR_INVALID;

@@ -386,15 +386,21 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
                                    float* __restrict__ coef, int G, long long Pg, int C, int training, float eps,
-                                   float momentum) {
+                                   float momentum, int replicas) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float rm = running_mean[c], rv = running_var[c];
   for (int g = 0; g < G; ++g) {
     float mean, rstd;
     if (training) {
-      const double m = sums[(static_cast<long long>(g) * C + c) * 2] / static_cast<double>(Pg);
-      double var = sums[(static_cast<long long>(g) * C + c) * 2 + 1] / static_cast<double>(Pg) - m * m;
+      double s1 = 0.0, s2 = 0.0;
+      for (int r = 0; r < replicas; ++r) {
+        const double* sp = sums + ((static_cast<long long>(r) * G + g) * C + c) * 2;
+        s1 += sp[0];
+        s2 += sp[1];
+      }
+      const double m = s1 / static_cast<double>(Pg);
+      double var = s2 / static_cast<double>(Pg) - m * m;
       if (var < 0.0) var = 0.0;
       mean = static_cast<float>(m);
       rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
@@ -421,9 +427,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
 
 int bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
                 long long* nbt, float* coef, int G, long long Pg, int C, int training, float eps, float momentum,
-                cudaStream_t s) {
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(sums, gamma, beta, running_mean, running_var, nbt, coef, G, Pg, C,
-                                                      training, eps, momentum);
+                cudaStream_t s, int replicas) {
+  bn_finalize_kernel<<<ceil_div(C, 64), 64, 0, s>>>(sums, gamma, beta, running_mean, running_var, nbt, coef, G, Pg, C,
+                                                    training, eps, momentum, replicas);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

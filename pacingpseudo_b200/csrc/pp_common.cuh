@@ -62,6 +62,8 @@ void prof_reset();
   } while (0)
 #define PP_LAUNCH_CHECK() PP_LAUNCH_CHECK_N(1)
 
+constexpr int kStatReplicas = 32;  // interleaved BatchNorm partial-sum accumulators written by the conv epilogue
+
 int sm_count();  // cached multiprocessor count of the current device (148 on B200)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

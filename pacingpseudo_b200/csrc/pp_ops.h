@@ -10,8 +10,10 @@ int init_device(int device);
 const char* last_error();
 
 // ---- convolutions -------------------------------------------------------------------------------
+// stats/groups (optional): fused BatchNorm partial sums [groups][cout][2] of the rounded output (caller zeroes)
 int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
-               int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil, cudaStream_t s);
+               int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil, cudaStream_t s,
+               double* stats = nullptr, int groups = 1);
 int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw, int N, int H,
                      int W, int dil, cudaStream_t s);
 int conv3x3_simt(int dtype, const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias,
@@ -34,7 +36,7 @@ int head_bwd(int dtype, const float* dlogits, const void* a, const float* w, voi
 int bn_stats(int dtype, const void* y, double* sums, int G, long long Pg, int C, cudaStream_t s);
 int bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
                 long long* nbt, float* coef, int G, long long Pg, int C, int training, float eps, float momentum,
-                cudaStream_t s);
+                cudaStream_t s, int replicas = 1);
 int bn_apply(int dtype, const void* y, const float* coef, void* a, int G, long long Pg, int C, float slope,
              cudaStream_t s);
 int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* bsums, float* bcoef, float* dgamma,

@@ -116,7 +116,7 @@ static UNetLayout make_layout(const UNetPlan& pl, int N, int H, int W, int G) {
   for (const ConvL& c : pl.convs) {
     L.yraw.push_back(take(act_bytes(pl.acts[c.out])));
     L.coef.push_back(take(sizeof(float) * 4 * G * c.cout));
-    L.sums.push_back(take(sizeof(double) * 2 * G * c.cout));
+    L.sums.push_back(take(sizeof(double) * 2 * G * c.cout * kStatReplicas));
     const long long wn = 9LL * c.cout * (c.cin0 + c.cin1);
     L.wf.push_back(take(wn * es));
     L.wd.push_back(take(wn * es));
@@ -160,6 +160,10 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
       const Act& ao = pl.acts[c.out];
       const int h = H / ao.res, w = W / ao.res;
       void* yraw = base + L.yraw[op.layer];
+      const long long Pg = static_cast<long long>(N / G) * h * w;
+      double* sums = reinterpret_cast<double*>(base + L.sums[op.layer]);
+      float* coef = reinterpret_cast<float*>(base + L.coef[op.layer]);
+      bool fused_stats = false;
       if (c.in0 < 0) {
         rc = first_conv_fwd(dt, x, static_cast<const float*>(pp[0]), static_cast<const float*>(pp[1]), yraw, N, h, w,
                             c.cout, s);
@@ -170,25 +174,30 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
         if (rc) return rc;
         const void* x0 = base + L.act_data[c.in0];
         const void* x1 = c.in1 >= 0 ? base + L.act_data[c.in1] : nullptr;
-        if (dt == PP_BF16)
+        if (dt == PP_BF16) {
+          // batch statistics ride in the conv epilogue when a pixel tile never straddles two statistics groups
+          int bw_ = 1, bh_ = 1;
+          while (bw_ < w && bw_ < 128) bw_ <<= 1;
+          while (bh_ < h && bw_ * bh_ < 128) bh_ <<= 1;
+          const int bn_ = 128 / (bw_ * bh_);
+          fused_stats = training && (bn_ == 1 || (N / G) % bn_ == 0);
+          if (fused_stats) PP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * G * c.cout * kStatReplicas, s));
           rc = conv3x3_tc(x0, c.cin0, x1, c.cin1, wf, static_cast<const float*>(pp[1]), yraw, c.cout, 0, nullptr, 0, 0,
-                          N, h, w, c.dil, s);
-        else
+                          N, h, w, c.dil, s, fused_stats ? sums : nullptr, G);
+        } else {
           rc = conv3x3_simt(dt, x0, c.cin0, x1, c.cin1, wf, static_cast<const float*>(pp[1]), yraw, c.cout, 0, nullptr,
                             0, 0, N, h, w, c.dil, s);
+        }
       }
       if (rc) return rc;
-      const long long Pg = static_cast<long long>(N / G) * h * w;
-      double* sums = reinterpret_cast<double*>(base + L.sums[op.layer]);
-      float* coef = reinterpret_cast<float*>(base + L.coef[op.layer]);
-      if (training) {
+      if (training && !fused_stats) {
         PP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * G * c.cout, s));
         rc = bn_stats(dt, yraw, sums, G, Pg, c.cout, s);
         if (rc) return rc;
       }
       rc = bn_finalize(sums, static_cast<const float*>(pp[2]), static_cast<const float*>(pp[3]),
                        static_cast<float*>(pp[4]), static_cast<float*>(pp[5]), static_cast<long long*>(pp[6]), coef, G,
-                       Pg, c.cout, training, 1e-5f, 0.1f, s);
+                       Pg, c.cout, training, 1e-5f, 0.1f, s, fused_stats ? kStatReplicas : 1);
       if (rc) return rc;
       rc = bn_apply(dt, yraw, coef, base + L.act_data[c.out], G, Pg, c.cout, 0.01f, s);
       if (rc) return rc;

@@ -14,7 +14,7 @@ namespace pp {
 int init_device(int device);
 const char* last_error();
 int conv3x3_tc(const void*, int, const void*, int, const void*, const float*, void*, int, int, void*, int, int, int,
-               int, int, int, cudaStream_t);
+               int, int, int, cudaStream_t, double* stats = nullptr, int groups = 1);
 int conv3x3_wgrad_tc(const void*, int, const void*, int, const void*, int, float*, int, int, int, int, cudaStream_t);
 int conv3x3_simt(int, const void*, int, const void*, int, const void*, const float*, void*, int, int, void*, int, int,
                  int, int, int, int, cudaStream_t);

@@ -110,6 +110,33 @@ def test_conv3x3_forward_dgrad_wgrad_vs_oracle(pp, case, precision):
         assert _rel(y.float(), y2.float()) < 2e-3
 
 
+@pytest.mark.parametrize("case", [(4, 32, 32, 64, 0, 128, 2), (2, 128, 128, 32, 0, 32, 1), (2, 64, 64, 128, 64, 64, 2),
+                                  (4, 8, 8, 64, 0, 64, 2)])
+def test_conv3x3_fused_batchnorm_statistics(pp, case):
+    """The conv epilogue's per-group sum / sum-of-squares equal a separate pass over the stored (rounded) output,
+    and two runs are bit-identical (the in-CTA reduction order is fixed)."""
+    L, PF, _ = pp
+    N, H, W, C0, C1, Co, G = case
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(N, H, W, C0, generator=g).bfloat16().cuda()
+    x1 = torch.randn(N, H, W, C1, generator=g).bfloat16().cuda() if C1 else None
+    w = (torch.randn(Co, C0 + C1, 3, 3, generator=g) / (3 * (C0 + C1) ** 0.5)).cuda()
+    b = torch.randn(Co, generator=g).cuda()
+    wf = torch.empty(9 * Co * (C0 + C1) * 2, dtype=torch.uint8, device="cuda")
+    wd = torch.empty_like(wf)
+    L.call("pp_pack_weights", PF.BF16, _p(w), _p(wf), _p(wd), Co, C0 + C1, _st())
+    R = L.cdll.pp_stat_replicas()
+    stats = torch.zeros(R, G, Co, 2, dtype=torch.float64, device="cuda")
+    y = torch.empty(N, H, W, Co, dtype=torch.bfloat16, device="cuda")
+    L.call("pp_conv3x3_bn_stats", _p(x0), C0, _p(x1), C1, _p(wf), _p(b), _p(y), Co, _p(stats), G, N, H, W, 1, _st())
+    y2 = torch.empty_like(y)
+    L.call("pp_conv3x3", PF.BF16, _p(x0), C0, _p(x1), C1, _p(wf), _p(b), _p(y2), Co, 0, None, 0, 0, N, H, W, 1, _st())
+    assert torch.equal(y, y2)
+    yg = y.double().view(G, -1, Co)
+    ref = torch.stack([yg.sum(1), (yg * yg).sum(1)], dim=-1)
+    assert _rel(stats.sum(0), ref) < 1e-6
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_first_conv_head_pool_upsample_bn_vs_oracle(pp, precision):
     L, PF, _ = pp
