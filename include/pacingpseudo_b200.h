@@ -155,9 +155,11 @@ int pp_dice_fwd(const float* z, const float* label, double* sums, float* coef, f
                 void* stream);
 int pp_dice_bwd(const float* z, const float* label, const float* coef, const float* g, float* dz, int N, int C,
                 int HW, int accumulate, void* stream);
-/* AuxPath.memory_update (aux_path_memory.py:68-116): sample 0 only; feat = aux_features [N,h,w,hid] */
-int pp_memory_update(int dtype, const void* feat, const float* scribble, float* bank, int C, int h, int w, int H,
-                     int W, int hid, int cosine_mode, float m, float one_minus_m, void* stream);
+/* AuxPath.memory_update (aux_path_memory.py:68-116): sample 0 only; feat = aux_features [N,h,w,hid].
+ * scratch: pp_memory_update_scratch_floats(C, hid) floats (per-slice partial sums, reduced in a fixed order). */
+int pp_memory_update_scratch_floats(int C, int hid);
+int pp_memory_update(int dtype, const void* feat, const float* scribble, float* bank, float* scratch, int C, int h,
+                     int w, int H, int W, int hid, int cosine_mode, float m, float one_minus_m, void* stream);
 /* cross_entropy_loss(fc_cls(memory_bank), arange(C)) (aux_path_memory.py:61; consistency_reglur_memory.py:94) */
 int pp_memory_loss_fwd(const float* bank, const float* wfc, float* loss, float* probs, int C, int hid,
                        void* stream);

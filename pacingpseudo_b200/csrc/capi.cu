@@ -79,7 +79,7 @@ int pp_conv3x3_bn_stats(const void* x0, int C0, const void* x1, int C1, const vo
 int pp_stat_replicas(void) { return kStatReplicas; }
 int pp_conv3x3_wgrad(int dtype, const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dwp,
                      int N, int H, int W, int dil, void* stream) {
-  if (dtype == PP_BF16) return conv3x3_wgrad_tc(dy, Cout, x0, C0, x1, C1, dwp, N, H, W, dil, ST(stream));
+  if (dtype == PP_BF16) return conv3x3_wgrad_tc(dy, Cout, x0, C0, x1, C1, dwp, nullptr, N, H, W, dil, ST(stream));
   return conv3x3_wgrad_simt(dtype, dy, Cout, x0, C0, x1, C1, dwp, N, H, W, dil, ST(stream));
 }
 int pp_conv3x3_reference(int dtype, const void* x0, int C0, const void* x1, int C1, const void* wpack,
@@ -190,9 +190,11 @@ int pp_dice_bwd(const float* z, const float* label, const float* coef, const flo
                 int HW, int accumulate, void* stream) {
   return dice_bwd(z, label, coef, g, dz, N, C, HW, accumulate, ST(stream));
 }
-int pp_memory_update(int dtype, const void* feat, const float* scribble, float* bank, int C, int h, int w, int H,
-                     int W, int hid, int cosine_mode, float m, float one_minus_m, void* stream) {
-  return memory_update(dtype, feat, scribble, bank, C, h, w, H, W, hid, cosine_mode, m, one_minus_m, ST(stream));
+int pp_memory_update_scratch_floats(int C, int hid) { return memory_update_scratch_floats(C, hid); }
+int pp_memory_update(int dtype, const void* feat, const float* scribble, float* bank, float* scratch, int C, int h,
+                     int w, int H, int W, int hid, int cosine_mode, float m, float one_minus_m, void* stream) {
+  return memory_update(dtype, feat, scribble, bank, scratch, C, h, w, H, W, hid, cosine_mode, m, one_minus_m,
+                       ST(stream));
 }
 int pp_memory_loss_fwd(const float* bank, const float* wfc, float* loss, float* probs, int C, int hid,
                        void* stream) {

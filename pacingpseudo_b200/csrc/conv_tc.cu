@@ -245,6 +245,7 @@ struct WgradTcParams {
   int Cout, C0, C1;
   int ci_tiles0, ci_tiles1;  // N tiles per source
   int ctot, cbase0, cbase1;  // row length of dw and the column offset of each source inside it
+  int oihw;                  // 1: dw is the OIHW gradient [Cout][ctot][9] itself (accumulated in place)
   int kb_per_split;
   int stages;
   float* dw;                 // [9][Cout][C0+C1] fp32, pre-zeroed, accumulated with red.global
@@ -361,10 +362,17 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_c
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c), v);
         tmem_wait_ld();
         if (co < p.Cout) {
-          float* o = p.dw + (static_cast<long long>(tap) * p.Cout + co) * ctot + cbase + c;
+          if (p.oihw) {
+            float* o = p.dw + (static_cast<long long>(co) * ctot + cbase + c) * 9 + tap;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (ci0 + c + j < csrc) atomicAdd(o + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j)
+              if (ci0 + c + j < csrc) atomicAdd(o + j * 9, __uint_as_float(v[j]));
+          } else {
+            float* o = p.dw + (static_cast<long long>(tap) * p.Cout + co) * ctot + cbase + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ci0 + c + j < csrc) atomicAdd(o + j, __uint_as_float(v[j]));
+          }
         }
       }
       tc_fence_before();
@@ -705,8 +713,9 @@ static int wgrad_narrow(const void* dy, int Cout, const void* x, int Csrc, int c
 
 // generic kernel over the given sources; ctot / cbase place them inside the rows of dw
 static int wgrad_wide(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, int ctot, int cbase0,
-                      int cbase1, float* dw, int N, int H, int W, int dil, cudaStream_t stream) {
+                      int cbase1, float* dw, int oihw, int N, int H, int W, int dil, cudaStream_t stream) {
   WgradTcParams p{};
+  p.oihw = oihw;
   p.N = N; p.H = H; p.W = W; p.dil = dil;
   pixel_box(W, H, 64, &p.bw, &p.bh, &p.bn);
   p.tiles_w = ceil_div(W, p.bw);
@@ -741,23 +750,45 @@ static int wgrad_wide(const void* dy, int Cout, const void* x0, int C0, const vo
   return launch_wgrad_tc<256>(tdy, tx0, tx1, p, grid, stream);
 }
 
-// dy:[N,H,W,Cout] bf16, x0/x1 as in forward; dw:[9][Cout][C0+C1] fp32, MUST be zeroed by the caller.
-int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw, int N,
-                     int H, int W, int dil, cudaStream_t stream) {
+int unpack_wgrad_range(const float* dwp, float* g, int Cout, int Cin, int ci_begin, int ci_count, int accumulate,
+                       cudaStream_t s);
+
+bool conv3x3_wgrad_tc_uses_scratch(int Cout, int C0, int C1) {
+  return narrow_ok(C0, Cout) || (C1 > 0 && narrow_ok(C1, Cout));
+}
+
+// dy:[N,H,W,Cout] bf16, x0/x1 as in forward.
+//   g_oihw == nullptr: dwp[9][Cout][C0+C1] fp32 packed gradient, accumulated (caller zeroes it).
+//   g_oihw != nullptr: the OIHW gradient [Cout][C0+C1][3][3] is accumulated in place. Wide sources go there
+//     directly from the epilogue; narrow sources go through dwp (caller zeroes it when
+//     conv3x3_wgrad_tc_uses_scratch()) and are folded in by a column-range unpack.
+int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dwp,
+                     float* g_oihw, int N, int H, int W, int dil, cudaStream_t stream) {
   PP_REQUIRE(N > 0 && H > 0 && W > 0 && dil >= 1, "conv3x3_wgrad_tc: bad shape");
   PP_REQUIRE(Cout % 8 == 0 && C0 % 8 == 0 && C1 % 8 == 0 && C0 > 0, "conv3x3_wgrad_tc: channels must be multiples of 8");
   PP_REQUIRE((x1 == nullptr) == (C1 == 0), "conv3x3_wgrad_tc: x1/C1 mismatch");
   const int ctot = C0 + C1;
   const bool n0 = narrow_ok(C0, Cout), n1 = C1 > 0 && narrow_ok(C1, Cout);
+  const int oihw = g_oihw != nullptr;
+  float* wide_dst = oihw ? g_oihw : dwp;
   int rc = PP_OK;
-  if (n0) rc = wgrad_narrow(dy, Cout, x0, C0, ctot, 0, dw, N, H, W, dil, stream);
+  if (n0) rc = wgrad_narrow(dy, Cout, x0, C0, ctot, 0, dwp, N, H, W, dil, stream);
   if (rc) return rc;
-  if (n1) rc = wgrad_narrow(dy, Cout, x1, C1, ctot, C0, dw, N, H, W, dil, stream);
+  if (n1) rc = wgrad_narrow(dy, Cout, x1, C1, ctot, C0, dwp, N, H, W, dil, stream);
   if (rc) return rc;
-  if (!n0 && C1 > 0 && !n1) return wgrad_wide(dy, Cout, x0, C0, x1, C1, ctot, 0, C0, dw, N, H, W, dil, stream);
-  if (!n0) rc = wgrad_wide(dy, Cout, x0, C0, nullptr, 0, ctot, 0, 0, dw, N, H, W, dil, stream);
+  if (!n0 && C1 > 0 && !n1) {
+    rc = wgrad_wide(dy, Cout, x0, C0, x1, C1, ctot, 0, C0, wide_dst, oihw, N, H, W, dil, stream);
+  } else {
+    if (!n0) rc = wgrad_wide(dy, Cout, x0, C0, nullptr, 0, ctot, 0, 0, wide_dst, oihw, N, H, W, dil, stream);
+    if (rc) return rc;
+    if (C1 > 0 && !n1) rc = wgrad_wide(dy, Cout, x1, C1, nullptr, 0, ctot, C0, 0, wide_dst, oihw, N, H, W, dil, stream);
+  }
   if (rc) return rc;
-  if (C1 > 0 && !n1 && n0) rc = wgrad_wide(dy, Cout, x1, C1, nullptr, 0, ctot, C0, 0, dw, N, H, W, dil, stream);
+  if (oihw) {
+    if (n0) rc = unpack_wgrad_range(dwp, g_oihw, Cout, ctot, 0, C0, 1, stream);
+    if (rc) return rc;
+    if (n1) rc = unpack_wgrad_range(dwp, g_oihw, Cout, ctot, C0, C1, 1, stream);
+  }
   return rc;
 }
 

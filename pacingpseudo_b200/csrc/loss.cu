@@ -508,37 +508,35 @@ int dice_bwd(const float* z, const float* label, const float* coef, const float*
 // 32x32 feature map is evaluated on the fly at that pixel only.
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxHidPerLane = 8;  // hid_ch <= 256
+constexpr int kMemSlices = 32;     // blocks per class in the gather phase
 
+// phase 1: grid (kMemSlices, C). Each block scans a slice of sample 0's scribble plane of its class and
+// writes its partial sums [U(hid) | E(hid) | S | count] to scratch[cls][slice][2*hid+2].
 template <typename T>
 __global__ void __launch_bounds__(256)
-memory_update_kernel(const T* __restrict__ feat /*[N][h][w][hid], sample 0 used*/, const float* __restrict__ scribble
-                     /*[N][K][H][W], sample 0 used*/, float* __restrict__ bank /*[C][hid]*/, int h, int w, int H, int W,
-                     int hid, int cosine_mode, float m, float one_minus_m, float sh, float sw) {
-  __shared__ float s_row[256], s_rhat[256];
+memory_gather_kernel(const T* __restrict__ feat /*[N][h][w][hid], sample 0 used*/, const float* __restrict__ scribble
+                     /*[N][K][H][W], sample 0 used*/, const float* __restrict__ bank /*[C][hid]*/,
+                     float* __restrict__ scratch, int h, int w, int H, int W, int hid, float sh, float sw) {
+  __shared__ float s_rhat[256];
   __shared__ float s_U[8][256], s_E[8][256];
-  __shared__ float s_S[8], s_cnt[8];
-  __shared__ int s_allzero;
-  const int cls = blockIdx.x;
+  __shared__ float s_S[8], s_cnt[8], s_red[8];
+  const int cls = blockIdx.y, slice = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int R = hid / 32;
-  if (threadIdx.x == 0) s_allzero = 1;
-  __syncthreads();
   float nrm_part = 0.f;
   for (int k = threadIdx.x; k < hid; k += blockDim.x) {
     const float v = bank[cls * hid + k];
-    s_row[k] = v;
-    if (v != 0.f) s_allzero = 0;
+    s_rhat[k] = v;
     nrm_part = fmaf(v, v, nrm_part);
   }
-  // block-wide sum of squares
-  __shared__ float s_red[8];
   nrm_part = warp_sum(nrm_part);
   if (lane == 0) s_red[warp] = nrm_part;
   __syncthreads();
   float nrm2 = 0.f;
   for (int i = 0; i < 8; ++i) nrm2 += s_red[i];
   const float rinv = 1.f / (sqrtf(nrm2) + 1e-8f);
-  for (int k = threadIdx.x; k < hid; k += blockDim.x) s_rhat[k] = s_row[k] * rinv;
+  __syncthreads();
+  for (int k = threadIdx.x; k < hid; k += blockDim.x) s_rhat[k] *= rinv;
   __syncthreads();
 
   float U[kMaxHidPerLane], E[kMaxHidPerLane];
@@ -547,9 +545,11 @@ memory_update_kernel(const T* __restrict__ feat /*[N][h][w][hid], sample 0 used*
   float S = 0.f, cnt = 0.f;
   const float* plane = scribble + static_cast<long long>(cls) * H * W;  // sample 0, channel cls
   const int HWp = H * W;
-  for (int base = warp * 32; base < HWp; base += 8 * 32) {
+  const int per = (HWp + kMemSlices - 1) / kMemSlices;
+  const int pbeg = slice * per, pend = min(pbeg + per, HWp);
+  for (int base = pbeg + warp * 32; base < pend; base += 8 * 32) {
     const int pix = base + lane;
-    const bool hit = (pix < HWp) && (plane[pix] == 1.f);
+    const bool hit = (pix < pend) && (plane[pix] == 1.f);
     unsigned bal = __ballot_sync(0xffffffffu, hit);
     while (bal) {
       const int b = __ffs(bal) - 1;
@@ -595,32 +595,72 @@ memory_update_kernel(const T* __restrict__ feat /*[N][h][w][hid], sample 0 used*
     if (r < R) { s_U[warp][r * 32 + lane] = U[r]; s_E[warp][r * 32 + lane] = E[r]; }
   if (lane == 0) { s_S[warp] = S; s_cnt[warp] = cnt; }
   __syncthreads();
-  float St = 0.f, ct = 0.f;
-  for (int i = 0; i < 8; ++i) { St += s_S[i]; ct += s_cnt[i]; }
-  if (ct == 0.f) return;  // class absent in sample 0: row untouched
+  float* out = scratch + (static_cast<long long>(cls) * kMemSlices + slice) * (2 * hid + 2);
   for (int k = threadIdx.x; k < hid; k += blockDim.x) {
     float Ut = 0.f, Et = 0.f;
     for (int i = 0; i < 8; ++i) { Ut += s_U[i][k]; Et += s_E[i][k]; }
-    float out;
-    if (s_allzero) out = Et / ct;                                             // first touch: plain mean
-    else if (cosine_mode) out = one_minus_m * s_rhat[k] + m * (Ut / (St + 1e-8f));
-    else out = one_minus_m * s_row[k] + m * (Et / ct);
-    bank[cls * hid + k] = out;
+    out[k] = Ut;
+    out[hid + k] = Et;
+  }
+  if (threadIdx.x == 0) {
+    float St = 0.f, ct = 0.f;
+    for (int i = 0; i < 8; ++i) { St += s_S[i]; ct += s_cnt[i]; }
+    out[2 * hid] = St;
+    out[2 * hid + 1] = ct;
   }
 }
 
-int memory_update(int dtype, const void* feat, const float* scribble, float* bank, int C, int h, int w, int H, int W,
-                  int hid, int cosine_mode, float m, float one_minus_m, cudaStream_t s) {
+// phase 2: grid C. Fixed-order reduction over the slices, then the update rule of aux_path_memory.py:84-114.
+__global__ void memory_apply_kernel(const float* __restrict__ scratch, float* __restrict__ bank, int hid, int cosine_mode,
+                                    float m, float one_minus_m) {
+  __shared__ float s_red[8];
+  __shared__ int s_nonzero;
+  const int cls = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_nonzero = 0;
+  __syncthreads();
+  const int k = threadIdx.x;  // blockDim.x == 256 >= hid
+  const float row = k < hid ? bank[cls * hid + k] : 0.f;
+  if (row != 0.f) s_nonzero = 1;
+  float part = warp_sum(row * row);
+  if (lane == 0) s_red[warp] = part;
+  __syncthreads();
+  float nrm2 = 0.f;
+  for (int i = 0; i < 8; ++i) nrm2 += s_red[i];
+  const float rhat = row / (sqrtf(nrm2) + 1e-8f);
+  const float* in = scratch + static_cast<long long>(cls) * kMemSlices * (2 * hid + 2);
+  float St = 0.f, ct = 0.f, Ut = 0.f, Et = 0.f;
+  for (int sl = 0; sl < kMemSlices; ++sl) {
+    const float* q = in + static_cast<long long>(sl) * (2 * hid + 2);
+    St += q[2 * hid];
+    ct += q[2 * hid + 1];
+    if (k < hid) { Ut += q[k]; Et += q[hid + k]; }
+  }
+  if (ct == 0.f || k >= hid) return;  // class absent in sample 0: row untouched
+  float out;
+  if (!s_nonzero) out = Et / ct;                                             // first touch: plain mean
+  else if (cosine_mode) out = one_minus_m * rhat + m * (Ut / (St + 1e-8f));
+  else out = one_minus_m * row + m * (Et / ct);
+  bank[cls * hid + k] = out;
+}
+
+int memory_update_scratch_floats(int C, int hid) { return C * kMemSlices * (2 * hid + 2); }
+
+int memory_update(int dtype, const void* feat, const float* scribble, float* bank, float* scratch, int C, int h, int w,
+                  int H, int W, int hid, int cosine_mode, float m, float one_minus_m, cudaStream_t s) {
   PP_REQUIRE(hid % 32 == 0 && hid <= 256, "memory_update: hid_ch=%d unsupported (multiple of 32, <= 256)", hid);
+  PP_REQUIRE(scratch != nullptr, "memory_update: scratch buffer required");
   const float sh = H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f;
   const float sw = W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f;
+  dim3 grid(kMemSlices, C);
   if (dtype == PP_F32)
-    memory_update_kernel<float><<<C, 256, 0, s>>>(static_cast<const float*>(feat), scribble, bank, h, w, H, W, hid,
-                                                  cosine_mode, m, one_minus_m, sh, sw);
+    memory_gather_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(feat), scribble, bank, scratch, h, w, H,
+                                                     W, hid, sh, sw);
   else
-    memory_update_kernel<__nv_bfloat16><<<C, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(feat), scribble, bank, h, w,
-                                                          H, W, hid, cosine_mode, m, one_minus_m, sh, sw);
-  PP_LAUNCH_CHECK();
+    memory_gather_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(feat), scribble, bank,
+                                                             scratch, h, w, H, W, hid, sh, sw);
+  memory_apply_kernel<<<C, 256, 0, s>>>(scratch, bank, hid, cosine_mode, m, one_minus_m);
+  PP_LAUNCH_CHECK_N(2);
   return PP_OK;
 }
 

@@ -54,11 +54,12 @@ int pack_weights(int dtype, const float* w, void* wf, void* wd, int Cout, int Ci
   return PP_OK;
 }
 
-// dwp [tap][Cout][Cin] fp32 -> OIHW grad [Cout][Cin][3][3] (accumulate ? += : =)
+// dwp [tap][Cout][Cin] fp32 -> OIHW grad [Cout][Cin][3][3] (accumulate ? += : =), for input channels
+// [ci_begin, ci_begin + ci_count) only (multiples of 32).
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ g,
-                                                           int Cout, int Cin, int accumulate) {
+                                                           int Cout, int Cin, int ci_begin, int accumulate) {
   __shared__ float tile[32][32 * 9 + 1];
-  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int co0 = blockIdx.y * 32, ci0 = ci_begin + blockIdx.x * 32;
   for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
     const int tap = i / 1024, a = (i / 32) % 32, b = i % 32;
     tile[a][b * 9 + tap] = dwp[(static_cast<long long>(tap) * Cout + co0 + a) * Cin + ci0 + b];
@@ -71,11 +72,17 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
   }
 }
 
-int unpack_wgrad(const float* dwp, float* g, int Cout, int Cin, int accumulate, cudaStream_t s) {
-  PP_REQUIRE(Cout % 32 == 0 && Cin % 32 == 0, "unpack_wgrad: Cout=%d Cin=%d must be multiples of 32", Cout, Cin);
-  unpack_wgrad_kernel<<<dim3(Cin / 32, Cout / 32), 256, 0, s>>>(dwp, g, Cout, Cin, accumulate);
+int unpack_wgrad_range(const float* dwp, float* g, int Cout, int Cin, int ci_begin, int ci_count, int accumulate,
+                       cudaStream_t s) {
+  PP_REQUIRE(Cout % 32 == 0 && ci_begin % 32 == 0 && ci_count % 32 == 0 && ci_begin + ci_count <= Cin,
+             "unpack_wgrad: Cout=%d Cin=%d range [%d,+%d) must be multiples of 32", Cout, Cin, ci_begin, ci_count);
+  unpack_wgrad_kernel<<<dim3(ci_count / 32, Cout / 32), 256, 0, s>>>(dwp, g, Cout, Cin, ci_begin, accumulate);
   PP_LAUNCH_CHECK();
   return PP_OK;
+}
+
+int unpack_wgrad(const float* dwp, float* g, int Cout, int Cin, int accumulate, cudaStream_t s) {
+  return unpack_wgrad_range(dwp, g, Cout, Cin, 0, Cin, accumulate, s);
 }
 
 // ==============================================================================================
@@ -146,17 +153,29 @@ __global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const T* __restri
     float acc[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[t] = 0.f;
-    for (long long p = pb; p < pe; ++p) {
-      const int px = int(p % W), py = int((p / W) % H);
-      const long long img = p / (static_cast<long long>(W) * H);
-      float xv = 0.f;
-      if (lane < 9) {
-        const int yy = py + lane / 3 - 1, xx = px + lane % 3 - 1;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) xv = __ldg(x + (img * H + yy) * W + xx);
-      }
-      const float g = (co < Cout) ? to_f32(dy[p * Cout + co]) : 0.f;
+    constexpr int U = 4;  // pixels in flight per warp (independent loads)
+    for (long long p0 = pb; p0 < pe; p0 += U) {
+      float xv[U], g[U];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) acc[t] = fmaf(g, __shfl_sync(0xffffffffu, xv, t), acc[t]);
+      for (int u = 0; u < U; ++u) {
+        const long long p = p0 + u;
+        xv[u] = 0.f;
+        g[u] = 0.f;
+        if (p < pe) {
+          const int px = int(p % W), py = int((p / W) % H);
+          const long long img = p / (static_cast<long long>(W) * H);
+          if (lane < 9) {
+            const int yy = py + lane / 3 - 1, xx = px + lane % 3 - 1;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) xv[u] = __ldg(x + (img * H + yy) * W + xx);
+          }
+          if (co < Cout) g[u] = to_f32(dy[p * Cout + co]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[t] = fmaf(g[u], __shfl_sync(0xffffffffu, xv[u], t), acc[t]);
+      }
     }
     if (co < Cout) {
 #pragma unroll
@@ -281,18 +300,31 @@ __global__ void __launch_bounds__(256) head_bwd_weight_kernel(const float* __res
   for (int c = 0; c < kMaxClasses; ++c)
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[c][r] = 0.f;
-  for (long long p = pb; p < pe; ++p) {
-    const long long n = p / HW, hw = p % HW;
-    const float dlv = (lane < C) ? dlogits[(n * C + lane) * HW + hw] : 0.f;
-    accb += dlv;
-    float av[R];
+  constexpr int U = 4;  // pixels in flight per warp
+  for (long long p0 = pb; p0 < pe; p0 += U) {
+    float dlv[U], av[U][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) av[r] = to_f32(a[p * CIN + r * 32 + lane]);
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u;
+      dlv[u] = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) {
-      const float d = __shfl_sync(0xffffffffu, dlv, c);
+      for (int r = 0; r < R; ++r) av[u][r] = 0.f;
+      if (p < pe) {
+        const long long n = p / HW, hw = p % HW;
+        if (lane < C) dlv[u] = dlogits[(n * C + lane) * HW + hw];
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[c][r] = fmaf(d, av[r], acc[c][r]);
+        for (int r = 0; r < R; ++r) av[u][r] = to_f32(a[p * CIN + r * 32 + lane]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      accb += dlv[u];
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c) {
+        const float d = __shfl_sync(0xffffffffu, dlv[u], c);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[c][r] = fmaf(d, av[u][r], acc[c][r]);
+      }
     }
   }
 #pragma unroll
@@ -345,14 +377,23 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, 
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
   if (l < pl) {
+    constexpr int U = 4;
     const T* base = y + (static_cast<long long>(g) * Pg) * C + v * 8;
-    for (long long p = p0 + l; p < p1; p += pl) {
-      Vec8<T> pk;
-      pk.load(base + p * C);
-      float f[8];
-      pk.get(f);
+    for (long long pb = p0 + l; pb < p1; pb += static_cast<long long>(pl) * U) {
+      Vec8<T> pk[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+      for (int u = 0; u < U; ++u) {
+        const long long p = pb + static_cast<long long>(u) * pl;
+        if (p < p1) pk[u].load(base + p * C);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pb + static_cast<long long>(u) * pl >= p1) break;
+        float f[8];
+        pk[u].get(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+      }
     }
   }
 #pragma unroll
@@ -434,26 +475,36 @@ int bn_finalize(const double* sums, const float* gamma, const float* beta, float
   return PP_OK;
 }
 
-// a = lrelu(y * scale + shift)
+// a = lrelu(y * scale + shift). Four independent 16-byte vectors per thread per iteration keep enough
+// bytes in flight per SM to approach the HBM roofline.
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ coef,
                                                        T* __restrict__ a, long long Pg, int C, long long total_vecs,
                                                        float slope) {
+  constexpr int U = 4;
   const int vecs = C / 8;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_vecs;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = int(i % vecs);
-    const long long p = i / vecs;
-    const int g = int(p / Pg);
-    const float* cf = coef + static_cast<long long>(g) * 4 * C + v * 8;
-    Vec8<T> pk;
-    pk.load(y + i * 8);
-    float f[8];
-    pk.get(f);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < total_vecs; i0 += stride * U) {
+    Vec8<T> pk[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = lrelu(fmaf(f[j], __ldg(cf + j), __ldg(cf + C + j)), slope);
-    pk.set(f);
-    pk.store(a + i * 8);
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < total_vecs) pk[u].load(y + i * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= total_vecs) break;
+      const int v = int(i % vecs);
+      const int g = int((i / vecs) / Pg);
+      const float* cf = coef + static_cast<long long>(g) * 4 * C + v * 8;
+      float f[8];
+      pk[u].get(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = lrelu(fmaf(f[j], __ldg(cf + j), __ldg(cf + C + j)), slope);
+      pk[u].set(f);
+      pk[u].store(a + i * 8);
+    }
   }
 }
 
@@ -489,20 +540,29 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
     sc[j] = cf[j]; sh[j] = cf[C + j]; mu[j] = cf[2 * C + j]; rs[j] = cf[3 * C + j];
   }
   if (l < pl) {
+    constexpr int U = 4;
     const long long base = (static_cast<long long>(g) * Pg) * C + v * 8;
-    for (long long p = p0 + l; p < p1; p += pl) {
-      Vec8<T> pa, py;
-      pa.load(da + base + p * C);
-      py.load(y + base + p * C);
-      float fa[8], fy[8];
-      pa.get(fa);
-      py.get(fy);
+    for (long long pb = p0 + l; pb < p1; pb += static_cast<long long>(pl) * U) {
+      Vec8<T> pa[U], py[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(fy[j], sc[j], sh[j]);
-        const float dz = z > 0.f ? fa[j] : fa[j] * slope;
-        s[j] += dz;
-        ss[j] = fmaf(dz, (fy[j] - mu[j]) * rs[j], ss[j]);
+      for (int u = 0; u < U; ++u) {
+        const long long p = pb + static_cast<long long>(u) * pl;
+        if (p < p1) { pa[u].load(da + base + p * C); py[u].load(y + base + p * C); }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long p = pb + static_cast<long long>(u) * pl;
+        if (p >= p1) break;
+        float fa[8], fy[8];
+        pa[u].get(fa);
+        py[u].get(fy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(fy[j], sc[j], sh[j]);
+          const float dz = z > 0.f ? fa[j] : fa[j] * slope;
+          s[j] += dz;
+          ss[j] = fmaf(dz, (fy[j] - mu[j]) * rs[j], ss[j]);
+        }
       }
     }
   }
@@ -552,30 +612,38 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                            const float* __restrict__ coef,
                                                            const float* __restrict__ bcoef, T* __restrict__ dy,
                                                            long long Pg, int C, long long total_vecs, float slope) {
+  constexpr int U = 2;
   const int vecs = C / 8;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_vecs;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = int(i % vecs);
-    const long long p = i / vecs;
-    const int g = int(p / Pg);
-    const float* cf = coef + static_cast<long long>(g) * 4 * C + v * 8;
-    const float* bc = bcoef + static_cast<long long>(g) * 2 * C + v * 8;
-    Vec8<T> pa, py;
-    pa.load(da + i * 8);
-    py.load(y + i * 8);
-    float fa[8], fy[8], o[8];
-    pa.get(fa);
-    py.get(fy);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < total_vecs; i0 += stride * U) {
+    Vec8<T> pa[U], py[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float sc = __ldg(cf + j);
-      const float z = fmaf(fy[j], sc, __ldg(cf + C + j));
-      const float dz = z > 0.f ? fa[j] : fa[j] * slope;
-      const float xhat = (fy[j] - __ldg(cf + 2 * C + j)) * __ldg(cf + 3 * C + j);
-      o[j] = sc * (dz - __ldg(bc + j) - xhat * __ldg(bc + C + j));
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < total_vecs) { pa[u].load(da + i * 8); py[u].load(y + i * 8); }
     }
-    pa.set(o);
-    pa.store(dy + i * 8);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= total_vecs) break;
+      const int v = int(i % vecs);
+      const int g = int((i / vecs) / Pg);
+      const float* cf = coef + static_cast<long long>(g) * 4 * C + v * 8;
+      const float* bc = bcoef + static_cast<long long>(g) * 2 * C + v * 8;
+      float fa[8], fy[8], o[8];
+      pa[u].get(fa);
+      py[u].get(fy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sc = __ldg(cf + j);
+        const float z = fmaf(fy[j], sc, __ldg(cf + C + j));
+        const float dz = z > 0.f ? fa[j] : fa[j] * slope;
+        const float xhat = (fy[j] - __ldg(cf + 2 * C + j)) * __ldg(cf + 3 * C + j);
+        o[j] = sc * (dz - __ldg(bc + j) - xhat * __ldg(bc + C + j));
+      }
+      pa[u].set(o);
+      pa[u].store(dy + i * 8);
+    }
   }
 }
 
@@ -783,19 +851,44 @@ __global__ void __launch_bounds__(256) upsample_nhwc_bwd_kernel(const T* __restr
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int Y = ylo; Y <= yhi; ++Y) {
-      const float wy = lerp_weight(Y, yi, h, sh);
-      if (wy == 0.f) continue;
-      for (int X = xlo; X <= xhi; ++X) {
-        const float wx = lerp_weight(X, xi, w, sw);
-        if (wx == 0.f) continue;
-        Vec8<T> pk;
-        pk.load(gy + ((n * H + Y) * W + X) * C + v * 8);
-        float f[8];
-        pk.get(f);
-        const float ww = wy * wx;
+    constexpr int KMAX = 8;   // candidate window per axis for scale factors >= 2 (wider windows take the slow path)
+    if (yhi - ylo < KMAX && xhi - xlo < KMAX) {
+      float wyv[KMAX], wxv[KMAX];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, f[j], acc[j]);
+      for (int k = 0; k < KMAX; ++k) {
+        wyv[k] = (ylo + k <= yhi) ? lerp_weight(ylo + k, yi, h, sh) : 0.f;
+        wxv[k] = (xlo + k <= xhi) ? lerp_weight(xlo + k, xi, w, sw) : 0.f;
+      }
+#pragma unroll
+      for (int a = 0; a < KMAX; ++a) {
+        if (wyv[a] == 0.f) continue;
+#pragma unroll
+        for (int b = 0; b < KMAX; ++b) {
+          if (wxv[b] == 0.f) continue;
+          Vec8<T> pk;
+          pk.load(gy + ((n * H + ylo + a) * W + xlo + b) * C + v * 8);
+          float f[8];
+          pk.get(f);
+          const float ww = wyv[a] * wxv[b];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, f[j], acc[j]);
+        }
+      }
+    } else {
+      for (int Y = ylo; Y <= yhi; ++Y) {
+        const float wy = lerp_weight(Y, yi, h, sh);
+        if (wy == 0.f) continue;
+        for (int X = xlo; X <= xhi; ++X) {
+          const float wx = lerp_weight(X, xi, w, sw);
+          if (wx == 0.f) continue;
+          Vec8<T> pk;
+          pk.load(gy + ((n * H + Y) * W + X) * C + v * 8);
+          float f[8];
+          pk.get(f);
+          const float ww = wy * wx;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, f[j], acc[j]);
+        }
       }
     }
     Vec8<T> out;

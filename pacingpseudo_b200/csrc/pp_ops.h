@@ -14,8 +14,13 @@ const char* last_error();
 int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
                int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil, cudaStream_t s,
                double* stats = nullptr, int groups = 1);
-int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw, int N, int H,
-                     int W, int dil, cudaStream_t s);
+// g_oihw == nullptr: packed dwp[9][Cout][C0+C1] += ; else the OIHW gradient is accumulated in place (dwp is scratch
+// for narrow sources, zeroed by the caller when conv3x3_wgrad_tc_uses_scratch())
+int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dwp,
+                     float* g_oihw, int N, int H, int W, int dil, cudaStream_t s);
+bool conv3x3_wgrad_tc_uses_scratch(int Cout, int C0, int C1);
+int unpack_wgrad_range(const float* dwp, float* g, int Cout, int Cin, int ci_begin, int ci_count, int accumulate,
+                       cudaStream_t s);
 int conv3x3_simt(int dtype, const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias,
                  void* out0, int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil,
                  cudaStream_t s);
@@ -71,8 +76,9 @@ int dice_fwd(const float* z, const float* label, double* sums, float* coef, floa
              cudaStream_t s);
 int dice_bwd(const float* z, const float* label, const float* coef, const float* g, float* dz, int N, int C, int HW,
              int accumulate, cudaStream_t s);
-int memory_update(int dtype, const void* feat, const float* scribble, float* bank, int C, int h, int w, int H, int W,
-                  int hid, int cosine_mode, float m, float one_minus_m, cudaStream_t s);
+int memory_update_scratch_floats(int C, int hid);
+int memory_update(int dtype, const void* feat, const float* scribble, float* bank, float* scratch, int C, int h, int w,
+                  int H, int W, int hid, int cosine_mode, float m, float one_minus_m, cudaStream_t s);
 int memory_loss_fwd(const float* bank, const float* wfc, float* loss, float* probs, int C, int hid, cudaStream_t s);
 int memory_loss_bwd(const float* bank, const float* probs, const float* g, float* dwfc, int C, int hid, cudaStream_t s);
 

@@ -279,14 +279,21 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
       }
       const int ctot = c.cin0 + c.cin1;
       float* dwp = reinterpret_cast<float*>(base + L.dwp_scratch);
-      PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * c.cout * ctot, s));
       const void* x0 = base + L.act_data[c.in0];
       const void* x1 = c.in1 >= 0 ? base + L.act_data[c.in1] : nullptr;
-      if (dt == PP_BF16) rc = conv3x3_wgrad_tc(dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, N, h, w, c.dil, s);
-      else rc = conv3x3_wgrad_simt(dt, dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, N, h, w, c.dil, s);
-      if (rc) return rc;
-      rc = unpack_wgrad(dwp, gg[0], c.cout, ctot, 1, s);
-      if (rc) return rc;
+      if (dt == PP_BF16) {
+        // wide sources accumulate straight into the OIHW gradient; narrow ones go through the packed scratch
+        if (conv3x3_wgrad_tc_uses_scratch(c.cout, c.cin0, c.cin1))
+          PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * c.cout * ctot, s));
+        rc = conv3x3_wgrad_tc(dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, gg[0], N, h, w, c.dil, s);
+        if (rc) return rc;
+      } else {
+        PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * c.cout * ctot, s));
+        rc = conv3x3_wgrad_simt(dt, dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, N, h, w, c.dil, s);
+        if (rc) return rc;
+        rc = unpack_wgrad(dwp, gg[0], c.cout, ctot, 1, s);
+        if (rc) return rc;
+      }
       // dgrad: forward kernel on the flipped/transposed pack, scattered to the two sources
       void* g0 = base + L.act_grad[c.in0];
       void* g1 = c.in1 >= 0 ? base + L.act_grad[c.in1] : nullptr;

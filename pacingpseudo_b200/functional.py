@@ -442,5 +442,6 @@ def memory_update(code, aux_features, scribble, bank, mode, m):
     C = bank.shape[0]
     scribble = scribble.contiguous().float()
     with torch.cuda.device(bank.device):
-        lib.call("pp_memory_update", code, ptr(aux_features), ptr(scribble), ptr(bank), C, h, w, H, W, hid,
+        scratch = torch.empty(lib.cdll.pp_memory_update_scratch_floats(C, hid), dtype=torch.float32, device=bank.device)
+        lib.call("pp_memory_update", code, ptr(aux_features), ptr(scribble), ptr(bank), ptr(scratch), C, h, w, H, W, hid,
                  1 if mode == "cosine_similarity" else 0, float(m), float(1.0 - m), current_stream(bank.device))

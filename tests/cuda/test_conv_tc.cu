@@ -15,7 +15,7 @@ int init_device(int device);
 const char* last_error();
 int conv3x3_tc(const void*, int, const void*, int, const void*, const float*, void*, int, int, void*, int, int, int,
                int, int, int, cudaStream_t, double* stats = nullptr, int groups = 1);
-int conv3x3_wgrad_tc(const void*, int, const void*, int, const void*, int, float*, int, int, int, int, cudaStream_t);
+int conv3x3_wgrad_tc(const void*, int, const void*, int, const void*, int, float*, float*, int, int, int, int, cudaStream_t);
 int conv3x3_simt(int, const void*, int, const void*, int, const void*, const float*, void*, int, int, void*, int, int,
                  int, int, int, int, cudaStream_t);
 int conv3x3_wgrad_simt(int, const void*, int, const void*, int, const void*, int, float*, int, int, int, int,
@@ -182,7 +182,7 @@ int main(int argc, char** argv) {
     CK(cudaMemset(dw_tc, 0, nw * 4)); CK(cudaMemset(dw_ref, 0, nw * 4));
     PPCK(pp::conv3x3_wgrad_simt(pp::PP_BF16, r0, c.oc0, x0, c.C0, x1p, c.C1, dw_ref, c.N, c.H, c.W, c.dil, 0));
     CK(cudaDeviceSynchronize());
-    PPCK(pp::conv3x3_wgrad_tc(r0, c.oc0, x0, c.C0, x1p, c.C1, dw_tc, c.N, c.H, c.W, c.dil, 0));
+    PPCK(pp::conv3x3_wgrad_tc(r0, c.oc0, x0, c.C0, x1p, c.C1, dw_tc, nullptr, c.N, c.H, c.W, c.dil, 0));
     CK(cudaDeviceSynchronize());
     std::vector<float> a(nw), r(nw);
     CK(cudaMemcpy(a.data(), dw_tc, nw * 4, cudaMemcpyDeviceToHost));
