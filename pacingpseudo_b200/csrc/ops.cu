@@ -17,6 +17,12 @@ static inline int grid_for(long long work, int block, int max_blocks_per_sm = 16
   return static_cast<int>(g);
 }
 
+// Hot loops index with 32-bit integers (a 64-bit div/mod costs ~100 instructions per element on the GPU); the
+// launchers check that the element counts fit.
+#define PP_REQUIRE_INT32(v, what) \
+  PP_REQUIRE(static_cast<long long>(v) < (1LL << 31), "%s: %lld elements exceed the 32-bit index range", what, \
+             static_cast<long long>(v))
+
 #define PP_DISPATCH_T(dtype, ...)                        \
   do {                                                   \
     if ((dtype) == PP_F32) { using T = float; __VA_ARGS__ } \
@@ -97,18 +103,17 @@ __global__ void __launch_bounds__(256) first_conv_fwd_kernel(const float* __rest
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[Cout * 9 + i] = bias ? bias[i] : 0.f;
   __syncthreads();
   const int vecs = Cout / 8;
-  const long long total = static_cast<long long>(N) * H * W * vecs;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = int(i % vecs);
-    const long long p = i / vecs;
-    const int px = int(p % W), py = int((p / W) % H);
-    const long long img = p / (static_cast<long long>(W) * H);
+  const int total = N * H * W * vecs;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % vecs;
+    const int p = i / vecs;
+    const int px = p % W, py = (p / W) % H;
+    const int img = p / (W * H);
     float xin[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
-      xin[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (img * H + yy) * W + xx) : 0.f;
+      xin[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (static_cast<size_t>(img) * H + yy) * W + xx) : 0.f;
     }
     float o[8];
 #pragma unroll
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(256) first_conv_fwd_kernel(const float* __rest
     }
     Vec8<T> pk;
     pk.set(o);
-    pk.store(y + p * Cout + v * 8);
+    pk.store(y + static_cast<size_t>(p) * Cout + v * 8);
   }
 }
 
@@ -129,6 +134,7 @@ int first_conv_fwd(int dtype, const float* x, const float* w, const float* bias,
                    cudaStream_t s) {
   PP_REQUIRE(Cout % 8 == 0 && Cout <= 256, "first_conv_fwd: Cout=%d unsupported", Cout);
   const long long total = static_cast<long long>(N) * H * W * (Cout / 8);
+  PP_REQUIRE_INT32(total * 8, "first_conv_fwd");
   PP_DISPATCH_T(dtype, first_conv_fwd_kernel<T><<<grid_for(total, 256), 256, (Cout * 10) * sizeof(float), s>>>(
                            x, w, bias, static_cast<T*>(y), N, H, W, Cout););
   PP_LAUNCH_CHECK();
@@ -143,32 +149,32 @@ __global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const T* __restri
   for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long long warp_id = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  const long long P = static_cast<long long>(N) * H * W;
-  const long long chunk = (P + nwarps - 1) / nwarps;
-  const long long pb = warp_id * chunk, pe = (pb + chunk < P) ? pb + chunk : P;
+  const int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int P = N * H * W;
+  const int chunk = (P + nwarps - 1) / nwarps;
+  const int pb = min(warp_id * chunk, P), pe = min(pb + chunk, P);
   for (int cb = 0; cb < Cout; cb += 32) {  // channel block handled by lane
     const int co = cb + lane;
     float acc[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[t] = 0.f;
     constexpr int U = 4;  // pixels in flight per warp (independent loads)
-    for (long long p0 = pb; p0 < pe; p0 += U) {
+    for (int p0 = pb; p0 < pe; p0 += U) {
       float xv[U], g[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const long long p = p0 + u;
+        const int p = p0 + u;
         xv[u] = 0.f;
         g[u] = 0.f;
         if (p < pe) {
-          const int px = int(p % W), py = int((p / W) % H);
-          const long long img = p / (static_cast<long long>(W) * H);
+          const int px = p % W, py = (p / W) % H;
+          const int img = p / (W * H);
           if (lane < 9) {
             const int yy = py + lane / 3 - 1, xx = px + lane % 3 - 1;
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) xv[u] = __ldg(x + (img * H + yy) * W + xx);
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) xv[u] = __ldg(x + (static_cast<size_t>(img) * H + yy) * W + xx);
           }
-          if (co < Cout) g[u] = to_f32(dy[p * Cout + co]);
+          if (co < Cout) g[u] = to_f32(dy[static_cast<size_t>(p) * Cout + co]);
         }
       }
 #pragma unroll
@@ -189,6 +195,7 @@ __global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const T* __restri
 int first_conv_wgrad(int dtype, const void* dy, const float* x, float* dw, int N, int H, int W, int Cout,
                      cudaStream_t s) {
   PP_REQUIRE(Cout <= 256, "first_conv_wgrad: Cout=%d unsupported", Cout);
+  PP_REQUIRE_INT32(static_cast<long long>(N) * H * W, "first_conv_wgrad");
   const int blocks = sm_count() * 4;
   PP_DISPATCH_T(dtype, first_conv_wgrad_kernel<T><<<blocks, 256, Cout * 9 * sizeof(float), s>>>(
                            static_cast<const T*>(dy), x, dw, N, H, W, Cout););
@@ -205,20 +212,19 @@ constexpr int kMaxClasses = 8;
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ a, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ logits,
-                                                       long long P, int HW, int C) {
+                                                       int P, int HW, int C) {
   __shared__ float sw[kMaxClasses * CIN + kMaxClasses];
   for (int i = threadIdx.x; i < C * CIN; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) sw[kMaxClasses * CIN + i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
     float acc[kMaxClasses];
 #pragma unroll
     for (int c = 0; c < kMaxClasses; ++c) acc[c] = (c < C) ? sw[kMaxClasses * CIN + c] : 0.f;
 #pragma unroll
     for (int v = 0; v < CIN / 8; ++v) {
       Vec8<T> pk;
-      pk.load(a + p * CIN + v * 8);
+      pk.load(a + static_cast<size_t>(p) * CIN + v * 8);
       float f[8];
       pk.get(f);
 #pragma unroll
@@ -228,10 +234,10 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ a, 
           for (int j = 0; j < 8; ++j) acc[c] = fmaf(f[j], sw[c * CIN + v * 8 + j], acc[c]);
         }
     }
-    const long long n = p / HW, hw = p % HW;
+    const int n = p / HW, hw = p % HW;
 #pragma unroll
     for (int c = 0; c < kMaxClasses; ++c)
-      if (c < C) logits[(n * C + c) * HW + hw] = acc[c];
+      if (c < C) logits[(static_cast<size_t>(n) * C + c) * HW + hw] = acc[c];
   }
 }
 
@@ -239,8 +245,9 @@ int head_fwd(int dtype, const void* a, const float* w, const float* bias, float*
              int C, cudaStream_t s) {
   PP_REQUIRE(C >= 1 && C <= kMaxClasses, "head_fwd: num_classes=%d unsupported (max %d)", C, kMaxClasses);
   PP_REQUIRE(Cin == 32 || Cin == 64 || Cin == 128 || Cin == 256, "head_fwd: Cin=%d unsupported (32/64/128/256)", Cin);
+  PP_REQUIRE_INT32(P * Cin, "head_fwd");
 #define PP_HEAD_FWD(CIN_) \
-  head_fwd_kernel<T, CIN_><<<grid_for(P, 256), 256, 0, s>>>(static_cast<const T*>(a), w, bias, logits, P, HW, C)
+  head_fwd_kernel<T, CIN_><<<grid_for(P, 256), 256, 0, s>>>(static_cast<const T*>(a), w, bias, logits, int(P), HW, C)
   PP_DISPATCH_T(dtype, if (Cin == 32) PP_HEAD_FWD(32); else if (Cin == 64) PP_HEAD_FWD(64);
                 else if (Cin == 128) PP_HEAD_FWD(128); else PP_HEAD_FWD(256););
 #undef PP_HEAD_FWD
@@ -252,16 +259,15 @@ int head_fwd(int dtype, const void* a, const float* w, const float* bias, float*
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restrict__ dlogits,
                                                             const float* __restrict__ w, T* __restrict__ da,
-                                                            long long P, int HW, int C) {
+                                                            int P, int HW, int C) {
   __shared__ float sw[kMaxClasses * CIN];
   for (int i = threadIdx.x; i < C * CIN; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
-  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long n = p / HW, hw = p % HW;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+    const int n = p / HW, hw = p % HW;
     float dl[kMaxClasses];
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) dl[c] = (c < C) ? dlogits[(n * C + c) * HW + hw] : 0.f;
+    for (int c = 0; c < kMaxClasses; ++c) dl[c] = (c < C) ? dlogits[(static_cast<size_t>(n) * C + c) * HW + hw] : 0.f;
 #pragma unroll
     for (int v = 0; v < CIN / 8; ++v) {
       float f[8];
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restr
       }
       Vec8<T> pk;
       pk.set(f);
-      pk.store(da + p * CIN + v * 8);
+      pk.store(da + static_cast<size_t>(p) * CIN + v * 8);
     }
   }
 }
@@ -284,16 +290,16 @@ __global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restr
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256) head_bwd_weight_kernel(const float* __restrict__ dlogits,
                                                               const T* __restrict__ a, float* __restrict__ dw,
-                                                              float* __restrict__ db, long long P, int HW, int C) {
+                                                              float* __restrict__ db, int P, int HW, int C) {
   __shared__ float sacc[kMaxClasses * CIN + kMaxClasses];
   for (int i = threadIdx.x; i < kMaxClasses * CIN + kMaxClasses; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
   constexpr int R = CIN / 32;
   const int lane = threadIdx.x & 31;
-  const long long warp_id = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  const long long chunk = (P + nwarps - 1) / nwarps;
-  const long long pb = warp_id * chunk, pe = (pb + chunk < P) ? pb + chunk : P;
+  const int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int chunk = (P + nwarps - 1) / nwarps;
+  const int pb = min(warp_id * chunk, P), pe = min(pb + chunk, P);
   float acc[kMaxClasses][R];
   float accb = 0.f;
 #pragma unroll
@@ -301,19 +307,19 @@ __global__ void __launch_bounds__(256) head_bwd_weight_kernel(const float* __res
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[c][r] = 0.f;
   constexpr int U = 4;  // pixels in flight per warp
-  for (long long p0 = pb; p0 < pe; p0 += U) {
+  for (int p0 = pb; p0 < pe; p0 += U) {
     float dlv[U], av[U][R];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long p = p0 + u;
+      const int p = p0 + u;
       dlv[u] = 0.f;
 #pragma unroll
       for (int r = 0; r < R; ++r) av[u][r] = 0.f;
       if (p < pe) {
-        const long long n = p / HW, hw = p % HW;
-        if (lane < C) dlv[u] = dlogits[(n * C + lane) * HW + hw];
+        const int n = p / HW, hw = p % HW;
+        if (lane < C) dlv[u] = dlogits[(static_cast<size_t>(n) * C + lane) * HW + hw];
 #pragma unroll
-        for (int r = 0; r < R; ++r) av[u][r] = to_f32(a[p * CIN + r * 32 + lane]);
+        for (int r = 0; r < R; ++r) av[u][r] = to_f32(a[static_cast<size_t>(p) * CIN + r * 32 + lane]);
       }
     }
 #pragma unroll
@@ -344,11 +350,12 @@ int head_bwd(int dtype, const float* dlogits, const void* a, const float* w, voi
              int HW, int Cin, int C, cudaStream_t s) {
   PP_REQUIRE(C >= 1 && C <= kMaxClasses, "head_bwd: num_classes=%d unsupported", C);
   PP_REQUIRE(Cin == 32 || Cin == 64 || Cin == 128 || Cin == 256, "head_bwd: Cin=%d unsupported (32/64/128/256)", Cin);
+  PP_REQUIRE_INT32(P * Cin, "head_bwd");
   const int wblocks = sm_count() * 4;
 #define PP_HEAD_BWD(CIN_)                                                                                          \
   do {                                                                                                             \
-    if (da) head_bwd_data_kernel<T, CIN_><<<grid_for(P, 256), 256, 0, s>>>(dlogits, w, static_cast<T*>(da), P, HW, C); \
-    head_bwd_weight_kernel<T, CIN_><<<wblocks, 256, 0, s>>>(dlogits, static_cast<const T*>(a), dw, db, P, HW, C);   \
+    if (da) head_bwd_data_kernel<T, CIN_><<<grid_for(P, 256), 256, 0, s>>>(dlogits, w, static_cast<T*>(da), int(P), HW, C); \
+    head_bwd_weight_kernel<T, CIN_><<<wblocks, 256, 0, s>>>(dlogits, static_cast<const T*>(a), dw, db, int(P), HW, C);   \
   } while (0)
   PP_DISPATCH_T(dtype, if (Cin == 32) PP_HEAD_BWD(32); else if (Cin == 64) PP_HEAD_BWD(64);
                 else if (Cin == 128) PP_HEAD_BWD(128); else PP_HEAD_BWD(256););
@@ -423,23 +430,30 @@ int bn_stats(int dtype, const void* y, double* sums, int G, long long Pg, int C,
 
 // Finalize: per-group scale/shift/mean/rstd; running statistics updated group by group (train).
 // coef layout: [G][4][C] floats = scale, shift, mean, rstd.
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
-                                   float* __restrict__ coef, int G, long long Pg, int C, int training, float eps,
-                                   float momentum, int replicas) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restrict__ sums,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta,
+                                                          float* __restrict__ running_mean,
+                                                          float* __restrict__ running_var,
+                                                          long long* __restrict__ num_batches_tracked,
+                                                          float* __restrict__ coef, int G, long long Pg, int C,
+                                                          int training, float eps, float momentum, int replicas) {
+  // one warp per channel; the lanes fetch the replicated partial sums in parallel
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   float rm = running_mean[c], rv = running_var[c];
   for (int g = 0; g < G; ++g) {
     float mean, rstd;
     if (training) {
       double s1 = 0.0, s2 = 0.0;
-      for (int r = 0; r < replicas; ++r) {
+      for (int r = lane; r < replicas; r += 32) {
         const double* sp = sums + ((static_cast<long long>(r) * G + g) * C + c) * 2;
         s1 += sp[0];
         s2 += sp[1];
       }
+      s1 = warp_sum_d(s1);
+      s2 = warp_sum_d(s2);
       const double m = s1 / static_cast<double>(Pg);
       double var = s2 / static_cast<double>(Pg) - m * m;
       if (var < 0.0) var = 0.0;
@@ -452,14 +466,16 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
       mean = rm;
       rstd = 1.f / sqrtf(rv + eps);
     }
-    const float sc = gamma[c] * rstd;
-    float* cf = coef + static_cast<long long>(g) * 4 * C;
-    cf[c] = sc;
-    cf[C + c] = beta[c] - mean * sc;
-    cf[2 * C + c] = mean;
-    cf[3 * C + c] = rstd;
+    if (lane == 0) {
+      const float sc = gamma[c] * rstd;
+      float* cf = coef + static_cast<long long>(g) * 4 * C;
+      cf[c] = sc;
+      cf[C + c] = beta[c] - mean * sc;
+      cf[2 * C + c] = mean;
+      cf[3 * C + c] = rstd;
+    }
   }
-  if (training) {
+  if (training && lane == 0) {
     running_mean[c] = rm;
     running_var[c] = rv;
     if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += G;
@@ -469,51 +485,66 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
 int bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
                 long long* nbt, float* coef, int G, long long Pg, int C, int training, float eps, float momentum,
                 cudaStream_t s, int replicas) {
-  bn_finalize_kernel<<<ceil_div(C, 64), 64, 0, s>>>(sums, gamma, beta, running_mean, running_var, nbt, coef, G, Pg, C,
+  bn_finalize_kernel<<<ceil_div(C, 4), 128, 0, s>>>(sums, gamma, beta, running_mean, running_var, nbt, coef, G, Pg, C,
                                                     training, eps, momentum, replicas);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
 
-// a = lrelu(y * scale + shift). Four independent 16-byte vectors per thread per iteration keep enough
-// bytes in flight per SM to approach the HBM roofline.
+// a = lrelu(y * scale + shift). Blocks own (group, pixel chunk); a thread keeps one 8-channel vector's
+// coefficients in registers and streams pixels with four independent 16-byte loads in flight.
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ coef,
-                                                       T* __restrict__ a, long long Pg, int C, long long total_vecs,
-                                                       float slope) {
+                                                       T* __restrict__ a, int Pg, int C, int chunk,
+                                                       int chunks_per_group, float slope) {
   constexpr int U = 4;
   const int vecs = C / 8;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < total_vecs; i0 += stride * U) {
+  const int pl = 256 / vecs;
+  const int v = threadIdx.x % vecs, l = threadIdx.x / vecs;
+  const int g = blockIdx.x / chunks_per_group;
+  const int p0 = (blockIdx.x % chunks_per_group) * chunk;
+  const int p1 = min(p0 + chunk, Pg);
+  if (l >= pl) return;
+  float sc[8], sh[8];
+  const float* cf = coef + static_cast<size_t>(g) * 4 * C + v * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = cf[j]; sh[j] = cf[C + j]; }
+  const size_t base = static_cast<size_t>(g) * Pg * C + v * 8;
+  for (int pb = p0 + l; pb < p1; pb += pl * U) {
     Vec8<T> pk[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < total_vecs) pk[u].load(y + i * 8);
-    }
+    for (int u = 0; u < U; ++u)
+      if (pb + u * pl < p1) pk[u].load(y + base + static_cast<size_t>(pb + u * pl) * C);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      if (i >= total_vecs) break;
-      const int v = int(i % vecs);
-      const int g = int((i / vecs) / Pg);
-      const float* cf = coef + static_cast<long long>(g) * 4 * C + v * 8;
+      if (pb + u * pl >= p1) break;
       float f[8];
       pk[u].get(f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = lrelu(fmaf(f[j], __ldg(cf + j), __ldg(cf + C + j)), slope);
+      for (int j = 0; j < 8; ++j) f[j] = lrelu(fmaf(f[j], sc[j], sh[j]), slope);
       pk[u].set(f);
-      pk[u].store(a + i * 8);
+      pk[u].store(a + base + static_cast<size_t>(pb + u * pl) * C);
     }
   }
 }
 
+static void bn_chunks(int G, long long Pg, int blocks_per_sm, int* chunk, int* cpg) {
+  int c = (sm_count() * blocks_per_sm) / G;
+  if (c < 1) c = 1;
+  long long ch = ceil_div_ll(Pg, c);
+  if (ch < 64) ch = 64;
+  *chunk = static_cast<int>(ch);
+  *cpg = static_cast<int>(ceil_div_ll(Pg, ch));
+}
+
 int bn_apply(int dtype, const void* y, const float* coef, void* a, int G, long long Pg, int C, float slope,
              cudaStream_t s) {
-  PP_REQUIRE(C % 8 == 0, "bn_apply: C=%d must be a multiple of 8", C);
-  const long long tv = static_cast<long long>(G) * Pg * (C / 8);
-  PP_DISPATCH_T(dtype, bn_apply_kernel<T><<<grid_for(tv, 256), 256, 0, s>>>(static_cast<const T*>(y), coef,
-                                                                            static_cast<T*>(a), Pg, C, tv, slope););
+  PP_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "bn_apply: C=%d unsupported", C);
+  PP_REQUIRE_INT32(Pg * C, "bn_apply");
+  int chunk, cpg;
+  bn_chunks(G, Pg, 8, &chunk, &cpg);
+  PP_DISPATCH_T(dtype, bn_apply_kernel<T><<<G * cpg, 256, 0, s>>>(static_cast<const T*>(y), coef, static_cast<T*>(a),
+                                                                  int(Pg), C, chunk, cpg, slope););
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -606,43 +637,53 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ bsums, const f
   if (dbias != nullptr) dbias[c] += static_cast<float>(dbs);  // exactly 0 under batch statistics
 }
 
-// dy = scale * (dz - k1 - xhat * k2)
+// dy = scale * (dz - k1 - xhat * k2); same (group, chunk) decomposition, coefficients in registers
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y,
                                                            const float* __restrict__ coef,
-                                                           const float* __restrict__ bcoef, T* __restrict__ dy,
-                                                           long long Pg, int C, long long total_vecs, float slope) {
+                                                           const float* __restrict__ bcoef, T* __restrict__ dy, int Pg,
+                                                           int C, int chunk, int chunks_per_group, float slope) {
   constexpr int U = 2;
   const int vecs = C / 8;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < total_vecs; i0 += stride * U) {
+  const int pl = 256 / vecs;
+  const int v = threadIdx.x % vecs, l = threadIdx.x / vecs;
+  const int g = blockIdx.x / chunks_per_group;
+  const int p0 = (blockIdx.x % chunks_per_group) * chunk;
+  const int p1 = min(p0 + chunk, Pg);
+  if (l >= pl) return;
+  float sc[8], sh[8], mu[8], rs[8], k1[8], k2[8];
+  const float* cf = coef + static_cast<size_t>(g) * 4 * C + v * 8;
+  const float* bc = bcoef + static_cast<size_t>(g) * 2 * C + v * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = cf[j]; sh[j] = cf[C + j]; mu[j] = cf[2 * C + j]; rs[j] = cf[3 * C + j];
+    k1[j] = bc[j]; k2[j] = bc[C + j];
+  }
+  const size_t base = static_cast<size_t>(g) * Pg * C + v * 8;
+  for (int pb = p0 + l; pb < p1; pb += pl * U) {
     Vec8<T> pa[U], py[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < total_vecs) { pa[u].load(da + i * 8); py[u].load(y + i * 8); }
-    }
+    for (int u = 0; u < U; ++u)
+      if (pb + u * pl < p1) {
+        const size_t o = base + static_cast<size_t>(pb + u * pl) * C;
+        pa[u].load(da + o);
+        py[u].load(y + o);
+      }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      if (i >= total_vecs) break;
-      const int v = int(i % vecs);
-      const int g = int((i / vecs) / Pg);
-      const float* cf = coef + static_cast<long long>(g) * 4 * C + v * 8;
-      const float* bc = bcoef + static_cast<long long>(g) * 2 * C + v * 8;
+      if (pb + u * pl >= p1) break;
       float fa[8], fy[8], o[8];
       pa[u].get(fa);
       py[u].get(fy);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float sc = __ldg(cf + j);
-        const float z = fmaf(fy[j], sc, __ldg(cf + C + j));
+        const float z = fmaf(fy[j], sc[j], sh[j]);
         const float dz = z > 0.f ? fa[j] : fa[j] * slope;
-        const float xhat = (fy[j] - __ldg(cf + 2 * C + j)) * __ldg(cf + 3 * C + j);
-        o[j] = sc * (dz - __ldg(bc + j) - xhat * __ldg(bc + C + j));
+        const float xhat = (fy[j] - mu[j]) * rs[j];
+        o[j] = sc[j] * (dz - k1[j] - xhat * k2[j]);
       }
       pa[u].set(o);
-      pa[u].store(dy + i * 8);
+      pa[u].store(dy + base + static_cast<size_t>(pb + u * pl) * C);
     }
   }
 }
@@ -651,21 +692,23 @@ int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* 
            float* dbeta, float* dbias, void* dy, int G, long long Pg, int C, int training, float slope,
            cudaStream_t s) {
   PP_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "bn_bwd: C=%d unsupported", C);
+  PP_REQUIRE_INT32(Pg * C, "bn_bwd");
   PP_CHECK_CUDA(cudaMemsetAsync(bsums, 0, sizeof(double) * 2 * G * C, s));
   int cpg = (sm_count() * 4) / G;
   if (cpg < 1) cpg = 1;
   long long chunk = ceil_div_ll(Pg, cpg);
   if (chunk < 256) chunk = 256;
   cpg = static_cast<int>(ceil_div_ll(Pg, chunk));
-  const long long tv = static_cast<long long>(G) * Pg * (C / 8);
+  int achunk, acpg;
+  bn_chunks(G, Pg, 8, &achunk, &acpg);
   PP_DISPATCH_T(dtype,
                 bn_bwd_reduce_kernel<T><<<G * cpg, 256, 0, s>>>(static_cast<const T*>(da), static_cast<const T*>(y),
                                                                 coef, bsums, Pg, C, chunk, cpg, slope);
                 bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(bsums, coef, dgamma, dbeta, dbias, bcoef, G, Pg,
                                                                         C, training);
-                bn_bwd_apply_kernel<T><<<grid_for(tv, 256), 256, 0, s>>>(static_cast<const T*>(da),
-                                                                         static_cast<const T*>(y), coef, bcoef,
-                                                                         static_cast<T*>(dy), Pg, C, tv, slope););
+                bn_bwd_apply_kernel<T><<<G * acpg, 256, 0, s>>>(static_cast<const T*>(da), static_cast<const T*>(y),
+                                                                coef, bcoef, static_cast<T*>(dy), int(Pg), C, achunk,
+                                                                acpg, slope););
   PP_LAUNCH_CHECK_N(3);
   return PP_OK;
 }
@@ -678,13 +721,12 @@ template <typename T>
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H,
                                                           int W, int C) {
   const int vecs = C / 8, Ho = H / 2, Wo = W / 2;
-  const long long total = static_cast<long long>(N) * Ho * Wo * vecs;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = int(i % vecs);
-    long long p = i / vecs;
-    const int xo = int(p % Wo), yo = int((p / Wo) % Ho);
-    const long long n = p / (static_cast<long long>(Wo) * Ho);
+  const int total = N * Ho * Wo * vecs;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % vecs;
+    const int p = i / vecs;
+    const int xo = p % Wo, yo = (p / Wo) % Ho;
+    const size_t n = p / (Wo * Ho);
     float m[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -697,7 +739,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ 
     }
     Vec8<T> o;
     o.set(m);
-    o.store(y + i * 8);
+    o.store(y + static_cast<size_t>(i) * 8);
   }
 }
 
@@ -706,13 +748,12 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
                                                           T* __restrict__ gx, int N, int H, int W, int C,
                                                           int accumulate) {
   const int vecs = C / 8, Ho = H / 2, Wo = W / 2;
-  const long long total = static_cast<long long>(N) * Ho * Wo * vecs;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = int(i % vecs);
-    long long p = i / vecs;
-    const int xo = int(p % Wo), yo = int((p / Wo) % Ho);
-    const long long n = p / (static_cast<long long>(Wo) * Ho);
+  const int total = N * Ho * Wo * vecs;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % vecs;
+    const int p = i / vecs;
+    const int xo = p % Wo, yo = (p / Wo) % Ho;
+    const size_t n = p / (Wo * Ho);
     float m[8];
     int am[8];
 #pragma unroll
@@ -726,7 +767,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
         if (k == 0 || f[j] > m[j]) { m[j] = f[j]; am[j] = k; }
     }
     Vec8<T> pg;
-    pg.load(gy + i * 8);
+    pg.load(gy + static_cast<size_t>(i) * 8);
     float g[8];
     pg.get(g);
 #pragma unroll
@@ -752,6 +793,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
 
 int maxpool_fwd(int dtype, const void* x, void* y, int N, int H, int W, int C, cudaStream_t s) {
   PP_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "maxpool_fwd: H=%d W=%d must be even, C=%d multiple of 8", H, W, C);
+  PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * C, "maxpool_fwd");
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
   PP_DISPATCH_T(dtype, maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(static_cast<const T*>(x),
                                                                                    static_cast<T*>(y), N, H, W, C););
@@ -761,6 +803,7 @@ int maxpool_fwd(int dtype, const void* x, void* y, int N, int H, int W, int C, c
 int maxpool_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int H, int W, int C, int accumulate,
                 cudaStream_t s) {
   PP_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "maxpool_bwd: H=%d W=%d must be even, C=%d multiple of 8", H, W, C);
+  PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * C, "maxpool_bwd");
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
   PP_DISPATCH_T(dtype, maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(
                            static_cast<const T*>(x), static_cast<const T*>(gy), static_cast<T*>(gx), N, H, W, C,
@@ -807,13 +850,12 @@ template <typename T>
 __global__ void __launch_bounds__(256) upsample_nhwc_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N,
                                                                 int h, int w, int H, int W, int C, float sh, float sw) {
   const int vecs = C / 8;
-  const long long total = static_cast<long long>(N) * H * W * vecs;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = int(i % vecs);
-    long long p = i / vecs;
-    const int X = int(p % W), Y = int((p / W) % H);
-    const long long n = p / (static_cast<long long>(W) * H);
+  const int total = N * H * W * vecs;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % vecs;
+    const int p = i / vecs;
+    const int X = p % W, Y = (p / W) % H;
+    const size_t n = p / (W * H);
     const Lerp ly = lerp_src(Y, h, sh), lx = lerp_src(X, w, sw);
     const T* b = x + n * h * w * C + v * 8;
     Vec8<T> p00, p01, p10, p11;
@@ -828,7 +870,7 @@ __global__ void __launch_bounds__(256) upsample_nhwc_fwd_kernel(const T* __restr
       o[j] = ly.w0 * (lx.w0 * f00[j] + lx.w1 * f01[j]) + ly.w1 * (lx.w0 * f10[j] + lx.w1 * f11[j]);
     Vec8<T> out;
     out.set(o);
-    out.store(y + i * 8);
+    out.store(y + static_cast<size_t>(i) * 8);
   }
 }
 
@@ -838,13 +880,12 @@ __global__ void __launch_bounds__(256) upsample_nhwc_bwd_kernel(const T* __restr
                                                                 int h, int w, int H, int W, int C, float sh, float sw,
                                                                 int accumulate) {
   const int vecs = C / 8;
-  const long long total = static_cast<long long>(N) * h * w * vecs;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = int(i % vecs);
-    long long p = i / vecs;
-    const int xi = int(p % w), yi = int((p / w) % h);
-    const long long n = p / (static_cast<long long>(w) * h);
+  const int total = N * h * w * vecs;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % vecs;
+    const int p = i / vecs;
+    const int xi = p % w, yi = (p / w) % h;
+    const size_t n = p / (w * h);
     int ylo, yhi, xlo, xhi;
     lerp_range(yi, H, sh, &ylo, &yhi);
     lerp_range(xi, W, sw, &xlo, &xhi);
@@ -894,18 +935,19 @@ __global__ void __launch_bounds__(256) upsample_nhwc_bwd_kernel(const T* __restr
     Vec8<T> out;
     if (accumulate) {
       float old[8];
-      out.load(gx + i * 8);
+      out.load(gx + static_cast<size_t>(i) * 8);
       out.get(old);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += old[j];
     }
     out.set(acc);
-    out.store(gx + i * 8);
+    out.store(gx + static_cast<size_t>(i) * 8);
   }
 }
 
 int upsample_nhwc_fwd(int dtype, const void* x, void* y, int N, int h, int w, int H, int W, int C, cudaStream_t s) {
   PP_REQUIRE(C % 8 == 0, "upsample_nhwc_fwd: C=%d must be a multiple of 8", C);
+  PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * C, "upsample_nhwc_fwd");
   const long long total = static_cast<long long>(N) * H * W * (C / 8);
   PP_DISPATCH_T(dtype, upsample_nhwc_fwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(
                            static_cast<const T*>(x), static_cast<T*>(y), N, h, w, H, W, C, ac_scale(h, H),
@@ -916,6 +958,7 @@ int upsample_nhwc_fwd(int dtype, const void* x, void* y, int N, int h, int w, in
 int upsample_nhwc_bwd(int dtype, const void* gy, void* gx, int N, int h, int w, int H, int W, int C, int accumulate,
                       cudaStream_t s) {
   PP_REQUIRE(C % 8 == 0, "upsample_nhwc_bwd: C=%d must be a multiple of 8", C);
+  PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * C, "upsample_nhwc_bwd");
   const long long total = static_cast<long long>(N) * h * w * (C / 8);
   PP_DISPATCH_T(dtype, upsample_nhwc_bwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(
                            static_cast<const T*>(gy), static_cast<T*>(gx), N, h, w, H, W, C, ac_scale(h, H),
