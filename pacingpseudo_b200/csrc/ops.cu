@@ -78,10 +78,29 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
   }
 }
 
+// small ranges (the narrow layers): one thread per OIHW element, strided gather from the packed layout
+__global__ void __launch_bounds__(256) unpack_wgrad_small_kernel(const float* __restrict__ dwp, float* __restrict__ g,
+                                                                 int Cout, int Cin, int ci_begin, int ci_count,
+                                                                 int accumulate) {
+  const int total = Cout * ci_count * 9;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int tap = i % 9, ci = ci_begin + (i / 9) % ci_count, co = i / (9 * ci_count);
+  const float v = dwp[(static_cast<size_t>(tap) * Cout + co) * Cin + ci];
+  float* o = g + (static_cast<size_t>(co) * Cin + ci) * 9 + tap;
+  *o = accumulate ? *o + v : v;
+}
+
 int unpack_wgrad_range(const float* dwp, float* g, int Cout, int Cin, int ci_begin, int ci_count, int accumulate,
                        cudaStream_t s) {
   PP_REQUIRE(Cout % 32 == 0 && ci_begin % 32 == 0 && ci_count % 32 == 0 && ci_begin + ci_count <= Cin,
              "unpack_wgrad: Cout=%d Cin=%d range [%d,+%d) must be multiples of 32", Cout, Cin, ci_begin, ci_count);
+  if (Cout * ci_count <= 64 * 64) {
+    unpack_wgrad_small_kernel<<<ceil_div(Cout * ci_count * 9, 256), 256, 0, s>>>(dwp, g, Cout, Cin, ci_begin, ci_count,
+                                                                                accumulate);
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+  }
   unpack_wgrad_kernel<<<dim3(ci_count / 32, Cout / 32), 256, 0, s>>>(dwp, g, Cout, Cin, ci_begin, accumulate);
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -160,6 +179,7 @@ __global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const T* __restri
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[t] = 0.f;
     constexpr int U = 4;  // pixels in flight per warp (independent loads)
+    int cx = pb % W, cy = (pb / W) % H, cimg = pb / (W * H);   // running coordinates of pixel p0 (no per-pixel division)
     for (int p0 = pb; p0 < pe; p0 += U) {
       float xv[U], g[U];
 #pragma unroll
@@ -168,8 +188,8 @@ __global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const T* __restri
         xv[u] = 0.f;
         g[u] = 0.f;
         if (p < pe) {
-          const int px = p % W, py = (p / W) % H;
-          const int img = p / (W * H);
+          const int px = cx, py = cy, img = cimg;
+          if (++cx == W) { cx = 0; if (++cy == H) { cy = 0; ++cimg; } }
           if (lane < 9) {
             const int yy = py + lane / 3 - 1, xx = px + lane % 3 - 1;
             if (yy >= 0 && yy < H && xx >= 0 && xx < W) xv[u] = __ldg(x + (static_cast<size_t>(img) * H + yy) * W + xx);
@@ -307,6 +327,7 @@ __global__ void __launch_bounds__(256) head_bwd_weight_kernel(const float* __res
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[c][r] = 0.f;
   constexpr int U = 4;  // pixels in flight per warp
+  int cn = pb / HW, chw = pb % HW;   // running (image, pixel) of p0
   for (int p0 = pb; p0 < pe; p0 += U) {
     float dlv[U], av[U][R];
 #pragma unroll
@@ -316,7 +337,8 @@ __global__ void __launch_bounds__(256) head_bwd_weight_kernel(const float* __res
 #pragma unroll
       for (int r = 0; r < R; ++r) av[u][r] = 0.f;
       if (p < pe) {
-        const int n = p / HW, hw = p % HW;
+        const int n = cn, hw = chw;
+        if (++chw == HW) { chw = 0; ++cn; }
         if (lane < C) dlv[u] = dlogits[(static_cast<size_t>(n) * C + lane) * HW + hw];
 #pragma unroll
         for (int r = 0; r < R; ++r) av[u][r] = to_f32(a[static_cast<size_t>(p) * CIN + r * 32 + lane]);

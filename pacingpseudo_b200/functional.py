@@ -124,6 +124,7 @@ class UNetFunction(torch.autograd.Function):
         ctx.shape = (N, H, W)
         ctx.set_materialize_grads(False)  # unused end points must arrive as None, not as zero tensors
         ctx.buffers = buffers
+        ctx.params = learnable  # the Parameter objects themselves (direct gradient accumulation, see backward)
         ctx.save_for_backward(x, ws, *learnable)
         return (logits, *feats)
 
@@ -145,9 +146,21 @@ class UNetFunction(torch.autograd.Function):
             if g_logits is None:
                 g_logits = torch.zeros((N, engine.num_classes, H, W), dtype=torch.float32, device=dev)
             g_logits = g_logits.contiguous().float()
-            sizes = [t.numel() for t in learnable]
+            # The kernels ACCUMULATE (+=) into the gradient buffers. Parameters whose .grad has been pre-attached by
+            # pacingpseudo_b200.optim.FlatAdam (views of one flat buffer, marked _pp_direct_grad) are written in place
+            # and reported to autograd as None: no per-parameter `grad += g` kernels, no temporary gradient copy.
+            direct = [getattr(t, "_pp_direct_grad", False) and t.grad is not None and t.grad.is_contiguous()
+                      and t.grad.dtype == torch.float32 for t in ctx.params]
+            sizes = [0 if d else t.numel() for d, t in zip(direct, ctx.params)]
             flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-            grads = [g.view_as(t) for g, t in zip(flat.split(sizes), learnable)]
+            grads, ret = [], []
+            for d, t, g in zip(direct, ctx.params, flat.split(sizes)):
+                if d:
+                    grads.append(t.grad)
+                    ret.append(None)
+                else:
+                    grads.append(g.view_as(t))
+                    ret.append(grads[-1])
             ids, dfeat = [], []
             for act, g in zip(ctx.act_ids, g_feats):
                 if g is not None:
@@ -157,7 +170,7 @@ class UNetFunction(torch.autograd.Function):
             lib.call("pp_unet_backward", engine.handle, ptr(x), _ptr_array(params), ptr(ws), N, H, W, ctx.groups,
                      ctx.training, ptr(g_logits), len(ids), id_arr, _ptr_array(dfeat) if dfeat else None,
                      _ptr_array(grads), current_stream(dev))
-        return (None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, *ret)
 
 
 # --------------------------------------------------------------------------------------------

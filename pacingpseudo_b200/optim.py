@@ -28,6 +28,7 @@ class FlatAdam:
             self.flat_param[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_param[off:off + n].view_as(p)
             p.grad = self.flat_grad[off:off + n].view_as(p)
+            p._pp_direct_grad = True  # UNetFunction.backward accumulates straight into this view
             off += n
         self.exp_avg = torch.zeros_like(self.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat_param)

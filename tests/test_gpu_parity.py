@@ -517,3 +517,39 @@ def test_data_parallel_equivalence_emulated(pp):
     avg = average_gradients_emulated(per_rank)
     for k in avg:
         assert torch.allclose(avg[k], 0.5 * (per_rank[0][k] + per_rank[1][k]), rtol=1e-6, atol=1e-9)
+
+
+def test_flat_adam_and_direct_gradient_accumulation(pp):
+    """pacingpseudo_b200.optim.FlatAdam == torch.optim.Adam(lr, weight_decay) (train_chaos.py:219), and gradients
+    accumulated directly into its flat buffer equal the gradients autograd would have delivered."""
+    from pacingpseudo_b200.optim import FlatAdam
+    from pacingpseudo_b200.synth import make_batch
+    case = dict(kind="pacing", C=4, os=8, training=True, cr="ce_loss", mode="cosine_similarity")
+    ma = Hn.build_cuda_model(case, "fp32")
+    mb = Hn.build_cuda_model(case, "fp32")
+    oa = torch.optim.Adam(ma.parameters(), lr=1e-3, weight_decay=3e-4)
+    ob = FlatAdam(mb.parameters(), lr=1e-3, weight_decay=3e-4)
+    assert all(p.grad is not None and p._pp_direct_grad for p in mb.parameters() if p.requires_grad)
+    for step in range(3):
+        b = {k: v.cuda() for k, v in make_batch(2, 4, 64, 64, seed=40 + step).items() if k != "label"}
+        for m, o in ((ma, oa), (mb, ob)):
+            loss = O.total_loss(m(b, mode="train", step=step), epoch=30)
+            o.zero_grad()
+            loss.backward()
+        if step == 0:
+            for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+                if pa.grad is not None:
+                    assert pb.grad.data_ptr() >= ob.flat_grad.data_ptr()
+                    assert _rel(pb.grad, pa.grad) < 1e-4 or float(pa.grad.abs().max()) < 1e-7, k
+        oa.step()
+        ob.step()
+        if step == 0:
+            # one Adam step from identical states: identical updates (lr * m_hat / (sqrt(v_hat) + eps)), except where the
+            # gradient is numerically zero (conv bias under batch-statistics BN: the sign of rounding noise decides)
+            for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+                if pa.requires_grad and not k.endswith("conv.bias") and not k.endswith("layer_bottleneck.1.bias"):
+                    d = (pa.detach() - pb.detach()).abs()
+                    assert float((d > 2e-6).float().mean()) < 2e-3, (k, float(d.max()))
+    # later steps: the two runs drift apart chaotically (tiny case), but every element moved by <= ~lr per step
+    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert float((pa.detach() - pb.detach()).abs().max()) <= 2.5 * 3 * 1e-3, k
