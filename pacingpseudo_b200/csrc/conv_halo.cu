@@ -1,0 +1,322 @@
+// conv_halo.cu — 3x3 convolution for the NARROW, HIGH-RESOLUTION layers (32..96 channels at 256^2 / 128^2):
+// shared-memory-resident im2col on tcgen05.
+//
+// The generic kernel (conv_tc.cu) re-streams the 128-pixel A tile from L2 once per tap (9x) and the weight tile once
+// per M tile; for the narrow layers that L2->SM traffic, not the tensor core, is the bound (ncu: tensor pipe 10 %,
+// ~2.5 us per tile). Here one CTA owns a strip of 128 output columns x L output rows of one image:
+//   * the packed weights of ALL 9 taps stay resident in shared memory (9 * Cout * Cin * 2 B <= ~72 KB);
+//   * each INPUT row segment (128 + 2 halo pixels, all channels) is loaded exactly once by TMA into a 4-slot ring;
+//   * the nine taps of an output row are nine views of three ring slots: the +-1 pixel shifts are shared-memory
+//     descriptor start offsets of +-1 row (128 B / 64 B). A B200 experiment (tests/cuda/exp_desc_shift.cu,
+//     profiles/r01_exp_umma_descriptor_row_shift.txt) shows the UMMA swizzle is a function of the absolute smem
+//     address, so a K-major swizzled descriptor may start at ANY row with base_offset = 0;
+//   * two TMEM accumulators: the epilogue of row y overlaps the MMAs of row y+1.
+// HBM traffic is the algorithmic minimum (input read once, output written once).
+//
+// Same semantics as conv3x3_tc (two concat sources, two dgrad destinations with accumulate flags, bias, fused
+// BatchNorm statistics). Reference call site: nn.Conv2d in /root/reference/models/unet.py:188.
+#include "pp_common.cuh"
+
+namespace pp {
+
+static constexpr int kHaloThreads = 192;
+static constexpr int kRing = 4;      // input-row ring slots (3 live rows + 1 in flight)
+static constexpr int kTW = 128;      // output columns per strip == MMA M
+static constexpr int kBoxW = kTW + 2;
+
+struct HaloParams {
+  int N, H, W;
+  int strips, segs, L;         // column strips per row, row segments per image, rows per segment
+  int kc0, kc1, c0;            // K chunks per source, channels of source 0
+  int ctot;
+  __nv_bfloat16* out0;
+  __nv_bfloat16* out1;
+  int outc0, outc1, acc0, acc1;
+  const float* bias;
+  double* stats;
+  int imgs_per_group, groups;
+  int chunk_bytes;             // bytes of one ring chunk (kBoxW rows, rounded up to 1 KB)
+};
+
+template <int BLOCK_N, int BK>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                       const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+  constexpr int ROW = BK * 2;
+  constexpr uint32_t SWZ = (BK == 64) ? SWZ_128B : SWZ_64B;
+  constexpr uint32_t SBO = 8 * ROW;
+  constexpr int WTILE = BLOCK_N * ROW;                      // one (tap, chunk) weight tile
+  constexpr int TMEM_BUF = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : 128);
+  constexpr int TMEM_COLS = 2 * TMEM_BUF;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int chunks = p.kc0 + p.kc1;
+  uint8_t* s_w = smem;                                      // [9][chunks][BLOCK_N][BK]
+  uint8_t* s_ring = s_w + 9 * chunks * WTILE;               // [kRing][chunks][chunk_bytes]
+  const int slot_bytes = chunks * p.chunk_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + kRing * slot_bytes);
+  uint64_t* w_full = bars;
+  uint64_t* row_full = bars + 1;
+  uint64_t* row_empty = row_full + kRing;
+  uint64_t* acc_full = row_empty + kRing;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 2);  // [4 warps][2][BLOCK_N]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // job = (image, column strip, row segment)
+  const int job = blockIdx.x;
+  const int seg = job % p.segs;
+  const int strip = (job / p.segs) % p.strips;
+  const int img = job / (p.segs * p.strips);
+  const int x0 = strip * kTW;
+  const int r0 = seg * p.L;
+  const int rows = min(p.L, p.H - r0);                       // output rows of this job
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.kc1 > 0) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    mbar_init(w_full, 1);
+    for (int s = 0; s < kRing; ++s) { mbar_init(&row_full[s], 1); mbar_init(&row_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (p.stats != nullptr)
+    for (int i = threadIdx.x; i < 8 * BLOCK_N; i += kHaloThreads) s_stats[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: resident weights, then one box per (input row, chunk) =====
+      mbar_arrive_expect_tx(w_full, 9 * chunks * WTILE);
+      for (int tap = 0; tap < 9; ++tap)
+        for (int kc = 0; kc < chunks; ++kc) {
+          const int kofs = kc < p.kc0 ? kc * BK : p.c0 + (kc - p.kc0) * BK;
+          tma_load_3d(s_w + (tap * chunks + kc) * WTILE, &tmB, w_full, kofs, 0, tap);
+        }
+      for (int i = 0; i < rows + 2; ++i) {                   // input row r0 - 1 + i (out-of-range rows load as zeros)
+        const int slot = i % kRing;
+        mbar_wait(&row_empty[slot], ((i / kRing) & 1) ^ 1);
+        mbar_arrive_expect_tx(&row_full[slot], chunks * kBoxW * ROW);
+        uint8_t* dst = s_ring + slot * slot_bytes;
+        for (int kc = 0; kc < chunks; ++kc) {
+          if (kc < p.kc0) tma_load_4d(dst + kc * p.chunk_bytes, &tmA0, &row_full[slot], kc * BK, x0 - 1, r0 - 1 + i, img);
+          else tma_load_4d(dst + kc * p.chunk_bytes, &tmA1, &row_full[slot], (kc - p.kc0) * BK, x0 - 1, r0 - 1 + i, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      mbar_wait(w_full, 0);
+      mbar_wait(&row_full[0], 0);
+      mbar_wait(&row_full[1], 0);
+      const uint32_t w_addr = smem_u32(s_w);
+      const uint32_t ring_addr = smem_u32(s_ring);
+      for (int t = 0; t < rows; ++t) {
+        const int inew = t + 2;
+        mbar_wait(&row_full[inew % kRing], (inew / kRing) & 1);
+        const int b = t & 1;
+        mbar_wait(&acc_empty[b], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + b * TMEM_BUF;
+        uint32_t first = 1;
+        for (int ky = 0; ky < 3; ++ky) {
+          const uint32_t slot_addr = ring_addr + ((t + ky) % kRing) * slot_bytes;
+          for (int kc = 0; kc < chunks; ++kc) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint32_t a_addr = slot_addr + kc * p.chunk_bytes + kx * ROW;     // +-1 pixel == +-1 smem row
+              const uint32_t b_addr = w_addr + ((ky * 3 + kx) * chunks + kc) * WTILE;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 16, SBO, SWZ),
+                          make_smem_desc(b_addr + k * 32, 16, SBO, SWZ), idesc, first ? 0u : 1u);
+                first = 0;
+              }
+            }
+          }
+        }
+        umma_commit(&acc_full[b]);                 // accumulator of output row t complete
+        umma_commit(&row_empty[t % kRing]);        // input row t is not needed by later output rows
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> (+bias, +old) -> bf16 NHWC (+ BatchNorm partial sums) =====
+    const int q = warp & 3;
+    const int px = x0 + q * 32 + lane;
+    const bool col_ok = px < p.W;
+    for (int t = 0; t < rows; ++t) {
+      const int b = t & 1;
+      mbar_wait(&acc_full[b], (t >> 1) & 1);
+      tc_fence_after();
+      const long long pix = (static_cast<long long>(img) * p.H + (r0 + t)) * p.W + px;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        __nv_bfloat16* dst;
+        int dstc, acc, ch;
+        if (c < p.outc0) { dst = p.out0; dstc = p.outc0; acc = p.acc0; ch = c; }
+        else             { dst = p.out1; dstc = p.outc1; acc = p.acc1; ch = c - p.outc0; }
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * TMEM_BUF + c), v);
+        tmem_wait_ld();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + c + j);
+        }
+        if (col_ok) {
+          __nv_bfloat16* o = dst + pix * dstc + ch;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            Vec8<__nv_bfloat16> pk;
+            float tt[8];
+            if (acc) {
+              pk.load(o + g * 8);
+              pk.get(tt);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[g * 8 + j] += tt[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tt[j] = f[g * 8 + j];
+            pk.set(tt);
+            pk.store(o + g * 8);
+            pk.get(tt);   // statistics of the ROUNDED values
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[g * 8 + j] = tt[j];
+          }
+        }
+        if (p.stats != nullptr) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s1[j] = col_ok ? f[j] : 0.f; s2[j] = s1[j] * s1[j]; }
+#pragma unroll
+          for (int w = 16; w >= 1; w >>= 1) {
+            const bool hi = (lane & w) != 0;
+#pragma unroll
+            for (int j = 0; j < w; ++j) {
+              const float a1 = hi ? s1[j] : s1[j + w], a2 = hi ? s2[j] : s2[j + w];
+              const float k1 = hi ? s1[j + w] : s1[j], k2 = hi ? s2[j + w] : s2[j];
+              s1[j] = k1 + __shfl_xor_sync(0xffffffffu, a1, w);
+              s2[j] = k2 + __shfl_xor_sync(0xffffffffu, a2, w);
+            }
+          }
+          s_stats[(q * 2 + 0) * BLOCK_N + c + lane] += s1[0];   // per-warp slot, fixed order: reproducible
+          s_stats[(q * 2 + 1) * BLOCK_N + c + lane] += s2[0];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+    }
+  }
+  __syncwarp();
+  __syncthreads();
+  if (p.stats != nullptr) {
+    const int grp = img / p.imgs_per_group;
+    const int cout = p.outc0 + p.outc1;
+    for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kHaloThreads) {
+      const int st = i / BLOCK_N, j = i % BLOCK_N;
+      const double tot = (static_cast<double>(s_stats[(0 * 2 + st) * BLOCK_N + j]) + s_stats[(1 * 2 + st) * BLOCK_N + j]) +
+                         (static_cast<double>(s_stats[(2 * 2 + st) * BLOCK_N + j]) + s_stats[(3 * 2 + st) * BLOCK_N + j]);
+      atomicAdd(p.stats + ((static_cast<long long>(job % kStatReplicas) * p.groups + grp) * cout + j) * 2 + st, tot);
+    }
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host
+// ----------------------------------------------------------------------------------------------
+static int halo_chunk_bytes(int bk) { return ((kBoxW * bk * 2) + 1023) / 1024 * 1024; }
+
+static long long halo_smem_bytes(int cout, int ctot, int bk) {
+  const int chunks = ctot / bk;
+  return 9LL * chunks * cout * bk * 2 + static_cast<long long>(kRing) * chunks * halo_chunk_bytes(bk) + 1024 + 256 +
+         8 * cout * 4;
+}
+
+bool conv3x3_halo_applicable(int C0, int C1, int cout, int outc0, int outc1, int H, int W, int dil) {
+  if (dil != 1 || W < 112 || H < 2) return false;
+  if (cout != 32 && cout != 64 && cout != 96) return false;
+  if (outc0 % 32 != 0 || outc1 % 32 != 0) return false;
+  const int bk = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
+  if (C0 % bk != 0 || C1 % bk != 0) return false;
+  return halo_smem_bytes(cout, C0 + C1, bk) <= 200 * 1024;
+}
+
+template <int BLOCK_N, int BK>
+static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const HaloParams& p, int jobs,
+                       int smem, double flops, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_tc_kernel<BLOCK_N, BK>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024));
+    attr_set = true;
+  }
+  const int slot = prof_begin(PROF_CONV, flops, stream);
+  conv3x3_halo_tc_kernel<BLOCK_N, BK><<<jobs, kHaloThreads, smem, stream>>>(a0, a1, b, p);
+  prof_end(slot, stream);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+int conv3x3_halo_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
+                    int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, cudaStream_t stream,
+                    double* stats, int groups) {
+  const int cout = outc0 + outc1, ctot = C0 + C1;
+  const int bk = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
+  HaloParams p{};
+  p.N = N; p.H = H; p.W = W;
+  p.strips = ceil_div(W, kTW);
+  // rows per job: aim for ~3 jobs per SM so the tail is short, but keep the 2-row halo overhead small
+  long long tiles = static_cast<long long>(N) * H * p.strips;
+  int L = static_cast<int>(tiles / (3LL * sm_count()));
+  if (L < 8) L = 8;
+  if (L > 64) L = 64;
+  if (L > H) L = H;
+  p.L = L;
+  p.segs = ceil_div(H, L);
+  p.kc0 = C0 / bk; p.kc1 = C1 / bk; p.c0 = C0; p.ctot = ctot;
+  p.out0 = static_cast<__nv_bfloat16*>(out0); p.out1 = static_cast<__nv_bfloat16*>(out1);
+  p.outc0 = outc0; p.outc1 = outc1; p.acc0 = acc0; p.acc1 = acc1; p.bias = bias;
+  p.stats = stats;
+  p.groups = groups > 0 ? groups : 1;
+  p.imgs_per_group = N / p.groups;
+  p.chunk_bytes = halo_chunk_bytes(bk);
+  const int jobs = N * p.strips * p.segs;
+
+  CUtensorMap a0, a1, b;
+  int rc = encode_tmap_nhwc(&a0, x0, N, H, W, C0, bk, kBoxW, 1, 1, bk == 64);
+  if (rc) return rc;
+  if (C1 > 0) rc = encode_tmap_nhwc(&a1, x1, N, H, W, C1, bk, kBoxW, 1, 1, bk == 64);
+  else a1 = a0;
+  if (rc) return rc;
+  rc = encode_tmap_weights(&b, wpack, 9, cout, ctot, bk, cout, bk == 64);
+  if (rc) return rc;
+  const int smem = static_cast<int>(halo_smem_bytes(cout, ctot, bk));
+  const double flops = 2.0 * N * H * W * 9.0 * ctot * cout;
+#define PP_HALO_CASE(BN_, BK_) \
+  if (cout == BN_ && bk == BK_) return launch_halo<BN_, BK_>(a0, a1, b, p, jobs, smem, flops, stream);
+  PP_HALO_CASE(32, 32) PP_HALO_CASE(64, 32) PP_HALO_CASE(96, 32) PP_HALO_CASE(32, 64) PP_HALO_CASE(64, 64)
+  PP_HALO_CASE(96, 64)
+#undef PP_HALO_CASE
+  set_error("conv3x3_halo_tc: no kernel for cout=%d bk=%d", cout, bk);
+  return PP_ERR_INVALID;
+}
+
+}  // namespace pp

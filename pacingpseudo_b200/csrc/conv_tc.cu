@@ -235,6 +235,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   }
 }
 
+bool conv3x3_halo_applicable(int C0, int C1, int cout, int outc0, int outc1, int H, int W, int dil);
+int conv3x3_halo_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
+                    int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, cudaStream_t stream,
+                    double* stats, int groups);
+
 // ----------------------------------------------------------------------------------------------
 // wgrad
 // ----------------------------------------------------------------------------------------------
@@ -591,6 +596,9 @@ int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack
   PP_REQUIRE((out1 == nullptr) == (outc1 == 0), "conv3x3_tc: out1/outc1 mismatch");
   PP_REQUIRE(outc0 % 32 == 0 && outc1 % 32 == 0, "conv3x3_tc: output channels must be multiples of 32 (outc0=%d outc1=%d)",
              outc0, outc1);
+  if (conv3x3_halo_applicable(C0, C1, cout, outc0, outc1, H, W, dil))   // narrow high-resolution layers
+    return conv3x3_halo_tc(x0, C0, x1, C1, wpack, bias, out0, outc0, acc0, out1, outc1, acc1, N, H, W, stream, stats,
+                           groups);
   const int bk = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
   // N tile: the largest of {256,192,128,96,64,32} that divides the total output channels (a tile may straddle the two
   // dgrad destinations: the epilogue picks the destination per 32-column chunk)

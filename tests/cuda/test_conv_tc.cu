@@ -40,6 +40,12 @@ static const Case kCases[] = {
     {2, 32, 32, 128, 64, 64, 0, 1, 0, "wgrad: wide source 0 + narrow source 1"},
     {1, 128, 128, 64, 0, 64, 0, 1, 0, "narrow wgrad 64->64 128x128"},
     {2, 64, 64, 32, 0, 64, 0, 2, 0, "narrow wgrad 32->64 dil2"},
+    {2, 128, 128, 64, 0, 64, 0, 1, 0, "halo conv 64->64 128x128"},
+    {1, 256, 256, 64, 32, 32, 0, 1, 0, "halo conv concat 64+32->32 256x256"},
+    {1, 256, 256, 32, 0, 64, 32, 1, 1, "halo dgrad 32->(64+32) accumulate"},
+    {2, 224, 224, 32, 0, 32, 0, 1, 0, "halo conv 224 ragged strip"},
+    {1, 112, 112, 32, 0, 64, 0, 1, 0, "halo conv 112 (single partial strip)"},
+    {3, 128, 128, 64, 0, 32, 0, 1, 0, "halo conv 64->32"},
 };
 
 static float bf16_round(float f) { return __bfloat162float(__float2bfloat16(f)); }

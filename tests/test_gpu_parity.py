@@ -391,7 +391,7 @@ def _full_model(C=5, precision="bf16", seed=1):
 def test_full_size_step_properties(pp):
     """N=12, 256x256, C=5 (config 2). Properties that hold at any size:
     (a) strong == weak image and eval-mode BN  =>  logits_strong == logits_weak and loss_cr == loss_ent;
-    (b) gradients are linear in the loss weight; (c) every loss/grad is finite; (d) weak-only val pass matches
+    (b) gradients are linear in the loss weight (x4: exact in bf16); (c) every loss/grad is finite; (d) weak-only val pass matches
     the weak half of the batched train pass."""
     from pacingpseudo_b200.synth import make_batch
     model, case = _full_model()
@@ -408,7 +408,7 @@ def test_full_size_step_properties(pp):
 
     model.train()
     grads = []
-    for wgt in (1.0, 3.0):
+    for wgt in (1.0, 4.0):   # a power of two: bf16 / fp32 scale exactly, so backward must be linear to rounding-order noise
         model.zero_grad(set_to_none=True)
         model.aux_path.memory_bank.data.zero_()
         sd0 = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "num_batches" in k}
@@ -420,7 +420,7 @@ def test_full_size_step_properties(pp):
             assert torch.isfinite(out[k]), k
     for a, b in zip(*grads):
         assert torch.isfinite(a).all()
-        assert _rel(3.0 * a, b) < 2e-2
+        assert _rel(4.0 * a, b) < 1e-3
 
 
 def _full_size_metrics(z, grads, z_ref, g_ref, names, tol_logits):
