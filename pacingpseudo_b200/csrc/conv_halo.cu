@@ -20,7 +20,7 @@
 namespace pp {
 
 static constexpr int kHaloThreads = 192;
-static constexpr int kRing = 4;      // input-row ring slots (3 live rows + 1 in flight)
+static constexpr int kMaxRing = 8;   // input-row ring slots: 3 live rows + up to 5 rows of TMA prefetch in flight
 static constexpr int kTW = 128;      // output columns per strip == MMA M
 static constexpr int kBoxW = kTW + 2;
 
@@ -36,6 +36,7 @@ struct HaloParams {
   double* stats;
   int imgs_per_group, groups;
   int chunk_bytes;             // bytes of one ring chunk (kBoxW rows, rounded up to 1 KB)
+  int ring;                    // ring slots in use (4..kMaxRing)
 };
 
 template <int BLOCK_N, int BK>
@@ -53,13 +54,14 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int chunks = p.kc0 + p.kc1;
   uint8_t* s_w = smem;                                      // [9][chunks][BLOCK_N][BK]
-  uint8_t* s_ring = s_w + 9 * chunks * WTILE;               // [kRing][chunks][chunk_bytes]
+  uint8_t* s_ring = s_w + 9 * chunks * WTILE;               // [ring][chunks][chunk_bytes]
   const int slot_bytes = chunks * p.chunk_bytes;
+  const int kRing = p.ring;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + kRing * slot_bytes);
   uint64_t* w_full = bars;
   uint64_t* row_full = bars + 1;
-  uint64_t* row_empty = row_full + kRing;
-  uint64_t* acc_full = row_empty + kRing;
+  uint64_t* row_empty = row_full + kMaxRing;
+  uint64_t* acc_full = row_empty + kMaxRing;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 2);  // [4 warps][2][BLOCK_N]
@@ -244,10 +246,17 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
 // ----------------------------------------------------------------------------------------------
 static int halo_chunk_bytes(int bk) { return ((kBoxW * bk * 2) + 1023) / 1024 * 1024; }
 
-static long long halo_smem_bytes(int cout, int ctot, int bk) {
+static long long halo_smem_bytes(int cout, int ctot, int bk, int ring) {
   const int chunks = ctot / bk;
-  return 9LL * chunks * cout * bk * 2 + static_cast<long long>(kRing) * chunks * halo_chunk_bytes(bk) + 1024 + 256 +
+  return 9LL * chunks * cout * bk * 2 + static_cast<long long>(ring) * chunks * halo_chunk_bytes(bk) + 1024 + 512 +
          8 * cout * 4;
+}
+// deepest ring that fits: 8 slots if two CTAs still fit an SM (~100 KB each), else whatever fits in 200 KB
+static int halo_ring(int cout, int ctot, int bk) {
+  if (halo_smem_bytes(cout, ctot, bk, kMaxRing) <= 100 * 1024) return kMaxRing;
+  int ring = kMaxRing;
+  while (ring > 4 && halo_smem_bytes(cout, ctot, bk, ring) > 200 * 1024) --ring;
+  return ring;
 }
 
 bool conv3x3_halo_applicable(int C0, int C1, int cout, int outc0, int outc1, int H, int W, int dil) {
@@ -256,7 +265,7 @@ bool conv3x3_halo_applicable(int C0, int C1, int cout, int outc0, int outc1, int
   if (outc0 % 32 != 0 || outc1 % 32 != 0) return false;
   const int bk = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
   if (C0 % bk != 0 || C1 % bk != 0) return false;
-  return halo_smem_bytes(cout, C0 + C1, bk) <= 200 * 1024;
+  return halo_smem_bytes(cout, C0 + C1, bk, 4) <= 200 * 1024;
 }
 
 template <int BLOCK_N, int BK>
@@ -283,11 +292,14 @@ int conv3x3_halo_tc(const void* x0, int C0, const void* x1, int C1, const void* 
   HaloParams p{};
   p.N = N; p.H = H; p.W = W;
   p.strips = ceil_div(W, kTW);
-  // rows per job: aim for ~3 jobs per SM so the tail is short, but keep the 2-row halo overhead small
-  long long tiles = static_cast<long long>(N) * H * p.strips;
-  int L = static_cast<int>(tiles / (3LL * sm_count()));
+  // rows per job: one wave of jobs over the resident CTA slots (2 per SM when the footprint allows), so that no
+  // second, mostly idle wave is needed and the 2-row halo overhead stays small
+  const int ring = halo_ring(cout, ctot, bk);
+  const int slots = sm_count() * (halo_smem_bytes(cout, ctot, bk, ring) <= 100 * 1024 ? 2 : 1);
+  int per = slots / (N * p.strips);
+  if (per < 1) per = 1;
+  int L = ceil_div(H, per);
   if (L < 8) L = 8;
-  if (L > 64) L = 64;
   if (L > H) L = H;
   p.L = L;
   p.segs = ceil_div(H, L);
@@ -298,6 +310,7 @@ int conv3x3_halo_tc(const void* x0, int C0, const void* x1, int C1, const void* 
   p.groups = groups > 0 ? groups : 1;
   p.imgs_per_group = N / p.groups;
   p.chunk_bytes = halo_chunk_bytes(bk);
+  p.ring = halo_ring(cout, ctot, bk);
   const int jobs = N * p.strips * p.segs;
 
   CUtensorMap a0, a1, b;
@@ -308,7 +321,7 @@ int conv3x3_halo_tc(const void* x0, int C0, const void* x1, int C1, const void* 
   if (rc) return rc;
   rc = encode_tmap_weights(&b, wpack, 9, cout, ctot, bk, cout, bk == 64);
   if (rc) return rc;
-  const int smem = static_cast<int>(halo_smem_bytes(cout, ctot, bk));
+  const int smem = static_cast<int>(halo_smem_bytes(cout, ctot, bk, p.ring));
   const double flops = 2.0 * N * H * W * 9.0 * ctot * cout;
 #define PP_HALO_CASE(BN_, BK_) \
   if (cout == BN_ && bk == BK_) return launch_halo<BN_, BK_>(a0, a1, b, p, jobs, smem, flops, stream);
