@@ -40,7 +40,7 @@ struct HaloParams {
 };
 
 template <int BLOCK_N, int BK>
-__global__ void __launch_bounds__(kHaloThreads, 1)
+__global__ void __launch_bounds__(kHaloThreads, BLOCK_N == 32 ? 2 : 1)
 conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                        const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
   constexpr int ROW = BK * 2;
@@ -88,15 +88,13 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
-  if (p.stats != nullptr)
-    for (int i = threadIdx.x; i < 8 * BLOCK_N; i += kHaloThreads) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== TMA producer: resident weights, then one box per (input row, chunk) =====
       mbar_arrive_expect_tx(w_full, 9 * chunks * WTILE);
       for (int tap = 0; tap < 9; ++tap)
@@ -116,54 +114,77 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== MMA issuer =====
+      // These MMAs are short (N = 32..96: 16..48 tensor cycles each), so the issue loop itself must be lean:
+      // descriptors advance by 32-bit adds on the uniform datapath (umma_bf16_lohi), the ring slot index is tracked
+      // incrementally, and the TMEM address is provably warp-uniform (warp_uniform() above).
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      constexpr uint32_t dhi = smem_desc_hi(SBO, SWZ);
+      constexpr uint32_t WT16 = WTILE >> 4;
       mbar_wait(w_full, 0);
       mbar_wait(&row_full[0], 0);
       mbar_wait(&row_full[1], 0);
-      const uint32_t w_addr = smem_u32(s_w);
-      const uint32_t ring_addr = smem_u32(s_ring);
+      const uint32_t w_lo = smem_desc_lo(smem_u32(s_w), 16);
+      const uint32_t ring_lo = smem_desc_lo(smem_u32(s_ring), 16);
+      const uint32_t slot16 = static_cast<uint32_t>(slot_bytes) >> 4, chunk16 = static_cast<uint32_t>(p.chunk_bytes) >> 4;
+      const uint32_t tap16 = static_cast<uint32_t>(chunks) * WT16;   // weight tiles of consecutive taps
+      int s0 = 0;                                                     // ring slot of input row t (== output row t - 1)
+      int snew = 2 % kRing;                                           // ring slot of the newest row needed (t + 2)
+      uint32_t pnew = 0;
       for (int t = 0; t < rows; ++t) {
-        const int inew = t + 2;
-        mbar_wait(&row_full[inew % kRing], (inew / kRing) & 1);
+        mbar_wait(&row_full[snew], pnew);
         const int b = t & 1;
         mbar_wait(&acc_empty[b], ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + b * TMEM_BUF;
-        uint32_t first = 1;
+        int sl = s0;
+#pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          const uint32_t slot_addr = ring_addr + ((t + ky) % kRing) * slot_bytes;
+          uint32_t a_lo = ring_lo + static_cast<uint32_t>(sl) * slot16;
+          uint32_t b_lo = w_lo + static_cast<uint32_t>(ky * 3) * tap16;
           for (int kc = 0; kc < chunks; ++kc) {
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-              const uint32_t a_addr = slot_addr + kc * p.chunk_bytes + kx * ROW;     // +-1 pixel == +-1 smem row
-              const uint32_t b_addr = w_addr + ((ky * 3 + kx) * chunks + kc) * WTILE;
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 16, SBO, SWZ),
-                          make_smem_desc(b_addr + k * 32, 16, SBO, SWZ), idesc, first ? 0u : 1u);
-                first = 0;
-              }
+              for (int k = 0; k < BK / 16; ++k)     // +-1 pixel == +-1 smem row; K step of 16 channels == 32 bytes
+                umma_bf16_lohi(d_tmem, a_lo + kx * (ROW >> 4) + k * 2, dhi, b_lo + kx * tap16 + k * 2, dhi, idesc,
+                               (kx | k) != 0 ? 1u : ((ky | kc) != 0 ? 1u : 0u));
             }
+            a_lo += chunk16;
+            b_lo += WT16;
           }
+          if (++sl == kRing) sl = 0;
         }
         umma_commit(&acc_full[b]);                 // accumulator of output row t complete
-        umma_commit(&row_empty[t % kRing]);        // input row t is not needed by later output rows
+        umma_commit(&row_empty[s0]);               // input row t is not needed by later output rows
+        if (++s0 == kRing) s0 = 0;
+        if (++snew == kRing) { snew = 0; pnew ^= 1; }
       }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> (+bias, +old) -> bf16 NHWC (+ BatchNorm partial sums) =====
+    // The epilogue is instruction-bound on these narrow tiles (ncu: issue slots 40 % busy, tensor pipe 15 %), so the
+    // bias lives in registers and the BatchNorm column sums are accumulated per thread across all rows of the job;
+    // the 32-lane transpose-reduce runs once per job instead of once per row.
+    constexpr int NCH = BLOCK_N / 32;
+    constexpr bool kStatsOk = BLOCK_N <= 64;   // statistics are a forward-pass feature (Cout 32 / 64)
     const int q = warp & 3;
     const int px = x0 + q * 32 + lane;
     const bool col_ok = px < p.W;
+    float s1[kStatsOk ? BLOCK_N : 1], s2[kStatsOk ? BLOCK_N : 1];
+    if constexpr (kStatsOk) {
+#pragma unroll
+      for (int j = 0; j < BLOCK_N; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    }
     for (int t = 0; t < rows; ++t) {
       const int b = t & 1;
       mbar_wait(&acc_full[b], (t >> 1) & 1);
       tc_fence_after();
       const long long pix = (static_cast<long long>(img) * p.H + (r0 + t)) * p.W + px;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+#pragma unroll
+      for (int cc = 0; cc < NCH; ++cc) {
+        const int c = cc * 32;
         __nv_bfloat16* dst;
         int dstc, acc, ch;
         if (c < p.outc0) { dst = p.out0; dstc = p.outc0; acc = p.acc0; ch = c; }
@@ -175,8 +196,17 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         if (p.bias != nullptr) {
+          if ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {   // 8 broadcast vector loads per chunk
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + c + j);
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(b4 + j);
+              f[4 * j] += bv.x; f[4 * j + 1] += bv.y; f[4 * j + 2] += bv.z; f[4 * j + 3] += bv.w;
+            }
+          } else {                                                 // any 4-byte aligned pointer is legal at the C ABI
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + c + j);
+          }
         }
         if (col_ok) {
           __nv_bfloat16* o = dst + pix * dstc + ch;
@@ -194,33 +224,44 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
             for (int j = 0; j < 8; ++j) tt[j] = f[g * 8 + j];
             pk.set(tt);
             pk.store(o + g * 8);
-            pk.get(tt);   // statistics of the ROUNDED values
+            if constexpr (kStatsOk) {
+              pk.get(tt);   // statistics of the ROUNDED values (what BatchNorm reads back)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[g * 8 + j] = tt[j];
-          }
-        }
-        if (p.stats != nullptr) {
-          float s1[32], s2[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { s1[j] = col_ok ? f[j] : 0.f; s2[j] = s1[j] * s1[j]; }
-#pragma unroll
-          for (int w = 16; w >= 1; w >>= 1) {
-            const bool hi = (lane & w) != 0;
-#pragma unroll
-            for (int j = 0; j < w; ++j) {
-              const float a1 = hi ? s1[j] : s1[j + w], a2 = hi ? s2[j] : s2[j + w];
-              const float k1 = hi ? s1[j + w] : s1[j], k2 = hi ? s2[j + w] : s2[j];
-              s1[j] = k1 + __shfl_xor_sync(0xffffffffu, a1, w);
-              s2[j] = k2 + __shfl_xor_sync(0xffffffffu, a2, w);
+              for (int j = 0; j < 8; ++j) {
+                s1[c + g * 8 + j] += tt[j];
+                s2[c + g * 8 + j] = fmaf(tt[j], tt[j], s2[c + g * 8 + j]);
+              }
             }
           }
-          s_stats[(q * 2 + 0) * BLOCK_N + c + lane] += s1[0];   // per-warp slot, fixed order: reproducible
-          s_stats[(q * 2 + 1) * BLOCK_N + c + lane] += s2[0];
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[b]);
+    }
+    if constexpr (kStatsOk) {
+      if (p.stats != nullptr) {
+#pragma unroll
+        for (int cc = 0; cc < NCH; ++cc) {
+          // column sums over this warp's 32 pixel columns: butterfly transpose-reduce, lane j ends with channel j
+          float a[32], bq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { a[j] = s1[cc * 32 + j]; bq[j] = s2[cc * 32 + j]; }
+#pragma unroll
+          for (int w = 16; w >= 1; w >>= 1) {
+            const bool hi = (lane & w) != 0;
+#pragma unroll
+            for (int j = 0; j < w; ++j) {
+              const float a1 = hi ? a[j] : a[j + w], a2 = hi ? bq[j] : bq[j + w];
+              const float k1 = hi ? a[j + w] : a[j], k2 = hi ? bq[j + w] : bq[j];
+              a[j] = k1 + __shfl_xor_sync(0xffffffffu, a1, w);
+              bq[j] = k2 + __shfl_xor_sync(0xffffffffu, a2, w);
+            }
+          }
+          s_stats[(q * 2 + 0) * BLOCK_N + cc * 32 + lane] = a[0];   // one slot per warp, summed in a fixed order below
+          s_stats[(q * 2 + 1) * BLOCK_N + cc * 32 + lane] = bq[0];
+        }
+      }
     }
   }
   __syncwarp();

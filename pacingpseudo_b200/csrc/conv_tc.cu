@@ -91,10 +91,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
@@ -119,24 +119,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    if (elect_one()) {
+      // ===== MMA issuer (elected thread; descriptors advance by 32-bit adds, see umma_bf16_lohi) =====
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      constexpr uint32_t dhi = smem_desc_hi(SBO, SWZ);
+      const uint32_t base_lo = smem_desc_lo(smem_u32(smem), 16);
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t a_lo = base_lo;
       for (int it = 0; it < num_k; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t da = make_smem_desc(sa + k * 32, 16, SBO, SWZ);
-          const uint64_t db = make_smem_desc(sb + k * 32, 16, SBO, SWZ);
-          umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16_lohi(tmem_base, a_lo + k * 2, dhi, a_lo + (A_BYTES >> 4) + k * 2, dhi, idesc, (it | k) != 0 ? 1u : 0u);
         umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        a_lo += STAGE_BYTES >> 4;
+        if (++stage == p.stages) { stage = 0; phase ^= 1; a_lo = base_lo; }
       }
       umma_commit(tmem_full_bar);  // accumulator complete
     }
@@ -168,8 +167,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
       if (p.bias != nullptr) {
+        if ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {   // 8 broadcast vector loads per chunk
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col + j);
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = __ldg(b4 + j);
+            f[4 * j] += bv.x; f[4 * j + 1] += bv.y; f[4 * j + 2] += bv.z; f[4 * j + 3] += bv.w;
+          }
+        } else {                                                 // any 4-byte aligned pointer is legal at the C ABI
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col + j);
+        }
       }
       if (valid) {
         __nv_bfloat16* o = dst + pix * dstc + ch;
@@ -305,11 +313,11 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
 
   if (num_k > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         const CUtensorMap* tmX = src1 ? &tmX1 : &tmX0;
         int stage = 0;
         uint32_t phase = 0;
@@ -331,25 +339,25 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_c
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (elect_one()) {
         constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);  // both operands MN-major
+        // 16 pixels (K) = 16 rows of 128 B; MN chunks of 64 channels are BOX_BYTES apart (LBO);
+        // groups of 8 K rows are 1024 B apart (SBO).
+        constexpr uint32_t dhi = smem_desc_hi(1024, SWZ_128B);
+        const uint32_t base_lo = smem_desc_lo(smem_u32(smem), BOX_BYTES);
         int stage = 0;
         uint32_t phase = 0;
+        uint32_t a_lo = base_lo;
         for (int it = 0; it < num_k; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-          for (int k = 0; k < PIXK / 16; ++k) {
-            // 16 pixels (K) = 16 rows of 128 B; MN chunks of 64 channels are BOX_BYTES apart (LBO);
-            // groups of 8 K rows are 1024 B apart (SBO).
-            const uint64_t da = make_smem_desc(sa + k * 2048, BOX_BYTES, 1024, SWZ_128B);
-            const uint64_t db = make_smem_desc(sb + k * 2048, BOX_BYTES, 1024, SWZ_128B);
-            umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < PIXK / 16; ++k)
+            umma_bf16_lohi(tmem_base, a_lo + k * (2048 >> 4), dhi, a_lo + (A_BYTES >> 4) + k * (2048 >> 4), dhi, idesc,
+                           (it | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          a_lo += STAGE_BYTES >> 4;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; a_lo = base_lo; }
         }
         umma_commit(tmem_full_bar);
       }
@@ -455,11 +463,11 @@ conv3x3_wgrad_narrow_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
 
   if (num_k > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -481,28 +489,31 @@ conv3x3_wgrad_narrow_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (elect_one()) {
         constexpr uint32_t idesc = make_idesc_bf16(128, NCOUT, 1, 1);  // both operands MN-major
+        // K step = 16 pixel rows; MN chunks (one tap each) are xbox bytes apart (LBO); 8-row groups 8*ROW apart (SBO)
+        constexpr uint32_t ahi = smem_desc_hi(8 * ROW_A, SWZ_A), bhi = smem_desc_hi(8 * ROW_B, SWZ_B);
         const int ksteps = p.pixk / 16;
+        const uint32_t base_a = smem_desc_lo(smem_u32(smem), xbox);
+        const uint32_t base_b = smem_desc_lo(smem_u32(smem) + 9 * xbox, ybox);
+        const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4, xbox16 = static_cast<uint32_t>(xbox) >> 4;
         int stage = 0;
         uint32_t phase = 0;
+        uint32_t soff = 0;
         for (int it = 0; it < num_k; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sx = smem_u32(smem + stage * stage_bytes);
-          const uint32_t sy = sx + 9 * xbox;
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
             const int g0 = (g == NG - 1) ? 9 - TPG : g * TPG;   // first tap of the group
-            for (int k = 0; k < ksteps; ++k) {
-              // K step = 16 pixel rows; MN chunks (one tap each) are xbox bytes apart; 8-row groups 8*ROW apart
-              const uint64_t da = make_smem_desc(sx + g0 * xbox + k * 16 * ROW_A, xbox, 8 * ROW_A, SWZ_A);
-              const uint64_t db = make_smem_desc(sy + k * 16 * ROW_B, ybox, 8 * ROW_B, SWZ_B);
-              umma_bf16(tmem_base + g * NCOUT, da, db, idesc, (it | k) != 0 ? 1u : 0u);
-            }
+            const uint32_t a_lo = base_a + soff + g0 * xbox16, b_lo = base_b + soff;
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16_lohi(tmem_base + g * NCOUT, a_lo + k * (16 * ROW_A >> 4), ahi, b_lo + k * (16 * ROW_B >> 4), bhi,
+                             idesc, (it | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          soff += stage16;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; soff = 0; }
         }
         umma_commit(tmem_full_bar);
       }

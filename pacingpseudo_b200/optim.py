@@ -19,17 +19,20 @@ class FlatAdam:
         dev = self.params[0].device
         if dev.type != "cuda":
             raise RuntimeError("FlatAdam: parameters must live on a CUDA device (no CPU path)")
-        sizes = [p.numel() for p in self.params]
-        self.numel = sum(sizes)
-        self.flat_param = torch.empty(self.numel, dtype=torch.float32, device=dev)
+        # every view starts on a 16-byte boundary (vector loads in the kernels); the padding elements stay zero
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.numel = off
+        self.flat_param = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(self.numel, dtype=torch.float32, device=dev)
-        off = 0
-        for p, n in zip(self.params, sizes):
+        for p, off in zip(self.params, self.offsets):
+            n = p.numel()
             self.flat_param[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_param[off:off + n].view_as(p)
             p.grad = self.flat_grad[off:off + n].view_as(p)
             p._pp_direct_grad = True  # UNetFunction.backward accumulates straight into this view
-            off += n
         self.exp_avg = torch.zeros_like(self.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
         self.param_groups = [dict(params=self.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)]
@@ -38,12 +41,9 @@ class FlatAdam:
 
     def zero_grad(self, set_to_none=False):
         self.flat_grad.zero_()
-        off = 0
-        for p in self.params:  # re-attach if a caller dropped the views
-            n = p.numel()
+        for p, off in zip(self.params, self.offsets):  # re-attach if a caller dropped the views
             if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
-                p.grad = self.flat_grad[off:off + n].view_as(p)
-            off += n
+                p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
 
     @torch.no_grad()
     def step(self):

@@ -110,6 +110,35 @@ def test_conv3x3_forward_dgrad_wgrad_vs_oracle(pp, case, precision):
         assert _rel(y.float(), y2.float()) < 2e-3
 
 
+@pytest.mark.parametrize("case", [(2, 16, 16, 64, 0, 128, 1), (1, 16, 128, 32, 0, 32, 1), (1, 8, 256, 64, 32, 32, 1)])
+def test_conv3x3_bias_pointer_alignment(pp, case):
+    """The C ABI accepts any 4-byte aligned bias pointer (parameters re-homed as views of a flat buffer need not be
+    16-byte aligned): generic and smem-resident (halo) kernels, aligned vs. misaligned pointer, bit-identical."""
+    L, PF, _ = pp
+    N, H, W, C0, C1, Co, dil = case
+    g = torch.Generator().manual_seed(11)
+    x0 = torch.randn(N, H, W, C0, generator=g).bfloat16().cuda()
+    x1 = torch.randn(N, H, W, C1, generator=g).bfloat16().cuda() if C1 else None
+    w = (torch.randn(Co, C0 + C1, 3, 3, generator=g) / (3 * (C0 + C1) ** 0.5)).cuda()
+    b = torch.randn(Co, generator=g)
+    wf = torch.empty(9 * Co * (C0 + C1) * 2, dtype=torch.uint8, device="cuda")
+    wd = torch.empty_like(wf)
+    L.call("pp_pack_weights", PF.BF16, _p(w), _p(wf), _p(wd), Co, C0 + C1, _st())
+    outs = []
+    for shift in (0, 1, 2, 3):
+        buf = torch.zeros(Co + 8, device="cuda")
+        assert buf.data_ptr() % 16 == 0
+        bias = buf[shift:shift + Co]
+        bias.copy_(b)
+        y = torch.empty(N, H, W, Co, dtype=torch.bfloat16, device="cuda")
+        L.call("pp_conv3x3", PF.BF16, _p(x0), C0, _p(x1), C1, _p(wf), _p(bias), _p(y), Co, 0, None, 0, 0, N, H, W, dil,
+               _st())
+        torch.cuda.synchronize()
+        outs.append(y)
+    for y in outs[1:]:
+        assert torch.equal(outs[0], y)
+
+
 @pytest.mark.parametrize("case", [(4, 32, 32, 64, 0, 128, 2), (2, 128, 128, 32, 0, 32, 1), (2, 64, 64, 128, 64, 64, 2),
                                   (4, 8, 8, 64, 0, 64, 2)])
 def test_conv3x3_fused_batchnorm_statistics(pp, case):
