@@ -125,27 +125,72 @@ def workload_config(args, pairs_override=None):
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: an NVML polling thread (every ~2 ms; the timed
+    region is only a few hundred ms long), falling back to `nvidia-smi -lms` when NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.handle, self.samples, self.mask, self.stop_flag = None, None, [], 0, False
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(self.index).uuid))
+        except Exception:
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        return pynvml, h
 
     def start(self):
         try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.smax = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.thr = threading.Thread(target=self._poll, daemon=True)
+            self.thr.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thr.join(timeout=2)
+            sm = sorted(self.samples)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax,
+                    "reasons": sorted(v for k, v in self.BITS.items() if self.mask & k), "samples": len(sm),
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -169,7 +214,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -180,6 +225,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from pacingpseudo_b200 import dp
+    from pacingpseudo_b200.data import DevicePrefetcher, LossReader
     from pacingpseudo_b200.dropin import DROPIN_PATH
     from pacingpseudo_b200.lib import get_lib
     from pacingpseudo_b200.optim import FlatAdam
@@ -207,7 +253,7 @@ def run_ours(args):
         args_parser=ns).to(dev)
     model.train(args.bn == "train")
     opt = FlatAdam(model.parameters(), lr=1e-4, weight_decay=3e-4)
-    reducer = dp.GradientAllReducer(opt.flat_grad, num_buckets=4)
+    reducer = dp.GradientAllReducer(opt.flat_grad, num_buckets=4, unet=model.backbone, optimizer=opt)
     opt.grad_scale = 1.0 / world
     if world > 1:
         model.aux_path.bank_sync = dp.make_bank_sync(0)
@@ -224,6 +270,9 @@ def run_ours(args):
     h2d_bytes = sum(v.numel() * v.element_size() for v in pool_host[0].values())
     w_ent = gaussian_ramp_up(args.epoch, 1.0, scale=8.0)
     w_cr = gaussian_ramp_up(args.epoch, 1.0, scale=8.0)
+
+    loss_reader = LossReader(dev)
+    prefetcher = DevicePrefetcher((), dev)
 
     def step(batch, read_back):
         out = model(batch, mode='train', step=args.epoch)
@@ -242,8 +291,10 @@ def run_ours(args):
         loss.backward()
         reducer.allreduce()
         opt.step()
-        if read_back:  # the five .item() reads of train_chaos.py:275-310
+        if read_back == "item":   # the five blocking .item() reads of train_chaos.py:275-310
             return [t.item() for t in (out['loss_pce'], loss_ent, loss_cr, loss_aux, loss_mem)]
+        if read_back == "async":  # same five scalars, non-blocking D2H, handed back one step later
+            return loss_reader.push([out['loss_pce'], loss_ent, loss_cr, loss_aux, loss_mem])
         return None
 
     def barrier():
@@ -258,11 +309,13 @@ def run_ours(args):
         l0 = lib.cdll.pp_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(nsteps):
-            if host_inputs:
-                batch = {k: v.to(dev, non_blocking=True) for k, v in pool_host[i % len(pool_host)].items()}
-                step(batch, True)
-            else:
+        if host_inputs:   # pinned host batches, H2D on a copy stream one step ahead (pacingpseudo_b200/data.py)
+            for batch in prefetcher.reset(pool_host[i % len(pool_host)] for i in range(nsteps)):
+                step(batch, host_inputs)
+            if host_inputs == "async":
+                assert len(loss_reader.flush()) == 5
+        else:
+            for i in range(nsteps):
                 step(pool_dev[i % len(pool_dev)], False)
         e1.record()
         barrier()
@@ -275,8 +328,10 @@ def run_ours(args):
     sampler = ClockSampler(dev.index)
     if rank == 0:
         sampler.start()
-    ms, launches = timed(args.steps, host_inputs=False, profile=True)
+    ms, launches = timed(args.steps, host_inputs=False, profile=False)
     clocks = sampler.stop() if rank == 0 else None
+    # the same K steps once more with every tcgen05 conv launch bracketed by CUDA events on its stream (roofline)
+    ms_prof, _ = timed(args.steps, host_inputs=False, profile=True)
     prof = {}
     for fam, name in ((0, "conv3x3_tc (fwd+dgrad)"), (1, "conv3x3_wgrad_tc")):
         t, f, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
@@ -284,11 +339,16 @@ def run_ours(args):
         prof[name] = dict(ms=t.value, flops=f.value, launches=n.value)
     e2e = None
     if not args.no_e2e:
-        for i in range(2):
-            step({k: v.to(dev, non_blocking=True) for k, v in pool_host[i].items()}, True)
-        ms_e2e, _ = timed(args.steps, host_inputs=True, profile=False)
+        for batch in prefetcher.reset(pool_host[i] for i in range(3)):   # allocates the staging buffers
+            step(batch, "async")
+        ms_e2e, _ = timed(args.steps, host_inputs="async", profile=False)
+        ms_e2e_item, _ = timed(args.steps, host_inputs="item", profile=False)
         e2e = {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": "img/s", "h2d_bytes_per_step": h2d_bytes,
-               "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / args.steps}
+               "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / args.steps,
+               "how": "pinned host batches -> DevicePrefetcher (H2D into persistent staging buffers on a copy stream, "
+                      "one step ahead) -> ConsistencyRegulr.forward / backward / FlatAdam.step -> LossReader (the five "
+                      "loss scalars, non-blocking D2H to pinned memory every step, read one step later)",
+               "ms_per_step_blocking_item_reads": ms_e2e_item / args.steps}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -312,7 +372,8 @@ def run_ours(args):
             "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
             "frac": achieved / peaks["tf_sustained"], "peak_source": peaks["src"] + " bf16 sustained",
             "traffic": None, "launches": int(conv_n), "kernel_ms_per_step": conv_ms / args.steps,
-            "share_of_step": conv_ms / ms if ms > 0 else None, "per_family": prof,
+            "share_of_step": conv_ms / ms_prof if ms_prof > 0 else None, "per_family": prof,
+            "profiled_pass_ms_per_step": ms_prof / args.steps,
             "step_tensor_frac": (value / world * gf / 1e12 / peaks["tf_sustained"]) if gf else None,
         },
     }

@@ -69,6 +69,13 @@ int pp_unet_forward(pp_unet_t u, const float* x, void* const* params, void* work
 int pp_unet_backward(pp_unet_t u, const float* x, void* const* params, void* workspace, int N, int H, int W, int G,
                      int training, const float* dlogits, int n_dfeat, const int* dfeat_act,
                      const void* const* dfeat, float* const* grads, void* stream);
+/* Data-parallel overlap (NEW functionality; the reference is single-GPU). pp_unet_backward walks the
+ * layers from the last to the first; after pp_unet_set_grad_events(u, n, layers) it records event i on its stream as
+ * soon as every parameter gradient of conv layers >= layers[i] (and of the head) has been enqueued.
+ * pp_unet_wait_grad_event makes `stream` (e.g. the NCCL stream) wait for event i, so the all-reduce of that slice of
+ * the gradient buffer overlaps the rest of the backward pass. The library owns the events. */
+int pp_unet_set_grad_events(pp_unet_t u, int n, const int* layers);
+int pp_unet_wait_grad_event(pp_unet_t u, int i, void* stream);
 
 /* ---- single operators (also used by the aux path and the op-level parity tests) --------------- */
 /* nn.Conv2d 3x3 stride 1 pad=dil (unet.py:188; aux_path_memory.py:24): y[N,H,W,oc0(+oc1)] from the virtual

@@ -9,6 +9,8 @@ namespace pp {
 struct UNetPlan;
 UNetPlan* unet_create(int input_ch, int init_ch, int max_ch, int num_classes, int output_stride, int dtype);
 void unet_destroy(UNetPlan* pl);
+int unet_set_grad_events(UNetPlan* pl, int n, const int* layers);
+int unet_wait_grad_event(const UNetPlan* pl, int i, cudaStream_t s);
 int unet_num_convs(const UNetPlan* pl);
 int unet_conv_info(const UNetPlan* pl, int layer, int* cin, int* cout, int* dil, const char** name);
 long long unet_workspace_bytes(const UNetPlan* pl, int N, int H, int W, int G);
@@ -42,6 +44,12 @@ int pp_unet_create(int input_ch, int init_ch, int max_ch, int num_classes, int o
   return *out ? PP_OK : PP_ERR_INVALID;
 }
 void pp_unet_destroy(pp_unet_t u) { unet_destroy(reinterpret_cast<pp::UNetPlan*>(u)); }
+int pp_unet_set_grad_events(pp_unet_t u, int n, const int* layers) {
+  return unet_set_grad_events(reinterpret_cast<pp::UNetPlan*>(u), n, layers);
+}
+int pp_unet_wait_grad_event(pp_unet_t u, int i, void* stream) {
+  return unet_wait_grad_event(reinterpret_cast<pp::UNetPlan*>(u), i, static_cast<cudaStream_t>(stream));
+}
 int pp_unet_num_convs(pp_unet_t u) { return unet_num_convs(reinterpret_cast<pp::UNetPlan*>(u)); }
 int pp_unet_conv_info(pp_unet_t u, int layer, int* cin, int* cout, int* dil, const char** name) {
   return unet_conv_info(reinterpret_cast<pp::UNetPlan*>(u), layer, cin, cout, dil, name);

@@ -36,6 +36,11 @@ struct UNetPlan {
   std::vector<Op> ops;
   int head_in = -1;
   std::map<std::string, int> named;
+  // data-parallel overlap: ev[i] is recorded on the backward stream as soon as every parameter gradient of
+  // conv layers >= ev_layer[i] (and of the head) is complete, so a communication stream can start reducing
+  // that slice of the gradient buffer while the rest of the backward pass still runs (dp.py).
+  std::vector<int> ev_layer;
+  std::vector<cudaEvent_t> ev;
 
   int new_act(int C, int res) { acts.push_back({C, res}); return int(acts.size()) - 1; }
 
@@ -272,8 +277,15 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
                   reinterpret_cast<const float*>(base + L.coef[op.layer]), reinterpret_cast<double*>(base + L.bsums),
                   reinterpret_cast<float*>(base + L.bcoef), gg[2], gg[3], gg[1], dy, G, Pg, c.cout, training, 0.01f, s);
       if (rc) return rc;
+      auto grads_ready = [&]() -> int {   // all parameter gradients of layers >= op.layer are enqueued
+        for (size_t e = 0; e < pl.ev_layer.size(); ++e)
+          if (pl.ev_layer[e] == op.layer) PP_CHECK_CUDA(cudaEventRecord(pl.ev[e], s));
+        return PP_OK;
+      };
       if (c.in0 < 0) {
         rc = first_conv_wgrad(dt, dy, x, gg[0], N, h, w, c.cout, s);
+        if (rc) return rc;
+        rc = grads_ready();
         if (rc) return rc;
         continue;
       }
@@ -294,6 +306,8 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
         rc = unpack_wgrad(dwp, gg[0], c.cout, ctot, 1, s);
         if (rc) return rc;
       }
+      rc = grads_ready();
+      if (rc) return rc;
       // dgrad: forward kernel on the flipped/transposed pack, scattered to the two sources
       void* g0 = base + L.act_grad[c.in0];
       void* g1 = c.in1 >= 0 ? base + L.act_grad[c.in1] : nullptr;
@@ -349,7 +363,29 @@ UNetPlan* unet_create(int input_ch, int init_ch, int max_ch, int num_classes, in
   pl->build();
   return pl;
 }
-void unet_destroy(UNetPlan* pl) { delete pl; }
+void unet_destroy(UNetPlan* pl) {
+  if (pl) for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
+  delete pl;
+}
+int unet_set_grad_events(UNetPlan* pl, int n, const int* layers) {
+  PP_REQUIRE(n >= 0 && (n == 0 || layers != nullptr), "unet_set_grad_events: bad arguments");
+  for (int i = 0; i < n; ++i)
+    PP_REQUIRE(layers[i] >= 0 && layers[i] < int(pl->convs.size()), "unet_set_grad_events: bad layer %d", layers[i]);
+  for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
+  pl->ev.clear();
+  pl->ev_layer.assign(layers, layers + n);
+  for (int i = 0; i < n; ++i) {
+    cudaEvent_t e;
+    PP_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    pl->ev.push_back(e);
+  }
+  return PP_OK;
+}
+int unet_wait_grad_event(const UNetPlan* pl, int i, cudaStream_t s) {
+  PP_REQUIRE(i >= 0 && i < int(pl->ev.size()), "unet_wait_grad_event: bad event index %d", i);
+  PP_CHECK_CUDA(cudaStreamWaitEvent(s, pl->ev[i], 0));
+  return PP_OK;
+}
 int unet_num_convs(const UNetPlan* pl) { return int(pl->convs.size()); }
 int unet_conv_info(const UNetPlan* pl, int layer, int* cin, int* cout, int* dil, const char** name) {
   PP_REQUIRE(layer >= 0 && layer < int(pl->convs.size()), "unet_conv_info: bad layer %d", layer);

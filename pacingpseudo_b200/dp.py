@@ -28,33 +28,107 @@ def init_distributed(backend=None):
     return rank, world, torch.device("cuda", local) if use_cuda else torch.device("cpu")
 
 
-class GradientAllReducer:
-    """Sum-all-reduce of a flat gradient buffer in `num_buckets` contiguous slices, on a side stream when on CUDA."""
+def plan_layer_buckets(layer_spans, num_buckets):
+    """Backward-ordered bucket plan over contiguous per-layer spans of the flat gradient buffer.
 
-    def __init__(self, flat_grad, num_buckets=4, group=None):
+    layer_spans: [(lo, hi)] per conv layer in FORWARD order (+ the head folded into the last span), contiguous and
+    increasing. The backward pass completes the layers last-to-first, so buckets are cut walking from the last
+    layer down, each closed once it holds >= 1/num_buckets of the elements; the remaining early layers form the
+    final bucket. Returns [(first_layer, lo, hi)]: bucket k = slice [lo, hi), complete once `first_layer`'s
+    gradients are; first_layer == 0 marks the final bucket (ready only when the whole backward pass is).
+    """
+    total = layer_spans[-1][1] - layer_spans[0][0]
+    target = max(1, total // max(1, num_buckets))
+    plan, hi, acc = [], layer_spans[-1][1], 0
+    for i in range(len(layer_spans) - 1, 0, -1):
+        acc += layer_spans[i][1] - layer_spans[i][0]
+        if acc >= target and len(plan) < num_buckets - 1:
+            plan.append((i, layer_spans[i][0], hi))
+            hi, acc = layer_spans[i][0], 0
+    plan.append((0, layer_spans[0][0], hi))
+    return plan
+
+
+class GradientAllReducer:
+    """Sum-all-reduce of a flat gradient buffer in contiguous bucket slices on a communication stream.
+
+    With `unet` (the drop-in models.unet.UNet whose parameters live in `optimizer`'s flat buffer) the buckets are cut
+    on layer boundaries in the order the backward pass completes them, and each bucket's all-reduce waits only for
+    the event pp_unet_backward records when those layers' gradients are done (include/pacingpseudo_b200.h,
+    pp_unet_set_grad_events): the exchange overlaps the remaining backward kernels. Gradients outside the UNet span
+    (aux path) and the earliest layers go last, after the whole backward pass. Without `unet`: `num_buckets` equal
+    slices after the backward pass (also the CPU / gloo path).
+    """
+
+    def __init__(self, flat_grad, num_buckets=4, group=None, unet=None, optimizer=None):
         self.flat = flat_grad
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         n = flat_grad.numel()
-        step = (n + num_buckets - 1) // num_buckets
-        step = (step + 127) // 128 * 128
-        self.buckets = [(o, min(o + step, n)) for o in range(0, n, step)]
         self.stream = torch.cuda.Stream(flat_grad.device) if flat_grad.is_cuda else None
+        self.unet = None
+        if unet is not None and optimizer is not None and flat_grad.is_cuda:
+            spans = self._layer_spans(unet, optimizer)
+            plan = plan_layer_buckets(spans, num_buckets)
+            self.overlapped = plan[:-1]                        # [(first_layer, lo, hi)] each with its own event
+            lo_tail, hi_tail = plan[-1][1], plan[-1][2]
+            self.tail = [(a, b) for a, b in ((0, hi_tail), (spans[-1][1], n)) if b > a]   # after the whole backward
+            assert lo_tail == spans[0][0]
+            self.buckets = [(lo, hi) for _, lo, hi in self.overlapped] + self.tail
+            self.unet = unet
+            import ctypes
+            layers = [fl for fl, _, _ in self.overlapped]
+            arr = (ctypes.c_int * max(1, len(layers)))(*layers)
+            unet.engine.lib.call("pp_unet_set_grad_events", unet.engine.handle, len(layers), arr)
+        else:
+            step = (n + num_buckets - 1) // num_buckets
+            step = (step + 127) // 128 * 128
+            self.buckets = [(o, min(o + step, n)) for o in range(0, n, step)]
+
+    @staticmethod
+    def _layer_spans(unet, optimizer):
+        where = {id(p): (off, p.numel()) for p, off in zip(optimizer.params, optimizer.offsets)}
+        spans = []
+        mods = unet._layer_modules()
+        for i, m in enumerate(mods):
+            ps = [m.conv.weight, m.conv.bias, m.norm_op.weight, m.norm_op.bias]
+            if i == len(mods) - 1:
+                ps += [unet.final_conv.weight, unet.final_conv.bias]
+            locs = [where[id(p)] for p in ps]
+            spans.append((min(o for o, _ in locs), max(o + k for o, k in locs)))
+        for a, b in zip(spans, spans[1:]):   # the flat buffer follows module registration order == layer order
+            if a[1] > b[0]:
+                raise RuntimeError("GradientAllReducer: UNet parameters are not laid out in layer order")
+        spans = [(lo, nxt[0]) for (lo, _), nxt in zip(spans, spans[1:])] + [spans[-1]]   # absorb alignment padding
+        return spans
 
     def allreduce(self):
+        """Call right after loss.backward() (all backward kernels enqueued on the current stream)."""
         if self.world == 1:
             return
-        if self.stream is not None:
-            self.stream.wait_stream(torch.cuda.current_stream(self.flat.device))
-            with torch.cuda.stream(self.stream):
-                works = [dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-                         for a, b in self.buckets]
-                for w in works:
-                    w.wait()
-            torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)
-        else:
+        if self.stream is None:
             for a, b in self.buckets:
                 dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group)
+            return
+        cur = torch.cuda.current_stream(self.flat.device)
+        works = []
+        with torch.cuda.stream(self.stream):
+            if self.unet is not None:
+                import ctypes
+                eng = self.unet.engine
+                st = ctypes.c_void_p(self.stream.cuda_stream)
+                for i, (_, a, b) in enumerate(self.overlapped):
+                    eng.lib.call("pp_unet_wait_grad_event", eng.handle, i, st)
+                    works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                tail = self.tail
+            else:
+                tail = self.buckets
+            self.stream.wait_stream(cur)
+            for a, b in tail:
+                works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            for w in works:
+                w.wait()
+        cur.wait_stream(self.stream)
 
 
 def make_bank_sync(src=0, group=None):

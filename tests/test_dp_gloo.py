@@ -52,3 +52,21 @@ def test_dp_host_logic_world2_gloo():
         assert p.exitcode == 0
     assert res[0][1:4] == (True, True, 1.0) and res[1][1:4] == (True, True, 1.0)
     assert res[0][4] == 1241 and res[1][4] == 2241
+
+
+def test_layer_bucket_plan_follows_backward_order():
+    """Buckets are cut on layer boundaries from the last layer down; the early layers form the final bucket."""
+    from pacingpseudo_b200.dp import plan_layer_buckets
+    sizes = [416, 9312, 18560, 36992, 73984, 147712, 295424, 590336, 1180672, 2360320, 2360320, 2360320, 4719616,
+             2360320, 1770240, 590336, 442624, 147712, 110720, 36992, 27712, 9477]   # the default UNet, head folded in
+    spans, off = [], 0
+    for n in sizes:
+        spans.append((off, off + n))
+        off += n
+    plan = plan_layer_buckets(spans, 4)
+    assert [b[0] for b in plan] == [13, 11, 8, 0]
+    assert plan[0][2] == off and plan[-1][1] == 0
+    for (_, lo, hi), (_, lo2, hi2) in zip(plan, plan[1:]):   # contiguous, descending, no gaps
+        assert lo == hi2 and lo2 < hi2
+    assert all(lo == spans[fl][0] for fl, lo, _ in plan)
+    assert plan_layer_buckets(spans, 1) == [(0, 0, off)]

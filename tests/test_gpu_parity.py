@@ -582,3 +582,35 @@ def test_flat_adam_and_direct_gradient_accumulation(pp):
     # later steps: the two runs drift apart chaotically (tiny case), but every element moved by <= ~lr per step
     for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         assert float((pa.detach() - pb.detach()).abs().max()) <= 2.5 * 3 * 1e-3, k
+
+
+def test_device_prefetcher_and_loss_reader(pp):
+    """Host->device staging (two persistent buffers, copy stream one batch ahead) delivers every batch intact even
+    when the consumer is slow, and LossReader returns each step's scalars exactly one push later."""
+    from pacingpseudo_b200.data import DevicePrefetcher, LossReader
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(3)
+    host = [{"image": torch.randn(4, 1, 64, 64, generator=g).pin_memory(),
+             "scribble": torch.randn(4, 6, 64, 64, generator=g).pin_memory(), "tag": i} for i in range(7)]
+    reader = LossReader(dev)
+    seen, lagged = 0, []
+    big = torch.randn(2048, 2048, device=dev)
+    pf = DevicePrefetcher(iter(host), dev)
+    for i, b in enumerate(pf):
+        assert b["tag"] == i
+        s = (b["image"].double().sum() + b["scribble"].double().sum()).float()
+        for _ in range(3):
+            big = big @ big * 1e-3     # keep the consumer stream busy so that copies really run ahead
+        lagged.append(reader.push([s, s * 2]))
+        assert torch.equal(b["image"].cpu(), host[i]["image"]) and torch.equal(b["scribble"].cpu(), host[i]["scribble"])
+        seen += 1
+    lagged.append(reader.flush())
+    assert seen == 7 and lagged[0] is None
+    for i in range(7):
+        ref = float(host[i]["image"].double().sum() + host[i]["scribble"].double().sum())
+        assert abs(lagged[i + 1][0] - ref) < 1e-3 * max(1.0, abs(ref)) and abs(lagged[i + 1][1] - 2 * ref) < 2e-3 * max(1.0, abs(ref))
+    assert pf.h2d_bytes == sum(v.numel() * 4 for b in host for v in b.values() if torch.is_tensor(v))
+    ptrs = {k: v.data_ptr() for s in pf.slots for k, v in s.items()}
+    for i, b in enumerate(pf.reset(iter(host[:3]))):     # next epoch: same staging buffers, data still intact
+        assert torch.equal(b["scribble"].cpu(), host[i]["scribble"])
+    assert ptrs == {k: v.data_ptr() for s in pf.slots for k, v in s.items()} and i == 2
