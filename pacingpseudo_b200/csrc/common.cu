@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -59,16 +60,34 @@ void prof_end(int slot, cudaStream_t s) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   cudaEventRecord(g_prof[slot].b, s);
 }
+// Time during which at least one launch of `family` (or of any family, family < 0) was running: the union of the
+// [start, end] intervals on the device timeline. With the weight-gradient kernels on a side stream, launches overlap,
+// and a plain sum of durations would count the shared time twice.
 int prof_collect(int family, double* ms, double* flops, long long* launches) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   *ms = 0; *flops = 0; *launches = 0;
+  if (g_prof_used == 0) return PP_OK;
+  std::vector<std::pair<float, float>> iv;
   for (size_t i = 0; i < g_prof_used; ++i) {
-    if (g_prof[i].family != family) continue;
+    if (family >= 0 && g_prof[i].family != family) continue;
     PP_CHECK_CUDA(cudaEventSynchronize(g_prof[i].b));
-    float t = 0.f;
-    PP_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b));
-    *ms += t; *flops += g_prof[i].flops; *launches += 1;
+    float ta = 0.f, tb = 0.f;
+    if (i > 0) PP_CHECK_CUDA(cudaEventElapsedTime(&ta, g_prof[0].a, g_prof[i].a));
+    PP_CHECK_CUDA(cudaEventElapsedTime(&tb, g_prof[0].a, g_prof[i].b));
+    iv.emplace_back(ta, tb);
+    *flops += g_prof[i].flops; *launches += 1;
   }
+  std::sort(iv.begin(), iv.end());
+  float cur_a = 0.f, cur_b = -1.f;
+  for (const auto& p : iv) {
+    if (cur_b < cur_a || p.first > cur_b) {
+      if (cur_b >= cur_a) *ms += cur_b - cur_a;
+      cur_a = p.first; cur_b = p.second;
+    } else if (p.second > cur_b) {
+      cur_b = p.second;
+    }
+  }
+  if (cur_b >= cur_a) *ms += cur_b - cur_a;
   return PP_OK;
 }
 void prof_reset() {

@@ -60,6 +60,61 @@ int pack_weights(int dtype, const float* w, void* wf, void* wd, int Cout, int Ci
   return PP_OK;
 }
 
+// All conv layers of a network in ONE launch (the per-layer kernels are launch-latency bound: 22 launches of a few
+// microseconds each per forward pass). The layer table travels as a kernel parameter.
+constexpr int kMaxPackLayers = 32;
+struct PackTable {
+  const float* w[kMaxPackLayers];
+  void* wf[kMaxPackLayers];
+  void* wd[kMaxPackLayers];
+  int cout[kMaxPackLayers], cin[kMaxPackLayers];
+  int tile_begin[kMaxPackLayers + 1];   // prefix sum of 32x32 tiles per layer
+  int n;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const __grid_constant__ PackTable tb) {
+  __shared__ float tile[32][32 * 9 + 1];
+  int l = 0;
+  while (l + 1 < tb.n && static_cast<int>(blockIdx.x) >= tb.tile_begin[l + 1]) ++l;
+  const int Cout = tb.cout[l], Cin = tb.cin[l];
+  const int tidx = blockIdx.x - tb.tile_begin[l];
+  const int tiles_ci = Cin / 32;
+  const int co0 = (tidx / tiles_ci) * 32, ci0 = (tidx % tiles_ci) * 32;
+  const float* __restrict__ w = tb.w[l];
+  T* __restrict__ wf = static_cast<T*>(tb.wf[l]);
+  T* __restrict__ wd = static_cast<T*>(tb.wd[l]);
+  for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+    const int r = i / 288, c = i % 288;
+    tile[r][c] = w[(static_cast<long long>(co0 + r) * Cin + ci0) * 9 + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
+    const int tap = i / 1024, a = (i / 32) % 32, b = i % 32;
+    wf[(static_cast<long long>(tap) * Cout + co0 + a) * Cin + ci0 + b] = from_f32<T>(tile[a][b * 9 + tap]);
+    wd[(static_cast<long long>(8 - tap) * Cin + ci0 + a) * Cout + co0 + b] = from_f32<T>(tile[b][a * 9 + tap]);
+  }
+}
+
+int pack_weights_multi(int dtype, int n, const float* const* w, void* const* wf, void* const* wd, const int* cout,
+                       const int* cin, cudaStream_t s) {
+  for (int base = 0; base < n; base += kMaxPackLayers) {
+    PackTable tb{};
+    tb.n = n - base < kMaxPackLayers ? n - base : kMaxPackLayers;
+    tb.tile_begin[0] = 0;
+    for (int i = 0; i < tb.n; ++i) {
+      const int k = base + i;
+      PP_REQUIRE(cout[k] % 32 == 0 && cin[k] % 32 == 0, "pack_weights: Cout=%d Cin=%d must be multiples of 32", cout[k],
+                 cin[k]);
+      tb.w[i] = w[k]; tb.wf[i] = wf[k]; tb.wd[i] = wd[k]; tb.cout[i] = cout[k]; tb.cin[i] = cin[k];
+      tb.tile_begin[i + 1] = tb.tile_begin[i] + (cout[k] / 32) * (cin[k] / 32);
+    }
+    if (tb.tile_begin[tb.n] == 0) continue;
+    PP_DISPATCH_T(dtype, pack_weights_multi_kernel<T><<<tb.tile_begin[tb.n], 256, 0, s>>>(tb););
+    PP_LAUNCH_CHECK();
+  }
+  return PP_OK;
+}
+
 // dwp [tap][Cout][Cin] fp32 -> OIHW grad [Cout][Cin][3][3] (accumulate ? += : =), for input channels
 // [ci_begin, ci_begin + ci_count) only (multiples of 32).
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ g,
@@ -112,35 +167,40 @@ int unpack_wgrad(const float* dwp, float* g, int Cout, int Cin, int accumulate, 
 
 // ==============================================================================================
 // First conv: Cin = 1, 3x3, pad 1 (unet.py:28 enc_block1.conv_layer1). Direct convolution.
+// Thread = (pixel, group of 8 output channels); the group is fixed per thread, so its 72 weights + 8 biases
+// live in registers and the inner loop is 9 broadcast loads of x, 72 FMAs and one 16-byte store.
 // ==============================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) first_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, T* __restrict__ y, int N,
                                                              int H, int W, int Cout) {
-  extern __shared__ float sw[];  // [Cout][9] + [Cout]
-  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[Cout * 9 + i] = bias ? bias[i] : 0.f;
-  __syncthreads();
-  const int vecs = Cout / 8;
-  const int total = N * H * W * vecs;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int v = i % vecs;
-    const int p = i / vecs;
-    const int px = p % W, py = (p / W) % H;
-    const int img = p / (W * H);
+  const int vecs = Cout / 8;                 // power of two, <= 32 (checked by the launcher)
+  const int v = threadIdx.x % vecs;
+  const int ppb = 256 / vecs;                // pixels per block iteration
+  float wr[8][9], br[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    br[j] = bias ? bias[v * 8 + j] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[j][t] = w[(v * 8 + j) * 9 + t];
+  }
+  const int P = N * H * W;
+  for (int p = blockIdx.x * ppb + threadIdx.x / vecs; p < P; p += gridDim.x * ppb) {
+    const int px = p % W, row = p / W, py = row % H;
+    const float* xr = x + static_cast<size_t>(row) * W + px;   // row = img * H + py
     float xin[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
-      xin[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (static_cast<size_t>(img) * H + yy) * W + xx) : 0.f;
+      const int dy = t / 3 - 1, dx = t % 3 - 1;
+      const bool ok = (py + dy >= 0) && (py + dy < H) && (px + dx >= 0) && (px + dx < W);
+      xin[t] = ok ? __ldg(xr + dy * W + dx) : 0.f;
     }
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int co = v * 8 + j;
-      float a = sw[Cout * 9 + co];
+      float a = br[j];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) a = fmaf(xin[t], sw[co * 9 + t], a);
+      for (int t = 0; t < 9; ++t) a = fmaf(xin[t], wr[j][t], a);
       o[j] = a;
     }
     Vec8<T> pk;
@@ -149,74 +209,89 @@ __global__ void __launch_bounds__(256) first_conv_fwd_kernel(const float* __rest
   }
 }
 
+static bool pow2_vecs(int C) { return C % 8 == 0 && C <= 256 && ((C / 8) & (C / 8 - 1)) == 0; }
+
 int first_conv_fwd(int dtype, const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
                    cudaStream_t s) {
-  PP_REQUIRE(Cout % 8 == 0 && Cout <= 256, "first_conv_fwd: Cout=%d unsupported", Cout);
-  const long long total = static_cast<long long>(N) * H * W * (Cout / 8);
-  PP_REQUIRE_INT32(total * 8, "first_conv_fwd");
-  PP_DISPATCH_T(dtype, first_conv_fwd_kernel<T><<<grid_for(total, 256), 256, (Cout * 10) * sizeof(float), s>>>(
+  PP_REQUIRE(pow2_vecs(Cout), "first_conv_fwd: Cout=%d unsupported (8,16,...,256)", Cout);
+  const long long P = static_cast<long long>(N) * H * W;
+  PP_REQUIRE_INT32(P * Cout, "first_conv_fwd");
+  const int ppb = 256 / (Cout / 8);
+  PP_DISPATCH_T(dtype, first_conv_fwd_kernel<T><<<grid_for(ceil_div_ll(P, ppb) * 256, 256, 8), 256, 0, s>>>(
                            x, w, bias, static_cast<T*>(y), N, H, W, Cout););
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
 
 // dW[co][tap] += sum_p dy[p][co] * x[p + off(tap)]   (dw is the OIHW fp32 grad [Cout][1][3][3])
+// Thread = (pixel, group of 8 channels): one 16-byte load of dy per pixel, 72 register accumulators; partial sums
+// are combined by warp shuffles (lanes holding the same channel group), then shared memory, then one atomic per
+// (block, weight).
 template <typename T>
 __global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const T* __restrict__ dy, const float* __restrict__ x,
                                                                float* __restrict__ dw, int N, int H, int W, int Cout) {
   extern __shared__ float sacc[];  // [Cout*9]
   for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int vecs = Cout / 8;
+  const int v = threadIdx.x % vecs;
+  const int ppb = 256 / vecs;
+  float acc[8][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
   const int P = N * H * W;
-  const int chunk = (P + nwarps - 1) / nwarps;
-  const int pb = min(warp_id * chunk, P), pe = min(pb + chunk, P);
-  for (int cb = 0; cb < Cout; cb += 32) {  // channel block handled by lane
-    const int co = cb + lane;
-    float acc[9];
+  constexpr int U = 2;   // pixels in flight per thread
+  for (int p0 = blockIdx.x * ppb + threadIdx.x / vecs; p0 < P; p0 += gridDim.x * ppb * U) {
+    Vec8<T> g[U];
+    float xin[U][9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
-    constexpr int U = 4;  // pixels in flight per warp (independent loads)
-    int cx = pb % W, cy = (pb / W) % H, cimg = pb / (W * H);   // running coordinates of pixel p0 (no per-pixel division)
-    for (int p0 = pb; p0 < pe; p0 += U) {
-      float xv[U], g[U];
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * gridDim.x * ppb;
+      if (p < P) {
+        g[u].load(dy + static_cast<size_t>(p) * Cout + v * 8);
+        const int px = p % W, row = p / W, py = row % H;
+        const float* xr = x + static_cast<size_t>(row) * W + px;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int p = p0 + u;
-        xv[u] = 0.f;
-        g[u] = 0.f;
-        if (p < pe) {
-          const int px = cx, py = cy, img = cimg;
-          if (++cx == W) { cx = 0; if (++cy == H) { cy = 0; ++cimg; } }
-          if (lane < 9) {
-            const int yy = py + lane / 3 - 1, xx = px + lane % 3 - 1;
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) xv[u] = __ldg(x + (static_cast<size_t>(img) * H + yy) * W + xx);
-          }
-          if (co < Cout) g[u] = to_f32(dy[static_cast<size_t>(p) * Cout + co]);
+        for (int t = 0; t < 9; ++t) {
+          const int ddy = t / 3 - 1, ddx = t % 3 - 1;
+          const bool ok = (py + ddy >= 0) && (py + ddy < H) && (px + ddx >= 0) && (px + ddx < W);
+          xin[u][t] = ok ? __ldg(xr + ddy * W + ddx) : 0.f;
         }
-      }
+      } else {
+        g[u].zero();
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-#pragma unroll
-        for (int t = 0; t < 9; ++t) acc[t] = fmaf(g[u], __shfl_sync(0xffffffffu, xv[u], t), acc[t]);
+        for (int t = 0; t < 9; ++t) xin[u][t] = 0.f;
       }
     }
-    if (co < Cout) {
 #pragma unroll
-      for (int t = 0; t < 9; ++t) atomicAdd(&sacc[co * 9 + t], acc[t]);
+    for (int u = 0; u < U; ++u) {
+      float f[8];
+      g[u].get(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(f[j], xin[u][t], acc[j][t]);
     }
   }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float a = acc[j][t];
+      for (int o = vecs; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);   // lanes with the same v
+      if (lane < vecs) atomicAdd(&sacc[(v * 8 + j) * 9 + t], a);
+    }
   __syncthreads();
   for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
 }
-
 int first_conv_wgrad(int dtype, const void* dy, const float* x, float* dw, int N, int H, int W, int Cout,
                      cudaStream_t s) {
-  PP_REQUIRE(Cout <= 256, "first_conv_wgrad: Cout=%d unsupported", Cout);
-  PP_REQUIRE_INT32(static_cast<long long>(N) * H * W, "first_conv_wgrad");
-  const int blocks = sm_count() * 4;
+  PP_REQUIRE(pow2_vecs(Cout), "first_conv_wgrad: Cout=%d unsupported (8,16,...,256)", Cout);
+  PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * Cout, "first_conv_wgrad");
+  const int blocks = sm_count() * 2;
   PP_DISPATCH_T(dtype, first_conv_wgrad_kernel<T><<<blocks, 256, Cout * 9 * sizeof(float), s>>>(
                            static_cast<const T*>(dy), x, dw, N, H, W, Cout););
   PP_LAUNCH_CHECK();
@@ -226,163 +301,174 @@ int first_conv_wgrad(int dtype, const void* dy, const float* x, float* dw, int N
 // ==============================================================================================
 // 1x1 heads (unet.py:60 final_conv with bias; aux_path_memory.py:32 fc_cls without bias).
 // Input NHWC T [P][Cin], output logits NCHW fp32 [N][C][HW]. C <= 8.
+// Thread = (pixel, group of 8 input channels): fully coalesced 16-byte loads, the class sums are combined across the
+// CIN/8 lanes of a pixel with xor-shuffles; weights of the thread's channel group live in registers.
 // ==============================================================================================
 constexpr int kMaxClasses = 8;
 
-template <typename T, int CIN>
+template <typename T, int CIN, int NC>
 __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ a, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ logits,
                                                        int P, int HW, int C) {
-  __shared__ float sw[kMaxClasses * CIN + kMaxClasses];
-  for (int i = threadIdx.x; i < C * CIN; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[kMaxClasses * CIN + i] = bias ? bias[i] : 0.f;
-  __syncthreads();
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
-    float acc[kMaxClasses];
+  constexpr int VECS = CIN / 8, PPB = 256 / VECS;
+  const int v = threadIdx.x % VECS;
+  float wr[NC][8], br[NC];
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) acc[c] = (c < C) ? sw[kMaxClasses * CIN + c] : 0.f;
+  for (int c = 0; c < NC; ++c) {
+    br[c] = (c < C && bias) ? bias[c] : 0.f;
 #pragma unroll
-    for (int v = 0; v < CIN / 8; ++v) {
-      Vec8<T> pk;
-      pk.load(a + static_cast<size_t>(p) * CIN + v * 8);
-      float f[8];
-      pk.get(f);
+    for (int j = 0; j < 8; ++j) wr[c][j] = c < C ? w[c * CIN + v * 8 + j] : 0.f;
+  }
+  constexpr int U = 2;
+  for (int p0 = blockIdx.x * PPB + threadIdx.x / VECS; p0 < P; p0 += gridDim.x * PPB * U) {
+    Vec8<T> pk[U];
 #pragma unroll
-      for (int c = 0; c < kMaxClasses; ++c)
-        if (c < C) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[c] = fmaf(f[j], sw[c * CIN + v * 8 + j], acc[c]);
-        }
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * gridDim.x * PPB;
+      if (p < P) pk[u].load(a + static_cast<size_t>(p) * CIN + v * 8);
+      else pk[u].zero();
     }
-    const int n = p / HW, hw = p % HW;
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c)
-      if (c < C) logits[(static_cast<size_t>(n) * C + c) * HW + hw] = acc[c];
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * gridDim.x * PPB;
+      float f[8], acc[NC];
+      pk[u].get(f);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t = fmaf(f[j], wr[c][j], t);
+#pragma unroll
+        for (int o = 1; o < VECS; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        acc[c] = t + br[c];
+      }
+      if (p < P) {
+        const int n = p / HW, hw = p % HW;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)   // the VECS lanes of a pixel share the stores: lane v writes classes v, v+VECS, ..
+          if (c < C && (c % VECS) == v) logits[(static_cast<size_t>(n) * C + c) * HW + hw] = acc[c];
+      }
+    }
   }
 }
+
+// Backward of the 1x1 head in ONE pass over dlogits and the activations:
+//   da[p][ci] = sum_c dl[c][p] * w[c][ci]            (skipped when da == nullptr)
+//   dW[c][ci] += sum_p dl[c][p] * a[p][ci];  db[c] += sum_p dl[c][p]
+template <typename T, int CIN, int NC>
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dlogits, const T* __restrict__ a,
+                                                       const float* __restrict__ w, T* __restrict__ da,
+                                                       float* __restrict__ dw, float* __restrict__ db, int P, int HW,
+                                                       int C) {
+  constexpr int VECS = CIN / 8, PPB = 256 / VECS;
+  __shared__ float sacc[NC * CIN + NC];
+  for (int i = threadIdx.x; i < NC * CIN + NC; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int v = threadIdx.x % VECS;
+  float wr[NC][8], accw[NC][8], accb[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    accb[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { wr[c][j] = c < C ? w[c * CIN + v * 8 + j] : 0.f; accw[c][j] = 0.f; }
+  }
+  constexpr int U = 2;
+  for (int p0 = blockIdx.x * PPB + threadIdx.x / VECS; p0 < P; p0 += gridDim.x * PPB * U) {
+    Vec8<T> pk[U];
+    float dl[U][NC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * gridDim.x * PPB;
+      if (p < P) {
+        pk[u].load(a + static_cast<size_t>(p) * CIN + v * 8);
+        const int n = p / HW, hw = p % HW;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) dl[u][c] = c < C ? __ldg(dlogits + (static_cast<size_t>(n) * C + c) * HW + hw) : 0.f;
+      } else {
+        pk[u].zero();
+#pragma unroll
+        for (int c = 0; c < NC; ++c) dl[u][c] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * gridDim.x * PPB;
+      float f[8], o[8];
+      pk[u].get(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        accb[c] += dl[u][c];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          accw[c][j] = fmaf(dl[u][c], f[j], accw[c][j]);
+          o[j] = fmaf(dl[u][c], wr[c][j], o[j]);
+        }
+      }
+      if (da != nullptr && p < P) {
+        Vec8<T> q;
+        q.set(o);
+        q.store(da + static_cast<size_t>(p) * CIN + v * 8);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = accw[c][j];
+#pragma unroll
+      for (int o = VECS; o < 32; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);   // lanes with the same v
+      if (lane < VECS && c < C) atomicAdd(&sacc[c * CIN + v * 8 + j], t);
+    }
+    float t = (v == 0) ? accb[c] : 0.f;   // every lane of a pixel saw the same dl: count it once
+    t = warp_sum(t);
+    if (lane == 0 && c < C) atomicAdd(&sacc[NC * CIN + c], t);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * CIN; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
+  if (db != nullptr)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(db + i, sacc[NC * CIN + i]);
+}
+
+#define PP_HEAD_DISPATCH(MACRO)                                                  \
+  do {                                                                           \
+    if (C <= 2)      { if (Cin == 32) MACRO(32, 2); else if (Cin == 64) MACRO(64, 2); else MACRO(128, 2); } \
+    else if (C <= 4) { if (Cin == 32) MACRO(32, 4); else if (Cin == 64) MACRO(64, 4); else MACRO(128, 4); } \
+    else if (C == 5) { if (Cin == 32) MACRO(32, 5); else if (Cin == 64) MACRO(64, 5); else MACRO(128, 5); } \
+    else             { if (Cin == 32) MACRO(32, 8); else if (Cin == 64) MACRO(64, 8); else MACRO(128, 8); } \
+  } while (0)
 
 int head_fwd(int dtype, const void* a, const float* w, const float* bias, float* logits, long long P, int HW, int Cin,
              int C, cudaStream_t s) {
   PP_REQUIRE(C >= 1 && C <= kMaxClasses, "head_fwd: num_classes=%d unsupported (max %d)", C, kMaxClasses);
-  PP_REQUIRE(Cin == 32 || Cin == 64 || Cin == 128 || Cin == 256, "head_fwd: Cin=%d unsupported (32/64/128/256)", Cin);
+  PP_REQUIRE(Cin == 32 || Cin == 64 || Cin == 128, "head_fwd: Cin=%d unsupported (32/64/128)", Cin);
   PP_REQUIRE_INT32(P * Cin, "head_fwd");
-#define PP_HEAD_FWD(CIN_) \
-  head_fwd_kernel<T, CIN_><<<grid_for(P, 256), 256, 0, s>>>(static_cast<const T*>(a), w, bias, logits, int(P), HW, C)
-  PP_DISPATCH_T(dtype, if (Cin == 32) PP_HEAD_FWD(32); else if (Cin == 64) PP_HEAD_FWD(64);
-                else if (Cin == 128) PP_HEAD_FWD(128); else PP_HEAD_FWD(256););
+  const int grid = grid_for(ceil_div_ll(P, 2 * (256 / (Cin / 8))) * 256, 256, 8);
+#define PP_HEAD_FWD(CIN_, NC_) \
+  head_fwd_kernel<T, CIN_, NC_><<<grid, 256, 0, s>>>(static_cast<const T*>(a), w, bias, logits, int(P), HW, C)
+  PP_DISPATCH_T(dtype, PP_HEAD_DISPATCH(PP_HEAD_FWD););
 #undef PP_HEAD_FWD
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
 
-// da[p][ci] = sum_c dl[c][p] * w[c][ci]
-template <typename T, int CIN>
-__global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restrict__ dlogits,
-                                                            const float* __restrict__ w, T* __restrict__ da,
-                                                            int P, int HW, int C) {
-  __shared__ float sw[kMaxClasses * CIN];
-  for (int i = threadIdx.x; i < C * CIN; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
-    const int n = p / HW, hw = p % HW;
-    float dl[kMaxClasses];
-#pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) dl[c] = (c < C) ? dlogits[(static_cast<size_t>(n) * C + c) * HW + hw] : 0.f;
-#pragma unroll
-    for (int v = 0; v < CIN / 8; ++v) {
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float acc = 0.f;
-#pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c)
-          if (c < C) acc = fmaf(dl[c], sw[c * CIN + v * 8 + j], acc);
-        f[j] = acc;
-      }
-      Vec8<T> pk;
-      pk.set(f);
-      pk.store(da + static_cast<size_t>(p) * CIN + v * 8);
-    }
-  }
-}
-
-// dW[c][ci] += sum_p dl[c][p] * a[p][ci];  db[c] += sum_p dl[c][p]
-template <typename T, int CIN>
-__global__ void __launch_bounds__(256) head_bwd_weight_kernel(const float* __restrict__ dlogits,
-                                                              const T* __restrict__ a, float* __restrict__ dw,
-                                                              float* __restrict__ db, int P, int HW, int C) {
-  __shared__ float sacc[kMaxClasses * CIN + kMaxClasses];
-  for (int i = threadIdx.x; i < kMaxClasses * CIN + kMaxClasses; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
-  constexpr int R = CIN / 32;
-  const int lane = threadIdx.x & 31;
-  const int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int chunk = (P + nwarps - 1) / nwarps;
-  const int pb = min(warp_id * chunk, P), pe = min(pb + chunk, P);
-  float acc[kMaxClasses][R];
-  float accb = 0.f;
-#pragma unroll
-  for (int c = 0; c < kMaxClasses; ++c)
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc[c][r] = 0.f;
-  constexpr int U = 4;  // pixels in flight per warp
-  int cn = pb / HW, chw = pb % HW;   // running (image, pixel) of p0
-  for (int p0 = pb; p0 < pe; p0 += U) {
-    float dlv[U], av[U][R];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = p0 + u;
-      dlv[u] = 0.f;
-#pragma unroll
-      for (int r = 0; r < R; ++r) av[u][r] = 0.f;
-      if (p < pe) {
-        const int n = cn, hw = chw;
-        if (++chw == HW) { chw = 0; ++cn; }
-        if (lane < C) dlv[u] = dlogits[(static_cast<size_t>(n) * C + lane) * HW + hw];
-#pragma unroll
-        for (int r = 0; r < R; ++r) av[u][r] = to_f32(a[static_cast<size_t>(p) * CIN + r * 32 + lane]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      accb += dlv[u];
-#pragma unroll
-      for (int c = 0; c < kMaxClasses; ++c) {
-        const float d = __shfl_sync(0xffffffffu, dlv[u], c);
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[c][r] = fmaf(d, av[u][r], acc[c][r]);
-      }
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < kMaxClasses; ++c)
-    if (c < C) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) atomicAdd(&sacc[c * CIN + r * 32 + lane], acc[c][r]);
-    }
-  if (lane < C) atomicAdd(&sacc[kMaxClasses * CIN + lane], accb);
-  __syncthreads();
-  for (int i = threadIdx.x; i < C * CIN; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
-  if (db != nullptr)
-    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(db + i, sacc[kMaxClasses * CIN + i]);
-}
-
 int head_bwd(int dtype, const float* dlogits, const void* a, const float* w, void* da, float* dw, float* db, long long P,
              int HW, int Cin, int C, cudaStream_t s) {
   PP_REQUIRE(C >= 1 && C <= kMaxClasses, "head_bwd: num_classes=%d unsupported", C);
-  PP_REQUIRE(Cin == 32 || Cin == 64 || Cin == 128 || Cin == 256, "head_bwd: Cin=%d unsupported (32/64/128/256)", Cin);
+  PP_REQUIRE(Cin == 32 || Cin == 64 || Cin == 128, "head_bwd: Cin=%d unsupported (32/64/128)", Cin);
   PP_REQUIRE_INT32(P * Cin, "head_bwd");
-  const int wblocks = sm_count() * 4;
-#define PP_HEAD_BWD(CIN_)                                                                                          \
-  do {                                                                                                             \
-    if (da) head_bwd_data_kernel<T, CIN_><<<grid_for(P, 256), 256, 0, s>>>(dlogits, w, static_cast<T*>(da), int(P), HW, C); \
-    head_bwd_weight_kernel<T, CIN_><<<wblocks, 256, 0, s>>>(dlogits, static_cast<const T*>(a), dw, db, int(P), HW, C);   \
-  } while (0)
-  PP_DISPATCH_T(dtype, if (Cin == 32) PP_HEAD_BWD(32); else if (Cin == 64) PP_HEAD_BWD(64);
-                else if (Cin == 128) PP_HEAD_BWD(128); else PP_HEAD_BWD(256););
+  int grid = sm_count() * 4;
+  const long long need = ceil_div_ll(P, 2 * (256 / (Cin / 8)));
+  if (grid > need) grid = static_cast<int>(need < 1 ? 1 : need);
+#define PP_HEAD_BWD(CIN_, NC_)                                                                                     \
+  head_bwd_kernel<T, CIN_, NC_><<<grid, 256, 0, s>>>(dlogits, static_cast<const T*>(a), w, static_cast<T*>(da), dw, db, \
+                                                     int(P), HW, C)
+  PP_DISPATCH_T(dtype, PP_HEAD_DISPATCH(PP_HEAD_BWD););
 #undef PP_HEAD_BWD
-  PP_LAUNCH_CHECK_N(da ? 2 : 1);
+  PP_LAUNCH_CHECK();
   return PP_OK;
 }
 
@@ -593,7 +679,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
     sc[j] = cf[j]; sh[j] = cf[C + j]; mu[j] = cf[2 * C + j]; rs[j] = cf[3 * C + j];
   }
   if (l < pl) {
-    constexpr int U = 4;
+    constexpr int U = 8;
     const long long base = (static_cast<long long>(g) * Pg) * C + v * 8;
     for (long long pb = p0 + l; pb < p1; pb += static_cast<long long>(pl) * U) {
       Vec8<T> pa[U], py[U];
@@ -630,42 +716,18 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
   }
 }
 
-// Backward finalize: parameter grads (+=) and the per-group coefficients of the apply pass.
-// bcoef layout [G][2][C]: k1 = sum dz / Pg, k2 = sum dz*xhat / Pg  (zeros in eval mode).
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ bsums, const float* __restrict__ coef,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ dbias, float* __restrict__ bcoef, int G, long long Pg, int C,
-                                       int training) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double dg = 0.0, dbt = 0.0, dbs = 0.0;
-  for (int g = 0; g < G; ++g) {
-    const double sdz = bsums[(static_cast<long long>(g) * C + c) * 2];
-    const double sdx = bsums[(static_cast<long long>(g) * C + c) * 2 + 1];
-    dg += sdx;
-    dbt += sdz;
-    float* bc = bcoef + static_cast<long long>(g) * 2 * C;
-    if (training) {
-      bc[c] = static_cast<float>(sdz / static_cast<double>(Pg));
-      bc[C + c] = static_cast<float>(sdx / static_cast<double>(Pg));
-    } else {
-      bc[c] = 0.f;
-      bc[C + c] = 0.f;
-      dbs += sdz * static_cast<double>(coef[static_cast<long long>(g) * 4 * C + c]);  // scale * sum dz
-    }
-  }
-  dgamma[c] += static_cast<float>(dg);
-  dbeta[c] += static_cast<float>(dbt);
-  if (dbias != nullptr) dbias[c] += static_cast<float>(dbs);  // exactly 0 under batch statistics
-}
-
-// dy = scale * (dz - k1 - xhat * k2); same (group, chunk) decomposition, coefficients in registers
+// dy = scale * (dz - k1 - xhat * k2) with k1 = sum dz / Pg, k2 = sum dz*xhat / Pg (zeros in eval mode); same
+// (group, chunk) decomposition, coefficients in registers. The former finalize kernel is folded in: every thread
+// derives k1/k2 of its 8 channels from the reduced sums, and block 0 also adds the parameter gradients
+// (dgamma += sum_g sum dz*xhat, dbeta += sum_g sum dz, eval mode: dbias += sum_g scale * sum dz).
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y,
                                                            const float* __restrict__ coef,
-                                                           const float* __restrict__ bcoef, T* __restrict__ dy, int Pg,
-                                                           int C, int chunk, int chunks_per_group, float slope) {
-  constexpr int U = 2;
+                                                           const double* __restrict__ bsums, T* __restrict__ dy,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           float* __restrict__ dbias, int G, int Pg, int C, int chunk,
+                                                           int chunks_per_group, int training, float slope) {
+  constexpr int U = 4;
   const int vecs = C / 8;
   const int pl = 256 / vecs;
   const int v = threadIdx.x % vecs, l = threadIdx.x / vecs;
@@ -673,13 +735,31 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
   const int p0 = (blockIdx.x % chunks_per_group) * chunk;
   const int p1 = min(p0 + chunk, Pg);
   if (l >= pl) return;
+  if (blockIdx.x == 0 && l == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = v * 8 + j;
+      double dg = 0.0, dbt = 0.0, dbs = 0.0;
+      for (int gg = 0; gg < G; ++gg) {
+        const double sdz = bsums[(static_cast<size_t>(gg) * C + c) * 2];
+        dbt += sdz;
+        dg += bsums[(static_cast<size_t>(gg) * C + c) * 2 + 1];
+        if (!training) dbs += sdz * static_cast<double>(coef[static_cast<size_t>(gg) * 4 * C + c]);  // scale * sum dz
+      }
+      dgamma[c] += static_cast<float>(dg);
+      dbeta[c] += static_cast<float>(dbt);
+      if (dbias != nullptr) dbias[c] += static_cast<float>(dbs);  // exactly 0 under batch statistics
+    }
+  }
   float sc[8], sh[8], mu[8], rs[8], k1[8], k2[8];
   const float* cf = coef + static_cast<size_t>(g) * 4 * C + v * 8;
-  const float* bc = bcoef + static_cast<size_t>(g) * 2 * C + v * 8;
+  const double* bs = bsums + (static_cast<size_t>(g) * C + v * 8) * 2;
+  const double inv = 1.0 / static_cast<double>(Pg);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     sc[j] = cf[j]; sh[j] = cf[C + j]; mu[j] = cf[2 * C + j]; rs[j] = cf[3 * C + j];
-    k1[j] = bc[j]; k2[j] = bc[C + j];
+    k1[j] = training ? static_cast<float>(bs[2 * j] * inv) : 0.f;
+    k2[j] = training ? static_cast<float>(bs[2 * j + 1] * inv) : 0.f;
   }
   const size_t base = static_cast<size_t>(g) * Pg * C + v * 8;
   for (int pb = p0 + l; pb < p1; pb += pl * U) {
@@ -713,25 +793,24 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
 int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* bsums, float* bcoef, float* dgamma,
            float* dbeta, float* dbias, void* dy, int G, long long Pg, int C, int training, float slope,
            cudaStream_t s) {
+  (void)bcoef;   // kept in the signature (workspace layout); the apply pass reads the reduced sums directly
   PP_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "bn_bwd: C=%d unsupported", C);
   PP_REQUIRE_INT32(Pg * C, "bn_bwd");
   PP_CHECK_CUDA(cudaMemsetAsync(bsums, 0, sizeof(double) * 2 * G * C, s));
   int cpg = (sm_count() * 4) / G;
   if (cpg < 1) cpg = 1;
   long long chunk = ceil_div_ll(Pg, cpg);
-  if (chunk < 256) chunk = 256;
+  if (chunk < 128) chunk = 128;
   cpg = static_cast<int>(ceil_div_ll(Pg, chunk));
   int achunk, acpg;
   bn_chunks(G, Pg, 8, &achunk, &acpg);
   PP_DISPATCH_T(dtype,
                 bn_bwd_reduce_kernel<T><<<G * cpg, 256, 0, s>>>(static_cast<const T*>(da), static_cast<const T*>(y),
                                                                 coef, bsums, Pg, C, chunk, cpg, slope);
-                bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(bsums, coef, dgamma, dbeta, dbias, bcoef, G, Pg,
-                                                                        C, training);
                 bn_bwd_apply_kernel<T><<<G * acpg, 256, 0, s>>>(static_cast<const T*>(da), static_cast<const T*>(y),
-                                                                coef, bcoef, static_cast<T*>(dy), int(Pg), C, achunk,
-                                                                acpg, slope););
-  PP_LAUNCH_CHECK_N(3);
+                                                                coef, bsums, static_cast<T*>(dy), dgamma, dbeta, dbias,
+                                                                G, int(Pg), C, achunk, acpg, training, slope););
+  PP_LAUNCH_CHECK_N(2);
   return PP_OK;
 }
 
@@ -868,110 +947,164 @@ __device__ __forceinline__ void lerp_range(int i, int out_size, float scale, int
   *hi = b > out_size - 1 ? out_size - 1 : b;
 }
 
+// Forward: one block row per output row (n, Y): the vertical taps are block-uniform, the thread loop walks
+// (X, channel vector) with a single integer division per element.
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_nhwc_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N,
                                                                 int h, int w, int H, int W, int C, float sh, float sw) {
   const int vecs = C / 8;
-  const int total = N * H * W * vecs;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int v = i % vecs;
-    const int p = i / vecs;
-    const int X = p % W, Y = (p / W) % H;
-    const size_t n = p / (W * H);
-    const Lerp ly = lerp_src(Y, h, sh), lx = lerp_src(X, w, sw);
-    const T* b = x + n * h * w * C + v * 8;
-    Vec8<T> p00, p01, p10, p11;
-    p00.load(b + (static_cast<long long>(ly.i0) * w + lx.i0) * C);
-    p01.load(b + (static_cast<long long>(ly.i0) * w + lx.i1) * C);
-    p10.load(b + (static_cast<long long>(ly.i1) * w + lx.i0) * C);
-    p11.load(b + (static_cast<long long>(ly.i1) * w + lx.i1) * C);
-    float f00[8], f01[8], f10[8], f11[8], o[8];
-    p00.get(f00); p01.get(f01); p10.get(f10); p11.get(f11);
+  const int rows = N * H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / H, Y = row % H;
+    const Lerp ly = lerp_src(Y, h, sh);
+    const T* r0 = x + (static_cast<size_t>(n) * h + ly.i0) * w * C;
+    const T* r1 = x + (static_cast<size_t>(n) * h + ly.i1) * w * C;
+    T* out = y + static_cast<size_t>(row) * W * C;
+    for (int t = threadIdx.x; t < W * vecs; t += blockDim.x) {
+      const int X = t / vecs, v = t - X * vecs;
+      const Lerp lx = lerp_src(X, w, sw);
+      Vec8<T> p00, p01, p10, p11;
+      p00.load(r0 + lx.i0 * C + v * 8);
+      p01.load(r0 + lx.i1 * C + v * 8);
+      p10.load(r1 + lx.i0 * C + v * 8);
+      p11.load(r1 + lx.i1 * C + v * 8);
+      float f00[8], f01[8], f10[8], f11[8], o[8];
+      p00.get(f00); p01.get(f01); p10.get(f10); p11.get(f11);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      o[j] = ly.w0 * (lx.w0 * f00[j] + lx.w1 * f01[j]) + ly.w1 * (lx.w0 * f10[j] + lx.w1 * f11[j]);
-    Vec8<T> out;
-    out.set(o);
-    out.store(y + static_cast<size_t>(i) * 8);
+      for (int j = 0; j < 8; ++j)
+        o[j] = ly.w0 * (lx.w0 * f00[j] + lx.w1 * f01[j]) + ly.w1 * (lx.w0 * f10[j] + lx.w1 * f11[j]);
+      Vec8<T> q;
+      q.set(o);
+      q.store(out + static_cast<size_t>(t) * 8);
+    }
   }
 }
 
-// gx[n,i,j,:] = sum over outputs (Y,X) reading (i,j) of wy*wx*gy[n,Y,X,:]  (gather, deterministic)
+// Exact inverse of the forward index map. A(i) = first output index whose lower tap lerp_src(.).i0 is >= i
+// (A(in_size) = out_size). Input i is read as the LOWER tap (weight w0) by outputs [A(i), A(i+1)) and as the UPPER
+// tap (weight w1) by outputs [A(i-1), A(i)); at the last input index the upper tap folds onto the lower one
+// (lerp_src: i1 == i0), where w1 == 0 up to rounding and is added all the same, exactly as the forward pass does.
+__device__ __forceinline__ int lerp_first_out(int i, int in_size, int out_size, float scale) {
+  if (i <= 0) return 0;
+  if (i >= in_size || scale <= 0.f) return out_size;
+  int a = static_cast<int>(static_cast<float>(i) / scale);
+  a = a < 0 ? 0 : (a > out_size ? out_size : a);
+  while (a > 0 && static_cast<int>(scale * static_cast<float>(a - 1)) >= i) --a;
+  while (a < out_size && static_cast<int>(scale * static_cast<float>(a)) < i) ++a;
+  return a;
+}
+constexpr int kUpWin = 12;   // widest candidate window handled from registers (scale factor <= ~5)
+
+struct UpTaps { int lo, n; float w[kUpWin]; };
+// all outputs that read input index i, with their weights (n == -1: window too wide, caller takes the slow path)
+__device__ __forceinline__ UpTaps up_taps(int i, int in_size, int out_size, float scale) {
+  UpTaps t;
+  const int a0 = lerp_first_out(i - 1, in_size, out_size, scale);
+  const int a1 = lerp_first_out(i, in_size, out_size, scale);
+  const int a2 = lerp_first_out(i + 1, in_size, out_size, scale);
+  t.lo = (i == 0) ? a1 : a0;
+  t.n = a2 - t.lo;
+  if (t.n > kUpWin) { t.n = -1; return t; }
+#pragma unroll
+  for (int k = 0; k < kUpWin; ++k) {
+    const int o = t.lo + k;
+    float wv = 0.f;
+    if (k < t.n) {
+      const Lerp l = lerp_src(o, in_size, scale);
+      if (l.i0 == i) wv += l.w0;
+      if (l.i1 == i) wv += l.w1;
+    }
+    t.w[k] = wv;
+  }
+  return t;
+}
+
+// gx[n,i,j,:] = sum over outputs (Y,X) reading (i,j) of wy*wx*gy[n,Y,X,:]  (gather, deterministic).
+// One block row per INPUT row (n, yi): the vertical taps are block-uniform; the horizontal taps of every input
+// column are computed once per block into shared memory (they do not depend on the row).
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_nhwc_bwd_kernel(const T* __restrict__ gy, T* __restrict__ gx, int N,
                                                                 int h, int w, int H, int W, int C, float sh, float sw,
                                                                 int accumulate) {
+  extern __shared__ float s_tx[];               // [w][kUpWin] weights, then [w] lo, [w] n (ints)
+  int* s_lo = reinterpret_cast<int*>(s_tx + w * kUpWin);
+  int* s_n = s_lo + w;
+  for (int xi = threadIdx.x; xi < w; xi += blockDim.x) {
+    const UpTaps tx = up_taps(xi, w, W, sw);
+    s_lo[xi] = tx.lo;
+    s_n[xi] = tx.n;
+#pragma unroll
+    for (int k = 0; k < kUpWin; ++k) s_tx[xi * kUpWin + k] = tx.w[k];
+  }
+  __syncthreads();
   const int vecs = C / 8;
-  const int total = N * h * w * vecs;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int v = i % vecs;
-    const int p = i / vecs;
-    const int xi = p % w, yi = (p / w) % h;
-    const size_t n = p / (w * h);
-    int ylo, yhi, xlo, xhi;
-    lerp_range(yi, H, sh, &ylo, &yhi);
-    lerp_range(xi, W, sw, &xlo, &xhi);
-    float acc[8];
+  const int rows = N * h;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / h, yi = row % h;
+    const UpTaps ty = up_taps(yi, h, H, sh);
+    T* out = gx + static_cast<size_t>(row) * w * C;
+    const T* gimg = gy + static_cast<size_t>(n) * H * W * C;
+    for (int t = threadIdx.x; t < w * vecs; t += blockDim.x) {
+      const int xi = t / vecs, v = t - xi * vecs;
+      const int xlo0 = s_lo[xi], xn = s_n[xi];
+      float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    constexpr int KMAX = 8;   // candidate window per axis for scale factors >= 2 (wider windows take the slow path)
-    if (yhi - ylo < KMAX && xhi - xlo < KMAX) {
-      float wyv[KMAX], wxv[KMAX];
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      if (ty.n >= 0 && xn >= 0) {
+        const float* wx = s_tx + xi * kUpWin;
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        wyv[k] = (ylo + k <= yhi) ? lerp_weight(ylo + k, yi, h, sh) : 0.f;
-        wxv[k] = (xlo + k <= xhi) ? lerp_weight(xlo + k, xi, w, sw) : 0.f;
-      }
+        for (int a = 0; a < kUpWin; ++a) {
+          if (a >= ty.n) break;
+          const T* grow = gimg + (static_cast<size_t>(ty.lo + a) * W + xlo0) * C + v * 8;
+          for (int b = 0; b < xn; ++b) {
+            Vec8<T> pk;
+            pk.load(grow + static_cast<size_t>(b) * C);
+            float f[8];
+            pk.get(f);
+            const float ww = ty.w[a] * wx[b];
 #pragma unroll
-      for (int a = 0; a < KMAX; ++a) {
-        if (wyv[a] == 0.f) continue;
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, f[j], acc[j]);
+          }
+        }
+      } else {   // very large scale factors: scan the candidate window
+        int ylo, yhi, xlo, xhi;
+        lerp_range(yi, H, sh, &ylo, &yhi);
+        lerp_range(xi, W, sw, &xlo, &xhi);
+        for (int Y = ylo; Y <= yhi; ++Y) {
+          const float wy = lerp_weight(Y, yi, h, sh);
+          if (wy == 0.f) continue;
+          for (int X = xlo; X <= xhi; ++X) {
+            const float wxv = lerp_weight(X, xi, w, sw);
+            if (wxv == 0.f) continue;
+            Vec8<T> pk;
+            pk.load(gimg + (static_cast<size_t>(Y) * W + X) * C + v * 8);
+            float f[8];
+            pk.get(f);
+            const float ww = wy * wxv;
 #pragma unroll
-        for (int b = 0; b < KMAX; ++b) {
-          if (wxv[b] == 0.f) continue;
-          Vec8<T> pk;
-          pk.load(gy + ((n * H + ylo + a) * W + xlo + b) * C + v * 8);
-          float f[8];
-          pk.get(f);
-          const float ww = wyv[a] * wxv[b];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, f[j], acc[j]);
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, f[j], acc[j]);
+          }
         }
       }
-    } else {
-      for (int Y = ylo; Y <= yhi; ++Y) {
-        const float wy = lerp_weight(Y, yi, h, sh);
-        if (wy == 0.f) continue;
-        for (int X = xlo; X <= xhi; ++X) {
-          const float wx = lerp_weight(X, xi, w, sw);
-          if (wx == 0.f) continue;
-          Vec8<T> pk;
-          pk.load(gy + ((n * H + Y) * W + X) * C + v * 8);
-          float f[8];
-          pk.get(f);
-          const float ww = wy * wx;
+      Vec8<T> q;
+      if (accumulate) {
+        float old[8];
+        q.load(out + static_cast<size_t>(t) * 8);
+        q.get(old);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(ww, f[j], acc[j]);
-        }
+        for (int j = 0; j < 8; ++j) acc[j] += old[j];
       }
+      q.set(acc);
+      q.store(out + static_cast<size_t>(t) * 8);
     }
-    Vec8<T> out;
-    if (accumulate) {
-      float old[8];
-      out.load(gx + static_cast<size_t>(i) * 8);
-      out.get(old);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += old[j];
-    }
-    out.set(acc);
-    out.store(gx + static_cast<size_t>(i) * 8);
   }
 }
 
 int upsample_nhwc_fwd(int dtype, const void* x, void* y, int N, int h, int w, int H, int W, int C, cudaStream_t s) {
   PP_REQUIRE(C % 8 == 0, "upsample_nhwc_fwd: C=%d must be a multiple of 8", C);
   PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * C, "upsample_nhwc_fwd");
-  const long long total = static_cast<long long>(N) * H * W * (C / 8);
-  PP_DISPATCH_T(dtype, upsample_nhwc_fwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(
+  const int threads = W * (C / 8) >= 256 ? 256 : 128;
+  PP_DISPATCH_T(dtype, upsample_nhwc_fwd_kernel<T><<<grid_for(static_cast<long long>(N) * H * 256, 256, 32), threads, 0, s>>>(
                            static_cast<const T*>(x), static_cast<T*>(y), N, h, w, H, W, C, ac_scale(h, H),
                            ac_scale(w, W)););
   PP_LAUNCH_CHECK();
@@ -981,64 +1114,77 @@ int upsample_nhwc_bwd(int dtype, const void* gy, void* gx, int N, int h, int w, 
                       cudaStream_t s) {
   PP_REQUIRE(C % 8 == 0, "upsample_nhwc_bwd: C=%d must be a multiple of 8", C);
   PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * C, "upsample_nhwc_bwd");
-  const long long total = static_cast<long long>(N) * h * w * (C / 8);
-  PP_DISPATCH_T(dtype, upsample_nhwc_bwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(
+  const int threads = w * (C / 8) >= 256 ? 256 : 128;
+  const size_t smem = static_cast<size_t>(w) * (kUpWin + 2) * sizeof(float);
+  PP_REQUIRE(smem <= 48 * 1024, "upsample_nhwc_bwd: input width %d too large", w);
+  PP_DISPATCH_T(dtype, upsample_nhwc_bwd_kernel<T><<<grid_for(static_cast<long long>(N) * h * 256, 256, 8), threads, smem, s>>>(
                            static_cast<const T*>(gy), static_cast<T*>(gx), N, h, w, H, W, C, ac_scale(h, H),
                            ac_scale(w, W), accumulate););
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
 
-// NCHW fp32 planes (the aux-path logits, C = num_classes): x [NC][h][w] -> y [NC][H][W]
+// NCHW fp32 planes (the aux-path logits, C = num_classes): x [NC][h][w] -> y [NC][H][W]. One block per output row.
 __global__ void __launch_bounds__(256) upsample_planes_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                   long long NC, int h, int w, int H, int W, float sh,
                                                                   float sw) {
-  const long long total = NC * H * W;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int X = int(i % W), Y = int((i / W) % H);
-    const long long pl = i / (static_cast<long long>(W) * H);
-    const Lerp ly = lerp_src(Y, h, sh), lx = lerp_src(X, w, sw);
-    const float* b = x + pl * h * w;
-    y[i] = ly.w0 * (lx.w0 * b[ly.i0 * w + lx.i0] + lx.w1 * b[ly.i0 * w + lx.i1]) +
-           ly.w1 * (lx.w0 * b[ly.i1 * w + lx.i0] + lx.w1 * b[ly.i1 * w + lx.i1]);
+  const long long rows = NC * H;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const long long pl = row / H;
+    const int Y = static_cast<int>(row - pl * H);
+    const Lerp ly = lerp_src(Y, h, sh);
+    const float* r0 = x + (pl * h + ly.i0) * w;
+    const float* r1 = x + (pl * h + ly.i1) * w;
+    for (int X = threadIdx.x; X < W; X += blockDim.x) {
+      const Lerp lx = lerp_src(X, w, sw);
+      y[row * W + X] = ly.w0 * (lx.w0 * __ldg(r0 + lx.i0) + lx.w1 * __ldg(r0 + lx.i1)) +
+                       ly.w1 * (lx.w0 * __ldg(r1 + lx.i0) + lx.w1 * __ldg(r1 + lx.i1));
+    }
   }
 }
-__global__ void __launch_bounds__(128) upsample_planes_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx,
+// Backward, separable inside a block: one block per INPUT row (plane, yi). Pass 1: tmp[X] = sum_Y wy(Y) gy[Y][X]
+// (coalesced row reads, block-uniform vertical taps) into shared memory; pass 2: gx[yi][xi] = sum_X wx(X) tmp[X].
+__global__ void __launch_bounds__(256) upsample_planes_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx,
                                                                   long long NC, int h, int w, int H, int W, float sh,
                                                                   float sw) {
-  // one warp per input element: lanes stride over the candidate output window
-  const long long total = NC * h * w;
-  const int lane = threadIdx.x & 31;
-  const long long warp_id = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  for (long long i = warp_id; i < total; i += nwarps) {
-    const int xi = int(i % w), yi = int((i / w) % h);
-    const long long pl = i / (static_cast<long long>(w) * h);
-    int ylo, yhi, xlo, xhi;
+  extern __shared__ float tmp[];   // [W]
+  const long long rows = NC * h;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const long long pl = row / h;
+    const int yi = static_cast<int>(row - pl * h);
+    int ylo, yhi;
     lerp_range(yi, H, sh, &ylo, &yhi);
-    lerp_range(xi, W, sw, &xlo, &xhi);
-    const int nx = xhi - xlo + 1, cnt = (yhi - ylo + 1) * nx;
-    float acc = 0.f;
-    for (int k = lane; k < cnt; k += 32) {
-      const int Y = ylo + k / nx, X = xlo + k % nx;
-      const float ww = lerp_weight(Y, yi, h, sh) * lerp_weight(X, xi, w, sw);
-      if (ww != 0.f) acc = fmaf(ww, gy[(pl * H + Y) * W + X], acc);
+    const float* g = gy + pl * H * W;
+    for (int X = threadIdx.x; X < W; X += blockDim.x) {
+      float a = 0.f;
+      for (int Y = ylo; Y <= yhi; ++Y) {
+        const float wy = lerp_weight(Y, yi, h, sh);   // block-uniform branch
+        if (wy != 0.f) a = fmaf(wy, __ldg(g + static_cast<size_t>(Y) * W + X), a);
+      }
+      tmp[X] = a;
     }
-    acc = warp_sum(acc);
-    if (lane == 0) gx[i] = acc;
+    __syncthreads();
+    for (int xi = threadIdx.x; xi < w; xi += blockDim.x) {
+      int xlo, xhi;
+      lerp_range(xi, W, sw, &xlo, &xhi);
+      float a = 0.f;
+      for (int X = xlo; X <= xhi; ++X) a = fmaf(lerp_weight(X, xi, w, sw), tmp[X], a);
+      gx[row * w + xi] = a;
+    }
+    __syncthreads();
   }
 }
 
 int upsample_planes_fwd(const float* x, float* y, long long NC, int h, int w, int H, int W, cudaStream_t s) {
-  upsample_planes_fwd_kernel<<<grid_for(NC * H * W, 256), 256, 0, s>>>(x, y, NC, h, w, H, W, ac_scale(h, H),
-                                                                       ac_scale(w, W));
+  upsample_planes_fwd_kernel<<<grid_for(NC * H * 256, 256, 32), W >= 256 ? 256 : 128, 0, s>>>(
+      x, y, NC, h, w, H, W, ac_scale(h, H), ac_scale(w, W));
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
 int upsample_planes_bwd(const float* gy, float* gx, long long NC, int h, int w, int H, int W, cudaStream_t s) {
-  upsample_planes_bwd_kernel<<<grid_for(NC * h * w * 32, 128), 128, 0, s>>>(gy, gx, NC, h, w, H, W, ac_scale(h, H),
-                                                                            ac_scale(w, W));
+  PP_REQUIRE(W <= 8192, "upsample_planes_bwd: W=%d too wide", W);
+  upsample_planes_bwd_kernel<<<grid_for(NC * h * 256, 256, 32), W >= 256 ? 256 : 128, W * sizeof(float), s>>>(
+      gy, gx, NC, h, w, H, W, ac_scale(h, H), ac_scale(w, W));
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

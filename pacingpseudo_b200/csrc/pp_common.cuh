@@ -102,6 +102,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 template <typename T> struct Vec8;
 template <> struct Vec8<__nv_bfloat16> {
   uint4 raw;
+  __device__ __forceinline__ void zero() { raw = make_uint4(0u, 0u, 0u, 0u); }
   __device__ __forceinline__ void load(const __nv_bfloat16* p) { raw = *reinterpret_cast<const uint4*>(p); }
   __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = raw; }
   __device__ __forceinline__ void get(float (&f)[8]) const {
@@ -124,6 +125,7 @@ template <> struct Vec8<__nv_bfloat16> {
 };
 template <> struct Vec8<float> {
   float4 a, b;
+  __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
   __device__ __forceinline__ void load(const float* p) {
     a = *reinterpret_cast<const float4*>(p);
     b = *reinterpret_cast<const float4*>(p + 4);

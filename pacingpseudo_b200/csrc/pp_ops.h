@@ -29,6 +29,8 @@ int conv3x3_wgrad_simt(int dtype, const void* dy, int Cout, const void* x0, int 
 
 // ---- ops.cu ---------------------------------------------------------------------------------------
 int pack_weights(int dtype, const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t s);
+int pack_weights_multi(int dtype, int n, const float* const* w, void* const* wf, void* const* wd, const int* cout,
+                       const int* cin, cudaStream_t s);
 int unpack_wgrad(const float* dwp, float* g, int Cout, int Cin, int accumulate, cudaStream_t s);
 int first_conv_fwd(int dtype, const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
                    cudaStream_t s);

@@ -5,6 +5,7 @@
 // carved from ONE caller-owned workspace. One C call launches the ~200 kernels of a pass, so the
 // Python side pays no per-layer overhead. The channel concat of the decoder is never materialised
 // (two-source K loop in the conv kernels); scale-1 "upsampling" (output_stride 8) is a no-op alias.
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -41,6 +42,13 @@ struct UNetPlan {
   // that slice of the gradient buffer while the rest of the backward pass still runs (dp.py).
   std::vector<int> ev_layer;
   std::vector<cudaEvent_t> ev;
+  // backward overlap: the weight-gradient kernels (tensor / L2 bound) run on an internal side stream while the
+  // critical chain (BatchNorm backward -> dgrad -> pool/upsample backward, mostly HBM bound) continues on the
+  // caller's stream. dY lives in kDyBufs rotating buffers guarded by events. PP_NO_OVERLAP=1 disables it.
+  static constexpr int kDyBufs = 3;
+  mutable cudaStream_t side = nullptr;
+  mutable cudaEvent_t dy_ready[kDyBufs] = {}, buf_free[kDyBufs] = {}, join = nullptr;
+  mutable int overlap = -1;   // -1: not initialised, 0: off, 1: on
 
   int new_act(int C, int res) { acts.push_back({C, res}); return int(acts.size()) - 1; }
 
@@ -102,7 +110,7 @@ struct UNetLayout {
   long long total = 0;
   std::vector<long long> act_data, act_grad;          // per activation
   std::vector<long long> yraw, coef, sums, wf, wd;     // per conv layer
-  long long dy_scratch = 0, dwp_scratch = 0, bsums = 0, bcoef = 0;
+  long long dy_scratch = 0, dy_stride = 0, dwp_scratch = 0, bsums = 0, bcoef = 0;
 };
 
 static UNetLayout make_layout(const UNetPlan& pl, int N, int H, int W, int G) {
@@ -129,6 +137,8 @@ static UNetLayout make_layout(const UNetPlan& pl, int N, int H, int W, int G) {
     max_c = std::max(max_c, c.cout);
   }
   L.dy_scratch = take(max_act);
+  L.dy_stride = align_up(max_act);
+  for (int k = 1; k < UNetPlan::kDyBufs; ++k) take(max_act);
   L.dwp_scratch = take(max_w * 4);
   L.bsums = take(sizeof(double) * 2 * G * max_c);
   L.bcoef = take(sizeof(float) * 2 * G * max_c);
@@ -158,6 +168,22 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
   const UNetLayout L = make_layout(pl, N, H, W, G);
   char* base = static_cast<char*>(ws);
   const int dt = pl.dtype;
+  {  // fp32 OIHW master weights -> packed forward / dgrad operands of every tensor-core layer, one launch
+    std::vector<const float*> pw;
+    std::vector<void*> pf, pd;
+    std::vector<int> co, ci;
+    for (size_t l = 0; l < pl.convs.size(); ++l) {
+      const ConvL& c = pl.convs[l];
+      if (c.in0 < 0) continue;
+      pw.push_back(static_cast<const float*>(params[l * kParamsPerConv]));
+      pf.push_back(base + L.wf[l]);
+      pd.push_back(base + L.wd[l]);
+      co.push_back(c.cout);
+      ci.push_back(c.cin0 + c.cin1);
+    }
+    rc = pack_weights_multi(dt, int(pw.size()), pw.data(), pf.data(), pd.data(), co.data(), ci.data(), s);
+    if (rc) return rc;
+  }
   for (const Op& op : pl.ops) {
     if (op.kind == OP_CONV) {
       const ConvL& c = pl.convs[op.layer];
@@ -174,9 +200,6 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
                             c.cout, s);
       } else {
         void* wf = base + L.wf[op.layer];
-        void* wd = base + L.wd[op.layer];
-        rc = pack_weights(dt, static_cast<const float*>(pp[0]), wf, wd, c.cout, c.cin0 + c.cin1, s);
-        if (rc) return rc;
         const void* x0 = base + L.act_data[c.in0];
         const void* x1 = c.in1 >= 0 ? base + L.act_data[c.in1] : nullptr;
         if (dt == PP_BF16) {
@@ -259,11 +282,28 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
     written[a] = 1;
   }
 
+  // ---- overlap plumbing (see UNetPlan) --------------------------------------------------------
+  if (pl.overlap < 0) {
+    const char* off = getenv("PP_NO_OVERLAP");
+    pl.overlap = (off != nullptr && off[0] == '1') ? 0 : 1;
+    if (pl.overlap) {
+      PP_CHECK_CUDA(cudaStreamCreateWithFlags(&pl.side, cudaStreamNonBlocking));
+      for (int k = 0; k < UNetPlan::kDyBufs; ++k) {
+        PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.dy_ready[k], cudaEventDisableTiming));
+        PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.buf_free[k], cudaEventDisableTiming));
+      }
+      PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.join, cudaEventDisableTiming));
+    }
+  }
+  const bool ov = pl.overlap == 1;
+  cudaStream_t ws_ = ov ? pl.side : s;       // stream of the weight-gradient kernels
+  bool buf_used[UNetPlan::kDyBufs] = {false, false, false};
+  int nbuf = 0;
+
   for (int oi = int(pl.ops.size()) - 1; oi >= 0; --oi) {
     const Op& op = pl.ops[oi];
     if (op.kind == OP_CONV) {
       const ConvL& c = pl.convs[op.layer];
-      void* const* pp = params + op.layer * kParamsPerConv;
       float* const* gg = grads + op.layer * kGradsPerConv;
       const Act& ao = pl.acts[c.out];
       const int h = H / ao.res, w = W / ao.res;
@@ -272,18 +312,28 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
         PP_CHECK_CUDA(cudaMemsetAsync(base + L.act_grad[c.out], 0, act_bytes(ao), s));
         written[c.out] = 1;
       }
-      void* dy = base + L.dy_scratch;
+      const int kb = ov ? (nbuf++ % UNetPlan::kDyBufs) : 0;
+      void* dy = base + L.dy_scratch + kb * L.dy_stride;
+      if (ov && buf_used[kb]) PP_CHECK_CUDA(cudaStreamWaitEvent(s, pl.buf_free[kb], 0));   // its last reader is done
       rc = bn_bwd(dt, base + L.act_grad[c.out], base + L.yraw[op.layer],
                   reinterpret_cast<const float*>(base + L.coef[op.layer]), reinterpret_cast<double*>(base + L.bsums),
                   reinterpret_cast<float*>(base + L.bcoef), gg[2], gg[3], gg[1], dy, G, Pg, c.cout, training, 0.01f, s);
       if (rc) return rc;
+      if (ov) {
+        PP_CHECK_CUDA(cudaEventRecord(pl.dy_ready[kb], s));
+        PP_CHECK_CUDA(cudaStreamWaitEvent(ws_, pl.dy_ready[kb], 0));
+      }
       auto grads_ready = [&]() -> int {   // all parameter gradients of layers >= op.layer are enqueued
         for (size_t e = 0; e < pl.ev_layer.size(); ++e)
-          if (pl.ev_layer[e] == op.layer) PP_CHECK_CUDA(cudaEventRecord(pl.ev[e], s));
+          if (pl.ev_layer[e] == op.layer) PP_CHECK_CUDA(cudaEventRecord(pl.ev[e], ws_));
+        if (ov) {
+          PP_CHECK_CUDA(cudaEventRecord(pl.buf_free[kb], ws_));
+          buf_used[kb] = true;
+        }
         return PP_OK;
       };
       if (c.in0 < 0) {
-        rc = first_conv_wgrad(dt, dy, x, gg[0], N, h, w, c.cout, s);
+        rc = first_conv_wgrad(dt, dy, x, gg[0], N, h, w, c.cout, ws_);
         if (rc) return rc;
         rc = grads_ready();
         if (rc) return rc;
@@ -296,14 +346,14 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
       if (dt == PP_BF16) {
         // wide sources accumulate straight into the OIHW gradient; narrow ones go through the packed scratch
         if (conv3x3_wgrad_tc_uses_scratch(c.cout, c.cin0, c.cin1))
-          PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * c.cout * ctot, s));
-        rc = conv3x3_wgrad_tc(dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, gg[0], N, h, w, c.dil, s);
+          PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * c.cout * ctot, ws_));
+        rc = conv3x3_wgrad_tc(dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, gg[0], N, h, w, c.dil, ws_);
         if (rc) return rc;
       } else {
-        PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * c.cout * ctot, s));
-        rc = conv3x3_wgrad_simt(dt, dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, N, h, w, c.dil, s);
+        PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * c.cout * ctot, ws_));
+        rc = conv3x3_wgrad_simt(dt, dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, N, h, w, c.dil, ws_);
         if (rc) return rc;
-        rc = unpack_wgrad(dwp, gg[0], c.cout, ctot, 1, s);
+        rc = unpack_wgrad(dwp, gg[0], c.cout, ctot, 1, ws_);
         if (rc) return rc;
       }
       rc = grads_ready();
@@ -344,6 +394,10 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
       written[op.src] = 1;
     }
   }
+  if (ov) {   // the caller's stream owns the result: every weight gradient is complete when its work is
+    PP_CHECK_CUDA(cudaEventRecord(pl.join, pl.side));
+    PP_CHECK_CUDA(cudaStreamWaitEvent(s, pl.join, 0));
+  }
   return PP_OK;
 }
 
@@ -364,7 +418,15 @@ UNetPlan* unet_create(int input_ch, int init_ch, int max_ch, int num_classes, in
   return pl;
 }
 void unet_destroy(UNetPlan* pl) {
-  if (pl) for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
+  if (pl) {
+    for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
+    for (int k = 0; k < UNetPlan::kDyBufs; ++k) {
+      if (pl->dy_ready[k]) cudaEventDestroy(pl->dy_ready[k]);
+      if (pl->buf_free[k]) cudaEventDestroy(pl->buf_free[k]);
+    }
+    if (pl->join) cudaEventDestroy(pl->join);
+    if (pl->side) cudaStreamDestroy(pl->side);
+  }
   delete pl;
 }
 int unet_set_grad_events(UNetPlan* pl, int n, const int* layers) {
