@@ -97,6 +97,14 @@ int pp_stat_replicas(void);
 /* weight gradient of the same conv: dwp[9][Cout][C0+C1] fp32 += (caller zeroes) */
 int pp_conv3x3_wgrad(int dtype, const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dwp,
                      int N, int H, int W, int dil, void* stream);
+/* bf16 weight gradient ACCUMULATED straight into the reference-layout gradient g_oihw[Cout][C0+C1][3][3] (the
+ * nn.Conv2d weight.grad, unet.py:188). dwp: packed scratch of 9*Cout*(C0+C1) floats (used, and zeroed here, only for
+ * 32/64-channel sources). ws_split (optional, ws_floats floats, ideally >= 2*9*Cout*(C0+C1)): scratch of the
+ * deterministic split-K path - every K split stores its partial gradient and a fixed-order reduction folds them in,
+ * so the result is bit-reproducible; without it the splits are accumulated with fp32 atomics. */
+int pp_conv3x3_wgrad_oihw(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dwp,
+                          float* g_oihw, float* ws_split, long long ws_floats, int N, int H, int W, int dil,
+                          void* stream);
 /* CUDA-core twin of the bf16 tcgen05 kernels (test cross-check only) */
 int pp_conv3x3_reference(int dtype, const void* x0, int C0, const void* x1, int C1, const void* wpack,
                          const float* bias, void* out0, int oc0, int acc0, void* out1, int oc1, int acc1, int N,

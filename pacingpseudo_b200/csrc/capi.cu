@@ -90,6 +90,14 @@ int pp_conv3x3_wgrad(int dtype, const void* dy, int Cout, const void* x0, int C0
   if (dtype == PP_BF16) return conv3x3_wgrad_tc(dy, Cout, x0, C0, x1, C1, dwp, nullptr, N, H, W, dil, ST(stream));
   return conv3x3_wgrad_simt(dtype, dy, Cout, x0, C0, x1, C1, dwp, N, H, W, dil, ST(stream));
 }
+int pp_conv3x3_wgrad_oihw(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dwp,
+                          float* g_oihw, float* ws_split, long long ws_floats, int N, int H, int W, int dil,
+                          void* stream) {
+  PP_REQUIRE(g_oihw != nullptr && dwp != nullptr, "pp_conv3x3_wgrad_oihw: null gradient / scratch pointer");
+  if (conv3x3_wgrad_tc_uses_scratch(Cout, C0, C1))
+    PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * Cout * (C0 + C1), ST(stream)));
+  return conv3x3_wgrad_tc(dy, Cout, x0, C0, x1, C1, dwp, g_oihw, N, H, W, dil, ST(stream), ws_split, ws_floats);
+}
 int pp_conv3x3_reference(int dtype, const void* x0, int C0, const void* x1, int C1, const void* wpack,
                          const float* bias, void* out0, int oc0, int acc0, void* out1, int oc1, int acc1, int N,
                          int H, int W, int dil, void* stream) {

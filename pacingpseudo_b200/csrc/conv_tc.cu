@@ -262,19 +262,26 @@ struct WgradTcParams {
   int kb_per_split;
   int stages;
   float* dw;                 // [9][Cout][C0+C1] fp32, pre-zeroed, accumulated with red.global
+  float* ws_split;           // != null: split s STORES its partial tile to ws_split[s][9][Cout][ctot] (no atomics,
+                             // coalesced 16-byte stores after a shared-memory transpose; summed by wgrad_reduce)
 };
 
-template <int BLOCK_N>
+// MT = number of 128-row output-channel blocks per CTA (1 or 2). MT = 2 gives a 256 x BLOCK_N tile in two TMEM
+// accumulators that share every X (B operand) stage: the L2 -> SM traffic per FLOP, which bounds this kernel, drops
+// by a third (48 KB -> 32 KB per 128x256x64 MMA block).
+template <int BLOCK_N, int MT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX0,
                         const __grid_constant__ CUtensorMap tmX1, const WgradTcParams p) {
   constexpr int PIXK = 64;                    // pixels (GEMM K) per pipeline stage
   constexpr int BOX_BYTES = PIXK * 128;       // one {64 ch x 64 px} box, 128-byte rows
-  constexpr int A_BYTES = 2 * BOX_BYTES;      // M = 128 output channels = 2 boxes
+  constexpr int A_BLOCK = 2 * BOX_BYTES;      // 128 output channels = 2 boxes
+  constexpr int A_BYTES = MT * A_BLOCK;
   constexpr int NB = BLOCK_N / 64;            // boxes on the N side
   constexpr int B_BYTES = NB * BOX_BYTES;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = BLOCK_N;
+  constexpr int TMEM_COLS = MT * BLOCK_N < 32 ? 32 : MT * BLOCK_N;
+  static_assert(MT * BLOCK_N <= 512, "accumulators do not fit TMEM");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -293,7 +300,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_c
   const int split = blockIdx.z;
   const bool src1 = ci_tile >= p.ci_tiles0;
   const int ci0 = (src1 ? ci_tile - p.ci_tiles0 : ci_tile) * BLOCK_N;  // channel offset inside the source
-  const int co0 = co_tile * 128;
+  const int co0 = co_tile * 128 * MT;
   const int kb_begin = split * p.kb_per_split;
   const int kb_end = min(kb_begin + p.kb_per_split, p.tiles_total);
   const int num_k = kb_end - kb_begin;
@@ -330,8 +337,9 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_c
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_4d(sa, &tmDY, &full_bar[stage], co0, x0, y0, n0);
-          tma_load_4d(sa + BOX_BYTES, &tmDY, &full_bar[stage], co0 + 64, x0, y0, n0);
+#pragma unroll
+          for (int b = 0; b < 2 * MT; ++b)
+            tma_load_4d(sa + b * BOX_BYTES, &tmDY, &full_bar[stage], co0 + b * 64, x0, y0, n0);
 #pragma unroll
           for (int b = 0; b < NB; ++b)
             tma_load_4d(sb + b * BOX_BYTES, tmX, &full_bar[stage], ci0 + b * 64, x0 + ox, y0 + oy, n0);
@@ -352,9 +360,12 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_c
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < PIXK / 16; ++k)
-            umma_bf16_lohi(tmem_base, a_lo + k * (2048 >> 4), dhi, a_lo + (A_BYTES >> 4) + k * (2048 >> 4), dhi, idesc,
-                           (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < PIXK / 16; ++k) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              umma_bf16_lohi(tmem_base + m * BLOCK_N, a_lo + m * (A_BLOCK >> 4) + k * (2048 >> 4), dhi,
+                             a_lo + (A_BYTES >> 4) + k * (2048 >> 4), dhi, idesc, (it | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty_bar[stage]);
           a_lo += STAGE_BYTES >> 4;
           if (++stage == p.stages) { stage = 0; phase ^= 1; a_lo = base_lo; }
@@ -363,32 +374,78 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_c
       }
     } else {
       const int q = warp & 3;
-      const int co = co0 + q * 32 + lane;
       const int csrc = src1 ? p.C1 : p.C0;
       const int ctot = p.ctot;
       const int cbase = (src1 ? p.cbase1 : p.cbase0) + ci0;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
+      if (p.ws_split != nullptr) {
+        // ---- split-scratch mode: TMEM -> registers -> shared-memory transpose -> coalesced 16-byte stores.
+        // The pipeline stages are idle now (every MMA has retired), so the transpose tile lives there.
+        constexpr int PITCH = BLOCK_N + 4;   // floats; +4 keeps the float4 row writes of 32 lanes conflict-free
+        float* tile = reinterpret_cast<float*>(smem);
+        float* dst = p.ws_split + static_cast<long long>(split) * 9 * p.Cout * ctot;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c), v);
-        tmem_wait_ld();
-        if (co < p.Cout) {
-          if (p.oihw) {
-            float* o = p.dw + (static_cast<long long>(co) * ctot + cbase + c) * 9 + tap;
+        for (int m = 0; m < MT; ++m) {
+          const int r = q * 32 + lane;
+#pragma unroll 1
+          for (int c = 0; c < BLOCK_N; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(m * BLOCK_N + c), v);
+            tmem_wait_ld();
+            float4* trow = reinterpret_cast<float4*>(tile + r * PITCH + c);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ci0 + c + j < csrc) atomicAdd(o + j * 9, __uint_as_float(v[j]));
-          } else {
-            float* o = p.dw + (static_cast<long long>(tap) * p.Cout + co) * ctot + cbase + c;
+            for (int j = 0; j < 8; ++j)
+              trow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+          for (int rr = q; rr < 128; rr += 4) {
+            const int co = co0 + m * 128 + rr;
+            if (co >= p.Cout) break;
+            float* orow = dst + (static_cast<long long>(tap) * p.Cout + co) * ctot + cbase;
+            for (int cc = lane * 4; cc < BLOCK_N; cc += 128)
+              if (ci0 + cc < csrc)
+                *reinterpret_cast<float4*>(orow + cc) = *reinterpret_cast<const float4*>(tile + rr * PITCH + cc);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+      } else {
+        const int co = co0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c), v);
+          tmem_wait_ld();
+          if (co < p.Cout) {
+            if (p.oihw) {
+              float* o = p.dw + (static_cast<long long>(co) * ctot + cbase + c) * 9 + tap;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ci0 + c + j < csrc) atomicAdd(o + j, __uint_as_float(v[j]));
+              for (int j = 0; j < 32; ++j)
+                if (ci0 + c + j < csrc) atomicAdd(o + j * 9, __uint_as_float(v[j]));
+            } else {
+              float* o = p.dw + (static_cast<long long>(tap) * p.Cout + co) * ctot + cbase + c;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ci0 + c + j < csrc) atomicAdd(o + j, __uint_as_float(v[j]));
+            }
           }
         }
       }
       tc_fence_before();
+    }
+  } else if (p.ws_split != nullptr && warp >= 2) {
+    // an empty split (cannot happen with the host's split sizing) must still define its scratch tile
+    const int q = warp & 3;
+    const int csrc = src1 ? p.C1 : p.C0;
+    const int cbase = (src1 ? p.cbase1 : p.cbase0) + ci0;
+    float* dst = p.ws_split + static_cast<long long>(split) * 9 * p.Cout * p.ctot;
+    for (int rr = q; rr < 128 * MT; rr += 4) {
+      const int co = co0 + rr;
+      if (co >= p.Cout) break;
+      float* orow = dst + (static_cast<long long>(tap) * p.Cout + co) * p.ctot + cbase;
+      for (int cc = lane * 4; cc < BLOCK_N; cc += 128)
+        if (ci0 + cc < csrc) *reinterpret_cast<float4*>(orow + cc) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   __syncwarp();
@@ -660,26 +717,53 @@ int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack
   return PP_ERR_INVALID;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MT>
 static int launch_wgrad_tc(const CUtensorMap& dy, const CUtensorMap& x0, const CUtensorMap& x1, WgradTcParams p,
                            dim3 grid, cudaStream_t stream) {
-  constexpr int STAGE_BYTES = (2 + BLOCK_N / 64) * 64 * 128;
+  constexpr int STAGE_BYTES = (2 * MT + BLOCK_N / 64) * 64 * 128;
   int stages = (200 * 1024) / STAGE_BYTES;
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
   const int smem = stages * STAGE_BYTES + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       200 * 1024 + 1024 + 256));
+    PP_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<BLOCK_N, MT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024 + 256));
     attr_set = true;
   }
   const double flops = 2.0 * p.N * p.H * p.W * 9.0 * (p.C0 + p.C1) * p.Cout;
   const int slot = prof_begin(PROF_WGRAD, flops, stream);
-  conv3x3_wgrad_tc_kernel<BLOCK_N><<<grid, kTcThreads, smem, stream>>>(dy, x0, x1, p);
+  conv3x3_wgrad_tc_kernel<BLOCK_N, MT><<<grid, kTcThreads, smem, stream>>>(dy, x0, x1, p);
   prof_end(slot, stream);
   PP_LAUNCH_CHECK();
   return PP_OK;
+}
+
+// Sum of the per-split partial gradients ws[split][tap][Cout][Cin] -> OIHW grad [Cout][Cin][3][3] (+=) for input
+// channels [ci_begin, ci_begin + ci_count): fixed summation order, so the weight gradient is bit-reproducible.
+// Thread = one (co, ci) pair: per split its 9 tap loads are independent and coalesced over ci across the warp; the 9
+// taps of a pair are contiguous in OIHW, so the warp's read-modify-write covers one contiguous 1152-byte span.
+__global__ void __launch_bounds__(256) wgrad_reduce_unpack_kernel(const float* __restrict__ ws, float* __restrict__ g,
+                                                                  int splits, int Cout, int Cin, int ci_begin,
+                                                                  int ci_count) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * ci_count) return;
+  const int co = idx / ci_count, ci = ci_begin + idx % ci_count;
+  const size_t split_stride = static_cast<size_t>(9) * Cout * Cin, tap_stride = static_cast<size_t>(Cout) * Cin;
+  const float* src = ws + static_cast<size_t>(co) * Cin + ci;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  for (int sp = 0; sp < splits; ++sp) {
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[t] = __ldg(src + sp * split_stride + t * tap_stride);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] += v[t];
+  }
+  float* o = g + (static_cast<size_t>(co) * Cin + ci) * 9;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) o[t] += acc[t];
 }
 
 template <int CI, int NCOUT>
@@ -730,9 +814,30 @@ static int wgrad_narrow(const void* dy, int Cout, const void* x, int Csrc, int c
   return launch_wgrad_narrow<64, 64>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, dil, stream);
 }
 
-// generic kernel over the given sources; ctot / cbase place them inside the rows of dw
+// K-split count: minimise  waves x (K blocks per CTA + fixed per-CTA cost) x time per K block  +  the reduction pass
+// over `splits` partial gradients (per_split_bytes each), one CTA per SM
+static int wgrad_plan_splits(int base_ctas, int tiles_total, int max_splits, double us_per_kb, double per_split_bytes) {
+  const int sms = sm_count();
+  const double ovh = 6.0;           // prologue + epilogue of a CTA, in units of one 64-pixel K block
+  const double reduce_bw = 2.5e6;   // bytes per microsecond the reduction pass sustains on these small tensors
+  int best = 1;
+  double best_cost = 1e300;
+  for (int sp = 1; sp <= max_splits && sp <= tiles_total; ++sp) {
+    const int kb = ceil_div(tiles_total, sp);
+    if (ceil_div(tiles_total, kb) != sp) continue;   // would leave an empty split
+    const double cost = static_cast<double>(ceil_div(base_ctas * sp, sms)) * (kb + ovh) * us_per_kb +
+                        sp * per_split_bytes / reduce_bw;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+  }
+  return best;
+}
+
+// generic kernel over the given sources; ctot / cbase place them inside the rows of dw.
+// ws_split != nullptr (and g_oihw): every K split stores its partial gradient to ws_split[split] and a fixed-order
+// reduction folds them into the OIHW gradient (no atomics, deterministic); 256-row tiles when Cout % 256 == 0.
 static int wgrad_wide(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, int ctot, int cbase0,
-                      int cbase1, float* dw, int oihw, int N, int H, int W, int dil, cudaStream_t stream) {
+                      int cbase1, float* dw, int oihw, int N, int H, int W, int dil, cudaStream_t stream,
+                      float* ws_split = nullptr, long long ws_floats = 0, float* g_oihw = nullptr) {
   WgradTcParams p{};
   p.oihw = oihw;
   p.N = N; p.H = H; p.W = W; p.dil = dil;
@@ -746,12 +851,25 @@ static int wgrad_wide(const void* dy, int Cout, const void* x0, int C0, const vo
   const int block_n = cmax <= 64 ? 64 : (cmax <= 128 ? 128 : 256);
   p.ci_tiles0 = ceil_div(C0, block_n);
   p.ci_tiles1 = C1 > 0 ? ceil_div(C1, block_n) : 0;
-  const int co_tiles = ceil_div(Cout, 128);
+  const long long per_split = 9LL * Cout * ctot;
+  const bool split_mode = ws_split != nullptr && g_oihw != nullptr && ws_floats >= per_split && Cout % 32 == 0 &&
+                          C0 % 32 == 0 && C1 % 32 == 0 && ctot % 4 == 0 && cbase0 % 4 == 0 && cbase1 % 4 == 0;
+  const int mt = (split_mode && Cout % 256 == 0 && block_n >= 128) ? 2 : 1;
+  const int co_tiles = ceil_div(Cout, 128 * mt);
   const int base_ctas = co_tiles * (p.ci_tiles0 + p.ci_tiles1) * 9;
-  // split K so that the grid is at most ~2 full waves of one CTA per SM (fewer partial-tile reductions)
-  int splits = (2 * sm_count()) / base_ctas;
-  if (splits > p.tiles_total) splits = p.tiles_total;
-  if (splits < 1) splits = 1;
+  int splits;
+  if (split_mode) {
+    long long cap = ws_floats / per_split;
+    if (cap > 64) cap = 64;
+    splits = wgrad_plan_splits(base_ctas, p.tiles_total, static_cast<int>(cap), 0.45 * mt * block_n / 256.0 + 0.1,
+                               4.0 * per_split);
+    p.ws_split = ws_split;
+  } else {
+    // atomic accumulation: at most ~2 full waves of one CTA per SM (fewer partial-tile reductions)
+    splits = (2 * sm_count()) / base_ctas;
+    if (splits > p.tiles_total) splits = p.tiles_total;
+    if (splits < 1) splits = 1;
+  }
   p.kb_per_split = ceil_div(p.tiles_total, splits);
   splits = ceil_div(p.tiles_total, p.kb_per_split);
 
@@ -764,9 +882,21 @@ static int wgrad_wide(const void* dy, int Cout, const void* x0, int C0, const vo
   else tx1 = tx0;
   if (rc) return rc;
   dim3 grid(co_tiles * (p.ci_tiles0 + p.ci_tiles1), 9, splits);
-  if (block_n == 64) return launch_wgrad_tc<64>(tdy, tx0, tx1, p, grid, stream);
-  if (block_n == 128) return launch_wgrad_tc<128>(tdy, tx0, tx1, p, grid, stream);
-  return launch_wgrad_tc<256>(tdy, tx0, tx1, p, grid, stream);
+  if (mt == 2) rc = block_n == 128 ? launch_wgrad_tc<128, 2>(tdy, tx0, tx1, p, grid, stream)
+                                   : launch_wgrad_tc<256, 2>(tdy, tx0, tx1, p, grid, stream);
+  else if (block_n == 64) rc = launch_wgrad_tc<64, 1>(tdy, tx0, tx1, p, grid, stream);
+  else if (block_n == 128) rc = launch_wgrad_tc<128, 1>(tdy, tx0, tx1, p, grid, stream);
+  else rc = launch_wgrad_tc<256, 1>(tdy, tx0, tx1, p, grid, stream);
+  if (rc || !split_mode) return rc;
+  // fold the splits into the OIHW gradient, source by source (their channel ranges inside a dw row)
+  const int begins[2] = {cbase0, cbase1}, counts[2] = {C0, C1};
+  for (int k = 0; k < 2; ++k) {
+    if (counts[k] == 0) continue;
+    wgrad_reduce_unpack_kernel<<<ceil_div(Cout * counts[k], 256), 256, 0, stream>>>(ws_split, g_oihw, splits, Cout, ctot,
+                                                                                   begins[k], counts[k]);
+    PP_LAUNCH_CHECK();
+  }
+  return PP_OK;
 }
 
 int unpack_wgrad_range(const float* dwp, float* g, int Cout, int Cin, int ci_begin, int ci_count, int accumulate,
@@ -781,8 +911,10 @@ bool conv3x3_wgrad_tc_uses_scratch(int Cout, int C0, int C1) {
 //   g_oihw != nullptr: the OIHW gradient [Cout][C0+C1][3][3] is accumulated in place. Wide sources go there
 //     directly from the epilogue; narrow sources go through dwp (caller zeroes it when
 //     conv3x3_wgrad_tc_uses_scratch()) and are folded in by a column-range unpack.
+//   ws_split (optional, ws_floats fp32 elements): scratch for the deterministic split-K path of the wide sources.
 int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dwp,
-                     float* g_oihw, int N, int H, int W, int dil, cudaStream_t stream) {
+                     float* g_oihw, int N, int H, int W, int dil, cudaStream_t stream, float* ws_split,
+                     long long ws_floats) {
   PP_REQUIRE(N > 0 && H > 0 && W > 0 && dil >= 1, "conv3x3_wgrad_tc: bad shape");
   PP_REQUIRE(Cout % 8 == 0 && C0 % 8 == 0 && C1 % 8 == 0 && C0 > 0, "conv3x3_wgrad_tc: channels must be multiples of 8");
   PP_REQUIRE((x1 == nullptr) == (C1 == 0), "conv3x3_wgrad_tc: x1/C1 mismatch");
@@ -796,11 +928,14 @@ int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const voi
   if (n1) rc = wgrad_narrow(dy, Cout, x1, C1, ctot, C0, dwp, N, H, W, dil, stream);
   if (rc) return rc;
   if (!n0 && C1 > 0 && !n1) {
-    rc = wgrad_wide(dy, Cout, x0, C0, x1, C1, ctot, 0, C0, wide_dst, oihw, N, H, W, dil, stream);
+    rc = wgrad_wide(dy, Cout, x0, C0, x1, C1, ctot, 0, C0, wide_dst, oihw, N, H, W, dil, stream, ws_split, ws_floats,
+                    g_oihw);
   } else {
-    if (!n0) rc = wgrad_wide(dy, Cout, x0, C0, nullptr, 0, ctot, 0, 0, wide_dst, oihw, N, H, W, dil, stream);
+    if (!n0) rc = wgrad_wide(dy, Cout, x0, C0, nullptr, 0, ctot, 0, 0, wide_dst, oihw, N, H, W, dil, stream, ws_split,
+                             ws_floats, g_oihw);
     if (rc) return rc;
-    if (C1 > 0 && !n1) rc = wgrad_wide(dy, Cout, x1, C1, nullptr, 0, ctot, C0, 0, wide_dst, oihw, N, H, W, dil, stream);
+    if (C1 > 0 && !n1) rc = wgrad_wide(dy, Cout, x1, C1, nullptr, 0, ctot, C0, 0, wide_dst, oihw, N, H, W, dil, stream,
+                                       ws_split, ws_floats, g_oihw);
   }
   if (rc) return rc;
   if (oihw) {

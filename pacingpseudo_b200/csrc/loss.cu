@@ -55,12 +55,11 @@ enum : int { ACC_PCE = 0, ACC_NLAB = 1, ACC_ENT = 2, ACC_MASK = 3, ACC_CR = 4, A
 struct Softmax {
   float p[kMaxC], lp[kMaxC];
 };
-__device__ __forceinline__ void load_softmax(const float* __restrict__ z, long long HW, int C, Softmax& s) {
-  float v[kMaxC];
+__device__ __forceinline__ void softmax_of(const float (&v)[kMaxC], int C, Softmax& s) {
   float mx = -INFINITY;
 #pragma unroll
   for (int c = 0; c < kMaxC; ++c)
-    if (c < C) { v[c] = z[c * HW]; mx = fmaxf(mx, v[c]); }
+    if (c < C) mx = fmaxf(mx, v[c]);
   float sum = 0.f;
 #pragma unroll
   for (int c = 0; c < kMaxC; ++c)
@@ -70,6 +69,59 @@ __device__ __forceinline__ void load_softmax(const float* __restrict__ z, long l
   for (int c = 0; c < kMaxC; ++c)
     if (c < C) { s.p[c] *= inv; s.lp[c] = v[c] - lse; }
     else { s.p[c] = 0.f; s.lp[c] = 0.f; }
+}
+__device__ __forceinline__ void load_softmax(const float* __restrict__ z, long long HW, int C, Softmax& s) {
+  float v[kMaxC];
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) v[c] = (c < C) ? z[c * HW] : 0.f;
+  softmax_of(v, C, s);
+}
+// V consecutive pixels of every class plane: one 16-byte load per plane when V == 4 (HW % 4 == 0 keeps the group
+// inside one image and 16-byte aligned), scalar loads when V == 1.
+template <int V>
+__device__ __forceinline__ void load_planes(const float* __restrict__ z, int HW, int C, float (&v)[V][kMaxC]) {
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) {
+    if (c < C) {
+      if constexpr (V == 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(z + static_cast<size_t>(c) * HW));
+        v[0][c] = q.x; v[1][c] = q.y; v[2][c] = q.z; v[3][c] = q.w;
+      } else {
+        v[0][c] = __ldg(z + static_cast<size_t>(c) * HW);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j][c] = 0.f;
+    }
+  }
+}
+template <int V>
+__device__ __forceinline__ void store_planes(float* __restrict__ z, int HW, int C, const float (&v)[V][kMaxC]) {
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c)
+    if (c < C) {
+      if constexpr (V == 4)
+        *reinterpret_cast<float4*>(z + static_cast<size_t>(c) * HW) = make_float4(v[0][c], v[1][c], v[2][c], v[3][c]);
+      else
+        z[static_cast<size_t>(c) * HW] = v[0][c];
+    }
+}
+template <int V>
+__device__ __forceinline__ void load_target_mask(const uint8_t* __restrict__ target, const float* __restrict__ mask,
+                                                 int p, int ignore_index, int (&t)[V], float (&m)[V]) {
+  if constexpr (V == 4) {
+    if (target) {
+      const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(target + p));
+      t[0] = q & 0xff; t[1] = (q >> 8) & 0xff; t[2] = (q >> 16) & 0xff; t[3] = q >> 24;
+    } else { t[0] = t[1] = t[2] = t[3] = ignore_index; }
+    if (mask) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(mask + p));
+      m[0] = q.x; m[1] = q.y; m[2] = q.z; m[3] = q.w;
+    } else { m[0] = m[1] = m[2] = m[3] = 1.f; }
+  } else {
+    t[0] = target ? target[p] : ignore_index;
+    m[0] = mask ? mask[p] : 1.f;
+  }
 }
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) - (v < 0.f); }
 
@@ -102,47 +154,62 @@ __device__ __forceinline__ void block_accumulate(float (&v)[6], double* __restri
   }
 }
 
+template <int V>
 __global__ void __launch_bounds__(256)
 scribble_loss_fwd_kernel(const float* __restrict__ zw, const float* __restrict__ zs, const float* __restrict__ za,
                          const uint8_t* __restrict__ target, const float* __restrict__ mask, double* __restrict__ acc,
-                         long long P, int HW, int C, int ignore_index, int do_ent, int cr_variant) {
+                         int P, int HW, int C, int ignore_index, int do_ent, int cr_variant) {
   float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long n = p / HW, hw = p % HW;
-    const long long off = n * C * HW + hw;
-    Softmax w;
-    load_softmax(zw + off, HW, C, w);
-    const int t = target ? target[p] : ignore_index;
-    const bool lab = (target != nullptr) && (t != ignore_index) && (t < C);
-    const float m = mask ? mask[p] : 1.f;
-    if (lab) {
-      float lpt = 0.f;
+  const int groups = P / V;
+  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
+    const int p = gi * V;
+    const int n = p / HW, hw = p - n * HW;
+    const size_t off = static_cast<size_t>(n) * C * HW + hw;
+    float vw[V][kMaxC], vs[V][kMaxC], va[V][kMaxC];
+    int tv[V];
+    float mv[V];
+    load_planes<V>(zw + off, HW, C, vw);
+    if (cr_variant != CR_NONE) load_planes<V>(zs + off, HW, C, vs);
+    load_target_mask<V>(target, mask, p, ignore_index, tv, mv);
+    bool any_lab = false;
 #pragma unroll
-      for (int c = 0; c < kMaxC; ++c) lpt = (c == t) ? w.lp[c] : lpt;
-      part[ACC_PCE] -= lpt;
-      part[ACC_NLAB] += 1.f;
-    }
-    part[ACC_MASK] += m;
-    if (do_ent) {
-      float H = 0.f;
+    for (int j = 0; j < V; ++j) any_lab |= (target != nullptr) && (tv[j] != ignore_index) && (tv[j] < C);
+    if (za != nullptr && any_lab) load_planes<V>(za + off, HW, C, va);   // aux logits matter on labelled pixels only
 #pragma unroll
-      for (int c = 0; c < kMaxC; ++c)
-        if (c < C) H -= w.p[c] * w.lp[c];
-      part[ACC_ENT] += m * H;
-    }
-    if (cr_variant != CR_NONE) {
-      Softmax s;
-      load_softmax(zs + off, HW, C, s);
-      part[ACC_CR] += m * cr_pixel(cr_variant, C, w, s);
-    }
-    if (za != nullptr && lab) {
-      Softmax a;
-      load_softmax(za + off, HW, C, a);
-      float lpt = 0.f;
+    for (int j = 0; j < V; ++j) {
+      Softmax w;
+      softmax_of(vw[j], C, w);
+      const int t = tv[j];
+      const bool lab = (target != nullptr) && (t != ignore_index) && (t < C);
+      const float m = mv[j];
+      if (lab) {
+        float lpt = 0.f;
 #pragma unroll
-      for (int c = 0; c < kMaxC; ++c) lpt = (c == t) ? a.lp[c] : lpt;
-      part[ACC_AUX] -= lpt;
+        for (int c = 0; c < kMaxC; ++c) lpt = (c == t) ? w.lp[c] : lpt;
+        part[ACC_PCE] -= lpt;
+        part[ACC_NLAB] += 1.f;
+      }
+      part[ACC_MASK] += m;
+      if (do_ent) {
+        float H = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c)
+          if (c < C) H -= w.p[c] * w.lp[c];
+        part[ACC_ENT] += m * H;
+      }
+      if (cr_variant != CR_NONE) {
+        Softmax sx;
+        softmax_of(vs[j], C, sx);
+        part[ACC_CR] += m * cr_pixel(cr_variant, C, w, sx);
+      }
+      if (za != nullptr && lab) {
+        Softmax a;
+        softmax_of(va[j], C, a);
+        float lpt = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) lpt = (c == t) ? a.lp[c] : lpt;
+        part[ACC_AUX] -= lpt;
+      }
     }
   }
   block_accumulate(part, acc);
@@ -168,6 +235,16 @@ __global__ void scribble_loss_finalize_kernel(const double* __restrict__ acc, fl
   }
 }
 
+// 4 pixels per thread need HW % 4 == 0 (a group never straddles two images) and 16 / 4-byte aligned base pointers
+static bool loss_vec4_ok(int HW, const void* a, const void* b, const void* c, const void* t, const void* m,
+                         const void* d = nullptr, const void* e = nullptr, const void* f = nullptr) {
+  if (HW % 4 != 0) return false;
+  const void* f4[] = {a, b, c, m, d, e, f};
+  for (const void* q : f4)
+    if (q != nullptr && (reinterpret_cast<uintptr_t>(q) & 15) != 0) return false;
+  return t == nullptr || (reinterpret_cast<uintptr_t>(t) & 3) == 0;
+}
+
 int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const uint8_t* target, const float* mask,
                       double* acc, float* loss_pce, float* loss_ent, float* loss_cr, float* loss_aux, int N, int C,
                       int HW, int ignore_index, int do_ent, int cr_variant, cudaStream_t s) {
@@ -175,9 +252,14 @@ int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const u
   PP_REQUIRE(cr_variant >= CR_NONE && cr_variant <= CR_KL, "scribble_loss: bad consistency variant %d", cr_variant);
   PP_REQUIRE((cr_variant == CR_NONE) == (zs == nullptr), "scribble_loss: strong logits / variant mismatch");
   const long long P = static_cast<long long>(N) * HW;
+  PP_REQUIRE(P * C < (1LL << 31), "scribble_loss: %lld logits exceed the 32-bit index range", P * C);
   PP_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ACC_SLOTS, s));
-  scribble_loss_fwd_kernel<<<grid_for_px(P, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, P, HW, C, ignore_index,
-                                                               do_ent, cr_variant);
+  if (loss_vec4_ok(HW, zw, zs, za, target, mask))
+    scribble_loss_fwd_kernel<4><<<grid_for_px(P / 4, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW, C,
+                                                                        ignore_index, do_ent, cr_variant);
+  else
+    scribble_loss_fwd_kernel<1><<<grid_for_px(P, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW, C,
+                                                                    ignore_index, do_ent, cr_variant);
   scribble_loss_finalize_kernel<<<1, 32, 0, s>>>(acc, loss_pce, do_ent ? loss_ent : nullptr,
                                                  cr_variant != CR_NONE ? loss_cr : nullptr,
                                                  za != nullptr ? loss_aux : nullptr, P, C, mask != nullptr, cr_variant);
@@ -185,13 +267,14 @@ int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const u
   return PP_OK;
 }
 
+template <int V>
 __global__ void __launch_bounds__(256)
 scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__ zs, const float* __restrict__ za,
                          const uint8_t* __restrict__ target, const float* __restrict__ mask,
                          const double* __restrict__ acc, const float* __restrict__ g_pce,
                          const float* __restrict__ g_ent, const float* __restrict__ g_cr,
                          const float* __restrict__ g_aux, float* __restrict__ dzw, float* __restrict__ dzs,
-                         float* __restrict__ dza, long long P, int HW, int C, int ignore_index, int do_ent,
+                         float* __restrict__ dza, int P, int HW, int C, int ignore_index, int do_ent,
                          int cr_variant, int detach_weak) {
   const float gp = g_pce ? *g_pce : 0.f, ge = (do_ent && g_ent) ? *g_ent : 0.f;
   const float gc = (cr_variant != CR_NONE && g_cr) ? *g_cr : 0.f, ga = (za && g_aux) ? *g_aux : 0.f;
@@ -203,81 +286,91 @@ scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__
   const float inv_cr = static_cast<float>(1.0 / masked_denom(acc, has_mask, ne));
   const bool weak_gets_cr = (cr_variant == CR_KL) || !detach_weak;
 
-  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long n = p / HW, hw = p % HW;
-    const long long off = n * C * HW + hw;
-    Softmax w;
-    load_softmax(zw + off, HW, C, w);
-    const int t = target ? target[p] : ignore_index;
-    const bool lab = (target != nullptr) && (t != ignore_index) && (t < C);
-    const float m = mask ? mask[p] : 1.f;
-    float d[kMaxC];
+  const int groups = P / V;
+  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
+    const int p = gi * V;
+    const int n = p / HW, hw = p - n * HW;
+    const size_t off = static_cast<size_t>(n) * C * HW + hw;
+    float vw[V][kMaxC], vs[V][kMaxC], va[V][kMaxC];
+    int tv[V];
+    float mv[V];
+    load_planes<V>(zw + off, HW, C, vw);
+    if (cr_variant != CR_NONE) load_planes<V>(zs + off, HW, C, vs);
+    load_target_mask<V>(target, mask, p, ignore_index, tv, mv);
+    bool any_lab = false;
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) d[c] = lab ? gp * inv_lab * (w.p[c] - (c == t ? 1.f : 0.f)) : 0.f;
-    if (do_ent) {
-      float H = 0.f;
+    for (int j = 0; j < V; ++j) any_lab |= (target != nullptr) && (tv[j] != ignore_index) && (tv[j] < C);
+    const bool do_aux = za != nullptr && dza != nullptr;
+    if (do_aux && any_lab) load_planes<V>(za + off, HW, C, va);
 #pragma unroll
-      for (int c = 0; c < kMaxC; ++c)
-        if (c < C) H -= w.p[c] * w.lp[c];
-      const float k = ge * m * inv_ent;
+    for (int j = 0; j < V; ++j) {
+      Softmax w;
+      softmax_of(vw[j], C, w);
+      const int t = tv[j];
+      const bool lab = (target != nullptr) && (t != ignore_index) && (t < C);
+      const float m = mv[j];
+      float d[kMaxC];
 #pragma unroll
-      for (int c = 0; c < kMaxC; ++c) d[c] -= k * w.p[c] * (w.lp[c] + H);
-    }
-    if (cr_variant != CR_NONE) {
-      Softmax s;
-      load_softmax(zs + off, HW, C, s);
-      const float k = gc * m * inv_cr;
-      float ds[kMaxC];
-      if (cr_variant == CR_CE || cr_variant == CR_KL) {
-        const float L = cr_pixel(cr_variant, C, w, s);
+      for (int c = 0; c < kMaxC; ++c) d[c] = lab ? gp * inv_lab * (w.p[c] - (c == t ? 1.f : 0.f)) : 0.f;
+      if (do_ent) {
+        float H = 0.f;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) {
-          ds[c] = k * (s.p[c] - w.p[c]);
-          if (weak_gets_cr) {
-            if (cr_variant == CR_CE) d[c] -= k * w.p[c] * (s.lp[c] + L);
-            else d[c] += k * w.p[c] * ((w.lp[c] - s.lp[c]) - L);
+        for (int c = 0; c < kMaxC; ++c)
+          if (c < C) H -= w.p[c] * w.lp[c];
+        const float k = ge * m * inv_ent;
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) d[c] -= k * w.p[c] * (w.lp[c] + H);
+      }
+      if (cr_variant != CR_NONE) {
+        Softmax sx;
+        softmax_of(vs[j], C, sx);
+        const float k = gc * m * inv_cr;
+        float ds[kMaxC];
+        if (cr_variant == CR_CE || cr_variant == CR_KL) {
+          const float L = cr_pixel(cr_variant, C, w, sx);
+#pragma unroll
+          for (int c = 0; c < kMaxC; ++c) {
+            ds[c] = k * (sx.p[c] - w.p[c]);
+            if (weak_gets_cr) {
+              if (cr_variant == CR_CE) d[c] -= k * w.p[c] * (sx.lp[c] + L);
+              else d[c] += k * w.p[c] * ((w.lp[c] - sx.lp[c]) - L);
+            }
+          }
+        } else {
+          float e[kMaxC], es = 0.f, ew = 0.f;
+#pragma unroll
+          for (int c = 0; c < kMaxC; ++c) {
+            const float df = sx.p[c] - w.p[c];
+            e[c] = (c < C) ? (cr_variant == CR_L1 ? sgn(df) : 2.f * df) : 0.f;
+            es = fmaf(e[c], sx.p[c], es);
+            ew = fmaf(e[c], w.p[c], ew);
+          }
+#pragma unroll
+          for (int c = 0; c < kMaxC; ++c) {
+            ds[c] = k * sx.p[c] * (e[c] - es);
+            if (weak_gets_cr) d[c] += k * w.p[c] * (ew - e[c]);
           }
         }
-      } else {
-        float e[kMaxC], es = 0.f, ew = 0.f;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) {
-          const float df = s.p[c] - w.p[c];
-          e[c] = (c < C) ? (cr_variant == CR_L1 ? sgn(df) : 2.f * df) : 0.f;
-          es = fmaf(e[c], s.p[c], es);
-          ew = fmaf(e[c], w.p[c], ew);
+        for (int c = 0; c < kMaxC; ++c) vs[j][c] = ds[c];     // the strong logits are consumed: reuse as output
+      }
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) vw[j][c] = d[c];
+      if (do_aux) {
+        if (lab) {
+          Softmax a;
+          softmax_of(va[j], C, a);
+#pragma unroll
+          for (int c = 0; c < kMaxC; ++c) va[j][c] = ga * inv_lab * (a.p[c] - (c == t ? 1.f : 0.f));
+        } else {
+#pragma unroll
+          for (int c = 0; c < kMaxC; ++c) va[j][c] = 0.f;
         }
-#pragma unroll
-        for (int c = 0; c < kMaxC; ++c) {
-          ds[c] = k * s.p[c] * (e[c] - es);
-          if (weak_gets_cr) d[c] += k * w.p[c] * (ew - e[c]);
-        }
-      }
-      if (dzs != nullptr) {
-#pragma unroll
-        for (int c = 0; c < kMaxC; ++c)
-          if (c < C) dzs[off + c * static_cast<long long>(HW)] = ds[c];
       }
     }
-    if (dzw != nullptr) {
-#pragma unroll
-      for (int c = 0; c < kMaxC; ++c)
-        if (c < C) dzw[off + c * static_cast<long long>(HW)] = d[c];
-    }
-    if (za != nullptr && dza != nullptr) {
-      if (lab) {
-        Softmax a;
-        load_softmax(za + off, HW, C, a);
-#pragma unroll
-        for (int c = 0; c < kMaxC; ++c)
-          if (c < C) dza[off + c * static_cast<long long>(HW)] = ga * inv_lab * (a.p[c] - (c == t ? 1.f : 0.f));
-      } else {
-#pragma unroll
-        for (int c = 0; c < kMaxC; ++c)
-          if (c < C) dza[off + c * static_cast<long long>(HW)] = 0.f;
-      }
-    }
+    if (cr_variant != CR_NONE && dzs != nullptr) store_planes<V>(dzs + off, HW, C, vs);
+    if (dzw != nullptr) store_planes<V>(dzw + off, HW, C, vw);
+    if (do_aux) store_planes<V>(dza + off, HW, C, va);
   }
 }
 
@@ -287,9 +380,15 @@ int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const u
                       int cr_variant, int detach_weak, cudaStream_t s) {
   PP_REQUIRE(C >= 1 && C <= kMaxC, "scribble_loss_bwd: num_classes=%d unsupported", C);
   const long long P = static_cast<long long>(N) * HW;
-  scribble_loss_bwd_kernel<<<grid_for_px(P, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent, g_cr, g_aux,
-                                                               dzw, dzs, dza, P, HW, C, ignore_index, do_ent, cr_variant,
-                                                               detach_weak);
+  PP_REQUIRE(P * C < (1LL << 31), "scribble_loss_bwd: %lld logits exceed the 32-bit index range", P * C);
+  if (loss_vec4_ok(HW, zw, zs, za, target, mask, dzw, dzs, dza))
+    scribble_loss_bwd_kernel<4><<<grid_for_px(P / 4, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent,
+                                                                        g_cr, g_aux, dzw, dzs, dza, int(P), HW, C,
+                                                                        ignore_index, do_ent, cr_variant, detach_weak);
+  else
+    scribble_loss_bwd_kernel<1><<<grid_for_px(P, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent, g_cr,
+                                                                    g_aux, dzw, dzs, dza, int(P), HW, C, ignore_index,
+                                                                    do_ent, cr_variant, detach_weak);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

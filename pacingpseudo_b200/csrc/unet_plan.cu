@@ -46,8 +46,11 @@ struct UNetPlan {
   // critical chain (BatchNorm backward -> dgrad -> pool/upsample backward, mostly HBM bound) continues on the
   // caller's stream. dY lives in kDyBufs rotating buffers guarded by events. PP_NO_OVERLAP=1 disables it.
   static constexpr int kDyBufs = 3;
+  static constexpr int kMaxParts = 2;   // forward: statistics groups on separate streams
   mutable cudaStream_t side = nullptr;
   mutable cudaEvent_t dy_ready[kDyBufs] = {}, buf_free[kDyBufs] = {}, join = nullptr;
+  mutable cudaStream_t part_stream[kMaxParts] = {};
+  mutable cudaEvent_t fork = nullptr, stat_order[kMaxParts] = {}, part_done[kMaxParts] = {};
   mutable int overlap = -1;   // -1: not initialised, 0: off, 1: on
 
   int new_act(int C, int res) { acts.push_back({C, res}); return int(acts.size()) - 1; }
@@ -110,7 +113,7 @@ struct UNetLayout {
   long long total = 0;
   std::vector<long long> act_data, act_grad;          // per activation
   std::vector<long long> yraw, coef, sums, wf, wd;     // per conv layer
-  long long dy_scratch = 0, dy_stride = 0, dwp_scratch = 0, bsums = 0, bcoef = 0;
+  long long dy_scratch = 0, dy_stride = 0, dwp_scratch = 0, dws_scratch = 0, dws_floats = 0, bsums = 0, bcoef = 0;
 };
 
 static UNetLayout make_layout(const UNetPlan& pl, int N, int H, int W, int G) {
@@ -140,6 +143,8 @@ static UNetLayout make_layout(const UNetPlan& pl, int N, int H, int W, int G) {
   L.dy_stride = align_up(max_act);
   for (int k = 1; k < UNetPlan::kDyBufs; ++k) take(max_act);
   L.dwp_scratch = take(max_w * 4);
+  L.dws_floats = 2 * max_w;                 // split-K partial gradients of the wide layers (>= 2 splits each)
+  L.dws_scratch = take(L.dws_floats * 4);
   L.bsums = take(sizeof(double) * 2 * G * max_c);
   L.bcoef = take(sizeof(float) * 2 * G * max_c);
   L.total = off;
@@ -158,6 +163,29 @@ static int check_shape(const UNetPlan& pl, int N, int H, int W, int G) {
   PP_REQUIRE(N > 0 && G > 0 && N % G == 0, "unet: batch %d not divisible into %d statistics groups", N, G);
   PP_REQUIRE(H % div == 0 && W % div == 0 && H >= div && W >= div,
              "unet: H=%d W=%d must be multiples of %d (maxpool stages)", H, W, div);
+  return PP_OK;
+}
+
+// internal streams / events of the overlap machinery (see UNetPlan), created on first use on the current device
+static int overlap_init(const UNetPlan& pl) {
+  if (pl.overlap >= 0) return PP_OK;
+  const char* off = getenv("PP_NO_OVERLAP");
+  const int on = (off != nullptr && off[0] == '1') ? 0 : 1;
+  if (on) {
+    PP_CHECK_CUDA(cudaStreamCreateWithFlags(&pl.side, cudaStreamNonBlocking));
+    for (int k = 0; k < UNetPlan::kDyBufs; ++k) {
+      PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.dy_ready[k], cudaEventDisableTiming));
+      PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.buf_free[k], cudaEventDisableTiming));
+    }
+    PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.join, cudaEventDisableTiming));
+    PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.fork, cudaEventDisableTiming));
+    for (int k = 0; k < UNetPlan::kMaxParts; ++k) {
+      if (k > 0) PP_CHECK_CUDA(cudaStreamCreateWithFlags(&pl.part_stream[k], cudaStreamNonBlocking));
+      PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.stat_order[k], cudaEventDisableTiming));
+      PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.part_done[k], cudaEventDisableTiming));
+    }
+  }
+  pl.overlap = on;
   return PP_OK;
 }
 
@@ -184,69 +212,106 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
     rc = pack_weights_multi(dt, int(pw.size()), pw.data(), pf.data(), pd.data(), co.data(), ci.data(), s);
     if (rc) return rc;
   }
+  // Statistics groups (the weak and the strong branch of the siamese step) are independent until the losses, so
+  // with overlap enabled every group runs on its own stream: the HBM-bound BatchNorm / pool / upsample kernels of one
+  // branch overlap the tensor-core kernels of the other. Only the running-statistics update is ordered (weak, then
+  // strong, as two reference forward passes would do): group g's finalize waits for group g-1's of the same layer.
+  rc = overlap_init(pl);
+  if (rc) return rc;
+  const int parts = (pl.overlap == 1 && G > 1 && G <= UNetPlan::kMaxParts) ? G : 1;
+  const int Np = N / parts, Gp = G / parts;   // images and statistics groups per part
+  const long long es = dt == PP_BF16 ? 2 : 4;
+  cudaStream_t st[UNetPlan::kMaxParts];
+  st[0] = s;
+  for (int k = 1; k < parts; ++k) {
+    st[k] = pl.part_stream[k];
+    PP_CHECK_CUDA(cudaEventRecord(pl.fork, s));
+    PP_CHECK_CUDA(cudaStreamWaitEvent(st[k], pl.fork, 0));
+  }
+  auto act_part = [&](long long off, const Act& a, int k) -> char* {   // images [k*Np, (k+1)*Np) of an activation
+    return base + off + static_cast<long long>(k) * Np * (H / a.res) * (W / a.res) * a.C * es;
+  };
   for (const Op& op : pl.ops) {
-    if (op.kind == OP_CONV) {
-      const ConvL& c = pl.convs[op.layer];
-      void* const* pp = params + op.layer * kParamsPerConv;
-      const Act& ao = pl.acts[c.out];
-      const int h = H / ao.res, w = W / ao.res;
-      void* yraw = base + L.yraw[op.layer];
-      const long long Pg = static_cast<long long>(N / G) * h * w;
-      double* sums = reinterpret_cast<double*>(base + L.sums[op.layer]);
-      float* coef = reinterpret_cast<float*>(base + L.coef[op.layer]);
-      bool fused_stats = false;
-      if (c.in0 < 0) {
-        rc = first_conv_fwd(dt, x, static_cast<const float*>(pp[0]), static_cast<const float*>(pp[1]), yraw, N, h, w,
-                            c.cout, s);
-      } else {
-        void* wf = base + L.wf[op.layer];
-        const void* x0 = base + L.act_data[c.in0];
-        const void* x1 = c.in1 >= 0 ? base + L.act_data[c.in1] : nullptr;
-        if (dt == PP_BF16) {
+    for (int k = 0; k < parts; ++k) {
+      cudaStream_t sk = st[k];
+      if (op.kind == OP_CONV) {
+        const ConvL& c = pl.convs[op.layer];
+        void* const* pp = params + op.layer * kParamsPerConv;
+        const Act& ao = pl.acts[c.out];
+        const int h = H / ao.res, w = W / ao.res;
+        void* yraw = act_part(L.yraw[op.layer], ao, k);
+        const long long Pg = static_cast<long long>(N / G) * h * w;
+        bool fused_stats = false;
+        if (dt == PP_BF16 && c.in0 >= 0) {
           // batch statistics ride in the conv epilogue when a pixel tile never straddles two statistics groups
           int bw_ = 1, bh_ = 1;
           while (bw_ < w && bw_ < 128) bw_ <<= 1;
           while (bh_ < h && bw_ * bh_ < 128) bh_ <<= 1;
           const int bn_ = 128 / (bw_ * bh_);
           fused_stats = training && (bn_ == 1 || (N / G) % bn_ == 0);
-          if (fused_stats) PP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * G * c.cout * kStatReplicas, s));
-          rc = conv3x3_tc(x0, c.cin0, x1, c.cin1, wf, static_cast<const float*>(pp[1]), yraw, c.cout, 0, nullptr, 0, 0,
-                          N, h, w, c.dil, s, fused_stats ? sums : nullptr, G);
-        } else {
-          rc = conv3x3_simt(dt, x0, c.cin0, x1, c.cin1, wf, static_cast<const float*>(pp[1]), yraw, c.cout, 0, nullptr,
-                            0, 0, N, h, w, c.dil, s);
         }
-      }
-      if (rc) return rc;
-      if (training && !fused_stats) {
-        PP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * G * c.cout, s));
-        rc = bn_stats(dt, yraw, sums, G, Pg, c.cout, s);
+        const int reps = fused_stats ? kStatReplicas : 1;
+        // sums: [replica][group][C][2] per part; coef: [group][4][C]
+        double* sums = reinterpret_cast<double*>(base + L.sums[op.layer]) + static_cast<long long>(k) * Gp * reps * c.cout * 2;
+        float* coef = reinterpret_cast<float*>(base + L.coef[op.layer]) + static_cast<long long>(k) * Gp * 4 * c.cout;
+        if (c.in0 < 0) {
+          rc = first_conv_fwd(dt, x + static_cast<long long>(k) * Np * H * W, static_cast<const float*>(pp[0]),
+                              static_cast<const float*>(pp[1]), yraw, Np, h, w, c.cout, sk);
+        } else {
+          void* wf = base + L.wf[op.layer];
+          const void* x0 = act_part(L.act_data[c.in0], pl.acts[c.in0], k);
+          const void* x1 = c.in1 >= 0 ? act_part(L.act_data[c.in1], pl.acts[c.in1], k) : nullptr;
+          if (dt == PP_BF16) {
+            if (fused_stats) PP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Gp * c.cout * kStatReplicas, sk));
+            rc = conv3x3_tc(x0, c.cin0, x1, c.cin1, wf, static_cast<const float*>(pp[1]), yraw, c.cout, 0, nullptr, 0,
+                            0, Np, h, w, c.dil, sk, fused_stats ? sums : nullptr, Gp);
+          } else {
+            rc = conv3x3_simt(dt, x0, c.cin0, x1, c.cin1, wf, static_cast<const float*>(pp[1]), yraw, c.cout, 0,
+                              nullptr, 0, 0, Np, h, w, c.dil, sk);
+          }
+        }
+        if (rc) return rc;
+        if (training && !fused_stats) {
+          PP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Gp * c.cout, sk));
+          rc = bn_stats(dt, yraw, sums, Gp, Pg, c.cout, sk);
+          if (rc) return rc;
+        }
+        if (k > 0) PP_CHECK_CUDA(cudaStreamWaitEvent(sk, pl.stat_order[k - 1], 0));   // running stats: group order
+        rc = bn_finalize(sums, static_cast<const float*>(pp[2]), static_cast<const float*>(pp[3]),
+                         static_cast<float*>(pp[4]), static_cast<float*>(pp[5]), static_cast<long long*>(pp[6]), coef,
+                         Gp, Pg, c.cout, training, 1e-5f, 0.1f, sk, reps);
+        if (rc) return rc;
+        if (parts > 1 && k + 1 < parts) PP_CHECK_CUDA(cudaEventRecord(pl.stat_order[k], sk));
+        rc = bn_apply(dt, yraw, coef, act_part(L.act_data[c.out], ao, k), Gp, Pg, c.cout, 0.01f, sk);
+        if (rc) return rc;
+      } else if (op.kind == OP_POOL) {
+        const Act& as = pl.acts[op.src];
+        rc = maxpool_fwd(dt, act_part(L.act_data[op.src], as, k), act_part(L.act_data[op.dst], pl.acts[op.dst], k), Np,
+                         H / as.res, W / as.res, as.C, sk);
+        if (rc) return rc;
+      } else {
+        const Act& as = pl.acts[op.src];
+        const Act& ad = pl.acts[op.dst];
+        rc = upsample_nhwc_fwd(dt, act_part(L.act_data[op.src], as, k), act_part(L.act_data[op.dst], ad, k), Np,
+                               H / as.res, W / as.res, H / ad.res, W / ad.res, as.C, sk);
         if (rc) return rc;
       }
-      rc = bn_finalize(sums, static_cast<const float*>(pp[2]), static_cast<const float*>(pp[3]),
-                       static_cast<float*>(pp[4]), static_cast<float*>(pp[5]), static_cast<long long*>(pp[6]), coef, G,
-                       Pg, c.cout, training, 1e-5f, 0.1f, s, fused_stats ? kStatReplicas : 1);
-      if (rc) return rc;
-      rc = bn_apply(dt, yraw, coef, base + L.act_data[c.out], G, Pg, c.cout, 0.01f, s);
-      if (rc) return rc;
-    } else if (op.kind == OP_POOL) {
-      const Act& as = pl.acts[op.src];
-      rc = maxpool_fwd(dt, base + L.act_data[op.src], base + L.act_data[op.dst], N, H / as.res, W / as.res, as.C, s);
-      if (rc) return rc;
-    } else {
-      const Act& as = pl.acts[op.src];
-      const Act& ad = pl.acts[op.dst];
-      rc = upsample_nhwc_fwd(dt, base + L.act_data[op.src], base + L.act_data[op.dst], N, H / as.res, W / as.res,
-                             H / ad.res, W / ad.res, as.C, s);
-      if (rc) return rc;
     }
   }
   void* const* hp = params + pl.convs.size() * kParamsPerConv;
   const Act& ah = pl.acts[pl.head_in];
   const int hh = H / ah.res, hw = W / ah.res;
-  return head_fwd(dt, base + L.act_data[pl.head_in], static_cast<const float*>(hp[0]),
-                  static_cast<const float*>(hp[1]), logits, static_cast<long long>(N) * hh * hw, hh * hw, ah.C,
-                  pl.num_classes, s);
+  for (int k = 0; k < parts; ++k) {
+    rc = head_fwd(dt, act_part(L.act_data[pl.head_in], ah, k), static_cast<const float*>(hp[0]),
+                  static_cast<const float*>(hp[1]), logits + static_cast<long long>(k) * Np * pl.num_classes * hh * hw,
+                  static_cast<long long>(Np) * hh * hw, hh * hw, ah.C, pl.num_classes, st[k]);
+    if (rc) return rc;
+  }
+  for (int k = 1; k < parts; ++k) {   // the caller's stream owns the result
+    PP_CHECK_CUDA(cudaEventRecord(pl.part_done[k], st[k]));
+    PP_CHECK_CUDA(cudaStreamWaitEvent(s, pl.part_done[k], 0));
+  }
+  return PP_OK;
 }
 
 // dfeat: optional external gradients w.r.t. named activations (NHWC, activation dtype), e.g. the
@@ -282,19 +347,8 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
     written[a] = 1;
   }
 
-  // ---- overlap plumbing (see UNetPlan) --------------------------------------------------------
-  if (pl.overlap < 0) {
-    const char* off = getenv("PP_NO_OVERLAP");
-    pl.overlap = (off != nullptr && off[0] == '1') ? 0 : 1;
-    if (pl.overlap) {
-      PP_CHECK_CUDA(cudaStreamCreateWithFlags(&pl.side, cudaStreamNonBlocking));
-      for (int k = 0; k < UNetPlan::kDyBufs; ++k) {
-        PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.dy_ready[k], cudaEventDisableTiming));
-        PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.buf_free[k], cudaEventDisableTiming));
-      }
-      PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.join, cudaEventDisableTiming));
-    }
-  }
+  rc = overlap_init(pl);
+  if (rc) return rc;
   const bool ov = pl.overlap == 1;
   cudaStream_t ws_ = ov ? pl.side : s;       // stream of the weight-gradient kernels
   bool buf_used[UNetPlan::kDyBufs] = {false, false, false};
@@ -347,7 +401,8 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
         // wide sources accumulate straight into the OIHW gradient; narrow ones go through the packed scratch
         if (conv3x3_wgrad_tc_uses_scratch(c.cout, c.cin0, c.cin1))
           PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * c.cout * ctot, ws_));
-        rc = conv3x3_wgrad_tc(dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, gg[0], N, h, w, c.dil, ws_);
+        rc = conv3x3_wgrad_tc(dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, gg[0], N, h, w, c.dil, ws_,
+                              reinterpret_cast<float*>(base + L.dws_scratch), L.dws_floats);
         if (rc) return rc;
       } else {
         PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * c.cout * ctot, ws_));
@@ -426,6 +481,12 @@ void unet_destroy(UNetPlan* pl) {
     }
     if (pl->join) cudaEventDestroy(pl->join);
     if (pl->side) cudaStreamDestroy(pl->side);
+    if (pl->fork) cudaEventDestroy(pl->fork);
+    for (int k = 0; k < UNetPlan::kMaxParts; ++k) {
+      if (pl->stat_order[k]) cudaEventDestroy(pl->stat_order[k]);
+      if (pl->part_done[k]) cudaEventDestroy(pl->part_done[k]);
+      if (pl->part_stream[k]) cudaStreamDestroy(pl->part_stream[k]);
+    }
   }
   delete pl;
 }

@@ -614,3 +614,35 @@ def test_device_prefetcher_and_loss_reader(pp):
     for i, b in enumerate(pf.reset(iter(host[:3]))):     # next epoch: same staging buffers, data still intact
         assert torch.equal(b["scribble"].cpu(), host[i]["scribble"])
     assert ptrs == {k: v.data_ptr() for s in pf.slots for k, v in s.items()} and i == 2
+
+
+@pytest.mark.parametrize("case", [(4, 8, 8, 512, 512, 512, 1), (3, 16, 16, 512, 256, 256, 1), (2, 32, 32, 128, 0, 256, 2),
+                                  (2, 32, 32, 128, 64, 64, 1), (5, 8, 8, 512, 0, 512, 4), (1, 28, 28, 256, 0, 128, 1)])
+def test_conv3x3_wgrad_oihw_split_k_deterministic(pp, case):
+    """Weight gradient accumulated into the OIHW gradient through the split-K scratch path (256-row tiles, fixed-order
+    reduction): matches torch CPU autograd, accumulates (+=), and two runs are bit-identical; the atomic path agrees."""
+    L, PF, _ = pp
+    N, H, W, C0, C1, Co, dil = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, C0 + C1, H, W, generator=g).bfloat16().float()
+    gy = torch.randn(N, Co, H, W, generator=g).bfloat16().float()
+    w = torch.zeros(Co, C0 + C1, 3, 3, requires_grad=True)
+    F.conv2d(x, w, None, 1, dil, dil).backward(gy)
+    x0 = _nhwc(x[:, :C0], torch.bfloat16)
+    x1 = _nhwc(x[:, C0:], torch.bfloat16) if C1 else None
+    dy = _nhwc(gy, torch.bfloat16)
+    n = 9 * Co * (C0 + C1)
+    dwp = torch.empty(n, device="cuda")
+    outs = []
+    for ws_floats in (2 * n, 2 * n, 5 * n, 0):
+        ws = torch.full((max(ws_floats, 1),), float("nan"), device="cuda")   # stale scratch must not leak into the result
+        gw = torch.ones(Co, C0 + C1, 3, 3, device="cuda")
+        L.call("pp_conv3x3_wgrad_oihw", _p(dy), Co, _p(x0), C0, _p(x1), C1, _p(dwp), _p(gw),
+               _p(ws) if ws_floats else None, ws_floats, N, H, W, dil, _st())
+        torch.cuda.synchronize()
+        outs.append(gw - 1.0)
+    for o in outs:
+        assert _rel(o, w.grad) < 1e-4
+    narrow = any(c in (32, 64) and Co in (32, 64) for c in (C0, C1))   # 32/64-channel sources accumulate atomically
+    if not narrow:
+        assert torch.equal(outs[0], outs[1])
