@@ -39,7 +39,8 @@ int pp_init(int device);                 /* selects the device, checks sm_100, r
 const char* pp_last_error(void);
 int pp_version(void);
 /* measurement hooks (bench.py): kernels launched so far by this library; optional CUDA-event bracketing of
- * every tcgen05 conv launch on its own stream. family 0 = conv3x3 forward/dgrad, 1 = conv3x3 wgrad, < 0 = both.
+ * every tcgen05 conv launch (and the fused loss passes) on its own stream. family 0 = conv3x3 forward/dgrad,
+ * 1 = conv3x3 wgrad, 2 = fused scribble loss forward/backward (its "flops" are algorithmic BYTES), < 0 = both conv families.
  * pp_profile_collect returns the device time during which at least one launch of the family was running (union of
  * the launch intervals: weight-gradient kernels overlap dgrad on a side stream), the algorithmic FLOPs and the
  * launch count (HOST pointers). */

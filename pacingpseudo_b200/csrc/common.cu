@@ -69,7 +69,7 @@ int prof_collect(int family, double* ms, double* flops, long long* launches) {
   if (g_prof_used == 0) return PP_OK;
   std::vector<std::pair<float, float>> iv;
   for (size_t i = 0; i < g_prof_used; ++i) {
-    if (family >= 0 && g_prof[i].family != family) continue;
+    if (family >= 0 ? g_prof[i].family != family : g_prof[i].family > PROF_WGRAD) continue;   // < 0: both conv families
     PP_CHECK_CUDA(cudaEventSynchronize(g_prof[i].b));
     float ta = 0.f, tb = 0.f;
     if (i > 0) PP_CHECK_CUDA(cudaEventElapsedTime(&ta, g_prof[0].a, g_prof[i].a));

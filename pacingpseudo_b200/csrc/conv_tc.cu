@@ -45,16 +45,23 @@ struct ConvTcParams {
   int imgs_per_group, groups;  // images per BatchNorm statistics group / number of groups (stats != null)
 };
 
-template <int BLOCK_N, int BK>
-__global__ void __launch_bounds__(kTcThreads, (BLOCK_N <= 96) ? 3 : 1)
+// MT = consecutive 128-pixel M tiles per CTA (1, 2 or 4), each with its own TMEM accumulator; they share every weight
+// (B operand) stage. The kernel is bound by L2 -> shared-memory traffic (TMA), not by the tensor pipe: per 64-channel
+// K block a CTA fetches MT*16 KB of activations + BLOCK_N*128 B of weights for MT*128*BLOCK_N*64 MACs, so a larger
+// MT x BLOCK_N footprint raises the FLOPs per fetched byte (128x256: 96 B/cycle/SM at full tensor rate, 256x256: 64).
+template <int BLOCK_N, int BK, int MT>
+__global__ void __launch_bounds__(kTcThreads, (BLOCK_N <= 96 && MT == 1) ? 3 : 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
-  constexpr int A_BYTES = 128 * BK * 2;
+  constexpr int A_TILE = 128 * BK * 2;
+  constexpr int A_BYTES = MT * A_TILE;
   constexpr int B_BYTES = BLOCK_N * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t SWZ = (BK == 64) ? SWZ_128B : SWZ_64B;
   constexpr uint32_t SBO = 8 * BK * 2;  // 8 rows of one swizzle atom
-  constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
+  constexpr int TMEM_NEED = MT * BLOCK_N;
+  constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : (TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512)));
+  static_assert(TMEM_NEED <= 512, "accumulators do not fit TMEM");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -67,13 +74,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // tile coordinates
-  const int m_tile = blockIdx.x;
   const int n_tile = blockIdx.y;
-  const int tw = m_tile % p.tiles_w;
-  const int th = (m_tile / p.tiles_w) % p.tiles_h;
-  const int tn = m_tile / (p.tiles_w * p.tiles_h);
-  const int x0 = tw * p.bw, y0 = th * p.bh, n0 = tn * p.bn;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int num_k = 9 * (p.kc0 + p.kc1);
 
   if (warp == 0 && lane == 0) {
@@ -96,6 +98,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 0) {
     if (elect_one()) {
       // ===== TMA producer =====
+      int tx0[MT], ty0[MT], tn0[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {   // tiles past the end load out-of-range images: zero fill, never stored
+        const int mt = blockIdx.x * MT + m;
+        tx0[m] = (mt % p.tiles_w) * p.bw;
+        ty0[m] = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+        tn0[m] = (mt / tiles_per_img) * p.bn;
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tap = 0; tap < 9; ++tap) {
@@ -107,10 +117,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           int kofs;
           if (kc < p.kc0) {
-            tma_load_4d(sa, &tmA0, &full_bar[stage], kc * BK, x0 + ox, y0 + oy, n0);
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              tma_load_4d(sa + m * A_TILE, &tmA0, &full_bar[stage], kc * BK, tx0[m] + ox, ty0[m] + oy, tn0[m]);
             kofs = kc * BK;
           } else {
-            tma_load_4d(sa, &tmA1, &full_bar[stage], (kc - p.kc0) * BK, x0 + ox, y0 + oy, n0);
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              tma_load_4d(sa + m * A_TILE, &tmA1, &full_bar[stage], (kc - p.kc0) * BK, tx0[m] + ox, ty0[m] + oy, tn0[m]);
             kofs = p.c0 + (kc - p.kc0) * BK;
           }
           tma_load_3d(sb, &tmB, &full_bar[stage], kofs, n_tile * BLOCK_N, tap);
@@ -131,112 +145,125 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma_bf16_lohi(tmem_base, a_lo + k * 2, dhi, a_lo + (A_BYTES >> 4) + k * 2, dhi, idesc, (it | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < BK / 16; ++k) {
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+            umma_bf16_lohi(tmem_base + m * BLOCK_N, a_lo + m * (A_TILE >> 4) + k * 2, dhi,
+                           a_lo + (A_BYTES >> 4) + k * 2, dhi, idesc, (it | k) != 0 ? 1u : 0u);
+        }
         umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
         a_lo += STAGE_BYTES >> 4;
         if (++stage == p.stages) { stage = 0; phase ^= 1; a_lo = base_lo; }
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
+      umma_commit(tmem_full_bar);  // accumulators complete
     }
   } else {
     // ===== epilogue: TMEM -> registers -> (+bias, +old) -> bf16 NHWC =====
     const int q = warp & 3;          // TMEM lane quarter accessible to this warp
     const int r = q * 32 + lane;     // tile row == pixel index inside the box
     const int lx = r % p.bw, ly = (r / p.bw) % p.bh, ln = r / (p.bw * p.bh);
-    const int px = x0 + lx, py = y0 + ly, pn = n0 + ln;
-    const bool valid = (px < p.W) && (py < p.H) && (pn < p.N);
-    const long long pix = (static_cast<long long>(pn) * p.H + py) * p.W + px;
-
     const int col0 = n_tile * BLOCK_N;  // first GEMM column of this CTA
+    const int et = threadIdx.x - 64;    // 0..127 among the epilogue threads
+    const int cout = p.outc0 + p.outc1;
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 32) {
-      // destination of this 32-column chunk (a CTA tile may straddle the two concat sources in dgrad)
-      const int col = col0 + c;
-      __nv_bfloat16* dst;
-      int dstc, acc, ch;
-      if (col < p.outc0) { dst = p.out0; dstc = p.outc0; acc = p.acc0; ch = col; }
-      else               { dst = p.out1; dstc = p.outc1; acc = p.acc1; ch = col - p.outc0; }
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c), v);
-      tmem_wait_ld();
-      float f[32];
+    for (int m = 0; m < MT; ++m) {
+      const int mt = blockIdx.x * MT + m;
+      const int x0 = (mt % p.tiles_w) * p.bw, y0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+      const int n0 = (mt / tiles_per_img) * p.bn;
+      const int px = x0 + lx, py = y0 + ly, pn = n0 + ln;
+      const bool valid = (px < p.W) && (py < p.H) && (pn < p.N);
+      const long long pix = (static_cast<long long>(pn) * p.H + py) * p.W + px;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        // destination of this 32-column chunk (a CTA tile may straddle the two concat sources in dgrad)
+        const int col = col0 + c;
+        __nv_bfloat16* dst;
+        int dstc, acc, ch;
+        if (col < p.outc0) { dst = p.out0; dstc = p.outc0; acc = p.acc0; ch = col; }
+        else               { dst = p.out1; dstc = p.outc1; acc = p.acc1; ch = col - p.outc0; }
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(m * BLOCK_N + c), v);
+        tmem_wait_ld();
+        float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (p.bias != nullptr) {
-        if ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {   // 8 broadcast vector loads per chunk
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+          if ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {   // 8 broadcast vector loads per chunk
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bv = __ldg(b4 + j);
-            f[4 * j] += bv.x; f[4 * j + 1] += bv.y; f[4 * j + 2] += bv.z; f[4 * j + 3] += bv.w;
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(b4 + j);
+              f[4 * j] += bv.x; f[4 * j + 1] += bv.y; f[4 * j + 2] += bv.z; f[4 * j + 3] += bv.w;
+            }
+          } else {                                                 // any 4-byte aligned pointer is legal at the C ABI
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col + j);
           }
-        } else {                                                 // any 4-byte aligned pointer is legal at the C ABI
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col + j);
         }
-      }
-      if (valid) {
-        __nv_bfloat16* o = dst + pix * dstc + ch;
+        if (valid) {
+          __nv_bfloat16* o = dst + pix * dstc + ch;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          Vec8<__nv_bfloat16> pk;
-          float t[8];
-          if (acc) {
-            pk.load(o + g * 8);
-            pk.get(t);
+          for (int g = 0; g < 4; ++g) {
+            Vec8<__nv_bfloat16> pk;
+            float t[8];
+            if (acc) {
+              pk.load(o + g * 8);
+              pk.get(t);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[g * 8 + j] += t[j];
+              for (int j = 0; j < 8; ++j) f[g * 8 + j] += t[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = f[g * 8 + j];
+            pk.set(t);
+            pk.store(o + g * 8);
+            pk.get(t);   // statistics are taken of the bf16-ROUNDED values (what BatchNorm will read back)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[g * 8 + j] = t[j];
           }
+        }
+        if (p.stats != nullptr) {
+          // column sums over this warp's 32 rows: butterfly transpose-reduce, lane j ends with column j
+          float s1[32], s2[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) t[j] = f[g * 8 + j];
-          pk.set(t);
-          pk.store(o + g * 8);
-          pk.get(t);   // statistics are taken of the bf16-ROUNDED values (what BatchNorm will read back)
+          for (int j = 0; j < 32; ++j) { s1[j] = valid ? f[j] : 0.f; s2[j] = s1[j] * s1[j]; }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[g * 8 + j] = t[j];
+          for (int w = 16; w >= 1; w >>= 1) {
+            const bool hi = (lane & w) != 0;
+#pragma unroll
+            for (int j = 0; j < w; ++j) {
+              const float a1 = hi ? s1[j] : s1[j + w], a2 = hi ? s2[j] : s2[j + w];
+              const float k1 = hi ? s1[j + w] : s1[j], k2 = hi ? s2[j + w] : s2[j];
+              s1[j] = k1 + __shfl_xor_sync(0xffffffffu, a1, w);
+              s2[j] = k2 + __shfl_xor_sync(0xffffffffu, a2, w);
+            }
+          }
+          s_stats[(q * 2 + 0) * BLOCK_N + c + lane] = s1[0];   // one slot per warp: summed in a fixed order below,
+          s_stats[(q * 2 + 1) * BLOCK_N + c + lane] = s2[0];   // so a forward pass is bit-reproducible
         }
       }
       if (p.stats != nullptr) {
-        // column sums over this warp's 32 rows: butterfly transpose-reduce, lane j ends with column j
-        float s1[32], s2[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { s1[j] = valid ? f[j] : 0.f; s2[j] = s1[j] * s1[j]; }
-#pragma unroll
-        for (int w = 16; w >= 1; w >>= 1) {
-          const bool hi = (lane & w) != 0;
-#pragma unroll
-          for (int j = 0; j < w; ++j) {
-            const float a1 = hi ? s1[j] : s1[j + w], a2 = hi ? s2[j] : s2[j + w];
-            const float k1 = hi ? s1[j + w] : s1[j], k2 = hi ? s2[j + w] : s2[j];
-            s1[j] = k1 + __shfl_xor_sync(0xffffffffu, a1, w);
-            s2[j] = k2 + __shfl_xor_sync(0xffffffffu, a2, w);
+        // all rows of a tile belong to one statistics group (host guarantees bn | imgs_per_group or bn == 1)
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+        if (n0 < p.N) {
+          const int grp = n0 / p.imgs_per_group;
+          for (int i = et; i < 2 * BLOCK_N; i += 128) {
+            const int st = i / BLOCK_N, j = i % BLOCK_N, cc = col0 + j;
+            // kStatReplicas interleaved copies of the accumulator spread the same-address atomics of thousands of CTAs
+            const double tot = (static_cast<double>(s_stats[(0 * 2 + st) * BLOCK_N + j]) + s_stats[(1 * 2 + st) * BLOCK_N + j]) +
+                               (static_cast<double>(s_stats[(2 * 2 + st) * BLOCK_N + j]) + s_stats[(3 * 2 + st) * BLOCK_N + j]);
+            atomicAdd(p.stats + ((static_cast<long long>(mt % kStatReplicas) * p.groups + grp) * cout + cc) * 2 + st, tot);
           }
         }
-        s_stats[(q * 2 + 0) * BLOCK_N + c + lane] = s1[0];   // one slot per warp: summed in a fixed order below,
-        s_stats[(q * 2 + 1) * BLOCK_N + c + lane] = s2[0];   // so a forward pass is bit-reproducible
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }
     tc_fence_before();
   }
   __syncwarp();
   __syncthreads();
-  if (p.stats != nullptr) {
-    // all rows of a tile belong to one statistics group (host guarantees bn | imgs_per_group or bn == 1)
-    const int grp = n0 / p.imgs_per_group;
-    const int cout = p.outc0 + p.outc1;
-    for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kTcThreads) {
-      const int st = i / BLOCK_N, cc = n_tile * BLOCK_N + i % BLOCK_N;
-      // kStatReplicas interleaved copies of the accumulator spread the same-address atomics of thousands of CTAs
-      const int j = i % BLOCK_N;
-      const double tot = (static_cast<double>(s_stats[(0 * 2 + st) * BLOCK_N + j]) + s_stats[(1 * 2 + st) * BLOCK_N + j]) +
-                         (static_cast<double>(s_stats[(2 * 2 + st) * BLOCK_N + j]) + s_stats[(3 * 2 + st) * BLOCK_N + j]);
-      atomicAdd(p.stats + ((static_cast<long long>(m_tile % kStatReplicas) * p.groups + grp) * cout + cc) * 2 + st, tot);
-    }
-  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -626,29 +653,67 @@ static void pixel_box(int W, int H, int pixels, int* bw, int* bh, int* bn) {
 }
 static int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
 
-template <int BLOCK_N, int BK>
+static constexpr int conv_tc_stages(int block_n, int bk, int mt) {
+  const int stage_bytes = mt * 128 * bk * 2 + block_n * bk * 2;
+  // narrow single tiles are latency-bound per CTA: keep the footprint small enough for 3 CTAs per SM
+  int stages = (((block_n <= 96 && mt == 1) ? 70 : 200) * 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  return stages;
+}
+
+template <int BLOCK_N, int BK, int MT>
 static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, ConvTcParams p,
                           int m_tiles, int n_tiles, cudaStream_t stream) {
-  constexpr int STAGE_BYTES = 128 * BK * 2 + BLOCK_N * BK * 2;
+  constexpr int STAGE_BYTES = MT * 128 * BK * 2 + BLOCK_N * BK * 2;
   constexpr int TAIL = 1024 + 256 + 8 * BLOCK_N * 4;
-  // narrow tiles are latency-bound per CTA: keep the footprint small enough for 3 CTAs per SM
-  int stages = ((BLOCK_N <= 96 ? 70 : 200) * 1024) / STAGE_BYTES;
-  if (stages > kMaxStages) stages = kMaxStages;
+  int stages = conv_tc_stages(BLOCK_N, BK, MT);
   if (stages < 2) stages = 2;
   p.stages = stages;
   const int smem = stages * STAGE_BYTES + TAIL;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<BLOCK_N, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PP_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<BLOCK_N, BK, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        200 * 1024 + TAIL));
     attr_set = true;
   }
   const double flops = 2.0 * p.N * p.H * p.W * 9.0 * p.ctot * (p.outc0 + p.outc1);
   const int slot = prof_begin(PROF_CONV, flops, stream);
-  conv3x3_tc_kernel<BLOCK_N, BK><<<dim3(m_tiles, n_tiles), kTcThreads, smem, stream>>>(a0, a1, b, p);
+  conv3x3_tc_kernel<BLOCK_N, BK, MT><<<dim3(ceil_div(m_tiles, MT), n_tiles), kTcThreads, smem, stream>>>(a0, a1, b, p);
   prof_end(slot, stream);
   PP_LAUNCH_CHECK();
   return PP_OK;
+}
+
+// Tile shape (output channels per CTA, M tiles per CTA) from a small cost model: a CTA's time is the larger of its
+// tensor-pipe cycles and its L2 -> shared-memory fetch cycles (the chip sustains ~5.9 KB/cycle, i.e. ~40 B/cycle per
+// SM when all SMs stream), plus a fixed prologue and a per-accumulator-chunk epilogue; the kernel's time is that times
+// the number of waves of one CTA per SM. PP_CONV_MT=1 pins single-tile CTAs (A/B experiments).
+static void conv_tc_pick_tile(int cout, int ktot, int bk, int m_tiles, int* block_n_out, int* mt_out) {
+  static const int kTiles[6] = {256, 192, 128, 96, 64, 32};
+  static int max_mt = -1;
+  if (max_mt < 0) {
+    const char* e = getenv("PP_CONV_MT");
+    max_mt = (e != nullptr && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 4;
+  }
+  const double sms = sm_count();
+  double best = 1e300;
+  *block_n_out = 32; *mt_out = 1;
+  for (int t = 0; t < 6; ++t) {
+    const int bn = kTiles[t];
+    if (cout % bn != 0) continue;
+    for (int mt = 1; mt <= max_mt; mt *= 2) {
+      if (mt * bn > 512) break;
+      if (mt > 1 && conv_tc_stages(bn, bk, mt) < 3) break;
+      const double ctas = static_cast<double>(ceil_div(m_tiles, mt)) * (cout / bn);
+      const int per_sm = (bn <= 96 && mt == 1) ? 3 : 1;               // co-resident CTAs
+      const double waves = ceil(ctas / (sms * per_sm));
+      const double mma = static_cast<double>(mt) * 128.0 * bn * 9.0 * ktot / 4096.0 * per_sm;
+      const double l2 = 9.0 * ktot * 2.0 * (128.0 * mt + bn) / 40.0 * per_sm;
+      const double cta = (mma > l2 ? mma : l2) + 5000.0 + mt * (bn / 32) * 350.0 * per_sm;
+      const double cost = waves * cta;
+      if (cost < best) { best = cost; *block_n_out = bn; *mt_out = mt; }
+    }
+  }
 }
 
 // x0:[N,H,W,C0] x1:[N,H,W,C1] (or null), wpack:[9][outc0+outc1][C0+C1] bf16.
@@ -668,13 +733,6 @@ int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack
     return conv3x3_halo_tc(x0, C0, x1, C1, wpack, bias, out0, outc0, acc0, out1, outc1, acc1, N, H, W, stream, stats,
                            groups);
   const int bk = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
-  // N tile: the largest of {256,192,128,96,64,32} that divides the total output channels (a tile may straddle the two
-  // dgrad destinations: the epilogue picks the destination per 32-column chunk)
-  static const int kTiles[6] = {256, 192, 128, 96, 64, 32};
-  int block_n = 32;
-  for (int t = 0; t < 6; ++t)
-    if (cout % kTiles[t] == 0) { block_n = kTiles[t]; break; }
-
   ConvTcParams p{};
   p.N = N; p.H = H; p.W = W; p.dil = dil;
   pixel_box(W, H, 128, &p.bw, &p.bh, &p.bn);
@@ -682,9 +740,10 @@ int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack
   p.tiles_h = ceil_div(H, p.bh);
   const int tiles_n = ceil_div(N, p.bn);
   const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
-  // keep at least ~2 waves of CTAs when the problem allows it
-  while (block_n > 64 && block_n % 64 == 0 && static_cast<long long>(m_tiles) * (cout / block_n) < 2LL * sm_count())
-    block_n >>= 1;
+  // N tile (a divisor of the output channels; a tile may straddle the two dgrad destinations: the epilogue picks the
+  // destination per 32-column chunk) and M tiles per CTA
+  int block_n, mt;
+  conv_tc_pick_tile(cout, ctot, bk, m_tiles, &block_n, &mt);
   p.stats = stats;
   p.imgs_per_group = groups > 0 ? N / groups : N;
   p.groups = groups > 0 ? groups : 1;
@@ -706,14 +765,18 @@ int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack
   if (rc) return rc;
 
   const int n_tiles = cout / block_n;
-#define PP_CONV_CASE(BN_, BK_) \
-  if (block_n == BN_ && bk == BK_) return launch_conv_tc<BN_, BK_>(a0, a1, b, p, m_tiles, n_tiles, stream);
-  PP_CONV_CASE(256, 64) PP_CONV_CASE(192, 64) PP_CONV_CASE(128, 64) PP_CONV_CASE(96, 64) PP_CONV_CASE(64, 64)
-  PP_CONV_CASE(32, 64)
-  PP_CONV_CASE(256, 32) PP_CONV_CASE(192, 32) PP_CONV_CASE(128, 32) PP_CONV_CASE(96, 32) PP_CONV_CASE(64, 32)
-  PP_CONV_CASE(32, 32)
+#define PP_CONV_CASE(BN_, BK_, MT_) \
+  if (block_n == BN_ && bk == BK_ && mt == MT_) return launch_conv_tc<BN_, BK_, MT_>(a0, a1, b, p, m_tiles, n_tiles, stream);
+#define PP_CONV_CASES(BK_)                                                                                        \
+  PP_CONV_CASE(256, BK_, 1) PP_CONV_CASE(256, BK_, 2) PP_CONV_CASE(192, BK_, 1) PP_CONV_CASE(192, BK_, 2)          \
+  PP_CONV_CASE(128, BK_, 1) PP_CONV_CASE(128, BK_, 2) PP_CONV_CASE(128, BK_, 4) PP_CONV_CASE(96, BK_, 1)           \
+  PP_CONV_CASE(96, BK_, 2) PP_CONV_CASE(96, BK_, 4) PP_CONV_CASE(64, BK_, 1) PP_CONV_CASE(64, BK_, 2)              \
+  PP_CONV_CASE(64, BK_, 4) PP_CONV_CASE(32, BK_, 1) PP_CONV_CASE(32, BK_, 2) PP_CONV_CASE(32, BK_, 4)
+  PP_CONV_CASES(64)
+  PP_CONV_CASES(32)
+#undef PP_CONV_CASES
 #undef PP_CONV_CASE
-  set_error("conv3x3_tc: no kernel for block_n=%d bk=%d", block_n, bk);
+  set_error("conv3x3_tc: no kernel for block_n=%d bk=%d mt=%d", block_n, bk, mt);
   return PP_ERR_INVALID;
 }
 

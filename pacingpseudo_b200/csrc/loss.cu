@@ -254,12 +254,17 @@ int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const u
   const long long P = static_cast<long long>(N) * HW;
   PP_REQUIRE(P * C < (1LL << 31), "scribble_loss: %lld logits exceed the 32-bit index range", P * C);
   PP_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ACC_SLOTS, s));
+  // algorithmic bytes: every logits tensor read once, u8 target + fp32 mask read once
+  const double bytes = static_cast<double>(P) * ((1 + (zs != nullptr) + (za != nullptr)) * 4.0 * C + (target != nullptr) +
+                                                 4.0 * (mask != nullptr));
+  const int slot = prof_begin(PROF_LOSS, bytes, s);
   if (loss_vec4_ok(HW, zw, zs, za, target, mask))
     scribble_loss_fwd_kernel<4><<<grid_for_px(P / 4, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW, C,
                                                                         ignore_index, do_ent, cr_variant);
   else
     scribble_loss_fwd_kernel<1><<<grid_for_px(P, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW, C,
                                                                     ignore_index, do_ent, cr_variant);
+  prof_end(slot, s);
   scribble_loss_finalize_kernel<<<1, 32, 0, s>>>(acc, loss_pce, do_ent ? loss_ent : nullptr,
                                                  cr_variant != CR_NONE ? loss_cr : nullptr,
                                                  za != nullptr ? loss_aux : nullptr, P, C, mask != nullptr, cr_variant);
@@ -381,6 +386,11 @@ int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const u
   PP_REQUIRE(C >= 1 && C <= kMaxC, "scribble_loss_bwd: num_classes=%d unsupported", C);
   const long long P = static_cast<long long>(N) * HW;
   PP_REQUIRE(P * C < (1LL << 31), "scribble_loss_bwd: %lld logits exceed the 32-bit index range", P * C);
+  // algorithmic bytes: forward reads + one write per gradient tensor
+  const double bytes = static_cast<double>(P) * ((1 + (zs != nullptr) + (za != nullptr)) * 4.0 * C + (target != nullptr) +
+                                                 4.0 * (mask != nullptr) +
+                                                 ((dzw != nullptr) + (dzs != nullptr) + (dza != nullptr)) * 4.0 * C);
+  const int slot = prof_begin(PROF_LOSS, bytes, s);
   if (loss_vec4_ok(HW, zw, zs, za, target, mask, dzw, dzs, dza))
     scribble_loss_bwd_kernel<4><<<grid_for_px(P / 4, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent,
                                                                         g_cr, g_aux, dzw, dzs, dza, int(P), HW, C,
@@ -389,6 +399,7 @@ int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const u
     scribble_loss_bwd_kernel<1><<<grid_for_px(P, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent, g_cr,
                                                                     g_aux, dzw, dzs, dza, int(P), HW, C, ignore_index,
                                                                     do_ent, cr_variant, detach_weak);
+  prof_end(slot, s);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

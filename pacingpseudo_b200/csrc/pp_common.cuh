@@ -48,7 +48,7 @@ void set_error(const char* fmt, ...);
 // the launching stream so bench.py can attribute time and algorithmic FLOPs to the dominant kernel.
 void count_launches(int n);
 long long launch_count();
-enum : int { PROF_CONV = 0, PROF_WGRAD = 1, PROF_FAMILIES = 2 };
+enum : int { PROF_CONV = 0, PROF_WGRAD = 1, PROF_LOSS = 2, PROF_FAMILIES = 3 };  // PROF_LOSS counts BYTES, not FLOPs
 void prof_enable(int on);
 int prof_begin(int family, double flops, cudaStream_t s);   // -> slot or -1 when profiling is off
 void prof_end(int slot, cudaStream_t s);
