@@ -19,7 +19,7 @@
 
 namespace pp {
 
-static constexpr int kHaloThreads = 192;
+static constexpr int kHaloThreads = 320;   // TMA producer + MMA issuer + 8 epilogue warps (two per TMEM lane quarter)
 static constexpr int kMaxRing = 8;   // input-row ring slots: 3 live rows + up to 5 rows of TMA prefetch in flight
 static constexpr int kTW = 128;      // output columns per strip == MMA M
 static constexpr int kBoxW = kTW + 2;
@@ -84,7 +84,7 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     tma_prefetch_desc(&tmB);
     mbar_init(w_full, 1);
     for (int s = 0; s < kRing; ++s) { mbar_init(&row_full[s], 1); mbar_init(&row_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -164,18 +164,22 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     }
   } else {
     // ===== epilogue: TMEM -> registers -> (+bias, +old) -> bf16 NHWC (+ BatchNorm partial sums) =====
-    // The epilogue is instruction-bound on these narrow tiles (ncu: issue slots 40 % busy, tensor pipe 15 %), so the
-    // bias lives in registers and the BatchNorm column sums are accumulated per thread across all rows of the job;
-    // the 32-lane transpose-reduce runs once per job instead of once per row.
-    constexpr int NCH = BLOCK_N / 32;
+    // The epilogue of a row is a serial instruction stream per warp (ncu: issue slots 40 % busy, tensor pipe 15 %) and
+    // paces these narrow tiles, so EIGHT warps share it: two per TMEM lane quarter, each owning half of the columns in
+    // units of 16. The bias lives in L1, the BatchNorm column sums are accumulated per thread across all rows of the
+    // job and the lane transpose-reduce runs once per job instead of once per row.
+    constexpr int UNITS = BLOCK_N / 32;        // 16-column units per warp (half of the tile's BLOCK_N / 16 units)
     constexpr bool kStatsOk = BLOCK_N <= 64;   // statistics are a forward-pass feature (Cout 32 / 64)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int cbeg = half * (BLOCK_N / 2);     // first column of this warp
     const int px = x0 + q * 32 + lane;
     const bool col_ok = px < p.W;
-    float s1[kStatsOk ? BLOCK_N : 1], s2[kStatsOk ? BLOCK_N : 1];
+    const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+    float s1[kStatsOk ? UNITS * 16 : 1], s2[kStatsOk ? UNITS * 16 : 1];
     if constexpr (kStatsOk) {
 #pragma unroll
-      for (int j = 0; j < BLOCK_N; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      for (int j = 0; j < UNITS * 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
     }
     for (int t = 0; t < rows; ++t) {
       const int b = t & 1;
@@ -183,35 +187,35 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       tc_fence_after();
       const long long pix = (static_cast<long long>(img) * p.H + (r0 + t)) * p.W + px;
 #pragma unroll
-      for (int cc = 0; cc < NCH; ++cc) {
-        const int c = cc * 32;
+      for (int u = 0; u < UNITS; ++u) {
+        const int c = cbeg + u * 16;
         __nv_bfloat16* dst;
         int dstc, acc, ch;
         if (c < p.outc0) { dst = p.out0; dstc = p.outc0; acc = p.acc0; ch = c; }
         else             { dst = p.out1; dstc = p.outc1; acc = p.acc1; ch = c - p.outc0; }
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * TMEM_BUF + c), v);
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * TMEM_BUF + c), v);
         tmem_wait_ld();
-        float f[32];
+        float f[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
         if (p.bias != nullptr) {
-          if ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {   // 8 broadcast vector loads per chunk
+          if (bias_vec) {   // broadcast vector loads
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               const float4 bv = __ldg(b4 + j);
               f[4 * j] += bv.x; f[4 * j + 1] += bv.y; f[4 * j + 2] += bv.z; f[4 * j + 3] += bv.w;
             }
-          } else {                                                 // any 4-byte aligned pointer is legal at the C ABI
+          } else {          // any 4-byte aligned pointer is legal at the C ABI
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + c + j);
+            for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + c + j);
           }
         }
         if (col_ok) {
           __nv_bfloat16* o = dst + pix * dstc + ch;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 2; ++g) {
             Vec8<__nv_bfloat16> pk;
             float tt[8];
             if (acc) {
@@ -228,8 +232,8 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
               pk.get(tt);   // statistics of the ROUNDED values (what BatchNorm reads back)
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                s1[c + g * 8 + j] += tt[j];
-                s2[c + g * 8 + j] = fmaf(tt[j], tt[j], s2[c + g * 8 + j]);
+                s1[u * 16 + g * 8 + j] += tt[j];
+                s2[u * 16 + g * 8 + j] = fmaf(tt[j], tt[j], s2[u * 16 + g * 8 + j]);
               }
             }
           }
@@ -242,13 +246,14 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     if constexpr (kStatsOk) {
       if (p.stats != nullptr) {
 #pragma unroll
-        for (int cc = 0; cc < NCH; ++cc) {
-          // column sums over this warp's 32 pixel columns: butterfly transpose-reduce, lane j ends with channel j
-          float a[32], bq[32];
+        for (int u = 0; u < UNITS; ++u) {
+          // column sums over this warp's 32 pixel columns: butterfly transpose-reduce of 16 values over lane bits
+          // 8,4,2,1 (lane j & 15 ends with channel j & 15), then one plain exchange across lane bit 16
+          float a[16], bq[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { a[j] = s1[cc * 32 + j]; bq[j] = s2[cc * 32 + j]; }
+          for (int j = 0; j < 16; ++j) { a[j] = s1[u * 16 + j]; bq[j] = s2[u * 16 + j]; }
 #pragma unroll
-          for (int w = 16; w >= 1; w >>= 1) {
+          for (int w = 8; w >= 1; w >>= 1) {
             const bool hi = (lane & w) != 0;
 #pragma unroll
             for (int j = 0; j < w; ++j) {
@@ -258,8 +263,12 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
               bq[j] = k2 + __shfl_xor_sync(0xffffffffu, a2, w);
             }
           }
-          s_stats[(q * 2 + 0) * BLOCK_N + cc * 32 + lane] = a[0];   // one slot per warp, summed in a fixed order below
-          s_stats[(q * 2 + 1) * BLOCK_N + cc * 32 + lane] = bq[0];
+          a[0] += __shfl_xor_sync(0xffffffffu, a[0], 16);
+          bq[0] += __shfl_xor_sync(0xffffffffu, bq[0], 16);
+          if (lane < 16) {   // one slot per (quarter, column): summed in a fixed order below
+            s_stats[(q * 2 + 0) * BLOCK_N + cbeg + u * 16 + lane] = a[0];
+            s_stats[(q * 2 + 1) * BLOCK_N + cbeg + u * 16 + lane] = bq[0];
+          }
         }
       }
     }

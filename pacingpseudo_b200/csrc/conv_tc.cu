@@ -24,7 +24,10 @@
 
 namespace pp {
 
-static constexpr int kTcThreads = 192;
+static constexpr int kTcThreads = 192;      // weight-gradient kernels: producer + MMA + 4 epilogue warps
+static constexpr int kConvThreads = 320;    // forward / dgrad: producer + MMA + 8 epilogue warps (two per TMEM lane
+                                            // quarter, alternating 32-column chunks): the epilogue of a tile is a
+                                            // serial instruction stream per warp and is NOT overlapped with MMAs
 static constexpr int kMaxStages = 8;
 
 struct ConvTcParams {
@@ -50,7 +53,7 @@ struct ConvTcParams {
 // K block a CTA fetches MT*16 KB of activations + BLOCK_N*128 B of weights for MT*128*BLOCK_N*64 MACs, so a larger
 // MT x BLOCK_N footprint raises the FLOPs per fetched byte (128x256: 96 B/cycle/SM at full tensor rate, 256x256: 64).
 template <int BLOCK_N, int BK, int MT>
-__global__ void __launch_bounds__(kTcThreads, (BLOCK_N <= 96 && MT == 1) ? 3 : 1)
+__global__ void __launch_bounds__(kConvThreads, (BLOCK_N <= 96 && MT == 1) ? 2 : 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
   constexpr int A_TILE = 128 * BK * 2;
@@ -160,10 +163,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   } else {
     // ===== epilogue: TMEM -> registers -> (+bias, +old) -> bf16 NHWC =====
     const int q = warp & 3;          // TMEM lane quarter accessible to this warp
+    const int half = (warp - 2) >> 2;   // the two warps of a quarter take alternating 32-column chunks
     const int r = q * 32 + lane;     // tile row == pixel index inside the box
     const int lx = r % p.bw, ly = (r / p.bw) % p.bh, ln = r / (p.bw * p.bh);
     const int col0 = n_tile * BLOCK_N;  // first GEMM column of this CTA
-    const int et = threadIdx.x - 64;    // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 64;    // 0..255 among the epilogue threads
     const int cout = p.outc0 + p.outc1;
 
     mbar_wait(tmem_full_bar, 0);
@@ -177,7 +181,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const bool valid = (px < p.W) && (py < p.H) && (pn < p.N);
       const long long pix = (static_cast<long long>(pn) * p.H + py) * p.W + px;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+      for (int c = half * 32; c < BLOCK_N; c += 64) {
         // destination of this 32-column chunk (a CTA tile may straddle the two concat sources in dgrad)
         const int col = col0 + c;
         __nv_bfloat16* dst;
@@ -246,10 +250,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
       if (p.stats != nullptr) {
         // all rows of a tile belong to one statistics group (host guarantees bn | imgs_per_group or bn == 1)
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
         if (n0 < p.N) {
           const int grp = n0 / p.imgs_per_group;
-          for (int i = et; i < 2 * BLOCK_N; i += 128) {
+          for (int i = et; i < 2 * BLOCK_N; i += 256) {
             const int st = i / BLOCK_N, j = i % BLOCK_N, cc = col0 + j;
             // kStatReplicas interleaved copies of the accumulator spread the same-address atomics of thousands of CTAs
             const double tot = (static_cast<double>(s_stats[(0 * 2 + st) * BLOCK_N + j]) + s_stats[(1 * 2 + st) * BLOCK_N + j]) +
@@ -257,7 +261,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             atomicAdd(p.stats + ((static_cast<long long>(mt % kStatReplicas) * p.groups + grp) * cout + cc) * 2 + st, tot);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
     tc_fence_before();
@@ -655,8 +659,8 @@ static int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
 
 static constexpr int conv_tc_stages(int block_n, int bk, int mt) {
   const int stage_bytes = mt * 128 * bk * 2 + block_n * bk * 2;
-  // narrow single tiles are latency-bound per CTA: keep the footprint small enough for 3 CTAs per SM
-  int stages = (((block_n <= 96 && mt == 1) ? 70 : 200) * 1024) / stage_bytes;
+  // narrow single tiles are latency-bound per CTA: keep the footprint small enough for 2 CTAs per SM
+  int stages = (((block_n <= 96 && mt == 1) ? 100 : 200) * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   return stages;
 }
@@ -678,7 +682,7 @@ static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CU
   }
   const double flops = 2.0 * p.N * p.H * p.W * 9.0 * p.ctot * (p.outc0 + p.outc1);
   const int slot = prof_begin(PROF_CONV, flops, stream);
-  conv3x3_tc_kernel<BLOCK_N, BK, MT><<<dim3(ceil_div(m_tiles, MT), n_tiles), kTcThreads, smem, stream>>>(a0, a1, b, p);
+  conv3x3_tc_kernel<BLOCK_N, BK, MT><<<dim3(ceil_div(m_tiles, MT), n_tiles), kConvThreads, smem, stream>>>(a0, a1, b, p);
   prof_end(slot, stream);
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -705,11 +709,11 @@ static void conv_tc_pick_tile(int cout, int ktot, int bk, int m_tiles, int* bloc
       if (mt * bn > 512) break;
       if (mt > 1 && conv_tc_stages(bn, bk, mt) < 3) break;
       const double ctas = static_cast<double>(ceil_div(m_tiles, mt)) * (cout / bn);
-      const int per_sm = (bn <= 96 && mt == 1) ? 3 : 1;               // co-resident CTAs
+      const int per_sm = (bn <= 96 && mt == 1) ? 2 : 1;               // co-resident CTAs
       const double waves = ceil(ctas / (sms * per_sm));
       const double mma = static_cast<double>(mt) * 128.0 * bn * 9.0 * ktot / 4096.0 * per_sm;
       const double l2 = 9.0 * ktot * 2.0 * (128.0 * mt + bn) / 40.0 * per_sm;
-      const double cta = (mma > l2 ? mma : l2) + 5000.0 + mt * (bn / 32) * 350.0 * per_sm;
+      const double cta = (mma > l2 ? mma : l2) + 5000.0 + mt * ((bn + 63) / 64) * 350.0 * per_sm;
       const double cost = waves * cta;
       if (cost < best) { best = cost; *block_n_out = bn; *mt_out = mt; }
     }
