@@ -47,8 +47,8 @@ struct UNetPlan {
   // caller's stream. dY lives in kDyBufs rotating buffers guarded by events. PP_NO_OVERLAP=1 disables it.
   static constexpr int kDyBufs = 3;
   static constexpr int kMaxParts = 2;   // forward: statistics groups on separate streams
-  mutable cudaStream_t side = nullptr;
-  mutable cudaEvent_t dy_ready[kDyBufs] = {}, buf_free[kDyBufs] = {}, join = nullptr;
+  mutable cudaStream_t side = nullptr, hi = nullptr;
+  mutable cudaEvent_t dy_ready[kDyBufs] = {}, buf_free[kDyBufs] = {}, join = nullptr, hi_done = nullptr;
   mutable cudaStream_t part_stream[kMaxParts] = {};
   mutable cudaEvent_t fork = nullptr, stat_order[kMaxParts] = {}, part_done[kMaxParts] = {};
   mutable int overlap = -1;   // -1: not initialised, 0: off, 1: on
@@ -173,6 +173,13 @@ static int overlap_init(const UNetPlan& pl) {
   const int on = (off != nullptr && off[0] == '1') ? 0 : 1;
   if (on) {
     PP_CHECK_CUDA(cudaStreamCreateWithFlags(&pl.side, cudaStreamNonBlocking));
+    const char* nohi = getenv("PP_NO_PRIORITY");
+    if (nohi == nullptr || nohi[0] != '1') {
+      int least = 0, greatest = 0;
+      PP_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      PP_CHECK_CUDA(cudaStreamCreateWithPriority(&pl.hi, cudaStreamNonBlocking, greatest));
+      PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.hi_done, cudaEventDisableTiming));
+    }
     for (int k = 0; k < UNetPlan::kDyBufs; ++k) {
       PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.dy_ready[k], cudaEventDisableTiming));
       PP_CHECK_CUDA(cudaEventCreateWithFlags(&pl.buf_free[k], cudaEventDisableTiming));
@@ -318,9 +325,21 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
 // aux path's gradient into encoder/stage5 and encoder/stage6. dfeat_act[i] = activation id.
 int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void* ws, int N, int H, int W, int G,
                   int training, const float* dlogits, int n_dfeat, const int* dfeat_act, const void* const* dfeat,
-                  float* const* grads, cudaStream_t s) {
+                  float* const* grads, cudaStream_t user_stream) {
   int rc = check_shape(pl, N, H, W, G);
   if (rc) return rc;
+  rc = overlap_init(pl);
+  if (rc) return rc;
+  // With overlap on, the critical chain (BatchNorm backward -> dgrad -> pool / upsample backward) runs on an internal
+  // HIGH-priority stream forked from the caller's stream, the weight gradients on an internal default-priority stream:
+  // when both have blocks pending, the block scheduler serves the chain first, so the HBM-bound chain kernels are not
+  // starved by the co-running wgrad CTAs. The caller's stream joins both at the end.
+  cudaStream_t s = user_stream;
+  if (pl.overlap == 1 && pl.hi != nullptr) {
+    PP_CHECK_CUDA(cudaEventRecord(pl.fork, user_stream));
+    PP_CHECK_CUDA(cudaStreamWaitEvent(pl.hi, pl.fork, 0));
+    s = pl.hi;
+  }
   const UNetLayout L = make_layout(pl, N, H, W, G);
   char* base = static_cast<char*>(ws);
   const int dt = pl.dtype;
@@ -347,8 +366,6 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
     written[a] = 1;
   }
 
-  rc = overlap_init(pl);
-  if (rc) return rc;
   const bool ov = pl.overlap == 1;
   cudaStream_t ws_ = ov ? pl.side : s;       // stream of the weight-gradient kernels
   bool buf_used[UNetPlan::kDyBufs] = {false, false, false};
@@ -449,9 +466,13 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
       written[op.src] = 1;
     }
   }
-  if (ov) {   // the caller's stream owns the result: every weight gradient is complete when its work is
+  if (ov) {   // the caller's stream owns the result: every gradient is complete when its work is
     PP_CHECK_CUDA(cudaEventRecord(pl.join, pl.side));
-    PP_CHECK_CUDA(cudaStreamWaitEvent(s, pl.join, 0));
+    PP_CHECK_CUDA(cudaStreamWaitEvent(user_stream, pl.join, 0));
+    if (s != user_stream) {
+      PP_CHECK_CUDA(cudaEventRecord(pl.hi_done, s));
+      PP_CHECK_CUDA(cudaStreamWaitEvent(user_stream, pl.hi_done, 0));
+    }
   }
   return PP_OK;
 }
@@ -480,6 +501,8 @@ void unet_destroy(UNetPlan* pl) {
       if (pl->buf_free[k]) cudaEventDestroy(pl->buf_free[k]);
     }
     if (pl->join) cudaEventDestroy(pl->join);
+    if (pl->hi_done) cudaEventDestroy(pl->hi_done);
+    if (pl->hi) cudaStreamDestroy(pl->hi);
     if (pl->side) cudaStreamDestroy(pl->side);
     if (pl->fork) cudaEventDestroy(pl->fork);
     for (int k = 0; k < UNetPlan::kMaxParts; ++k) {

@@ -646,3 +646,35 @@ def test_conv3x3_wgrad_oihw_split_k_deterministic(pp, case):
     narrow = any(c in (32, 64) and Co in (32, 64) for c in (C0, C1))   # 32/64-channel sources accumulate atomically
     if not narrow:
         assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("case", [(2, 32, 32, 2, 128), (1, 28, 28, 2, 256), (2, 64, 64, 2, 64), (3, 6, 4, 2, 32),
+                                  (1, 4, 5, 8, 32), (2, 16, 16, 1, 64), (1, 8, 8, 3, 64)])
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_upsample_nhwc_forward_backward_shapes(pp, case, precision):
+    """nn.Upsample(bilinear, align_corners=True) (unet.py:144) forward and backward at realistic sizes: the separable
+    shared-memory backward, its accumulate (+=) mode, and the gather fallback for large scale factors."""
+    L, PF, _ = pp
+    N, h, w, sc, C = case
+    code = PF.dtype_code(precision)
+    adt = PF.act_dtype(code)
+    tol = 1e-2 if precision == "bf16" else 1e-5
+    g = torch.Generator().manual_seed(h * 131 + w + sc)
+    a = torch.randn(N, C, h, w, generator=g)
+    gu = torch.randn(N, C, h * sc, w * sc, generator=g)
+    base = torch.randn(N, C, h, w, generator=g)
+    if precision == "bf16":
+        a, gu, base = a.bfloat16().float(), gu.bfloat16().float(), base.bfloat16().float()
+    ar = a.clone().requires_grad_()
+    u_ref = F.interpolate(ar, size=(h * sc, w * sc), mode="bilinear", align_corners=True)
+    u_ref.backward(gu)
+    u = torch.empty(N, h * sc, w * sc, C, dtype=adt, device="cuda")
+    L.call("pp_upsample_nhwc_fwd", code, _p(_nhwc(a, adt)), _p(u), N, h, w, h * sc, w * sc, C, _st())
+    assert _rel(u.float().permute(0, 3, 1, 2), u_ref.detach()) < tol
+    gu_d = _nhwc(gu, adt)
+    ga = torch.empty(N, h, w, C, dtype=adt, device="cuda")
+    L.call("pp_upsample_nhwc_bwd", code, _p(gu_d), _p(ga), N, h, w, h * sc, w * sc, C, 0, _st())
+    assert _rel(ga.float().permute(0, 3, 1, 2), ar.grad) < tol
+    gacc = _nhwc(base, adt)
+    L.call("pp_upsample_nhwc_bwd", code, _p(gu_d), _p(gacc), N, h, w, h * sc, w * sc, C, 1, _st())
+    assert _rel(gacc.float().permute(0, 3, 1, 2), ar.grad + base) < 2 * tol
