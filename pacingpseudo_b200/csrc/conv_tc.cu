@@ -642,6 +642,146 @@ conv3x3_wgrad_narrow_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __
 }
 
 // ----------------------------------------------------------------------------------------------
+// Row variant of the narrow wgrad (dilation 1, W % 64 == 0): the kernel above fetches NINE shifted X boxes per K block
+// and is bound by that L2 -> shared-memory re-fetch (ncu: ~1 GB through TMA for 200 MB of operands). Here a K block
+// is 64 consecutive pixels of one image row, and X arrives as THREE boxes of 66 pixels (rows y-1, y, y+1 with a
+// one-pixel halo each side); the horizontal taps are shared-memory row offsets of the MN-major descriptor (+0, +1, +2
+// pixel rows), the vertical taps are its MN chunks (LBO = box stride), so taps (ky = 0..2, kx) pack into one M = 128
+// MMA per kx (CI = 32: 3 x 32 rows used) or two (CI = 64: ky {0,1} and {2,-}). The unused chunk reads whatever follows
+// in shared memory; its accumulator rows are never stored.
+// ----------------------------------------------------------------------------------------------
+template <int CI, int NCOUT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3x3_wgrad_rows_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                             const WgradNarrowParams p) {
+  static_assert(NCOUT <= 64, "one dY box");
+  constexpr int PIXK = 64, XROWS = PIXK + 2;
+  constexpr int ROW_A = CI * 2, ROW_B = NCOUT * 2;
+  constexpr uint32_t SWZ_A = CI == 64 ? SWZ_128B : SWZ_64B;
+  constexpr uint32_t SWZ_B = NCOUT == 64 ? SWZ_128B : SWZ_64B;
+  constexpr int XBOX = (XROWS * ROW_A + 1023) / 1024 * 1024;   // box stride (1 KB aligned)
+  constexpr int YBOX = PIXK * ROW_B;
+  constexpr int STAGE_BYTES = 3 * XBOX + YBOX;
+  constexpr int GPK = CI == 32 ? 1 : 2;                         // MMA groups per kx
+  constexpr int NG = 3 * GPK;
+  constexpr int TMEM_NEED = NG * NCOUT;
+  constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+  static_assert(TMEM_NEED <= 512, "accumulators do not fit TMEM");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // one spare X box after the last stage: the unused MN chunk of the last stage's MMAs reads up to XBOX bytes past it
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * STAGE_BYTES + XBOX);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kb_begin = blockIdx.x * p.kb_per_cta;
+  const int kb_end = min(kb_begin + p.kb_per_cta, p.tiles_total);
+  const int num_k = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
+
+  if (num_k > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          const int tw = kb % p.tiles_w;
+          const int y = (kb / p.tiles_w) % p.H;
+          const int n = kb / (p.tiles_w * p.H);
+          const int x0 = tw * PIXK;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sx = smem + stage * STAGE_BYTES;
+          uint8_t* sy = sx + 3 * XBOX;
+          mbar_arrive_expect_tx(&full_bar[stage], 3 * XROWS * ROW_A + YBOX);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)   // out-of-range rows / columns arrive as zeros: the conv's padding
+            tma_load_4d(sx + ky * XBOX, &tmX, &full_bar[stage], 0, x0 - 1, y + ky - 1, n);
+          tma_load_4d(sy, &tmDY, &full_bar[stage], 0, x0, y, n);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, NCOUT, 1, 1);  // both operands MN-major
+        constexpr uint32_t ahi = smem_desc_hi(8 * ROW_A, SWZ_A), bhi = smem_desc_hi(8 * ROW_B, SWZ_B);
+        const uint32_t base_a = smem_desc_lo(smem_u32(smem), XBOX);
+        const uint32_t base_b = smem_desc_lo(smem_u32(smem) + 3 * XBOX, YBOX);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t soff = 0;
+        for (int it = 0; it < num_k; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            const int kx = g / GPK, kyb = (g % GPK) * 2;              // first vertical tap of the group
+            const uint32_t a_lo = base_a + soff + kyb * (XBOX >> 4) + kx * (ROW_A >> 4), b_lo = base_b + soff;
+#pragma unroll
+            for (int k = 0; k < PIXK / 16; ++k)
+              umma_bf16_lohi(tmem_base + g * NCOUT, a_lo + k * ROW_A, ahi, b_lo + k * ROW_B, bhi, idesc,
+                             (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          soff += STAGE_BYTES >> 4;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; soff = 0; }
+        }
+        umma_commit(tmem_full_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int r = q * 32 + lane;          // accumulator row = chunk * CI + ci
+      const int ci = r % CI, chunk = r / CI;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < NG; ++g) {
+        const int kx = g / GPK, ky = (g % GPK) * 2 + chunk;
+        const bool row_ok = (ky < 3) && (chunk < (CI == 32 ? 3 : 2)) && (ci < p.Csrc);
+        const int tap = ky * 3 + kx;
+#pragma unroll 1
+        for (int c = 0; c < NCOUT; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(g * NCOUT + c), v);
+          tmem_wait_ld();
+          if (row_ok) {
+            float* o = p.dw + (static_cast<long long>(tap) * p.Cout + c) * p.ctot + p.cbase + ci;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c + j < p.Cout) atomicAdd(o + static_cast<long long>(j) * p.ctot, __uint_as_float(v[j]));
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncwarp();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // Host launchers
 // ----------------------------------------------------------------------------------------------
 static int pow2_ceil(int v) {
@@ -871,10 +1011,60 @@ static int launch_wgrad_narrow(const void* dy, int Cout, const void* x, int Csrc
   return PP_OK;
 }
 
+template <int CI, int NCOUT>
+static int launch_wgrad_rows(const void* dy, int Cout, const void* x, int Csrc, int ctot, int cbase, float* dw, int N,
+                             int H, int W, cudaStream_t stream) {
+  WgradNarrowParams p{};
+  p.N = N; p.H = H; p.W = W; p.dil = 1;
+  constexpr int ROW_A = CI * 2, ROW_B = NCOUT * 2;
+  constexpr int XBOX = (66 * ROW_A + 1023) / 1024 * 1024;
+  constexpr int STAGE_BYTES = 3 * XBOX + 64 * ROW_B;
+  p.pixk = 64;
+  p.bw = 64; p.bh = 1; p.bn = 1;
+  p.tiles_w = W / 64;
+  p.tiles_h = H;
+  p.tiles_total = p.tiles_w * H * N;
+  p.Cout = Cout; p.Csrc = Csrc; p.ctot = ctot; p.cbase = cbase; p.dw = dw;
+  p.stages = (200 * 1024 - XBOX) / STAGE_BYTES;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  int ctas = sm_count() < p.tiles_total ? sm_count() : p.tiles_total;
+  p.kb_per_cta = ceil_div(p.tiles_total, ctas);
+  ctas = ceil_div(p.tiles_total, p.kb_per_cta);
+  CUtensorMap tx, tdy;
+  int rc = encode_tmap_nhwc(&tx, x, N, H, W, Csrc, CI, 66, 1, 1, CI == 64);
+  if (rc) return rc;
+  rc = encode_tmap_nhwc(&tdy, dy, N, H, W, Cout, NCOUT, 64, 1, 1, NCOUT == 64);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_rows_tc_kernel<CI, NCOUT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024 + 256));
+    attr_set = true;
+  }
+  const int smem = p.stages * STAGE_BYTES + XBOX + 1024 + 256;
+  const double flops = 2.0 * N * H * W * 9.0 * Csrc * Cout;
+  const int slot = prof_begin(PROF_WGRAD, flops, stream);
+  conv3x3_wgrad_rows_tc_kernel<CI, NCOUT><<<ctas, kTcThreads, smem, stream>>>(tx, tdy, p);
+  prof_end(slot, stream);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
 static bool narrow_ok(int Csrc, int Cout) { return (Csrc == 32 || Csrc == 64) && (Cout == 32 || Cout == 64); }
 
 static int wgrad_narrow(const void* dy, int Cout, const void* x, int Csrc, int ctot, int cbase, float* dw, int N, int H,
                         int W, int dil, cudaStream_t stream) {
+  static int rows_on = -1;
+  if (rows_on < 0) {
+    const char* e = getenv("PP_WGRAD_ROWS");
+    rows_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (rows_on && dil == 1 && W % 64 == 0) {   // row variant: X fetched 3x instead of 9x
+    if (Csrc == 32 && Cout == 32) return launch_wgrad_rows<32, 32>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, stream);
+    if (Csrc == 32 && Cout == 64) return launch_wgrad_rows<32, 64>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, stream);
+    if (Csrc == 64 && Cout == 32) return launch_wgrad_rows<64, 32>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, stream);
+    return launch_wgrad_rows<64, 64>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, stream);
+  }
   if (Csrc == 32 && Cout == 32) return launch_wgrad_narrow<32, 32>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, dil, stream);
   if (Csrc == 32 && Cout == 64) return launch_wgrad_narrow<32, 64>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, dil, stream);
   if (Csrc == 64 && Cout == 32) return launch_wgrad_narrow<64, 32>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, dil, stream);

@@ -17,6 +17,11 @@ static inline int grid_for(long long work, int block, int max_blocks_per_sm = 16
   return static_cast<int>(g);
 }
 
+// Block size of the BatchNorm apply / backward kernels. These HBM-bound kernels run CONCURRENTLY with the conv CTAs of
+// another stream (unet_plan.cu); a conv CTA holds ~36K of an SM's 64K registers, so small blocks (128 threads x <=128
+// registers = 16K) are what still fits beside it.
+static constexpr int kBnThreads = 128;
+
 // Hot loops index with 32-bit integers (a 64-bit div/mod costs ~100 instructions per element on the GPU); the
 // launchers check that the element counts fit.
 #define PP_REQUIRE_INT32(v, what) \
@@ -602,12 +607,12 @@ int bn_finalize(const double* sums, const float* gamma, const float* beta, float
 // a = lrelu(y * scale + shift). Blocks own (group, pixel chunk); a thread keeps one 8-channel vector's
 // coefficients in registers and streams pixels with four independent 16-byte loads in flight.
 template <typename T>
-__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ coef,
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ coef,
                                                        T* __restrict__ a, int Pg, int C, int chunk,
                                                        int chunks_per_group, float slope) {
   constexpr int U = 4;
   const int vecs = C / 8;
-  const int pl = 256 / vecs;
+  const int pl = kBnThreads / vecs;
   const int v = threadIdx.x % vecs, l = threadIdx.x / vecs;
   const int g = blockIdx.x / chunks_per_group;
   const int p0 = (blockIdx.x % chunks_per_group) * chunk;
@@ -647,11 +652,11 @@ static void bn_chunks(int G, long long Pg, int blocks_per_sm, int* chunk, int* c
 
 int bn_apply(int dtype, const void* y, const float* coef, void* a, int G, long long Pg, int C, float slope,
              cudaStream_t s) {
-  PP_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "bn_apply: C=%d unsupported", C);
+  PP_REQUIRE(C % 8 == 0 && C / 8 <= kBnThreads && kBnThreads % (C / 8) == 0, "bn_apply: C=%d unsupported", C);
   PP_REQUIRE_INT32(Pg * C, "bn_apply");
   int chunk, cpg;
-  bn_chunks(G, Pg, 8, &chunk, &cpg);
-  PP_DISPATCH_T(dtype, bn_apply_kernel<T><<<G * cpg, 256, 0, s>>>(static_cast<const T*>(y), coef, static_cast<T*>(a),
+  bn_chunks(G, Pg, 16, &chunk, &cpg);
+  PP_DISPATCH_T(dtype, bn_apply_kernel<T><<<G * cpg, kBnThreads, 0, s>>>(static_cast<const T*>(y), coef, static_cast<T*>(a),
                                                                   int(Pg), C, chunk, cpg, slope););
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -660,13 +665,13 @@ int bn_apply(int dtype, const void* y, const float* coef, void* a, int G, long l
 // Backward reduce: bsums[g][c][0..1] += sum dz, sum dz * xhat   with  z = y*scale+shift,
 // dz = da * (z > 0 ? 1 : slope),  xhat = (y - mean) * rstd.
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y,
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y,
                                                             const float* __restrict__ coef, double* __restrict__ bsums,
                                                             long long Pg, int C, long long chunk, int chunks_per_group,
                                                             float slope) {
-  __shared__ float red[256][17];
+  __shared__ float red[kBnThreads][17];
   const int vecs = C / 8;
-  const int pl = 256 / vecs;
+  const int pl = kBnThreads / vecs;
   const int v = threadIdx.x % vecs, l = threadIdx.x / vecs;
   const int g = blockIdx.x / chunks_per_group;
   const long long p0 = static_cast<long long>(blockIdx.x % chunks_per_group) * chunk;
@@ -708,7 +713,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
 #pragma unroll
   for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s[j]; red[threadIdx.x][8 + j] = ss[j]; }
   __syncthreads();
-  for (int t = threadIdx.x; t < 2 * C; t += 256) {
+  for (int t = threadIdx.x; t < 2 * C; t += kBnThreads) {
     const int c = t % C, st = t / C;
     double acc = 0.0;
     for (int k = 0; k < pl; ++k) acc += static_cast<double>(red[k * vecs + c / 8][st * 8 + c % 8]);
@@ -721,7 +726,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
 // derives k1/k2 of its 8 channels from the reduced sums, and block 0 also adds the parameter gradients
 // (dgamma += sum_g sum dz*xhat, dbeta += sum_g sum dz, eval mode: dbias += sum_g scale * sum dz).
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y,
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y,
                                                            const float* __restrict__ coef,
                                                            const double* __restrict__ bsums, T* __restrict__ dy,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -729,7 +734,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                            int chunks_per_group, int training, float slope) {
   constexpr int U = 4;
   const int vecs = C / 8;
-  const int pl = 256 / vecs;
+  const int pl = kBnThreads / vecs;
   const int v = threadIdx.x % vecs, l = threadIdx.x / vecs;
   const int g = blockIdx.x / chunks_per_group;
   const int p0 = (blockIdx.x % chunks_per_group) * chunk;
@@ -794,20 +799,20 @@ int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* 
            float* dbeta, float* dbias, void* dy, int G, long long Pg, int C, int training, float slope,
            cudaStream_t s) {
   (void)bcoef;   // kept in the signature (workspace layout); the apply pass reads the reduced sums directly
-  PP_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "bn_bwd: C=%d unsupported", C);
+  PP_REQUIRE(C % 8 == 0 && C / 8 <= kBnThreads && kBnThreads % (C / 8) == 0, "bn_bwd: C=%d unsupported", C);
   PP_REQUIRE_INT32(Pg * C, "bn_bwd");
   PP_CHECK_CUDA(cudaMemsetAsync(bsums, 0, sizeof(double) * 2 * G * C, s));
-  int cpg = (sm_count() * 4) / G;
+  int cpg = (sm_count() * 8) / G;
   if (cpg < 1) cpg = 1;
   long long chunk = ceil_div_ll(Pg, cpg);
-  if (chunk < 128) chunk = 128;
+  if (chunk < 64) chunk = 64;
   cpg = static_cast<int>(ceil_div_ll(Pg, chunk));
   int achunk, acpg;
-  bn_chunks(G, Pg, 8, &achunk, &acpg);
+  bn_chunks(G, Pg, 16, &achunk, &acpg);
   PP_DISPATCH_T(dtype,
-                bn_bwd_reduce_kernel<T><<<G * cpg, 256, 0, s>>>(static_cast<const T*>(da), static_cast<const T*>(y),
+                bn_bwd_reduce_kernel<T><<<G * cpg, kBnThreads, 0, s>>>(static_cast<const T*>(da), static_cast<const T*>(y),
                                                                 coef, bsums, Pg, C, chunk, cpg, slope);
-                bn_bwd_apply_kernel<T><<<G * acpg, 256, 0, s>>>(static_cast<const T*>(da), static_cast<const T*>(y),
+                bn_bwd_apply_kernel<T><<<G * acpg, kBnThreads, 0, s>>>(static_cast<const T*>(da), static_cast<const T*>(y),
                                                                 coef, bsums, static_cast<T*>(dy), dgamma, dbeta, dbias,
                                                                 G, int(Pg), C, achunk, acpg, training, slope););
   PP_LAUNCH_CHECK_N(2);

@@ -53,6 +53,8 @@ CONV_CASES = [
     (2, 32, 32, 64, 0, 64, 1), (2, 32, 32, 32, 0, 32, 1), (2, 16, 16, 256, 0, 512, 2), (2, 8, 8, 512, 512, 512, 1),
     (3, 16, 16, 64, 32, 32, 1), (1, 64, 64, 128, 64, 64, 1), (2, 8, 8, 512, 0, 512, 4), (1, 28, 28, 64, 0, 128, 1),
     (2, 8, 8, 512, 512, 64, 1),
+    # wide rows: smem-resident (halo) forward / dgrad and the row variant of the narrow weight gradient
+    (1, 8, 128, 32, 0, 32, 1), (1, 6, 192, 64, 32, 32, 1), (2, 4, 64, 64, 0, 64, 1), (1, 5, 128, 32, 0, 64, 1),
 ]
 
 
@@ -617,7 +619,10 @@ def test_device_prefetcher_and_loss_reader(pp):
 
 
 @pytest.mark.parametrize("case", [(4, 8, 8, 512, 512, 512, 1), (3, 16, 16, 512, 256, 256, 1), (2, 32, 32, 128, 0, 256, 2),
-                                  (2, 32, 32, 128, 64, 64, 1), (5, 8, 8, 512, 0, 512, 4), (1, 28, 28, 256, 0, 128, 1)])
+                                  (2, 32, 32, 128, 64, 64, 1), (5, 8, 8, 512, 0, 512, 4), (1, 28, 28, 256, 0, 128, 1),
+                                  # row variant of the narrow kernel with more K blocks per CTA than pipeline stages
+                                  # (regression: the unused MN chunk of the last stage read past the allocation)
+                                  (3, 256, 256, 64, 0, 32, 1), (4, 128, 128, 32, 0, 64, 1), (2, 256, 256, 64, 32, 32, 1)])
 def test_conv3x3_wgrad_oihw_split_k_deterministic(pp, case):
     """Weight gradient accumulated into the OIHW gradient through the split-K scratch path (256-row tiles, fixed-order
     reduction): matches torch CPU autograd, accumulates (+=), and two runs are bit-identical; the atomic path agrees."""
