@@ -1,6 +1,5 @@
 // common.cu — library state, error buffer, TMA tensor-map encoding.
 #include <stdarg.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -30,15 +29,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 
 int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
-
-bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("PP_PDL");
-    on = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return on == 1;
-}
 
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

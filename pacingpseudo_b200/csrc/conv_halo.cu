@@ -43,7 +43,6 @@ template <int BLOCK_N, int BK>
 __global__ void __launch_bounds__(kHaloThreads, BLOCK_N == 32 ? 2 : 1)
 conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                        const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
-  pdl_launch_dependents();
   constexpr int ROW = BK * 2;
   constexpr uint32_t SWZ = (BK == 64) ? SWZ_128B : SWZ_64B;
   constexpr uint32_t SBO = 8 * ROW;
@@ -93,7 +92,6 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = warp_uniform(*tmem_slot);
-  pdl_wait();   // everything above overlapped the previous kernel's tail; no global access before this point
 
   if (warp == 0) {
     if (elect_one()) {
@@ -330,7 +328,7 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     attr_set = true;
   }
   const int slot = prof_begin(PROF_CONV, flops, stream);
-  PP_KLAUNCH((conv3x3_halo_tc_kernel<BLOCK_N, BK>), jobs, kHaloThreads, smem, stream, a0, a1, b, p);
+  conv3x3_halo_tc_kernel<BLOCK_N, BK><<<jobs, kHaloThreads, smem, stream>>>(a0, a1, b, p);
   prof_end(slot, stream);
   PP_LAUNCH_CHECK();
   return PP_OK;

@@ -56,7 +56,6 @@ template <int BLOCK_N, int BK, int MT>
 __global__ void __launch_bounds__(kConvThreads, (BLOCK_N <= 96 && MT == 1) ? 2 : 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
-  pdl_launch_dependents();
   constexpr int A_TILE = 128 * BK * 2;
   constexpr int A_BYTES = MT * A_TILE;
   constexpr int B_BYTES = BLOCK_N * BK * 2;
@@ -98,7 +97,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = warp_uniform(*tmem_slot);
-  pdl_wait();   // everything above overlapped the previous kernel's tail; no global access before this point
 
   if (warp == 0) {
     if (elect_one()) {
@@ -306,7 +304,6 @@ template <int BLOCK_N, int MT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX0,
                         const __grid_constant__ CUtensorMap tmX1, const WgradTcParams p) {
-  pdl_launch_dependents();
   constexpr int PIXK = 64;                    // pixels (GEMM K) per pipeline stage
   constexpr int BOX_BYTES = PIXK * 128;       // one {64 ch x 64 px} box, 128-byte rows
   constexpr int A_BLOCK = 2 * BOX_BYTES;      // 128 output channels = 2 boxes
@@ -355,7 +352,6 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = warp_uniform(*tmem_slot);
-  pdl_wait();   // everything above overlapped the previous kernel's tail; no global access before this point
 
   if (num_k > 0) {
     if (warp == 0) {
@@ -514,7 +510,6 @@ template <int CI, int NCOUT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3x3_wgrad_narrow_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                                const WgradNarrowParams p) {
-  pdl_launch_dependents();
   constexpr int TPG = 128 / CI;                       // taps per MMA group
   constexpr int NG = (9 + TPG - 1) / TPG;             // 3 (CI = 32) or 5 (CI = 64)
   constexpr int ROW_A = CI * 2, ROW_B = (NCOUT < 64 ? NCOUT : 64) * 2;   // bytes per pixel row of a box
@@ -557,7 +552,6 @@ conv3x3_wgrad_narrow_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = warp_uniform(*tmem_slot);
-  pdl_wait();   // everything above overlapped the previous kernel's tail; no global access before this point
 
   if (num_k > 0) {
     if (warp == 0) {
@@ -660,7 +654,6 @@ template <int CI, int NCOUT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3x3_wgrad_rows_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                              const WgradNarrowParams p) {
-  pdl_launch_dependents();
   static_assert(NCOUT <= 64, "one dY box");
   constexpr int PIXK = 64, XROWS = PIXK + 2;
   constexpr int ROW_A = CI * 2, ROW_B = NCOUT * 2;
@@ -704,7 +697,6 @@ conv3x3_wgrad_rows_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = warp_uniform(*tmem_slot);
-  pdl_wait();   // everything above overlapped the previous kernel's tail; no global access before this point
 
   if (num_k > 0) {
     if (warp == 0) {
@@ -830,7 +822,7 @@ static int launch_conv_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CU
   }
   const double flops = 2.0 * p.N * p.H * p.W * 9.0 * p.ctot * (p.outc0 + p.outc1);
   const int slot = prof_begin(PROF_CONV, flops, stream);
-  PP_KLAUNCH((conv3x3_tc_kernel<BLOCK_N, BK, MT>), dim3(ceil_div(m_tiles, MT), n_tiles), kConvThreads, smem, stream, a0, a1, b, p);
+  conv3x3_tc_kernel<BLOCK_N, BK, MT><<<dim3(ceil_div(m_tiles, MT), n_tiles), kConvThreads, smem, stream>>>(a0, a1, b, p);
   prof_end(slot, stream);
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -948,7 +940,7 @@ static int launch_wgrad_tc(const CUtensorMap& dy, const CUtensorMap& x0, const C
   }
   const double flops = 2.0 * p.N * p.H * p.W * 9.0 * (p.C0 + p.C1) * p.Cout;
   const int slot = prof_begin(PROF_WGRAD, flops, stream);
-  PP_KLAUNCH((conv3x3_wgrad_tc_kernel<BLOCK_N, MT>), grid, kTcThreads, smem, stream, dy, x0, x1, p);
+  conv3x3_wgrad_tc_kernel<BLOCK_N, MT><<<grid, kTcThreads, smem, stream>>>(dy, x0, x1, p);
   prof_end(slot, stream);
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -961,8 +953,6 @@ static int launch_wgrad_tc(const CUtensorMap& dy, const CUtensorMap& x0, const C
 __global__ void __launch_bounds__(256) wgrad_reduce_unpack_kernel(const float* __restrict__ ws, float* __restrict__ g,
                                                                   int splits, int Cout, int Cin, int ci_begin,
                                                                   int ci_count) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Cout * ci_count) return;
   const int co = idx / ci_count, ci = ci_begin + idx % ci_count;
@@ -1015,7 +1005,7 @@ static int launch_wgrad_narrow(const void* dy, int Cout, const void* x, int Csrc
   const int smem = p.stages * stage_bytes + 1024 + 256;
   const double flops = 2.0 * N * H * W * 9.0 * Csrc * Cout;
   const int slot = prof_begin(PROF_WGRAD, flops, stream);
-  PP_KLAUNCH((conv3x3_wgrad_narrow_tc_kernel<CI, NCOUT>), ctas, kTcThreads, smem, stream, tx, tdy, p);
+  conv3x3_wgrad_narrow_tc_kernel<CI, NCOUT><<<ctas, kTcThreads, smem, stream>>>(tx, tdy, p);
   prof_end(slot, stream);
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -1054,7 +1044,7 @@ static int launch_wgrad_rows(const void* dy, int Cout, const void* x, int Csrc, 
   const int smem = p.stages * STAGE_BYTES + XBOX + 1024 + 256;
   const double flops = 2.0 * N * H * W * 9.0 * Csrc * Cout;
   const int slot = prof_begin(PROF_WGRAD, flops, stream);
-  PP_KLAUNCH((conv3x3_wgrad_rows_tc_kernel<CI, NCOUT>), ctas, kTcThreads, smem, stream, tx, tdy, p);
+  conv3x3_wgrad_rows_tc_kernel<CI, NCOUT><<<ctas, kTcThreads, smem, stream>>>(tx, tdy, p);
   prof_end(slot, stream);
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -1159,7 +1149,7 @@ static int wgrad_wide(const void* dy, int Cout, const void* x0, int C0, const vo
   const int begins[2] = {cbase0, cbase1}, counts[2] = {C0, C1};
   for (int k = 0; k < 2; ++k) {
     if (counts[k] == 0) continue;
-    PP_KLAUNCH((wgrad_reduce_unpack_kernel), ceil_div(Cout * counts[k], 256), 256, 0, stream, ws_split, g_oihw, splits, Cout, ctot,
+    wgrad_reduce_unpack_kernel<<<ceil_div(Cout * counts[k], 256), 256, 0, stream>>>(ws_split, g_oihw, splits, Cout, ctot,
                                                                                    begins[k], counts[k]);
     PP_LAUNCH_CHECK();
   }

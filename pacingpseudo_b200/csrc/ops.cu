@@ -78,8 +78,6 @@ struct PackTable {
 };
 template <typename T>
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const __grid_constant__ PackTable tb) {
-  pdl_launch_dependents();
-  pdl_wait();
   __shared__ float tile[32][32 * 9 + 1];
   int l = 0;
   while (l + 1 < tb.n && static_cast<int>(blockIdx.x) >= tb.tile_begin[l + 1]) ++l;
@@ -116,7 +114,7 @@ int pack_weights_multi(int dtype, int n, const float* const* w, void* const* wf,
       tb.tile_begin[i + 1] = tb.tile_begin[i] + (cout[k] / 32) * (cin[k] / 32);
     }
     if (tb.tile_begin[tb.n] == 0) continue;
-    PP_DISPATCH_T(dtype, PP_KLAUNCH((pack_weights_multi_kernel<T>), tb.tile_begin[tb.n], 256, 0, s, tb););
+    PP_DISPATCH_T(dtype, pack_weights_multi_kernel<T><<<tb.tile_begin[tb.n], 256, 0, s>>>(tb););
     PP_LAUNCH_CHECK();
   }
   return PP_OK;
@@ -126,8 +124,6 @@ int pack_weights_multi(int dtype, int n, const float* const* w, void* const* wf,
 // [ci_begin, ci_begin + ci_count) only (multiples of 32).
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ g,
                                                            int Cout, int Cin, int ci_begin, int accumulate) {
-  pdl_launch_dependents();
-  pdl_wait();
   __shared__ float tile[32][32 * 9 + 1];
   const int co0 = blockIdx.y * 32, ci0 = ci_begin + blockIdx.x * 32;
   for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
@@ -146,8 +142,6 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
 __global__ void __launch_bounds__(256) unpack_wgrad_small_kernel(const float* __restrict__ dwp, float* __restrict__ g,
                                                                  int Cout, int Cin, int ci_begin, int ci_count,
                                                                  int accumulate) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int total = Cout * ci_count * 9;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -162,12 +156,12 @@ int unpack_wgrad_range(const float* dwp, float* g, int Cout, int Cin, int ci_beg
   PP_REQUIRE(Cout % 32 == 0 && ci_begin % 32 == 0 && ci_count % 32 == 0 && ci_begin + ci_count <= Cin,
              "unpack_wgrad: Cout=%d Cin=%d range [%d,+%d) must be multiples of 32", Cout, Cin, ci_begin, ci_count);
   if (Cout * ci_count <= 64 * 64) {
-    PP_KLAUNCH((unpack_wgrad_small_kernel), ceil_div(Cout * ci_count * 9, 256), 256, 0, s, dwp, g, Cout, Cin, ci_begin, ci_count,
+    unpack_wgrad_small_kernel<<<ceil_div(Cout * ci_count * 9, 256), 256, 0, s>>>(dwp, g, Cout, Cin, ci_begin, ci_count,
                                                                                 accumulate);
     PP_LAUNCH_CHECK();
     return PP_OK;
   }
-  PP_KLAUNCH((unpack_wgrad_kernel), dim3(ci_count / 32, Cout / 32), 256, 0, s, dwp, g, Cout, Cin, ci_begin, accumulate);
+  unpack_wgrad_kernel<<<dim3(ci_count / 32, Cout / 32), 256, 0, s>>>(dwp, g, Cout, Cin, ci_begin, accumulate);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -185,8 +179,6 @@ template <typename T>
 __global__ void __launch_bounds__(256) first_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, T* __restrict__ y, int N,
                                                              int H, int W, int Cout) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int vecs = Cout / 8;                 // power of two, <= 32 (checked by the launcher)
   const int v = threadIdx.x % vecs;
   const int ppb = 256 / vecs;                // pixels per block iteration
@@ -230,7 +222,8 @@ int first_conv_fwd(int dtype, const float* x, const float* w, const float* bias,
   const long long P = static_cast<long long>(N) * H * W;
   PP_REQUIRE_INT32(P * Cout, "first_conv_fwd");
   const int ppb = 256 / (Cout / 8);
-  PP_DISPATCH_T(dtype, PP_KLAUNCH((first_conv_fwd_kernel<T>), grid_for(ceil_div_ll(P, ppb) * 256, 256, 8), 256, 0, s, x, w, bias, static_cast<T*>(y), N, H, W, Cout););
+  PP_DISPATCH_T(dtype, first_conv_fwd_kernel<T><<<grid_for(ceil_div_ll(P, ppb) * 256, 256, 8), 256, 0, s>>>(
+                           x, w, bias, static_cast<T*>(y), N, H, W, Cout););
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -242,8 +235,6 @@ int first_conv_fwd(int dtype, const float* x, const float* w, const float* bias,
 template <typename T>
 __global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const T* __restrict__ dy, const float* __restrict__ x,
                                                                float* __restrict__ dw, int N, int H, int W, int Cout) {
-  pdl_launch_dependents();
-  pdl_wait();
   extern __shared__ float sacc[];  // [Cout*9]
   for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
@@ -306,7 +297,8 @@ int first_conv_wgrad(int dtype, const void* dy, const float* x, float* dw, int N
   PP_REQUIRE(pow2_vecs(Cout), "first_conv_wgrad: Cout=%d unsupported (8,16,...,256)", Cout);
   PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * Cout, "first_conv_wgrad");
   const int blocks = sm_count() * 2;
-  PP_DISPATCH_T(dtype, PP_KLAUNCH((first_conv_wgrad_kernel<T>), blocks, 256, Cout * 9 * sizeof(float), s, static_cast<const T*>(dy), x, dw, N, H, W, Cout););
+  PP_DISPATCH_T(dtype, first_conv_wgrad_kernel<T><<<blocks, 256, Cout * 9 * sizeof(float), s>>>(
+                           static_cast<const T*>(dy), x, dw, N, H, W, Cout););
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -323,8 +315,6 @@ template <typename T, int CIN, int NC>
 __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ a, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ logits,
                                                        int P, int HW, int C) {
-  pdl_launch_dependents();
-  pdl_wait();
   constexpr int VECS = CIN / 8, PPB = 256 / VECS;
   const int v = threadIdx.x % VECS;
   float wr[NC][8], br[NC];
@@ -375,8 +365,6 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ w, T* __restrict__ da,
                                                        float* __restrict__ dw, float* __restrict__ db, int P, int HW,
                                                        int C) {
-  pdl_launch_dependents();
-  pdl_wait();
   constexpr int VECS = CIN / 8, PPB = 256 / VECS;
   __shared__ float sacc[NC * CIN + NC];
   for (int i = threadIdx.x; i < NC * CIN + NC; i += blockDim.x) sacc[i] = 0.f;
@@ -465,7 +453,7 @@ int head_fwd(int dtype, const void* a, const float* w, const float* bias, float*
   PP_REQUIRE_INT32(P * Cin, "head_fwd");
   const int grid = grid_for(ceil_div_ll(P, 2 * (256 / (Cin / 8))) * 256, 256, 8);
 #define PP_HEAD_FWD(CIN_, NC_) \
-  PP_KLAUNCH((head_fwd_kernel<T, CIN_, NC_>), grid, 256, 0, s, static_cast<const T*>(a), w, bias, logits, int(P), HW, C)
+  head_fwd_kernel<T, CIN_, NC_><<<grid, 256, 0, s>>>(static_cast<const T*>(a), w, bias, logits, int(P), HW, C)
   PP_DISPATCH_T(dtype, PP_HEAD_DISPATCH(PP_HEAD_FWD););
 #undef PP_HEAD_FWD
   PP_LAUNCH_CHECK();
@@ -481,7 +469,7 @@ int head_bwd(int dtype, const float* dlogits, const void* a, const float* w, voi
   const long long need = ceil_div_ll(P, 2 * (256 / (Cin / 8)));
   if (grid > need) grid = static_cast<int>(need < 1 ? 1 : need);
 #define PP_HEAD_BWD(CIN_, NC_)                                                                                     \
-  PP_KLAUNCH((head_bwd_kernel<T, CIN_, NC_>), grid, 256, 0, s, dlogits, static_cast<const T*>(a), w, static_cast<T*>(da), dw, db, \
+  head_bwd_kernel<T, CIN_, NC_><<<grid, 256, 0, s>>>(dlogits, static_cast<const T*>(a), w, static_cast<T*>(da), dw, db, \
                                                      int(P), HW, C)
   PP_DISPATCH_T(dtype, PP_HEAD_DISPATCH(PP_HEAD_BWD););
 #undef PP_HEAD_BWD
@@ -498,8 +486,6 @@ int head_bwd(int dtype, const float* dlogits, const void* a, const float* w, voi
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, double* __restrict__ sums, long long Pg,
                                                        int C, long long chunk, int chunks_per_group) {
-  pdl_launch_dependents();
-  pdl_wait();
   __shared__ float red[256][17];
   const int vecs = C / 8;
   const int pl = 256 / vecs;                 // pixel lanes per block
@@ -550,7 +536,7 @@ int bn_stats(int dtype, const void* y, double* sums, int G, long long Pg, int C,
   long long chunk = ceil_div_ll(Pg, cpg);
   if (chunk < 256) chunk = 256;
   cpg = static_cast<int>(ceil_div_ll(Pg, chunk));
-  PP_DISPATCH_T(dtype, PP_KLAUNCH((bn_stats_kernel<T>), G * cpg, 256, 0, s, static_cast<const T*>(y), sums, Pg, C, chunk, cpg););
+  PP_DISPATCH_T(dtype, bn_stats_kernel<T><<<G * cpg, 256, 0, s>>>(static_cast<const T*>(y), sums, Pg, C, chunk, cpg););
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -565,8 +551,6 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restri
                                                           long long* __restrict__ num_batches_tracked,
                                                           float* __restrict__ coef, int G, long long Pg, int C,
                                                           int training, float eps, float momentum, int replicas) {
-  pdl_launch_dependents();
-  pdl_wait();
   // one warp per channel; the lanes fetch the replicated partial sums in parallel
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -614,7 +598,7 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restri
 int bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
                 long long* nbt, float* coef, int G, long long Pg, int C, int training, float eps, float momentum,
                 cudaStream_t s, int replicas) {
-  PP_KLAUNCH((bn_finalize_kernel), ceil_div(C, 4), 128, 0, s, sums, gamma, beta, running_mean, running_var, nbt, coef, G, Pg, C,
+  bn_finalize_kernel<<<ceil_div(C, 4), 128, 0, s>>>(sums, gamma, beta, running_mean, running_var, nbt, coef, G, Pg, C,
                                                     training, eps, momentum, replicas);
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -626,8 +610,6 @@ template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ coef,
                                                        T* __restrict__ a, int Pg, int C, int chunk,
                                                        int chunks_per_group, float slope) {
-  pdl_launch_dependents();
-  pdl_wait();
   constexpr int U = 4;
   const int vecs = C / 8;
   const int pl = kBnThreads / vecs;
@@ -674,7 +656,7 @@ int bn_apply(int dtype, const void* y, const float* coef, void* a, int G, long l
   PP_REQUIRE_INT32(Pg * C, "bn_apply");
   int chunk, cpg;
   bn_chunks(G, Pg, 16, &chunk, &cpg);
-  PP_DISPATCH_T(dtype, PP_KLAUNCH((bn_apply_kernel<T>), G * cpg, kBnThreads, 0, s, static_cast<const T*>(y), coef, static_cast<T*>(a),
+  PP_DISPATCH_T(dtype, bn_apply_kernel<T><<<G * cpg, kBnThreads, 0, s>>>(static_cast<const T*>(y), coef, static_cast<T*>(a),
                                                                   int(Pg), C, chunk, cpg, slope););
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -687,8 +669,6 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __re
                                                             const float* __restrict__ coef, double* __restrict__ bsums,
                                                             long long Pg, int C, long long chunk, int chunks_per_group,
                                                             float slope) {
-  pdl_launch_dependents();
-  pdl_wait();
   __shared__ float red[kBnThreads][17];
   const int vecs = C / 8;
   const int pl = kBnThreads / vecs;
@@ -752,8 +732,6 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            float* __restrict__ dbias, int G, int Pg, int C, int chunk,
                                                            int chunks_per_group, int training, float slope) {
-  pdl_launch_dependents();
-  pdl_wait();
   constexpr int U = 4;
   const int vecs = C / 8;
   const int pl = kBnThreads / vecs;
@@ -832,9 +810,9 @@ int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* 
   int achunk, acpg;
   bn_chunks(G, Pg, 16, &achunk, &acpg);
   PP_DISPATCH_T(dtype,
-                PP_KLAUNCH((bn_bwd_reduce_kernel<T>), G * cpg, kBnThreads, 0, s, static_cast<const T*>(da), static_cast<const T*>(y),
+                bn_bwd_reduce_kernel<T><<<G * cpg, kBnThreads, 0, s>>>(static_cast<const T*>(da), static_cast<const T*>(y),
                                                                 coef, bsums, Pg, C, chunk, cpg, slope);
-                PP_KLAUNCH((bn_bwd_apply_kernel<T>), G * acpg, kBnThreads, 0, s, static_cast<const T*>(da), static_cast<const T*>(y),
+                bn_bwd_apply_kernel<T><<<G * acpg, kBnThreads, 0, s>>>(static_cast<const T*>(da), static_cast<const T*>(y),
                                                                 coef, bsums, static_cast<T*>(dy), dgamma, dbeta, dbias,
                                                                 G, int(Pg), C, achunk, acpg, training, slope););
   PP_LAUNCH_CHECK_N(2);
@@ -848,8 +826,6 @@ int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* 
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H,
                                                           int W, int C) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int vecs = C / 8, Ho = H / 2, Wo = W / 2;
   const int total = N * Ho * Wo * vecs;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -877,8 +853,6 @@ template <typename T>
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy,
                                                           T* __restrict__ gx, int N, int H, int W, int C,
                                                           int accumulate) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int vecs = C / 8, Ho = H / 2, Wo = W / 2;
   const int total = N * Ho * Wo * vecs;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -927,7 +901,7 @@ int maxpool_fwd(int dtype, const void* x, void* y, int N, int H, int W, int C, c
   PP_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "maxpool_fwd: H=%d W=%d must be even, C=%d multiple of 8", H, W, C);
   PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * C, "maxpool_fwd");
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
-  PP_DISPATCH_T(dtype, PP_KLAUNCH((maxpool_fwd_kernel<T>), grid_for(total, 256), 256, 0, s, static_cast<const T*>(x),
+  PP_DISPATCH_T(dtype, maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(static_cast<const T*>(x),
                                                                                    static_cast<T*>(y), N, H, W, C););
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -937,7 +911,8 @@ int maxpool_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int H
   PP_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "maxpool_bwd: H=%d W=%d must be even, C=%d multiple of 8", H, W, C);
   PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * C, "maxpool_bwd");
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
-  PP_DISPATCH_T(dtype, PP_KLAUNCH((maxpool_bwd_kernel<T>), grid_for(total, 256), 256, 0, s, static_cast<const T*>(x), static_cast<const T*>(gy), static_cast<T*>(gx), N, H, W, C,
+  PP_DISPATCH_T(dtype, maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(
+                           static_cast<const T*>(x), static_cast<const T*>(gy), static_cast<T*>(gx), N, H, W, C,
                            accumulate););
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -982,8 +957,6 @@ __device__ __forceinline__ void lerp_range(int i, int out_size, float scale, int
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_nhwc_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N,
                                                                 int h, int w, int H, int W, int C, float sh, float sw) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int vecs = C / 8;
   const int rows = N * H;
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -1058,8 +1031,6 @@ template <typename T>
 __global__ void __launch_bounds__(256) upsample_nhwc_bwd_kernel(const T* __restrict__ gy, T* __restrict__ gx, int N,
                                                                 int h, int w, int H, int W, int C, float sh, float sw,
                                                                 int accumulate) {
-  pdl_launch_dependents();
-  pdl_wait();
   extern __shared__ float s_tx[];               // [w][kUpWin] weights, then [w] lo, [w] n (ints)
   int* s_lo = reinterpret_cast<int*>(s_tx + w * kUpWin);
   int* s_n = s_lo + w;
@@ -1138,7 +1109,8 @@ int upsample_nhwc_fwd(int dtype, const void* x, void* y, int N, int h, int w, in
   PP_REQUIRE(C % 8 == 0, "upsample_nhwc_fwd: C=%d must be a multiple of 8", C);
   PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * C, "upsample_nhwc_fwd");
   const int threads = W * (C / 8) >= 256 ? 256 : 128;
-  PP_DISPATCH_T(dtype, PP_KLAUNCH((upsample_nhwc_fwd_kernel<T>), grid_for(static_cast<long long>(N) * H * 256, 256, 32), threads, 0, s, static_cast<const T*>(x), static_cast<T*>(y), N, h, w, H, W, C, ac_scale(h, H),
+  PP_DISPATCH_T(dtype, upsample_nhwc_fwd_kernel<T><<<grid_for(static_cast<long long>(N) * H * 256, 256, 32), threads, 0, s>>>(
+                           static_cast<const T*>(x), static_cast<T*>(y), N, h, w, H, W, C, ac_scale(h, H),
                            ac_scale(w, W)););
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -1152,7 +1124,8 @@ int upsample_nhwc_bwd(int dtype, const void* gy, void* gx, int N, int h, int w, 
   PP_REQUIRE(smem <= 48 * 1024, "upsample_nhwc_bwd: input width %d too large", w);
   // (A separable variant that stages an fp32 row in 64 KB of shared memory halves the global loads, but its blocks can
   // no longer co-reside with the 200 KB conv CTAs this kernel overlaps with in the backward pass: 7.30 -> 7.51 ms/step.)
-  PP_DISPATCH_T(dtype, PP_KLAUNCH((upsample_nhwc_bwd_kernel<T>), grid_for(static_cast<long long>(N) * h * 256, 256, 8), threads, smem, s, static_cast<const T*>(gy), static_cast<T*>(gx), N, h, w, H, W, C, ac_scale(h, H),
+  PP_DISPATCH_T(dtype, upsample_nhwc_bwd_kernel<T><<<grid_for(static_cast<long long>(N) * h * 256, 256, 8), threads, smem, s>>>(
+                           static_cast<const T*>(gy), static_cast<T*>(gx), N, h, w, H, W, C, ac_scale(h, H),
                            ac_scale(w, W), accumulate););
   PP_LAUNCH_CHECK();
   return PP_OK;

@@ -62,30 +62,6 @@ void prof_reset();
   } while (0)
 #define PP_LAUNCH_CHECK() PP_LAUNCH_CHECK_N(1)
 
-// Programmatic dependent launch (PDL): kernels launched through PP_KLAUNCH may be scheduled while the previous kernel
-// of the stream is still draining; their prologue (barrier init, TMEM allocation, descriptor prefetch, index math)
-// overlaps that tail, and `pdl_wait()` blocks until the previous kernel has completed and its writes are visible.
-// EVERY kernel launched through PP_KLAUNCH must call pdl_wait() before its first global-memory access.
-// PP_PDL=0 turns the launch attribute off (then pdl_wait() is a no-op).
-bool pdl_enabled();
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                 Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-#define PP_KLAUNCH(kernel, grid, block, smem, stream, ...) \
-  (void)::pp::launch_kernel(kernel, grid, block, smem, stream, __VA_ARGS__)
-
 constexpr int kStatReplicas = 32;  // interleaved BatchNorm partial-sum accumulators written by the conv epilogue
 
 int sm_count();  // cached multiprocessor count of the current device (148 on B200)
@@ -227,10 +203,6 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       "r"(c3)
       : "memory");
 }
-
-// ---- programmatic dependent launch ------------------------------------------------------------------
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- tcgen05 / TMEM ---------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
