@@ -642,7 +642,7 @@ conv3x3_wgrad_narrow_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __
 }
 
 // ----------------------------------------------------------------------------------------------
-// Row variant of the narrow wgrad (dilation 1, W % 64 == 0): the kernel above fetches NINE shifted X boxes per K block
+// Row variant of the narrow wgrad (dilation 1, W >= 64): the kernel above fetches NINE shifted X boxes per K block
 // and is bound by that L2 -> shared-memory re-fetch (ncu: ~1 GB through TMA for 200 MB of operands). Here a K block
 // is 64 consecutive pixels of one image row, and X arrives as THREE boxes of 66 pixels (rows y-1, y, y+1 with a
 // one-pixel halo each side); the horizontal taps are shared-memory row offsets of the MN-major descriptor (+0, +1, +2
@@ -1021,7 +1021,7 @@ static int launch_wgrad_rows(const void* dy, int Cout, const void* x, int Csrc, 
   constexpr int STAGE_BYTES = 3 * XBOX + 64 * ROW_B;
   p.pixk = 64;
   p.bw = 64; p.bh = 1; p.bn = 1;
-  p.tiles_w = W / 64;
+  p.tiles_w = ceil_div(W, 64);
   p.tiles_h = H;
   p.tiles_total = p.tiles_w * H * N;
   p.Cout = Cout; p.Csrc = Csrc; p.ctot = ctot; p.cbase = cbase; p.dw = dw;
@@ -1059,7 +1059,8 @@ static int wgrad_narrow(const void* dy, int Cout, const void* x, int Csrc, int c
     const char* e = getenv("PP_WGRAD_ROWS");
     rows_on = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
-  if (rows_on && dil == 1 && W % 64 == 0) {   // row variant: X fetched 3x instead of 9x
+  if (rows_on && dil == 1 && W >= 64) {   // row variant: X fetched 3x instead of 9x (a ragged last 64-pixel block
+                                          // is zero-filled by TMA and contributes nothing)
     if (Csrc == 32 && Cout == 32) return launch_wgrad_rows<32, 32>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, stream);
     if (Csrc == 32 && Cout == 64) return launch_wgrad_rows<32, 64>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, stream);
     if (Csrc == 64 && Cout == 32) return launch_wgrad_rows<64, 32>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, stream);

@@ -797,11 +797,11 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
 
 int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* bsums, float* bcoef, float* dgamma,
            float* dbeta, float* dbias, void* dy, int G, long long Pg, int C, int training, float slope,
-           cudaStream_t s) {
+           cudaStream_t s, bool sums_zeroed) {
   (void)bcoef;   // kept in the signature (workspace layout); the apply pass reads the reduced sums directly
   PP_REQUIRE(C % 8 == 0 && C / 8 <= kBnThreads && kBnThreads % (C / 8) == 0, "bn_bwd: C=%d unsupported", C);
   PP_REQUIRE_INT32(Pg * C, "bn_bwd");
-  PP_CHECK_CUDA(cudaMemsetAsync(bsums, 0, sizeof(double) * 2 * G * C, s));
+  if (!sums_zeroed) PP_CHECK_CUDA(cudaMemsetAsync(bsums, 0, sizeof(double) * 2 * G * C, s));
   int cpg = (sm_count() * 8) / G;
   if (cpg < 1) cpg = 1;
   long long chunk = ceil_div_ll(Pg, cpg);

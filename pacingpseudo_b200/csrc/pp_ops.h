@@ -48,7 +48,8 @@ int bn_finalize(const double* sums, const float* gamma, const float* beta, float
 int bn_apply(int dtype, const void* y, const float* coef, void* a, int G, long long Pg, int C, float slope,
              cudaStream_t s);
 int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* bsums, float* bcoef, float* dgamma,
-           float* dbeta, float* dbias, void* dy, int G, long long Pg, int C, int training, float slope, cudaStream_t s);
+           float* dbeta, float* dbias, void* dy, int G, long long Pg, int C, int training, float slope, cudaStream_t s,
+           bool sums_zeroed = false);
 int maxpool_fwd(int dtype, const void* x, void* y, int N, int H, int W, int C, cudaStream_t s);
 int maxpool_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int H, int W, int C, int accumulate,
                 cudaStream_t s);

@@ -114,6 +114,8 @@ struct UNetLayout {
   std::vector<long long> act_data, act_grad;          // per activation
   std::vector<long long> yraw, coef, sums, wf, wd;     // per conv layer
   long long dy_scratch = 0, dy_stride = 0, dwp_scratch = 0, dws_scratch = 0, dws_floats = 0, bsums = 0, bcoef = 0;
+  long long sums_begin = 0, sums_bytes = 0, bsums_begin = 0, bsums_bytes = 0;
+  std::vector<long long> bsums_layer;
 };
 
 static UNetLayout make_layout(const UNetPlan& pl, int N, int H, int W, int G) {
@@ -132,13 +134,20 @@ static UNetLayout make_layout(const UNetPlan& pl, int N, int H, int W, int G) {
   for (const ConvL& c : pl.convs) {
     L.yraw.push_back(take(act_bytes(pl.acts[c.out])));
     L.coef.push_back(take(sizeof(float) * 4 * G * c.cout));
-    L.sums.push_back(take(sizeof(double) * 2 * G * c.cout * kStatReplicas));
     const long long wn = 9LL * c.cout * (c.cin0 + c.cin1);
     L.wf.push_back(take(wn * es));
     L.wd.push_back(take(wn * es));
     max_w = std::max(max_w, wn);
     max_c = std::max(max_c, c.cout);
   }
+  // BatchNorm partial sums of every layer, forward ([replica][group][C][2]) and backward ([group][C][2]), in ONE
+  // contiguous region each: a single memset per pass instead of one tiny memset per layer on the critical chain
+  L.sums_begin = off;
+  for (const ConvL& c : pl.convs) L.sums.push_back(take(sizeof(double) * 2 * G * c.cout * kStatReplicas));
+  L.sums_bytes = off - L.sums_begin;
+  L.bsums_begin = off;
+  for (const ConvL& c : pl.convs) L.bsums_layer.push_back(take(sizeof(double) * 2 * G * c.cout));
+  L.bsums_bytes = off - L.bsums_begin;
   L.dy_scratch = take(max_act);
   L.dy_stride = align_up(max_act);
   for (int k = 1; k < UNetPlan::kDyBufs; ++k) take(max_act);
@@ -218,6 +227,7 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
     }
     rc = pack_weights_multi(dt, int(pw.size()), pw.data(), pf.data(), pd.data(), co.data(), ci.data(), s);
     if (rc) return rc;
+    if (training) PP_CHECK_CUDA(cudaMemsetAsync(base + L.sums_begin, 0, L.sums_bytes, s));   // all layers' statistics
   }
   // Statistics groups (the weak and the strong branch of the siamese step) are independent until the losses, so
   // with overlap enabled every group runs on its own stream: the HBM-bound BatchNorm / pool / upsample kernels of one
@@ -269,7 +279,6 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
           const void* x0 = act_part(L.act_data[c.in0], pl.acts[c.in0], k);
           const void* x1 = c.in1 >= 0 ? act_part(L.act_data[c.in1], pl.acts[c.in1], k) : nullptr;
           if (dt == PP_BF16) {
-            if (fused_stats) PP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Gp * c.cout * kStatReplicas, sk));
             rc = conv3x3_tc(x0, c.cin0, x1, c.cin1, wf, static_cast<const float*>(pp[1]), yraw, c.cout, 0, nullptr, 0,
                             0, Np, h, w, c.dil, sk, fused_stats ? sums : nullptr, Gp);
           } else {
@@ -279,7 +288,6 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
         }
         if (rc) return rc;
         if (training && !fused_stats) {
-          PP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * Gp * c.cout, sk));
           rc = bn_stats(dt, yraw, sums, Gp, Pg, c.cout, sk);
           if (rc) return rc;
         }
@@ -368,6 +376,7 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
 
   const bool ov = pl.overlap == 1;
   cudaStream_t ws_ = ov ? pl.side : s;       // stream of the weight-gradient kernels
+  PP_CHECK_CUDA(cudaMemsetAsync(base + L.bsums_begin, 0, L.bsums_bytes, s));   // BatchNorm-backward sums of all layers
   bool buf_used[UNetPlan::kDyBufs] = {false, false, false};
   int nbuf = 0;
 
@@ -387,8 +396,9 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
       void* dy = base + L.dy_scratch + kb * L.dy_stride;
       if (ov && buf_used[kb]) PP_CHECK_CUDA(cudaStreamWaitEvent(s, pl.buf_free[kb], 0));   // its last reader is done
       rc = bn_bwd(dt, base + L.act_grad[c.out], base + L.yraw[op.layer],
-                  reinterpret_cast<const float*>(base + L.coef[op.layer]), reinterpret_cast<double*>(base + L.bsums),
-                  reinterpret_cast<float*>(base + L.bcoef), gg[2], gg[3], gg[1], dy, G, Pg, c.cout, training, 0.01f, s);
+                  reinterpret_cast<const float*>(base + L.coef[op.layer]),
+                  reinterpret_cast<double*>(base + L.bsums_layer[op.layer]), reinterpret_cast<float*>(base + L.bcoef),
+                  gg[2], gg[3], gg[1], dy, G, Pg, c.cout, training, 0.01f, s, /*sums_zeroed=*/true);
       if (rc) return rc;
       if (ov) {
         PP_CHECK_CUDA(cudaEventRecord(pl.dy_ready[kb], s));

@@ -55,6 +55,7 @@ CONV_CASES = [
     (2, 8, 8, 512, 512, 64, 1),
     # wide rows: smem-resident (halo) forward / dgrad and the row variant of the narrow weight gradient
     (1, 8, 128, 32, 0, 32, 1), (1, 6, 192, 64, 32, 32, 1), (2, 4, 64, 64, 0, 64, 1), (1, 5, 128, 32, 0, 64, 1),
+    (1, 7, 112, 64, 32, 32, 1), (1, 5, 224, 32, 0, 32, 1),   # ragged last 64-pixel block (ACDC / LVSC crops)
 ]
 
 
