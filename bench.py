@@ -19,6 +19,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_RESULT_OUT = sys.stdout
 
 GF_PER_PAIR = {  # algorithmic conv FLOPs per weak+strong pair, BASELINE.md section 3 (fwd F, bwd 2F)
     (256, 5): 348.25e9, (256, 4): 348.22e9, (224, 4): 266.61e9, (224, 2): 266.57e9,
@@ -115,7 +116,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 def workload_config(args, pairs_override=None):
@@ -416,12 +417,17 @@ def run_ours(args):
             "value": v, "unit": "img/s", "cores": cores, "kind": "port",
             "sample": "oracle port of the same pacingpseudo step, %d pair(s) of %dx%d per step, %d timed steps (%.1f s)" % (
                 pairs, S, S, len(times), sum(times))}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE JSON line: library chatter written to file descriptor 1 (e.g. NCCL's version banner)
+    # is sent to stderr for the whole run, and the result line goes to the saved descriptor.
+    global _RESULT_OUT
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

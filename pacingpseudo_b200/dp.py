@@ -22,6 +22,8 @@ def init_distributed(backend=None):
     if use_cuda:
         torch.cuda.set_device(local)
     if world > 1 and not dist.is_initialized():
+        # NCCL writes its banner / debug lines to stdout by default; keep stdout for the caller's own output
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         dist.init_process_group(backend or ("nccl" if use_cuda else "gloo"), rank=rank, world_size=world)
