@@ -411,7 +411,7 @@ def run_ours(args):
         },
     }
     if world == 1 and not args.no_cpu_baseline:
-        times, cores, pairs = cpu_pacing_steps(args, steps=2, warmup=1, pairs=1)
+        times, cores, pairs = cpu_pacing_steps(args, steps=12, warmup=1, pairs=2)   # ~10-15 s of host work
         v = pairs * len(times) / sum(times)
         line["cpu_baseline"] = {
             "value": v, "unit": "img/s", "cores": cores, "kind": "port",
