@@ -52,21 +52,26 @@ enum : int { CR_NONE = 0, CR_CE = 1, CR_L1 = 2, CR_L2 = 3, CR_KL = 4 };
 // accumulator slots (double)
 enum : int { ACC_PCE = 0, ACC_NLAB = 1, ACC_ENT = 2, ACC_MASK = 3, ACC_CR = 4, ACC_AUX = 5, ACC_SLOTS = 8 };
 
-struct Softmax {
-  float p[kMaxC], lp[kMaxC];
+// NC = compile-time class capacity of the per-pixel arrays: the fused scribble-loss kernels are instantiated for
+// NC in {2, 4, 5, 8} so that C = 5 (CHAOS) does not carry 8-wide register arrays (162 -> ~100 registers, 2x occupancy)
+template <int NC>
+struct SoftmaxT {
+  float p[NC], lp[NC];
 };
-__device__ __forceinline__ void softmax_of(const float (&v)[kMaxC], int C, Softmax& s) {
+using Softmax = SoftmaxT<kMaxC>;
+template <int NC>
+__device__ __forceinline__ void softmax_of(const float (&v)[NC], int C, SoftmaxT<NC>& s) {
   float mx = -INFINITY;
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c)
+  for (int c = 0; c < NC; ++c)
     if (c < C) mx = fmaxf(mx, v[c]);
   float sum = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c)
+  for (int c = 0; c < NC; ++c)
     if (c < C) { s.p[c] = __expf(v[c] - mx); sum += s.p[c]; }
   const float inv = 1.f / sum, lse = mx + __logf(sum);
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c)
+  for (int c = 0; c < NC; ++c)
     if (c < C) { s.p[c] *= inv; s.lp[c] = v[c] - lse; }
     else { s.p[c] = 0.f; s.lp[c] = 0.f; }
 }
@@ -78,10 +83,10 @@ __device__ __forceinline__ void load_softmax(const float* __restrict__ z, long l
 }
 // V consecutive pixels of every class plane: one 16-byte load per plane when V == 4 (HW % 4 == 0 keeps the group
 // inside one image and 16-byte aligned), scalar loads when V == 1.
-template <int V>
-__device__ __forceinline__ void load_planes(const float* __restrict__ z, int HW, int C, float (&v)[V][kMaxC]) {
+template <int V, int NC>
+__device__ __forceinline__ void load_planes(const float* __restrict__ z, int HW, int C, float (&v)[V][NC]) {
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c) {
+  for (int c = 0; c < NC; ++c) {
     if (c < C) {
       if constexpr (V == 4) {
         const float4 q = __ldg(reinterpret_cast<const float4*>(z + static_cast<size_t>(c) * HW));
@@ -95,10 +100,10 @@ __device__ __forceinline__ void load_planes(const float* __restrict__ z, int HW,
     }
   }
 }
-template <int V>
-__device__ __forceinline__ void store_planes(float* __restrict__ z, int HW, int C, const float (&v)[V][kMaxC]) {
+template <int V, int NC>
+__device__ __forceinline__ void store_planes(float* __restrict__ z, int HW, int C, const float (&v)[V][NC]) {
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c)
+  for (int c = 0; c < NC; ++c)
     if (c < C) {
       if constexpr (V == 4)
         *reinterpret_cast<float4*>(z + static_cast<size_t>(c) * HW) = make_float4(v[0][c], v[1][c], v[2][c], v[3][c]);
@@ -125,10 +130,11 @@ __device__ __forceinline__ void load_target_mask(const uint8_t* __restrict__ tar
 }
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) - (v < 0.f); }
 
-__device__ __forceinline__ float cr_pixel(int variant, int C, const Softmax& w, const Softmax& s) {
+template <int NC>
+__device__ __forceinline__ float cr_pixel(int variant, int C, const SoftmaxT<NC>& w, const SoftmaxT<NC>& s) {
   float L = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c)
+  for (int c = 0; c < NC; ++c)
     if (c < C) {
       if (variant == CR_CE) L -= w.p[c] * s.lp[c];
       else if (variant == CR_L1) L += fabsf(s.p[c] - w.p[c]);
@@ -154,7 +160,7 @@ __device__ __forceinline__ void block_accumulate(float (&v)[6], double* __restri
   }
 }
 
-template <int V>
+template <int V, int NC>
 __global__ void __launch_bounds__(256)
 scribble_loss_fwd_kernel(const float* __restrict__ zw, const float* __restrict__ zs, const float* __restrict__ za,
                          const uint8_t* __restrict__ target, const float* __restrict__ mask, double* __restrict__ acc,
@@ -165,19 +171,19 @@ scribble_loss_fwd_kernel(const float* __restrict__ zw, const float* __restrict__
     const int p = gi * V;
     const int n = p / HW, hw = p - n * HW;
     const size_t off = static_cast<size_t>(n) * C * HW + hw;
-    float vw[V][kMaxC], vs[V][kMaxC], va[V][kMaxC];
+    float vw[V][NC], vs[V][NC], va[V][NC];
     int tv[V];
     float mv[V];
-    load_planes<V>(zw + off, HW, C, vw);
-    if (cr_variant != CR_NONE) load_planes<V>(zs + off, HW, C, vs);
+    load_planes<V, NC>(zw + off, HW, C, vw);
+    if (cr_variant != CR_NONE) load_planes<V, NC>(zs + off, HW, C, vs);
     load_target_mask<V>(target, mask, p, ignore_index, tv, mv);
     bool any_lab = false;
 #pragma unroll
     for (int j = 0; j < V; ++j) any_lab |= (target != nullptr) && (tv[j] != ignore_index) && (tv[j] < C);
-    if (za != nullptr && any_lab) load_planes<V>(za + off, HW, C, va);   // aux logits matter on labelled pixels only
+    if (za != nullptr && any_lab) load_planes<V, NC>(za + off, HW, C, va);   // aux logits matter on labelled pixels only
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      Softmax w;
+      SoftmaxT<NC> w;
       softmax_of(vw[j], C, w);
       const int t = tv[j];
       const bool lab = (target != nullptr) && (t != ignore_index) && (t < C);
@@ -185,7 +191,7 @@ scribble_loss_fwd_kernel(const float* __restrict__ zw, const float* __restrict__
       if (lab) {
         float lpt = 0.f;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) lpt = (c == t) ? w.lp[c] : lpt;
+        for (int c = 0; c < NC; ++c) lpt = (c == t) ? w.lp[c] : lpt;
         part[ACC_PCE] -= lpt;
         part[ACC_NLAB] += 1.f;
       }
@@ -193,21 +199,21 @@ scribble_loss_fwd_kernel(const float* __restrict__ zw, const float* __restrict__
       if (do_ent) {
         float H = 0.f;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c)
+        for (int c = 0; c < NC; ++c)
           if (c < C) H -= w.p[c] * w.lp[c];
         part[ACC_ENT] += m * H;
       }
       if (cr_variant != CR_NONE) {
-        Softmax sx;
+        SoftmaxT<NC> sx;
         softmax_of(vs[j], C, sx);
         part[ACC_CR] += m * cr_pixel(cr_variant, C, w, sx);
       }
       if (za != nullptr && lab) {
-        Softmax a;
+        SoftmaxT<NC> a;
         softmax_of(va[j], C, a);
         float lpt = 0.f;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) lpt = (c == t) ? a.lp[c] : lpt;
+        for (int c = 0; c < NC; ++c) lpt = (c == t) ? a.lp[c] : lpt;
         part[ACC_AUX] -= lpt;
       }
     }
@@ -258,12 +264,16 @@ int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const u
   const double bytes = static_cast<double>(P) * ((1 + (zs != nullptr) + (za != nullptr)) * 4.0 * C + (target != nullptr) +
                                                  4.0 * (mask != nullptr));
   const int slot = prof_begin(PROF_LOSS, bytes, s);
-  if (loss_vec4_ok(HW, zw, zs, za, target, mask))
-    scribble_loss_fwd_kernel<4><<<grid_for_px(P / 4, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW, C,
-                                                                        ignore_index, do_ent, cr_variant);
-  else
-    scribble_loss_fwd_kernel<1><<<grid_for_px(P, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW, C,
-                                                                    ignore_index, do_ent, cr_variant);
+#define PP_LOSS_FWD(V_, NC_, P_)                                                                              \
+  scribble_loss_fwd_kernel<V_, NC_><<<grid_for_px(P_, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW, C, \
+                                                                         ignore_index, do_ent, cr_variant)
+  if (loss_vec4_ok(HW, zw, zs, za, target, mask)) {
+    if (C <= 2) PP_LOSS_FWD(4, 2, P / 4); else if (C <= 4) PP_LOSS_FWD(4, 4, P / 4);
+    else if (C == 5) PP_LOSS_FWD(4, 5, P / 4); else PP_LOSS_FWD(4, 8, P / 4);
+  } else {
+    PP_LOSS_FWD(1, 8, P);
+  }
+#undef PP_LOSS_FWD
   prof_end(slot, s);
   scribble_loss_finalize_kernel<<<1, 32, 0, s>>>(acc, loss_pce, do_ent ? loss_ent : nullptr,
                                                  cr_variant != CR_NONE ? loss_cr : nullptr,
@@ -272,7 +282,7 @@ int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const u
   return PP_OK;
 }
 
-template <int V>
+template <int V, int NC>
 __global__ void __launch_bounds__(256)
 scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__ zs, const float* __restrict__ za,
                          const uint8_t* __restrict__ target, const float* __restrict__ mask,
@@ -296,45 +306,45 @@ scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__
     const int p = gi * V;
     const int n = p / HW, hw = p - n * HW;
     const size_t off = static_cast<size_t>(n) * C * HW + hw;
-    float vw[V][kMaxC], vs[V][kMaxC], va[V][kMaxC];
+    float vw[V][NC], vs[V][NC], va[V][NC];
     int tv[V];
     float mv[V];
-    load_planes<V>(zw + off, HW, C, vw);
-    if (cr_variant != CR_NONE) load_planes<V>(zs + off, HW, C, vs);
+    load_planes<V, NC>(zw + off, HW, C, vw);
+    if (cr_variant != CR_NONE) load_planes<V, NC>(zs + off, HW, C, vs);
     load_target_mask<V>(target, mask, p, ignore_index, tv, mv);
     bool any_lab = false;
 #pragma unroll
     for (int j = 0; j < V; ++j) any_lab |= (target != nullptr) && (tv[j] != ignore_index) && (tv[j] < C);
     const bool do_aux = za != nullptr && dza != nullptr;
-    if (do_aux && any_lab) load_planes<V>(za + off, HW, C, va);
+    if (do_aux && any_lab) load_planes<V, NC>(za + off, HW, C, va);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      Softmax w;
+      SoftmaxT<NC> w;
       softmax_of(vw[j], C, w);
       const int t = tv[j];
       const bool lab = (target != nullptr) && (t != ignore_index) && (t < C);
       const float m = mv[j];
-      float d[kMaxC];
+      float d[NC];
 #pragma unroll
-      for (int c = 0; c < kMaxC; ++c) d[c] = lab ? gp * inv_lab * (w.p[c] - (c == t ? 1.f : 0.f)) : 0.f;
+      for (int c = 0; c < NC; ++c) d[c] = lab ? gp * inv_lab * (w.p[c] - (c == t ? 1.f : 0.f)) : 0.f;
       if (do_ent) {
         float H = 0.f;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c)
+        for (int c = 0; c < NC; ++c)
           if (c < C) H -= w.p[c] * w.lp[c];
         const float k = ge * m * inv_ent;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) d[c] -= k * w.p[c] * (w.lp[c] + H);
+        for (int c = 0; c < NC; ++c) d[c] -= k * w.p[c] * (w.lp[c] + H);
       }
       if (cr_variant != CR_NONE) {
-        Softmax sx;
+        SoftmaxT<NC> sx;
         softmax_of(vs[j], C, sx);
         const float k = gc * m * inv_cr;
-        float ds[kMaxC];
+        float ds[NC];
         if (cr_variant == CR_CE || cr_variant == CR_KL) {
           const float L = cr_pixel(cr_variant, C, w, sx);
 #pragma unroll
-          for (int c = 0; c < kMaxC; ++c) {
+          for (int c = 0; c < NC; ++c) {
             ds[c] = k * (sx.p[c] - w.p[c]);
             if (weak_gets_cr) {
               if (cr_variant == CR_CE) d[c] -= k * w.p[c] * (sx.lp[c] + L);
@@ -342,40 +352,40 @@ scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__
             }
           }
         } else {
-          float e[kMaxC], es = 0.f, ew = 0.f;
+          float e[NC], es = 0.f, ew = 0.f;
 #pragma unroll
-          for (int c = 0; c < kMaxC; ++c) {
+          for (int c = 0; c < NC; ++c) {
             const float df = sx.p[c] - w.p[c];
             e[c] = (c < C) ? (cr_variant == CR_L1 ? sgn(df) : 2.f * df) : 0.f;
             es = fmaf(e[c], sx.p[c], es);
             ew = fmaf(e[c], w.p[c], ew);
           }
 #pragma unroll
-          for (int c = 0; c < kMaxC; ++c) {
+          for (int c = 0; c < NC; ++c) {
             ds[c] = k * sx.p[c] * (e[c] - es);
             if (weak_gets_cr) d[c] += k * w.p[c] * (ew - e[c]);
           }
         }
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) vs[j][c] = ds[c];     // the strong logits are consumed: reuse as output
+        for (int c = 0; c < NC; ++c) vs[j][c] = ds[c];     // the strong logits are consumed: reuse as output
       }
 #pragma unroll
-      for (int c = 0; c < kMaxC; ++c) vw[j][c] = d[c];
+      for (int c = 0; c < NC; ++c) vw[j][c] = d[c];
       if (do_aux) {
         if (lab) {
-          Softmax a;
+          SoftmaxT<NC> a;
           softmax_of(va[j], C, a);
 #pragma unroll
-          for (int c = 0; c < kMaxC; ++c) va[j][c] = ga * inv_lab * (a.p[c] - (c == t ? 1.f : 0.f));
+          for (int c = 0; c < NC; ++c) va[j][c] = ga * inv_lab * (a.p[c] - (c == t ? 1.f : 0.f));
         } else {
 #pragma unroll
-          for (int c = 0; c < kMaxC; ++c) va[j][c] = 0.f;
+          for (int c = 0; c < NC; ++c) va[j][c] = 0.f;
         }
       }
     }
-    if (cr_variant != CR_NONE && dzs != nullptr) store_planes<V>(dzs + off, HW, C, vs);
-    if (dzw != nullptr) store_planes<V>(dzw + off, HW, C, vw);
-    if (do_aux) store_planes<V>(dza + off, HW, C, va);
+    if (cr_variant != CR_NONE && dzs != nullptr) store_planes<V, NC>(dzs + off, HW, C, vs);
+    if (dzw != nullptr) store_planes<V, NC>(dzw + off, HW, C, vw);
+    if (do_aux) store_planes<V, NC>(dza + off, HW, C, va);
   }
 }
 
@@ -391,14 +401,17 @@ int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const u
                                                  4.0 * (mask != nullptr) +
                                                  ((dzw != nullptr) + (dzs != nullptr) + (dza != nullptr)) * 4.0 * C);
   const int slot = prof_begin(PROF_LOSS, bytes, s);
-  if (loss_vec4_ok(HW, zw, zs, za, target, mask, dzw, dzs, dza))
-    scribble_loss_bwd_kernel<4><<<grid_for_px(P / 4, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent,
-                                                                        g_cr, g_aux, dzw, dzs, dza, int(P), HW, C,
-                                                                        ignore_index, do_ent, cr_variant, detach_weak);
-  else
-    scribble_loss_bwd_kernel<1><<<grid_for_px(P, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent, g_cr,
-                                                                    g_aux, dzw, dzs, dza, int(P), HW, C, ignore_index,
-                                                                    do_ent, cr_variant, detach_weak);
+#define PP_LOSS_BWD(V_, NC_, P_)                                                                                    \
+  scribble_loss_bwd_kernel<V_, NC_><<<grid_for_px(P_, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent, g_cr, \
+                                                                         g_aux, dzw, dzs, dza, int(P), HW, C,          \
+                                                                         ignore_index, do_ent, cr_variant, detach_weak)
+  if (loss_vec4_ok(HW, zw, zs, za, target, mask, dzw, dzs, dza)) {
+    if (C <= 2) PP_LOSS_BWD(4, 2, P / 4); else if (C <= 4) PP_LOSS_BWD(4, 4, P / 4);
+    else if (C == 5) PP_LOSS_BWD(4, 5, P / 4); else PP_LOSS_BWD(4, 8, P / 4);
+  } else {
+    PP_LOSS_BWD(1, 8, P);
+  }
+#undef PP_LOSS_BWD
   prof_end(slot, s);
   PP_LAUNCH_CHECK();
   return PP_OK;
