@@ -10,16 +10,11 @@
 
 #include "../../pacingpseudo_b200/csrc/pp_common.cuh"
 
+#include "../../pacingpseudo_b200/csrc/pp_ops.h"
+
 namespace pp {
 int init_device(int device);
 const char* last_error();
-int conv3x3_tc(const void*, int, const void*, int, const void*, const float*, void*, int, int, void*, int, int, int,
-               int, int, int, cudaStream_t, double* stats = nullptr, int groups = 1);
-int conv3x3_wgrad_tc(const void*, int, const void*, int, const void*, int, float*, float*, int, int, int, int, cudaStream_t);
-int conv3x3_simt(int, const void*, int, const void*, int, const void*, const float*, void*, int, int, void*, int, int,
-                 int, int, int, int, cudaStream_t);
-int conv3x3_wgrad_simt(int, const void*, int, const void*, int, const void*, int, float*, int, int, int, int,
-                       cudaStream_t);
 }  // namespace pp
 
 struct Case { int N, H, W, C0, C1, oc0, oc1, dil, acc; const char* name; };

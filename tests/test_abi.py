@@ -114,3 +114,13 @@ def test_dropin_modules_mirror_reference_state_dict():
         UNet(is_stride_conv=True, is_trans_conv=True)
     with pytest.raises(RuntimeError, match="CUDA"):
         UNet(1, 32, 512, 5, 8)(torch.zeros(1, 1, 16, 16))  # no CPU fallback
+
+
+def test_graft_build_compiles_library_and_standalone_checker():
+    """__graft_entry__.build() (the driver's 'does it build' check): the shared library and the standalone
+    tcgen05 cross-check binary (tests/cuda/test_conv_tc.cu, linked against the kernel objects) must both build, so a
+    changed kernel-launcher signature cannot silently break the binary."""
+    import __graft_entry__ as g
+    path = g.build()
+    assert os.path.exists(path)
+    assert os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "test_conv_tc"))
