@@ -5,12 +5,13 @@
 // per M tile; for the narrow layers that L2->SM traffic, not the tensor core, is the bound (ncu: tensor pipe 10 %,
 // ~2.5 us per tile). Here one CTA owns a strip of 128 output columns x L output rows of one image:
 //   * the packed weights of ALL 9 taps stay resident in shared memory (9 * Cout * Cin * 2 B <= ~72 KB);
-//   * each INPUT row segment (128 + 2 halo pixels, all channels) is loaded exactly once by TMA into a 4-slot ring;
+//   * each INPUT row segment (128 + 2 halo pixels, all channels) is loaded exactly once by TMA into a 4..8-slot ring;
 //   * the nine taps of an output row are nine views of three ring slots: the +-1 pixel shifts are shared-memory
 //     descriptor start offsets of +-1 row (128 B / 64 B). A B200 experiment (tests/cuda/exp_desc_shift.cu,
 //     profiles/r01_exp_umma_descriptor_row_shift.txt) shows the UMMA swizzle is a function of the absolute smem
 //     address, so a K-major swizzled descriptor may start at ANY row with base_offset = 0;
-//   * two TMEM accumulators: the epilogue of row y overlaps the MMAs of row y+1.
+//   * two TMEM accumulators: the epilogue of row y (eight warps, two per TMEM lane quarter) overlaps the MMAs of
+//     row y+1.
 // HBM traffic is the algorithmic minimum (input read once, output written once).
 //
 // Same semantics as conv3x3_tc (two concat sources, two dgrad destinations with accumulate flags, bias, fused

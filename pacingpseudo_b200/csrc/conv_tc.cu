@@ -6,20 +6,21 @@
 // (/root/reference/models/aux_path_memory.py:24): forward, data gradient and weight gradient.
 //
 //   forward / dgrad :  D[pixel, co] = sum_{tap, ci} X[pixel + off(tap), ci] * Wp[tap, co, ci]
-//       M = 128 output pixels (a {bw x bh x bn} box of the NHWC tensor), N = BLOCK_N channels,
-//       K = 9 taps x (C0 + C1) input channels walked in BK-channel slices. The A slice of one tap is
-//       ONE TMA box of the activation tensor shifted by (dx*dil, dy*dil): out-of-bounds rows/cols are
-//       zero-filled by the TMA unit, which is exactly the conv's zero padding. The channel concat
-//       of the decoder (torch.cat((up, skip), 1), unet.py:151) is never materialised: the K loop
-//       walks two tensor maps. dgrad is the same kernel on spatially flipped, transposed weights
-//       and can scatter its N tiles to two destination tensors (the two concat sources).
-//   wgrad :  dW[tap, co, ci] = sum_pixel dY[pixel, co] * X[pixel + off(tap), ci]
-//       M = 128 output channels, N = BLOCK_N input channels, K = pixels; both operands are the
-//       same NHWC TMA boxes, consumed as MN-major UMMA operands. Split-K over pixel ranges with
-//       fp32 red.global accumulation.
+//       M = MT x 128 output pixels (MT consecutive {bw x bh x bn} boxes of the NHWC tensor, one TMEM accumulator
+//       each), N = BLOCK_N channels, K = 9 taps x (C0 + C1) input channels walked in BK-channel slices. The A slice
+//       of one tap is ONE TMA box of the activation tensor shifted by (dx*dil, dy*dil): out-of-bounds rows/cols are
+//       zero-filled by the TMA unit, which is exactly the conv's zero padding. The channel concat of the decoder
+//       (torch.cat((up, skip), 1), unet.py:151) is never materialised: the K loop walks two tensor maps. dgrad is
+//       the same kernel on spatially flipped, transposed weights and can scatter its N tiles to two destination
+//       tensors (the two concat sources). 320 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer
+//       (one elected lane each), warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter).
+//   wgrad (wide) :  dW[tap, co, ci] = sum_pixel dY[pixel, co] * X[pixel + off(tap), ci]
+//       M = MT x 128 output channels, N = BLOCK_N input channels, K = pixels; both operands are the same NHWC TMA
+//       boxes, consumed as MN-major UMMA operands. Split-K over pixel ranges: either fp32 red.global accumulation,
+//       or (training step) per-split scratch slabs + a fixed-order reduction (deterministic). 192 threads.
+//   wgrad (32/64-channel sources) :  taps packed into the MMA M dimension; the row variant fetches X as three
+//       66-pixel row boxes per K block and realises the horizontal taps as descriptor row offsets.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
-// (one lane), warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
 #include "pp_common.cuh"
 
 namespace pp {
