@@ -235,7 +235,12 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
   // strong, as two reference forward passes would do): group g's finalize waits for group g-1's of the same layer.
   rc = overlap_init(pl);
   if (rc) return rc;
-  const int parts = (pl.overlap == 1 && G > 1 && G <= UNetPlan::kMaxParts) ? G : 1;
+  static int fwd_parts_on = -1;
+  if (fwd_parts_on < 0) {
+    const char* e = getenv("PP_FWD_PARTS");
+    fwd_parts_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const int parts = (pl.overlap == 1 && fwd_parts_on && G > 1 && G <= UNetPlan::kMaxParts) ? G : 1;
   const int Np = N / parts, Gp = G / parts;   // images and statistics groups per part
   const long long es = dt == PP_BF16 ? 2 : 4;
   cudaStream_t st[UNetPlan::kMaxParts];
