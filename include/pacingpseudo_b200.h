@@ -184,6 +184,14 @@ int pp_memory_loss_fwd(const float* bank, const float* wfc, float* loss, float* 
 int pp_memory_loss_bwd(const float* bank, const float* probs, const float* g, float* dwfc, int C, int hid,
                        void* stream);
 
+/* ---- validation metric --------------------------------------------------------------
+ * utils/metrics.py:7-34 compute_dice, which train_chaos.py:386-390 calls per sample on host copies of the softmax
+ * values: here for the whole batch in one pass. scores, label: fp32 NCHW [N][C][HW] (label one-hot); dice: fp32
+ * [N][C], NaN where the class is absent from both the arg-max prediction and the label (the caller skips those);
+ * scratch: 3*N*C doubles followed by N*C uint32 (zeroed by the call). */
+int pp_dice_metric(const float* scores, const float* label, float* dice, void* scratch, int N, int C, int HW,
+                   void* stream);
+
 /* ---- optimizer (train_chaos.py:219 torch.optim.Adam(lr, weight_decay)) --------------------------- */
 int pp_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                  float eps, float weight_decay, int step, float grad_scale, void* stream);

@@ -162,6 +162,29 @@ def loss_function_vectors():
     return rec
 
 
+def dice_metric_inputs():
+    """Seeded inputs of the Dice-metric vectors (shared with the tests): softmax scores and one-hot labels of 4 samples,
+    with a class absent from prediction and label (-> nan), one absent from the label only, and exact score ties."""
+    g = torch.Generator().manual_seed(11)
+    N, C, H, W = 4, 5, 24, 20
+    z = 2 * torch.randn(N, C, H, W, generator=g)
+    z[0, 4] = -50.0                       # class 4 never predicted in sample 0 ...
+    z[1, 2] = -50.0
+    z[3, :, :4] = 0.25                    # exact ties: the first maximum wins
+    lab = torch.randint(0, C, (N, H, W), generator=g)
+    lab[0][lab[0] == 4] = 0               # ... and absent from its label: nan
+    lab[2][lab[2] == 1] = 3               # absent from the label only: 0
+    onehot = torch.nn.functional.one_hot(lab, C).permute(0, 3, 1, 2).float()
+    return torch.softmax(z, 1).numpy(), onehot.numpy()
+
+
+def dice_metric_vectors():
+    """Known answers of utils/metrics.py compute_dice (the reference's own function) on the seeded inputs."""
+    from utils.metrics import compute_dice
+    scores, onehot = dice_metric_inputs()
+    return {"dice": np.array([compute_dice(scores[n], onehot[n]) for n in range(scores.shape[0])], dtype=np.float64)}
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference not found at %s" % REF)
@@ -172,6 +195,8 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     np.savez_compressed(os.path.join(out_dir, "loss_functions.npz"), **loss_function_vectors())
     print("wrote loss_functions.npz")
+    np.savez_compressed(os.path.join(out_dir, "dice_metric.npz"), **dice_metric_vectors())
+    print("wrote dice_metric.npz")
     for name, case in CASES.items():
         rec = run_reference(name, case)
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **rec)

@@ -262,6 +262,24 @@ def dice(logits, onehot):
 # ------------------------------------------------------------------------------------------------
 # aux path + memory bank (models/aux_path_memory.py)
 # ------------------------------------------------------------------------------------------------
+def compute_dice_np(scores, target):
+    """utils/metrics.py:7-34 compute_dice, restated: scores, target (C, H, W) numpy -> list of C Dice values. pred =
+    argmax over classes (first maximum); per class 2*sum(pred_c*t_c) / (sum(pred_c) + sum(t_c) + 1e-5); np.nan when
+    the class is absent from both the prediction and the target."""
+    import numpy as np
+    C = scores.shape[0]
+    pred = np.argmax(scores, axis=0)
+    out = []
+    for c in range(C):
+        pc = (pred == c).astype(np.float64).reshape(-1)
+        tc = np.asarray(target[c], dtype=np.float64).reshape(-1)
+        if not pc.any() and not tc.any():
+            out.append(np.nan)
+        else:
+            out.append(2.0 * float((pc * tc).sum()) / (float(pc.sum()) + float(tc.sum()) + 1e-5))
+    return out
+
+
 def ramp_up_mo(step, max_step, base_mo=0.9, gamma=0.9):
     """aux_path_memory.py:118-120."""
     return (1 - step / max_step) ** gamma * base_mo

@@ -220,6 +220,10 @@ int pp_memory_loss_bwd(const float* bank, const float* probs, const float* g, fl
                        void* stream) {
   return memory_loss_bwd(bank, probs, g, dwfc, C, hid, ST(stream));
 }
+int pp_dice_metric(const float* scores, const float* label, float* dice, void* scratch, int N, int C, int HW,
+                   void* stream) {
+  return dice_metric(scores, label, dice, scratch, N, C, HW, ST(stream));
+}
 int pp_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                  float eps, float weight_decay, int step, float grad_scale, void* stream) {
   return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, ST(stream));

@@ -625,6 +625,95 @@ int dice_bwd(const float* z, const float* label, const float* coef, const float*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Validation Dice metric (utils/metrics.py:7-34 compute_dice, called per sample by train_chaos.py:386-390 on softmax
+// values copied to the host): for every sample n and class c, with pred = argmax_c score (first maximum wins, as
+// np.argmax) and the one-hot label t,   dice = 2 * sum[pred == c] * t_c / (sum[pred == c] + sum t_c + 1e-5),
+// NaN when the class is absent from both prediction and label. One pass over scores + label for the whole batch.
+// counts: [N][C][3] (intersection, predicted, labelled) as fp64 sums of the label VALUES (the reference multiplies by
+// the label array, so non-binary labels behave the same), plus [N][C] flags "label plane has a non-zero entry".
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dice_metric_count_kernel(const float* __restrict__ scores,
+                                                                const float* __restrict__ label,
+                                                                double* __restrict__ counts,
+                                                                unsigned int* __restrict__ nonzero, int HW, int C) {
+  const int n = blockIdx.y;
+  const float* sc = scores + static_cast<size_t>(n) * C * HW;
+  const float* lb = label + static_cast<size_t>(n) * C * HW;
+  float inter[kMaxC], predc[kMaxC], labc[kMaxC];
+  unsigned int nz = 0;
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) { inter[c] = 0.f; predc[c] = 0.f; labc[c] = 0.f; }
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    int best = 0;
+    float bv = sc[p];
+#pragma unroll
+    for (int c = 1; c < kMaxC; ++c)
+      if (c < C) {
+        const float v = sc[static_cast<size_t>(c) * HW + p];
+        if (v > bv) { bv = v; best = c; }
+      }
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c)
+      if (c < C) {
+        const float t = lb[static_cast<size_t>(c) * HW + p];
+        const float pr = (c == best) ? 1.f : 0.f;
+        inter[c] = fmaf(pr, t, inter[c]);
+        predc[c] += pr;
+        labc[c] += t;
+        if (t != 0.f) nz |= 1u << c;
+      }
+  }
+  __shared__ float red[3 * kMaxC][8];
+  __shared__ unsigned int red_nz[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) {
+    const float a = warp_sum(inter[c]), b = warp_sum(predc[c]), d = warp_sum(labc[c]);
+    if (lane == 0) { red[c][warp] = a; red[kMaxC + c][warp] = b; red[2 * kMaxC + c][warp] = d; }
+  }
+  nz = __reduce_or_sync(0xffffffffu, nz);
+  if (lane == 0) red_nz[warp] = nz;
+  __syncthreads();
+  if (threadIdx.x < 3 * kMaxC) {
+    const int k = threadIdx.x / kMaxC, c = threadIdx.x % kMaxC;
+    if (c < C) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += static_cast<double>(red[threadIdx.x][w]);
+      atomicAdd(counts + (static_cast<size_t>(n) * C + c) * 3 + k, t);
+    }
+  }
+  if (threadIdx.x == 0) {
+    unsigned int all = 0;
+    for (int w = 0; w < 8; ++w) all |= red_nz[w];
+    for (int c = 0; c < C; ++c)
+      if (all & (1u << c)) atomicOr(nonzero + n * C + c, 1u);
+  }
+}
+__global__ void dice_metric_finalize_kernel(const double* __restrict__ counts, const unsigned int* __restrict__ nonzero,
+                                            float* __restrict__ dice, int NC) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NC) return;
+  const double inter = counts[i * 3], pred = counts[i * 3 + 1], lab = counts[i * 3 + 2];
+  if (pred == 0.0 && nonzero[i] == 0u) dice[i] = nanf("");                       // absent from both: skipped by the caller
+  else dice[i] = static_cast<float>(2.0 * inter / (pred + lab + 1e-5));
+}
+// scratch: 3*N*C doubles + N*C uint32 (zeroed here)
+int dice_metric(const float* scores, const float* label, float* dice, void* scratch, int N, int C, int HW,
+                cudaStream_t s) {
+  PP_REQUIRE(C >= 1 && C <= kMaxC, "dice_metric: num_classes=%d unsupported (max %d)", C, kMaxC);
+  PP_REQUIRE(N >= 1 && N <= 65535 && HW >= 1, "dice_metric: bad shape N=%d HW=%d", N, HW);
+  double* counts = static_cast<double*>(scratch);
+  unsigned int* nonzero = reinterpret_cast<unsigned int*>(counts + 3LL * N * C);
+  PP_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 3 * N * C + sizeof(unsigned int) * N * C, s));
+  int bx = ceil_div(HW, 256 * 4);
+  if (bx > 64) bx = 64;
+  dice_metric_count_kernel<<<dim3(bx, N), 256, 0, s>>>(scores, label, counts, nonzero, HW, C);
+  dice_metric_finalize_kernel<<<ceil_div(N * C, 128), 128, 0, s>>>(counts, nonzero, dice, N * C);
+  PP_LAUNCH_CHECK_N(2);
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Memory-bank update (aux_path_memory.py:68-116). Only sample 0 of the batch is visited (the
 // reference returns from inside its per-sample loop). One block per class; a warp owns one
 // labelled pixel at a time: lanes split the hidden channels, the 8x bilinear upsample of the

@@ -86,4 +86,8 @@ int memory_update(int dtype, const void* feat, const float* scribble, float* ban
 int memory_loss_fwd(const float* bank, const float* wfc, float* loss, float* probs, int C, int hid, cudaStream_t s);
 int memory_loss_bwd(const float* bank, const float* probs, const float* g, float* dwfc, int C, int hid, cudaStream_t s);
 
+// validation Dice metric (utils/metrics.py:7-34), whole batch in one pass; scratch = 3*N*C doubles + N*C uint32
+int dice_metric(const float* scores, const float* label, float* dice, void* scratch, int N, int C, int HW,
+                cudaStream_t s);
+
 }  // namespace pp

@@ -684,3 +684,27 @@ def test_upsample_nhwc_forward_backward_shapes(pp, case, precision):
     gacc = _nhwc(base, adt)
     L.call("pp_upsample_nhwc_bwd", code, _p(gu_d), _p(gacc), N, h, w, h * sc, w * sc, C, 1, _st())
     assert _rel(gacc.float().permute(0, 3, 1, 2), ar.grad + base) < 2 * tol
+
+
+def test_dice_metric_vs_reference_golden_and_oracle(pp):
+    """pp_dice_metric (whole batch, one pass) against the reference's compute_dice vectors (tests/golden/dice_metric.npz)
+    and the oracle at a full-size batch; the per-sample wrapper keeps the reference's return type."""
+    from oracle.gen_golden import dice_metric_inputs
+    from pacingpseudo_b200.metrics import compute_dice, compute_dice_batch
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dice_metric.npz"))["dice"]
+    scores, onehot = dice_metric_inputs()
+    got = compute_dice_batch(torch.from_numpy(scores).cuda(), torch.from_numpy(onehot).cuda()).cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(gold))
+    assert np.allclose(got, gold, rtol=1e-6, atol=1e-7, equal_nan=True)
+    one = compute_dice(scores[0], onehot[0])
+    assert isinstance(one, list) and len(one) == 5 and np.isnan(one[4])
+    assert np.allclose(one, gold[0], rtol=1e-6, equal_nan=True)
+    # full size (12 x 5 x 256 x 256), logits instead of softmax values (same arg-max)
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(12, 5, 256, 256, generator=g)
+    lab = F.one_hot(torch.randint(0, 4, (12, 256, 256), generator=g), 5).permute(0, 3, 1, 2).float()   # class 4 never labelled
+    z[:, 4] -= 100.0                                                                                     # ... nor predicted
+    ref = np.array([O.compute_dice_np(z[n].numpy(), lab[n].numpy()) for n in range(12)])
+    got = compute_dice_batch(z.cuda(), lab.cuda()).cpu().numpy()
+    assert np.isnan(got[:, 4]).all() and np.isnan(ref[:, 4]).all()
+    assert np.allclose(got, ref, rtol=1e-6, atol=1e-7, equal_nan=True)

@@ -114,3 +114,18 @@ def test_oracle_matches_live_reference_upsample_and_unet():
         sys.path.remove("/root/reference")
         for mod in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "losses" or k.startswith("losses.")]:
             del sys.modules[mod]
+
+
+def test_dice_metric_oracle_matches_reference_golden():
+    """oracle.compute_dice_np (restating utils/metrics.py:7-34) against the vectors the reference's own compute_dice
+    produced (tests/golden/dice_metric.npz, oracle/gen_golden.py): incl. nan for a class absent from prediction and
+    label, 0 for a class absent from the label only, and first-maximum tie breaking."""
+    import numpy as np
+    from oracle import pp_oracle as O
+    from oracle.gen_golden import dice_metric_inputs
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dice_metric.npz"))["dice"]
+    scores, onehot = dice_metric_inputs()
+    mine = np.array([O.compute_dice_np(scores[n], onehot[n]) for n in range(scores.shape[0])])
+    assert np.isnan(gold[0, 4]) and gold[1, 2] == 0.0 and gold[2, 1] == 0.0
+    assert np.array_equal(np.isnan(mine), np.isnan(gold))
+    assert np.allclose(mine, gold, rtol=1e-12, atol=0, equal_nan=True)
