@@ -241,7 +241,7 @@ def run_ours(args):
     from pacingpseudo_b200.lib import get_lib
     from pacingpseudo_b200.optim import FlatAdam
     from pacingpseudo_b200.synth import make_batch
-    from oracle.pp_oracle import gaussian_ramp_up  # host scalar schedule only (utils/utils.py:53-65)
+    from pacingpseudo_b200.schedules import loss_weight_ramp_up
     sys.path.insert(0, DROPIN_PATH)
     from models.consistency_reglur_memory import ConsistencyRegulr
 
@@ -279,8 +279,8 @@ def run_ours(args):
         pool_host.append({k: b[k].pin_memory() for k in keys})
     pool_dev = [{k: v.to(dev) for k, v in b.items()} for b in pool_host]
     h2d_bytes = sum(v.numel() * v.element_size() for v in pool_host[0].values())
-    w_ent = gaussian_ramp_up(args.epoch, 1.0, scale=8.0)
-    w_cr = gaussian_ramp_up(args.epoch, 1.0, scale=8.0)
+    w_ent = loss_weight_ramp_up(args.epoch, 1.0, scale=8.0)
+    w_cr = loss_weight_ramp_up(args.epoch, 1.0, scale=8.0)
 
     loss_reader = LossReader(dev)
     prefetcher = DevicePrefetcher((), dev)

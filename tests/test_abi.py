@@ -124,3 +124,25 @@ def test_graft_build_compiles_library_and_standalone_checker():
     path = g.build()
     assert os.path.exists(path)
     assert os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "test_conv_tc"))
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under pacingpseudo_b200/ may import it, and bench.py may do so only
+    inside the CPU-baseline / reference-arm function."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "pacingpseudo_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
+    bench = open(os.path.join(root, "bench.py")).read()
+    ours = bench[bench.index("def run_ours("):bench.index("def main(")]
+    assert not re.search(r"^\s*(from|import)\s+oracle\b", ours, re.M)
+
+
+def test_loss_weight_ramp_up_matches_the_oracle_schedule():
+    from oracle.pp_oracle import gaussian_ramp_up
+    from pacingpseudo_b200.schedules import loss_weight_ramp_up
+    for t in (0, 1, 40, 79, 80, 200):
+        assert loss_weight_ramp_up(t, 1.0, scale=8.0) == gaussian_ramp_up(t, 1.0, scale=8.0)
