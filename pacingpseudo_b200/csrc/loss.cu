@@ -6,6 +6,7 @@
 //     bank classification loss (consistency_reglur_memory.py:94).
 // Thread = pixel; per-class planes are read with unit stride across the warp (coalesced).
 #include "pp_common.cuh"
+#include <stdlib.h>
 
 namespace pp {
 
@@ -241,6 +242,280 @@ __global__ void scribble_loss_finalize_kernel(const double* __restrict__ acc, fl
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lean instantiations of the fused scribble loss: class count C and consistency variant CR are compile-time, four
+// pixels per thread, softmax in the log2 domain on MUFU.EX2 / LG2 / RCP. Per pixel and logits tensor:
+//   d_c = z_c - max,  e_c = 2^(d_c*log2e),  S = sum e,  lS = ln S,  p_c = e_c / S,  log p_c = d_c - lS
+// so that  H = lS - (sum e_c d_c)/S  and  CE(p_w, s) = lS_s - (sum e_w,c d_s,c)/S_w  need neither p nor log p in the
+// forward pass (both are sums of non-negative terms: no cancellation). ~70 instructions per pixel forward instead of
+// ~430 in the generic kernel (runtime C / variant predicates), which made that kernel issue- rather than HBM-bound.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+template <int C>
+struct LeanSoftmax {
+  float d[C], e[C], inv, lS;   // shifted logits, unnormalised exponentials, 1/S, ln S
+  __device__ __forceinline__ void of(const float (&v)[C]) {
+    float mx = v[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, v[c]);
+    float S = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { d[c] = v[c] - mx; e[c] = fast_ex2(d[c] * kLog2e); S += e[c]; }
+    inv = fast_rcp(S);
+    lS = fast_lg2(S) * kLn2;
+  }
+  __device__ __forceinline__ float p(int c) const { return e[c] * inv; }
+  __device__ __forceinline__ float lp(int c) const { return d[c] - lS; }
+};
+
+template <int C>
+__device__ __forceinline__ void load_planes4(const float* __restrict__ z, int HW, float (&v)[4][C]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(z + static_cast<size_t>(c) * HW));
+    v[0][c] = q.x; v[1][c] = q.y; v[2][c] = q.z; v[3][c] = q.w;
+  }
+}
+template <int C>
+__device__ __forceinline__ void store_planes4(float* __restrict__ z, int HW, const float (&v)[4][C]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    __stcs(reinterpret_cast<float4*>(z + static_cast<size_t>(c) * HW), make_float4(v[0][c], v[1][c], v[2][c], v[3][c]));
+}
+template <int C>
+__device__ __forceinline__ float pick(const float (&a)[C], int t) {
+  float r = a[0];
+#pragma unroll
+  for (int c = 1; c < C; ++c) r = (c == t) ? a[c] : r;
+  return r;
+}
+
+// per-pixel consistency term from two softmaxes (w = weak = target side, s = strong)
+template <int C, int CR>
+__device__ __forceinline__ float lean_cr_pixel(const LeanSoftmax<C>& w, const LeanSoftmax<C>& s) {
+  float acc = 0.f;
+  if constexpr (CR == CR_CE) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc = fmaf(w.e[c], s.d[c], acc);
+    return s.lS - acc * w.inv;
+  } else if constexpr (CR == CR_KL) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc = fmaf(w.e[c], w.d[c] - s.d[c], acc);
+    return (s.lS - w.lS) + acc * w.inv;
+  } else if constexpr (CR == CR_L1) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc += fabsf(s.p(c) - w.p(c));
+    return acc;
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) { const float df = s.p(c) - w.p(c); acc = fmaf(df, df, acc); }
+    return acc;
+  }
+}
+
+template <int C, int CR>
+__global__ void __launch_bounds__(256, 3)
+scribble_loss_fwd_lean_kernel(const float* __restrict__ zw, const float* __restrict__ zs, const float* __restrict__ za,
+                              const uint8_t* __restrict__ target, const float* __restrict__ mask,
+                              double* __restrict__ acc, int P, int HW, int ignore_index, int do_ent) {
+  float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int groups = P >> 2;
+  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
+    const int p = gi << 2;
+    const int n = p / HW, hw = p - n * HW;
+    const size_t off = static_cast<size_t>(n) * C * HW + hw;
+    float vw[4][C], vs[4][C];
+    int tv[4];
+    float mv[4];
+    load_planes4<C>(zw + off, HW, vw);
+    if constexpr (CR != CR_NONE) load_planes4<C>(zs + off, HW, vs);
+    load_target_mask<4>(target, mask, p, ignore_index, tv, mv);
+    bool any_lab = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) any_lab |= (tv[j] != ignore_index) && (tv[j] < C);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      LeanSoftmax<C> w;
+      w.of(vw[j]);
+      const float m = mv[j];
+      part[ACC_MASK] += m;
+      if (do_ent) {
+        float ed = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) ed = fmaf(w.e[c], w.d[c], ed);
+        part[ACC_ENT] = fmaf(m, w.lS - ed * w.inv, part[ACC_ENT]);
+      }
+      if constexpr (CR != CR_NONE) {
+        LeanSoftmax<C> s;
+        s.of(vs[j]);
+        part[ACC_CR] = fmaf(m, lean_cr_pixel<C, CR>(w, s), part[ACC_CR]);
+      }
+      if (any_lab) {                                   // scribble pixels are ~1 % of the image
+        const int t = tv[j];
+        if ((t != ignore_index) && (t < C)) {
+          part[ACC_PCE] += w.lS - pick<C>(w.d, t);
+          part[ACC_NLAB] += 1.f;
+        }
+      }
+    }
+    if (za != nullptr && any_lab) {                    // aux logits matter on labelled pixels only
+      float va[4][C];
+      load_planes4<C>(za + off, HW, va);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int t = tv[j];
+        if ((t != ignore_index) && (t < C)) {
+          LeanSoftmax<C> a;
+          a.of(va[j]);
+          part[ACC_AUX] += a.lS - pick<C>(a.d, t);
+        }
+      }
+    }
+  }
+  block_accumulate(part, acc);
+}
+
+template <int C, int CR>
+__global__ void __launch_bounds__(256, 3)
+scribble_loss_bwd_lean_kernel(const float* __restrict__ zw, const float* __restrict__ zs, const float* __restrict__ za,
+                              const uint8_t* __restrict__ target, const float* __restrict__ mask,
+                              const double* __restrict__ acc, const float* __restrict__ g_pce,
+                              const float* __restrict__ g_ent, const float* __restrict__ g_cr,
+                              const float* __restrict__ g_aux, float* __restrict__ dzw, float* __restrict__ dzs,
+                              float* __restrict__ dza, int P, int HW, int ignore_index, int do_ent, int detach_weak) {
+  const float gp = g_pce ? *g_pce : 0.f, ge = (do_ent && g_ent) ? *g_ent : 0.f;
+  const float gc = (CR != CR_NONE && g_cr) ? *g_cr : 0.f, ga = (za && g_aux) ? *g_aux : 0.f;
+  const int has_mask = mask != nullptr;
+  const double nlab = acc[ACC_NLAB];
+  const float inv_lab = nlab > 0.0 ? static_cast<float>(1.0 / nlab) : 0.f;
+  const float k_ent = ge * static_cast<float>(1.0 / masked_denom(acc, has_mask, double(P) * C));
+  const double ne = (CR == CR_L1 || CR == CR_L2) ? double(P) : double(P) * C;
+  const float k_cr = gc * static_cast<float>(1.0 / masked_denom(acc, has_mask, ne));
+  const float k_pce = gp * inv_lab, k_aux = ga * inv_lab;
+  const bool weak_gets_cr = (CR == CR_KL) || !detach_weak;
+  const bool do_aux = za != nullptr && dza != nullptr;
+
+  const int groups = P >> 2;
+  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
+    const int p = gi << 2;
+    const int n = p / HW, hw = p - n * HW;
+    const size_t off = static_cast<size_t>(n) * C * HW + hw;
+    float vw[4][C], vs[4][C];
+    int tv[4];
+    float mv[4];
+    load_planes4<C>(zw + off, HW, vw);
+    if constexpr (CR != CR_NONE) load_planes4<C>(zs + off, HW, vs);
+    load_target_mask<4>(target, mask, p, ignore_index, tv, mv);
+    bool any_lab = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) any_lab |= (tv[j] != ignore_index) && (tv[j] < C);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      LeanSoftmax<C> w;
+      w.of(vw[j]);
+      const float m = mv[j];
+      float pw[C], coef[C];                        // dz_w = p_w * coef (+ the pCE term on labelled pixels)
+#pragma unroll
+      for (int c = 0; c < C; ++c) { pw[c] = w.p(c); coef[c] = 0.f; }
+      if (do_ent) {                                // -k p (log p + H)
+        float ed = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) ed = fmaf(pw[c], w.d[c], ed);
+        const float k = k_ent * m;                 // log p + H = d - lS + lS - sum p d = d - sum p d
+#pragma unroll
+        for (int c = 0; c < C; ++c) coef[c] = k * (ed - w.d[c]);
+      }
+      if constexpr (CR != CR_NONE) {
+        LeanSoftmax<C> s;
+        s.of(vs[j]);
+        const float k = k_cr * m;
+        if constexpr (CR == CR_CE || CR == CR_KL) {
+          // strong: k (p_s - p_w). weak, ce: -k p_w (log p_s + L) with log p_s + L = d_s - sum p_w d_s;
+          // kl: k p_w ((log p_w - log p_s) - L) with that bracket = (d_w - d_s) - sum p_w (d_w - d_s)
+          float q[C], qs = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            q[c] = (CR == CR_CE) ? s.d[c] : (s.d[c] - w.d[c]);
+            qs = fmaf(pw[c], q[c], qs);
+          }
+          if (weak_gets_cr) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) coef[c] = fmaf(k, qs - q[c], coef[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) vs[j][c] = k * (s.p(c) - pw[c]);
+        } else {
+          float e[C], es = 0.f, ew = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float df = s.p(c) - pw[c];
+            e[c] = (CR == CR_L1) ? sgn(df) : 2.f * df;
+            es = fmaf(e[c], s.p(c), es);
+            ew = fmaf(e[c], pw[c], ew);
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            vs[j][c] = k * s.p(c) * (e[c] - es);
+            if (weak_gets_cr) coef[c] = fmaf(k, ew - e[c], coef[c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) vw[j][c] = pw[c] * coef[c];
+      if (any_lab) {
+        const int t = tv[j];
+        if ((t != ignore_index) && (t < C)) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) vw[j][c] = fmaf(k_pce, pw[c] - (c == t ? 1.f : 0.f), vw[j][c]);
+        }
+      }
+    }
+    if constexpr (CR != CR_NONE) {
+      if (dzs != nullptr) store_planes4<C>(dzs + off, HW, vs);
+    }
+    if (dzw != nullptr) store_planes4<C>(dzw + off, HW, vw);
+    if (do_aux) {
+      float va[4][C];
+      if (any_lab) {
+        load_planes4<C>(za + off, HW, va);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int t = tv[j];
+          const bool lab = (t != ignore_index) && (t < C);
+          LeanSoftmax<C> a;
+          a.of(va[j]);
+#pragma unroll
+          for (int c = 0; c < C; ++c) va[j][c] = lab ? k_aux * (a.p(c) - (c == t ? 1.f : 0.f)) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < C; ++c) va[j][c] = 0.f;
+      }
+      store_planes4<C>(dza + off, HW, va);
+    }
+  }
+}
+
+// persistent-style grid for the lean kernels: three 256-thread blocks per SM (launch bounds), grid-stride loop
+static inline int lean_grid(long long groups) {
+  long long g = ceil_div_ll(groups, 256);
+  const long long cap = static_cast<long long>(sm_count()) * 3;
+  if (g > cap) g = cap;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+static inline bool lean_classes(int C) { return C >= 2 && C <= 5; }
+// PP_LOSS_GENERIC=1 routes every call to the generic (runtime C / variant) kernels: A/B timing and cross-checks
+static bool generic_loss_forced() {   // read per call so a test can toggle it inside one process
+  const char* e = getenv("PP_LOSS_GENERIC");
+  return e != nullptr && e[0] == '1';
+}
+
 // 4 pixels per thread need HW % 4 == 0 (a group never straddles two images) and 16 / 4-byte aligned base pointers
 static bool loss_vec4_ok(int HW, const void* a, const void* b, const void* c, const void* t, const void* m,
                          const void* d = nullptr, const void* e = nullptr, const void* f = nullptr) {
@@ -267,13 +542,30 @@ int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const u
 #define PP_LOSS_FWD(V_, NC_, P_)                                                                              \
   scribble_loss_fwd_kernel<V_, NC_><<<grid_for_px(P_, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW, C, \
                                                                          ignore_index, do_ent, cr_variant)
-  if (loss_vec4_ok(HW, zw, zs, za, target, mask)) {
+#define PP_LEAN_FWD(C_, CR_)                                                                                       \
+  scribble_loss_fwd_lean_kernel<C_, CR_><<<lean_grid(P / 4), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW,  \
+                                                                         ignore_index, do_ent)
+#define PP_LEAN_FWD_C(C_)                                                                                           \
+  switch (cr_variant) {                                                                                             \
+    case CR_NONE: PP_LEAN_FWD(C_, CR_NONE); break;                                                                  \
+    case CR_CE: PP_LEAN_FWD(C_, CR_CE); break;                                                                      \
+    case CR_L1: PP_LEAN_FWD(C_, CR_L1); break;                                                                      \
+    case CR_L2: PP_LEAN_FWD(C_, CR_L2); break;                                                                      \
+    default: PP_LEAN_FWD(C_, CR_KL); break;                                                                         \
+  }
+  const bool vec4 = loss_vec4_ok(HW, zw, zs, za, target, mask);
+  if (vec4 && target != nullptr && lean_classes(C) && !generic_loss_forced()) {
+    if (C == 2) { PP_LEAN_FWD_C(2); } else if (C == 3) { PP_LEAN_FWD_C(3); }
+    else if (C == 4) { PP_LEAN_FWD_C(4); } else { PP_LEAN_FWD_C(5); }
+  } else if (vec4) {
     if (C <= 2) PP_LOSS_FWD(4, 2, P / 4); else if (C <= 4) PP_LOSS_FWD(4, 4, P / 4);
     else if (C == 5) PP_LOSS_FWD(4, 5, P / 4); else PP_LOSS_FWD(4, 8, P / 4);
   } else {
     PP_LOSS_FWD(1, 8, P);
   }
 #undef PP_LOSS_FWD
+#undef PP_LEAN_FWD_C
+#undef PP_LEAN_FWD
   prof_end(slot, s);
   scribble_loss_finalize_kernel<<<1, 32, 0, s>>>(acc, loss_pce, do_ent ? loss_ent : nullptr,
                                                  cr_variant != CR_NONE ? loss_cr : nullptr,
@@ -405,13 +697,31 @@ int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const u
   scribble_loss_bwd_kernel<V_, NC_><<<grid_for_px(P_, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent, g_cr, \
                                                                          g_aux, dzw, dzs, dza, int(P), HW, C,          \
                                                                          ignore_index, do_ent, cr_variant, detach_weak)
-  if (loss_vec4_ok(HW, zw, zs, za, target, mask, dzw, dzs, dza)) {
+#define PP_LEAN_BWD(C_, CR_)                                                                                       \
+  scribble_loss_bwd_lean_kernel<C_, CR_><<<lean_grid(P / 4), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent, \
+                                                                         g_cr, g_aux, dzw, dzs, dza, int(P), HW,     \
+                                                                         ignore_index, do_ent, detach_weak)
+#define PP_LEAN_BWD_C(C_)                                                                                           \
+  switch (cr_variant) {                                                                                             \
+    case CR_NONE: PP_LEAN_BWD(C_, CR_NONE); break;                                                                  \
+    case CR_CE: PP_LEAN_BWD(C_, CR_CE); break;                                                                      \
+    case CR_L1: PP_LEAN_BWD(C_, CR_L1); break;                                                                      \
+    case CR_L2: PP_LEAN_BWD(C_, CR_L2); break;                                                                      \
+    default: PP_LEAN_BWD(C_, CR_KL); break;                                                                         \
+  }
+  const bool vec4 = loss_vec4_ok(HW, zw, zs, za, target, mask, dzw, dzs, dza);
+  if (vec4 && target != nullptr && lean_classes(C) && !generic_loss_forced()) {
+    if (C == 2) { PP_LEAN_BWD_C(2); } else if (C == 3) { PP_LEAN_BWD_C(3); }
+    else if (C == 4) { PP_LEAN_BWD_C(4); } else { PP_LEAN_BWD_C(5); }
+  } else if (vec4) {
     if (C <= 2) PP_LOSS_BWD(4, 2, P / 4); else if (C <= 4) PP_LOSS_BWD(4, 4, P / 4);
     else if (C == 5) PP_LOSS_BWD(4, 5, P / 4); else PP_LOSS_BWD(4, 8, P / 4);
   } else {
     PP_LOSS_BWD(1, 8, P);
   }
 #undef PP_LOSS_BWD
+#undef PP_LEAN_BWD_C
+#undef PP_LEAN_BWD
   prof_end(slot, s);
   PP_LAUNCH_CHECK();
   return PP_OK;

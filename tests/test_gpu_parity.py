@@ -360,6 +360,66 @@ def test_loss_functions_vs_reference_golden(pp):
     np.testing.assert_allclose(z.grad.cpu().numpy(), ref.grad.numpy(), rtol=1e-3, atol=1e-7)
 
 
+def _oracle_fused_losses(zw, zs, za, target, mask, C, variant, detach_weak):
+    """The four terms of consistency_reglur_memory.py:32-81 from the oracle's loss functions (fp64, CPU)."""
+    pce = O.partial_cross_entropy(zw, target, C)
+    ent = O.entropy_minimization(zw, mask)
+    pw = torch.softmax(zw.detach() if detach_weak else zw, 1)
+    if variant == "ce_loss":
+        cr = O.soft_label_cross_entropy(zs, pw, mask)
+    elif variant == "l1_loss":
+        cr = O.l1(torch.softmax(zs, 1), pw, mask)
+    elif variant == "l2_loss":
+        cr = O.l2(torch.softmax(zs, 1), pw, mask)
+    else:
+        cr = O.kl(zs, zw, mask)
+    aux = O.partial_cross_entropy(za, target, C)
+    return pce, ent, cr, aux
+
+
+@pytest.mark.parametrize("variant", ["ce_loss", "l1_loss", "l2_loss", "kl_loss"])
+@pytest.mark.parametrize("C,shape,use_mask,detach", [(5, (3, 16, 24), True, False), (2, (2, 12, 20), True, True),
+                                                      (3, (2, 8, 16), False, False), (4, (2, 14, 16), True, False),
+                                                      (7, (1, 8, 12), True, False), (5, (2, 5, 7), True, False)])
+def test_fused_scribble_loss_all_terms_vs_oracle(pp, variant, C, shape, use_mask, detach):
+    """All four terms in one call, with different upstream weights per term: the compile-time-C kernels
+    (C in 2..5, H*W % 4 == 0), the generic kernels (C = 7, ragged 5x7, or PP_LOSS_GENERIC=1) and the fp64 oracle."""
+    L, PF, _ = pp
+    N, H, W = shape
+    g = torch.Generator().manual_seed(100 * C + H)
+    zw0, zs0, za0 = (3.0 * torch.randn(N, C, H, W, generator=g, dtype=torch.float64) for _ in range(3))
+    target = torch.randint(0, C + 1, (N, H, W), generator=g)
+    target[torch.rand(N, H, W, generator=g) < 0.6] = C
+    target[0, 0, :4] = torch.tensor([0, C, 1, C])
+    mask = (torch.rand(N, 1, H, W, generator=g) < 0.7).double() if use_mask else None
+    wts = (1.0, 0.37, 0.81, 0.01)
+
+    ref_in = [t.clone().requires_grad_() for t in (zw0, zs0, za0)]
+    ref_terms = _oracle_fused_losses(*ref_in, target, mask, C, variant, detach)
+    sum(w * t for w, t in zip(wts, ref_terms)).backward()
+
+    results = {}
+    for forced in ("0", "1"):
+        os.environ["PP_LOSS_GENERIC"] = forced
+        try:
+            dev_in = [t.float().cuda().requires_grad_() for t in (zw0, zs0, za0)]
+            out = PF.scribble_losses(dev_in[0], target.cuda(), C, zs=dev_in[1], za=dev_in[2],
+                                     mask=None if mask is None else mask.float().cuda(), do_ent=True,
+                                     cr_variant=variant, detach_weak=detach)
+            terms = [out["loss_pce"], out["loss_ent"], out["loss_cr"], out["loss_aux"]]
+            sum(w * t for w, t in zip(wts, terms)).backward()
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("PP_LOSS_GENERIC", None)
+        for name, t, r in zip(("pce", "ent", "cr", "aux"), terms, ref_terms):
+            assert abs(t.item() - r.item()) <= 1e-4 * max(1.0, abs(r.item())), (forced, name, t.item(), r.item())
+        for name, t, r in zip(("dzw", "dzs", "dza"), dev_in, ref_in):
+            assert _rel(t.grad, r.grad) < 1e-4, (forced, name, _rel(t.grad, r.grad))
+        results[forced] = [t.grad.clone() for t in dev_in]
+    for a, b in zip(results["0"], results["1"]):
+        assert _rel(a, b) < 1e-5
+
+
 @pytest.mark.parametrize("mode", ["cosine_similarity", "mean"])
 def test_memory_update_vs_oracle(pp, mode):
     """aux_path_memory.py:68-116 incl. sample-0-only, first-touch mean, absent classes, in-place normalisation."""
