@@ -272,19 +272,36 @@ struct LeanSoftmax {
   __device__ __forceinline__ float lp(int c) const { return d[c] - lS; }
 };
 
-template <int C>
-__device__ __forceinline__ void load_planes4(const float* __restrict__ z, int HW, float (&v)[4][C]) {
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const float4 q = __ldg(reinterpret_cast<const float4*>(z + static_cast<size_t>(c) * HW));
-    v[0][c] = q.x; v[1][c] = q.y; v[2][c] = q.z; v[3][c] = q.w;
-  }
-}
-template <int C>
-__device__ __forceinline__ void store_planes4(float* __restrict__ z, int HW, const float (&v)[4][C]) {
+template <int C, int V>
+__device__ __forceinline__ void load_planes4(const float* __restrict__ z, int HW, float (&v)[V][C]) {
 #pragma unroll
   for (int c = 0; c < C; ++c)
-    __stcs(reinterpret_cast<float4*>(z + static_cast<size_t>(c) * HW), make_float4(v[0][c], v[1][c], v[2][c], v[3][c]));
+#pragma unroll
+    for (int h = 0; h < V; h += 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(z + static_cast<size_t>(c) * HW + h));
+      v[h][c] = q.x; v[h + 1][c] = q.y; v[h + 2][c] = q.z; v[h + 3][c] = q.w;
+    }
+}
+template <int C, int V>
+__device__ __forceinline__ void store_planes4(float* __restrict__ z, int HW, const float (&v)[V][C]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int h = 0; h < V; h += 4)
+      *reinterpret_cast<float4*>(z + static_cast<size_t>(c) * HW + h) =
+          make_float4(v[h][c], v[h + 1][c], v[h + 2][c], v[h + 3][c]);
+}
+template <int V>
+__device__ __forceinline__ void load_target_mask_v(const uint8_t* __restrict__ target, const float* __restrict__ mask,
+                                                   int p, int ignore_index, int (&t)[V], float (&m)[V]) {
+#pragma unroll
+  for (int h = 0; h < V; h += 4) {
+    int t4[4];
+    float m4[4];
+    load_target_mask<4>(target, mask, p + h, ignore_index, t4, m4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { t[h + j] = t4[j]; m[h + j] = m4[j]; }
+  }
 }
 template <int C>
 __device__ __forceinline__ float pick(const float (&a)[C], int t) {
@@ -317,28 +334,41 @@ __device__ __forceinline__ float lean_cr_pixel(const LeanSoftmax<C>& w, const Le
   }
 }
 
-template <int C, int CR>
+// Balanced contiguous spans instead of a grid-stride loop: block b owns groups [G*b/nb, G*(b+1)/nb) rounded to
+// 8 groups (128 bytes per class plane), so with ~1.7 groups per thread (12 pairs of 256^2 on 148 x 3 blocks) every
+// block finishes at the same time instead of 73 % of the blocks running a second full iteration.
+template <int V>
+__device__ __forceinline__ void lean_span(int groups, int& begin, int& end) {
+  constexpr int U = 32 / V;                     // groups per 128-byte line of one class plane
+  const long long units = (groups + U - 1) / U;
+  const int u0 = static_cast<int>(units * blockIdx.x / gridDim.x), u1 = static_cast<int>(units * (blockIdx.x + 1) / gridDim.x);
+  begin = u0 * U + threadIdx.x;
+  end = min(u1 * U, groups);
+}
+
+template <int C, int CR, int V>
 __global__ void __launch_bounds__(256, 3)
 scribble_loss_fwd_lean_kernel(const float* __restrict__ zw, const float* __restrict__ zs, const float* __restrict__ za,
                               const uint8_t* __restrict__ target, const float* __restrict__ mask,
                               double* __restrict__ acc, int P, int HW, int ignore_index, int do_ent) {
   float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const int groups = P >> 2;
-  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
-    const int p = gi << 2;
+  int gi, g_end;
+  lean_span<V>(P / V, gi, g_end);
+  for (; gi < g_end; gi += blockDim.x) {
+    const int p = gi * V;
     const int n = p / HW, hw = p - n * HW;
     const size_t off = static_cast<size_t>(n) * C * HW + hw;
-    float vw[4][C], vs[4][C];
-    int tv[4];
-    float mv[4];
-    load_planes4<C>(zw + off, HW, vw);
-    if constexpr (CR != CR_NONE) load_planes4<C>(zs + off, HW, vs);
-    load_target_mask<4>(target, mask, p, ignore_index, tv, mv);
+    float vw[V][C], vs[V][C];
+    int tv[V];
+    float mv[V];
+    load_planes4<C, V>(zw + off, HW, vw);
+    if constexpr (CR != CR_NONE) load_planes4<C, V>(zs + off, HW, vs);
+    load_target_mask_v<V>(target, mask, p, ignore_index, tv, mv);
     bool any_lab = false;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) any_lab |= (tv[j] != ignore_index) && (tv[j] < C);
+    for (int j = 0; j < V; ++j) any_lab |= (tv[j] != ignore_index) && (tv[j] < C);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < V; ++j) {
       LeanSoftmax<C> w;
       w.of(vw[j]);
       const float m = mv[j];
@@ -363,10 +393,10 @@ scribble_loss_fwd_lean_kernel(const float* __restrict__ zw, const float* __restr
       }
     }
     if (za != nullptr && any_lab) {                    // aux logits matter on labelled pixels only
-      float va[4][C];
-      load_planes4<C>(za + off, HW, va);
+      float va[V][C];
+      load_planes4<C, V>(za + off, HW, va);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < V; ++j) {
         const int t = tv[j];
         if ((t != ignore_index) && (t < C)) {
           LeanSoftmax<C> a;
@@ -379,7 +409,7 @@ scribble_loss_fwd_lean_kernel(const float* __restrict__ zw, const float* __restr
   block_accumulate(part, acc);
 }
 
-template <int C, int CR>
+template <int C, int CR, int V>
 __global__ void __launch_bounds__(256, 3)
 scribble_loss_bwd_lean_kernel(const float* __restrict__ zw, const float* __restrict__ zs, const float* __restrict__ za,
                               const uint8_t* __restrict__ target, const float* __restrict__ mask,
@@ -399,22 +429,23 @@ scribble_loss_bwd_lean_kernel(const float* __restrict__ zw, const float* __restr
   const bool weak_gets_cr = (CR == CR_KL) || !detach_weak;
   const bool do_aux = za != nullptr && dza != nullptr;
 
-  const int groups = P >> 2;
-  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
-    const int p = gi << 2;
+  int gi, g_end;
+  lean_span<V>(P / V, gi, g_end);
+  for (; gi < g_end; gi += blockDim.x) {
+    const int p = gi * V;
     const int n = p / HW, hw = p - n * HW;
     const size_t off = static_cast<size_t>(n) * C * HW + hw;
-    float vw[4][C], vs[4][C];
-    int tv[4];
-    float mv[4];
-    load_planes4<C>(zw + off, HW, vw);
-    if constexpr (CR != CR_NONE) load_planes4<C>(zs + off, HW, vs);
-    load_target_mask<4>(target, mask, p, ignore_index, tv, mv);
+    float vw[V][C], vs[V][C];
+    int tv[V];
+    float mv[V];
+    load_planes4<C, V>(zw + off, HW, vw);
+    if constexpr (CR != CR_NONE) load_planes4<C, V>(zs + off, HW, vs);
+    load_target_mask_v<V>(target, mask, p, ignore_index, tv, mv);
     bool any_lab = false;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) any_lab |= (tv[j] != ignore_index) && (tv[j] < C);
+    for (int j = 0; j < V; ++j) any_lab |= (tv[j] != ignore_index) && (tv[j] < C);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < V; ++j) {
       LeanSoftmax<C> w;
       w.of(vw[j]);
       const float m = mv[j];
@@ -475,15 +506,15 @@ scribble_loss_bwd_lean_kernel(const float* __restrict__ zw, const float* __restr
       }
     }
     if constexpr (CR != CR_NONE) {
-      if (dzs != nullptr) store_planes4<C>(dzs + off, HW, vs);
+      if (dzs != nullptr) store_planes4<C, V>(dzs + off, HW, vs);
     }
-    if (dzw != nullptr) store_planes4<C>(dzw + off, HW, vw);
+    if (dzw != nullptr) store_planes4<C, V>(dzw + off, HW, vw);
     if (do_aux) {
-      float va[4][C];
+      float va[V][C];
       if (any_lab) {
-        load_planes4<C>(za + off, HW, va);
+        load_planes4<C, V>(za + off, HW, va);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < V; ++j) {
           const int t = tv[j];
           const bool lab = (t != ignore_index) && (t < C);
           LeanSoftmax<C> a;
@@ -493,11 +524,11 @@ scribble_loss_bwd_lean_kernel(const float* __restrict__ zw, const float* __restr
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < V; ++j)
 #pragma unroll
           for (int c = 0; c < C; ++c) va[j][c] = 0.f;
       }
-      store_planes4<C>(dza + off, HW, va);
+      store_planes4<C, V>(dza + off, HW, va);
     }
   }
 }
@@ -510,6 +541,7 @@ static inline int lean_grid(long long groups) {
   return static_cast<int>(g < 1 ? 1 : g);
 }
 static inline bool lean_classes(int C) { return C >= 2 && C <= 5; }
+// (eight pixels per thread were measured too: no gain at C = 2, spills at C = 5; V stays a template parameter)
 // PP_LOSS_GENERIC=1 routes every call to the generic (runtime C / variant) kernels: A/B timing and cross-checks
 static bool generic_loss_forced() {   // read per call so a test can toggle it inside one process
   const char* e = getenv("PP_LOSS_GENERIC");
@@ -543,8 +575,8 @@ int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const u
   scribble_loss_fwd_kernel<V_, NC_><<<grid_for_px(P_, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW, C, \
                                                                          ignore_index, do_ent, cr_variant)
 #define PP_LEAN_FWD(C_, CR_)                                                                                       \
-  scribble_loss_fwd_lean_kernel<C_, CR_><<<lean_grid(P / 4), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW,  \
-                                                                         ignore_index, do_ent)
+  scribble_loss_fwd_lean_kernel<C_, CR_, 4><<<lean_grid(P / 4), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW, \
+                                                                            ignore_index, do_ent)
 #define PP_LEAN_FWD_C(C_)                                                                                           \
   switch (cr_variant) {                                                                                             \
     case CR_NONE: PP_LEAN_FWD(C_, CR_NONE); break;                                                                  \
@@ -698,9 +730,9 @@ int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const u
                                                                          g_aux, dzw, dzs, dza, int(P), HW, C,          \
                                                                          ignore_index, do_ent, cr_variant, detach_weak)
 #define PP_LEAN_BWD(C_, CR_)                                                                                       \
-  scribble_loss_bwd_lean_kernel<C_, CR_><<<lean_grid(P / 4), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent, \
-                                                                         g_cr, g_aux, dzw, dzs, dza, int(P), HW,     \
-                                                                         ignore_index, do_ent, detach_weak)
+  scribble_loss_bwd_lean_kernel<C_, CR_, 4><<<lean_grid(P / 4), 256, 0, s>>>(                                        \
+      zw, zs, za, target, mask, acc, g_pce, g_ent, g_cr, g_aux, dzw, dzs, dza, int(P), HW, ignore_index, do_ent,     \
+      detach_weak)
 #define PP_LEAN_BWD_C(C_)                                                                                           \
   switch (cr_variant) {                                                                                             \
     case CR_NONE: PP_LEAN_BWD(C_, CR_NONE); break;                                                                  \

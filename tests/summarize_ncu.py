@@ -15,7 +15,9 @@ caps = (('prof_conv256', 'conv3x3_tc_kernel<256,64,2> (forward / dgrad, 256 px x
         ('prof_conv128', 'conv3x3_tc_kernel<128,64,2>'),
         ('prof_wgrad256', 'conv3x3_wgrad_tc_kernel<256,2> (256 co x 256 ci per CTA)'),
         ('prof_halo32', 'conv3x3_halo_tc_kernel<32,32> (narrow full-resolution layers)'),
-        ('prof_loss', 'scribble_loss_fwd / bwd (C = 5 instantiation)'), ('prof_bnbwd', 'bn_bwd_reduce / bn_bwd_apply'))
+        ('prof_loss', 'scribble_loss_fwd / bwd (C = 5 instantiation of the generic kernels; superseded)'),
+        ('prof_loss_lean', 'scribble_loss_fwd/bwd_lean_kernel<5, ce> (compile-time C and variant; 12 pairs of 256^2)'),
+        ('prof_loss_lean_lvsc', 'scribble_loss_fwd/bwd_lean_kernel<2, ce> (96 pairs of 224^2)'), ('prof_bnbwd', 'bn_bwd_reduce / bn_bwd_apply'))
 out = ["# Round-1 ncu captures (`--set full --clock-control none --import-source on`; tests/run_ncu_kernels.sh, tests/run_ncu_final.sh)\n",
        "Raw pages: `profiles/r01_ncu_prof_*_raw.csv`. Durations are cold-cache and serialised (every launch is replayed ~40x).\n"]
 for f, title in caps:
