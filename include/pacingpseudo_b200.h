@@ -53,10 +53,19 @@ int pp_profile_collect(int family, double* ms, double* flops, long long* launche
 typedef struct UNetPlan* pp_unet_t;
 int pp_unet_create(int input_ch, int init_ch, int max_ch, int num_classes, int output_stride, int dtype,
                    pp_unet_t* out);
+/* strided = 1: the is_stride_conv + is_trans_conv variant (unet.py:25,113-116,141): the first conv of every
+ * sub-sampling encoder block has stride 2 (no max-pool) and every decoder block up-samples with
+ * ConvTranspose2d(lower_ch, skip_ch, k = s, stride = s, bias=False). pp_unet_create == strided 0. */
+int pp_unet_create_ex(int input_ch, int init_ch, int max_ch, int num_classes, int output_stride, int dtype,
+                      int strided, pp_unet_t* out);
 void pp_unet_destroy(pp_unet_t u);
 int pp_unet_num_convs(pp_unet_t u);
 /* layer -> Cin, Cout, dilation and module path ("enc_block1.conv_block.conv_layer1", ...) */
 int pp_unet_conv_info(pp_unet_t u, int layer, int* cin, int* cout, int* dil, const char** name);
+/* kind 0: Conv2d 3x3 stride 1 + BN + LeakyReLU; 1: the same with stride 2 (scale = 2); 2: ConvTranspose2d with
+ * kernel = stride = scale, weight [Cin][Cout][scale][scale], no bias / BN: its params slots 1..6 and grads slots 1..3
+ * are NULL. pp_unet_conv_info reports the PARAMETER's Cin / Cout for every kind. */
+int pp_unet_conv_kind(pp_unet_t u, int layer, int* kind, int* scale);
 long long pp_unet_workspace_bytes(pp_unet_t u, int N, int H, int W, int G);
 /* byte offset / shape of a named end point ("encoder/stage6", ... unet.py:82-97) inside the workspace */
 int pp_unet_activation(pp_unet_t u, const char* name, int N, int H, int W, int G, int* act_id, long long* offset,

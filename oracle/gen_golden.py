@@ -31,6 +31,11 @@ CASES = {
     "upperbound_ce_dice": dict(kind="upper", N=2, C=5, H=64, W=64, os=8, training=True),
     "unet_os16": dict(kind="baseline", N=2, C=4, H=64, W=64, os=16, training=True),
     "unet_os32": dict(kind="baseline", N=2, C=4, H=64, W=64, os=32, training=True),
+    # is_stride_conv + is_trans_conv (unet.py:113-116,141): stride-2 first convs, ConvTranspose2d up-sampling
+    "unet_strided_os32": dict(kind="baseline", N=2, C=4, H=64, W=64, os=32, training=True, strided=True),
+    "unet_strided_os16_eval": dict(kind="upper", N=2, C=5, H=64, W=64, os=16, training=False, strided=True),
+    "pacing_strided_os8": dict(kind="pacing", N=2, C=5, H=64, W=64, os=8, training=True, cr="ce_loss",
+                               mode="cosine_similarity", steps=2, strided=True),
 }
 
 
@@ -46,7 +51,7 @@ def summarize(t):
 
 def build_state(case):
     shapes = {}
-    for k, s in O.unet_param_shapes(1, 32, 512, case["C"], case["os"]).items():
+    for k, s in O.unet_param_shapes(1, 32, 512, case["C"], case["os"], strided=bool(case.get("strided"))).items():
         shapes["backbone." + k if case["kind"] == "pacing" else k] = s
     if case["kind"] == "pacing":
         for k, s in O.aux_param_shapes(case["C"], (512, 512), 64).items():
@@ -70,13 +75,14 @@ def run_reference(name, case):
     if case["kind"] == "pacing":
         model = ConsistencyRegulr(
             kwargs_unet=dict(input_ch=1, init_ch=32, max_ch=512, num_classes=C, output_stride=case["os"],
-                             is_stride_conv=False, is_trans_conv=False, elab_end_points=True),
+                             is_stride_conv=bool(case.get("strided")), is_trans_conv=bool(case.get("strided")),
+                             elab_end_points=True),
             kwargs_aux_path=dict(num_classes=C, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[512, 512],
                                  hid_ch=64, aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
                                  ensemble_mode=case["mode"]),
             args_parser=ref_args(case))
     else:
-        model = UNet(1, 32, 512, C, case["os"], False, False, True)
+        model = UNet(1, 32, 512, C, case["os"], bool(case.get("strided")), bool(case.get("strided")), True)
     model.load_state_dict(sd, strict=True)
     model.train(case["training"])
     for step in range(case.get("steps", 1)):
@@ -193,11 +199,15 @@ def main():
     torch.set_num_threads(8)
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
-    np.savez_compressed(os.path.join(out_dir, "loss_functions.npz"), **loss_function_vectors())
-    print("wrote loss_functions.npz")
-    np.savez_compressed(os.path.join(out_dir, "dice_metric.npz"), **dice_metric_vectors())
-    print("wrote dice_metric.npz")
+    if len(sys.argv) == 1:
+        np.savez_compressed(os.path.join(out_dir, "loss_functions.npz"), **loss_function_vectors())
+        print("wrote loss_functions.npz")
+        np.savez_compressed(os.path.join(out_dir, "dice_metric.npz"), **dice_metric_vectors())
+        print("wrote dice_metric.npz")
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]   # optional: regenerate the named cases only
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         rec = run_reference(name, case)
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **rec)
         print("wrote", name, {k: float(v) for k, v in rec.items() if k.startswith("s0/loss")})

@@ -39,8 +39,9 @@ def unet_structure(init_ch=32, max_ch=512, output_stride=8):
     return ch, enc, scales
 
 
-def unet_param_shapes(input_ch=1, init_ch=32, max_ch=512, num_classes=5, output_stride=8):
-    """Ordered {state-dict key: shape} of models.unet.UNet (165-entry ConsistencyRegulr minus aux)."""
+def unet_param_shapes(input_ch=1, init_ch=32, max_ch=512, num_classes=5, output_stride=8, strided=False):
+    """Ordered {state-dict key: shape} of models.unet.UNet (165-entry ConsistencyRegulr minus aux).
+    strided: the is_stride_conv + is_trans_conv variant adds dec_blockK.up_samp.weight (unet.py:141)."""
     ch, _enc, _sc = unet_structure(init_ch, max_ch, output_stride)
     shapes = {}
 
@@ -64,6 +65,10 @@ def unet_param_shapes(input_ch=1, init_ch=32, max_ch=512, num_classes=5, output_
     for stage in (5, 4, 3, 2, 1):  # DecBlock(lower, skip, .): DoubleConv(lower + skip, skip), unet.py:145
         lower = ch[stage]
         skip = ch[stage - 1]
+        if strided:   # ConvTranspose2d(lower, skip, ks, stride, bias=False) then DoubleConv(2 * skip, skip)
+            ks = _sc[5 - stage]
+            shapes['dec_block%d.up_samp.weight' % stage] = (lower, skip, ks, ks)
+            lower = skip
         block('dec_block%d' % stage, lower + skip, skip)
     shapes['final_conv.weight'] = (num_classes, ch[0], 1, 1)
     shapes['final_conv.bias'] = (num_classes,)
@@ -102,6 +107,8 @@ def synth_state_dict(shapes, seed, dtype=torch.float32):
             sd[k] = (0.05 * torch.randn(shp, generator=g)).to(dtype)
         elif k == 'memory_bank':
             sd[k] = torch.zeros(shp, dtype=dtype)
+        elif k.endswith('up_samp.weight'):   # (Cin, Cout, ks, ks)
+            sd[k] = (torch.randn(shp, generator=g) * math.sqrt(1.0 / shp[0])).to(dtype)
         else:
             fan_in = shp[1] * shp[2] * shp[3]
             sd[k] = (torch.randn(shp, generator=g) * math.sqrt(2.0 / fan_in)).to(dtype)
@@ -136,11 +143,11 @@ def _qw(w, quant):
 # ------------------------------------------------------------------------------------------------
 # layers
 # ------------------------------------------------------------------------------------------------
-def conv_bn_lrelu(x, sd, prefix, dilation, training, quant=False):
-    """ConvLayer (unet.py:178-193): Conv2d(3x3, pad=dil, bias) -> BatchNorm2d -> LeakyReLU(0.01).
+def conv_bn_lrelu(x, sd, prefix, dilation, training, quant=False, stride=1):
+    """ConvLayer (unet.py:178-193): Conv2d(3x3, stride, pad=dil, bias) -> BatchNorm2d -> LeakyReLU(0.01).
     Running statistics in `sd` are updated in place when training (momentum 0.1, unbiased variance)."""
     w = sd[prefix + '.conv.weight']
-    y = F.conv2d(x, _qw(w, quant and w.shape[1] > 1), sd[prefix + '.conv.bias'], 1, dilation, dilation)
+    y = F.conv2d(x, _qw(w, quant and w.shape[1] > 1), sd[prefix + '.conv.bias'], stride, dilation, dilation)
     y = _q(y, quant)
     g, b = sd[prefix + '.norm_op.weight'], sd[prefix + '.norm_op.bias']
     rm, rv = sd[prefix + '.norm_op.running_mean'], sd[prefix + '.norm_op.running_var']
@@ -159,8 +166,8 @@ def conv_bn_lrelu(x, sd, prefix, dilation, training, quant=False):
     return _q(torch.where(z > 0, z, z * SLOPE), quant)
 
 
-def double_conv(x, sd, prefix, dilation, training, quant=False):
-    x = conv_bn_lrelu(x, sd, prefix + '.conv_block.conv_layer1', dilation, training, quant)
+def double_conv(x, sd, prefix, dilation, training, quant=False, stride1=1):
+    x = conv_bn_lrelu(x, sd, prefix + '.conv_block.conv_layer1', dilation, training, quant, stride1)
     return conv_bn_lrelu(x, sd, prefix + '.conv_block.conv_layer2', dilation, training, quant)
 
 
@@ -185,22 +192,37 @@ def upsample_bilinear_ac(x, size):
     return top * wy0[:, None] + bot * wy1[:, None]
 
 
-def unet_forward(sd, x, training, init_ch=32, max_ch=512, output_stride=8, prefix='', quant=False):
-    """UNet.forward (unet.py:62-98) -> dict of the 12 end points."""
+def conv_transpose_ks(x, w):
+    """ConvTranspose2d(kernel = stride = S, bias=False) (unet.py:141) restated without F.conv_transpose2d:
+    out[n, co, S*y + a, S*x + b] = sum_ci x[n, ci, y, x] * w[ci, co, a, b]."""
+    n, _ci, h, wd = x.shape
+    co, S = w.shape[1], w.shape[2]
+    y = torch.einsum('nihw,ioab->nohawb', x, w)
+    return y.reshape(n, co, h * S, wd * S)
+
+
+def unet_forward(sd, x, training, init_ch=32, max_ch=512, output_stride=8, prefix='', quant=False, strided=False):
+    """UNet.forward (unet.py:62-98) -> dict of the 12 end points. strided: stride-2 first conv instead of the
+    max-pool (unet.py:113-116) and ConvTranspose2d instead of the bilinear up-sampling (unet.py:141)."""
     _ch, enc_cfg, scales = unet_structure(init_ch, max_ch, output_stride)
     ep = {}
     enc = []
     cur = x
     for k, (pool, dil) in enumerate(enc_cfg):
-        if pool:
+        if pool and not strided:
             cur = F.max_pool2d(cur, 2, 2)  # unet.py:109
-        cur = double_conv(cur, sd, '%senc_block%d' % (prefix, k + 1), dil, training, quant)
+        cur = double_conv(cur, sd, '%senc_block%d' % (prefix, k + 1), dil, training, quant,
+                          stride1=2 if (pool and strided) else 1)
         enc.append(cur)
         ep['encoder/stage%d' % (k + 1)] = cur
     for i, stage in enumerate((5, 4, 3, 2, 1)):
         skip = enc[stage - 1]
         s = scales[i]
-        up = _q(upsample_bilinear_ac(cur, (cur.shape[2] * s, cur.shape[3] * s)), quant) if s > 1 else cur
+        if strided:
+            wt = sd['%sdec_block%d.up_samp.weight' % (prefix, stage)]
+            up = _q(conv_transpose_ks(cur, _qw(wt, quant)), quant)
+        else:
+            up = _q(upsample_bilinear_ac(cur, (cur.shape[2] * s, cur.shape[3] * s)), quant) if s > 1 else cur
         cur = double_conv(torch.cat((up, skip), 1), sd, '%sdec_block%d' % (prefix, stage), 1, training, quant)  # :151
         ep['decoder/stage%d' % stage] = cur
     ep['segmentation/logits'] = F.conv2d(cur, sd[prefix + 'final_conv.weight'], sd[prefix + 'final_conv.bias'])
@@ -344,7 +366,7 @@ class StepConfig:
     def __init__(self, num_classes=5, ignored_index=5, do_loss_ent=True, do_decoder_consistency=True,
                  detach_weak_cr=False, loss_cr_variants='ce_loss', do_aux_path=True, do_memory=True,
                  feat_stage=('encoder/stage6', 'encoder/stage5'), max_step=400, update_momentum=0.9,
-                 ensemble_mode='cosine_similarity', init_ch=32, max_ch=512, output_stride=8, quant=False):
+                 ensemble_mode='cosine_similarity', init_ch=32, max_ch=512, output_stride=8, quant=False, strided=False):
         self.__dict__.update(locals())
         del self.__dict__['self']
 
@@ -355,7 +377,7 @@ def consistency_forward(sd, batch, cfg, mode='train', step=0, training=True):
     net = cfg
     out = {}
     kw = dict(init_ch=net.init_ch, max_ch=net.max_ch, output_stride=net.output_stride, prefix='backbone.',
-              quant=net.quant)
+              quant=net.quant, strided=net.strided)
     ep = unet_forward(sd, batch['image'], training, **kw)
     zw = ep['segmentation/logits']
     target = batch['scribble'].argmax(1)

@@ -7,7 +7,9 @@
 
 namespace pp {
 struct UNetPlan;
-UNetPlan* unet_create(int input_ch, int init_ch, int max_ch, int num_classes, int output_stride, int dtype);
+UNetPlan* unet_create(int input_ch, int init_ch, int max_ch, int num_classes, int output_stride, int dtype,
+                      int strided);
+int unet_conv_kind(const UNetPlan* pl, int layer, int* kind, int* scale);
 void unet_destroy(UNetPlan* pl);
 int unet_set_grad_events(UNetPlan* pl, int n, const int* layers);
 int unet_wait_grad_event(const UNetPlan* pl, int i, cudaStream_t s);
@@ -40,8 +42,17 @@ int pp_profile_collect(int family, double* ms, double* flops, long long* launche
 
 int pp_unet_create(int input_ch, int init_ch, int max_ch, int num_classes, int output_stride, int dtype,
                    pp_unet_t* out) {
-  *out = reinterpret_cast<pp_unet_t>(unet_create(input_ch, init_ch, max_ch, num_classes, output_stride, dtype));
+  *out = reinterpret_cast<pp_unet_t>(unet_create(input_ch, init_ch, max_ch, num_classes, output_stride, dtype, 0));
   return *out ? PP_OK : PP_ERR_INVALID;
+}
+int pp_unet_create_ex(int input_ch, int init_ch, int max_ch, int num_classes, int output_stride, int dtype,
+                      int strided, pp_unet_t* out) {
+  *out = reinterpret_cast<pp_unet_t>(
+      unet_create(input_ch, init_ch, max_ch, num_classes, output_stride, dtype, strided));
+  return *out ? PP_OK : PP_ERR_INVALID;
+}
+int pp_unet_conv_kind(pp_unet_t u, int layer, int* kind, int* scale) {
+  return unet_conv_kind(reinterpret_cast<pp::UNetPlan*>(u), layer, kind, scale);
 }
 void pp_unet_destroy(pp_unet_t u) { unet_destroy(reinterpret_cast<pp::UNetPlan*>(u)); }
 int pp_unet_set_grad_events(pp_unet_t u, int n, const int* layers) {

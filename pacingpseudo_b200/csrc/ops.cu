@@ -1247,6 +1247,147 @@ int nhwc_to_nchw(int dtype, const void* src, float* dst, int N, int C, int HW, c
 }
 
 // ==============================================================================================
+// The strided-conv / transposed-conv UNet variant (unet.py:113-116 stride-2 first conv of an encoder block,
+// unet.py:141 ConvTranspose2d(k = s, stride = s, bias=False) in the decoder) runs on the SAME stride-1 tcgen05
+// kernels through two exact identities:
+//   * conv3x3(stride 2, pad 1)(x) == conv3x3(stride 1, pad 1)(space_to_depth(x)) with the zero-embedded kernel
+//       We[co, (sy,sx,c), ty, tx] = W[co, c, ky, kx],  ky -> (ty, sy): 0 -> (0,1), 1 -> (1,0), 2 -> (1,1)  (same for x)
+//     because input row 2y + ky - 1 is block row y - 1 / sub-row 1 (ky = 0) or block row y / sub-row ky - 1;
+//   * ConvTranspose2d(k = s = S)(x) == depth_to_space(conv1x1(x) to S*S*Cout channels), the 1x1 conv being the centre
+//     tap of a 3x3 kernel:  We[(a*S+b)*Cout + co, ci, 1, 1] = Wt[ci, co, a, b].
+// Zero taps contribute exactly 0, so results equal the direct computation up to summation order. The embedded fp32
+// kernels are rebuilt from the master weights every forward pass; weight gradients are gathered back from the
+// embedded gradient. space_to_depth / depth_to_space: big[n, 2Y+sy, 2X+sx, c] <-> small[n, Y, X, (sy*2+sx)*C + c].
+// ==============================================================================================
+template <typename T, bool TO_DEPTH>
+__global__ void __launch_bounds__(256) space_depth_kernel(const T* __restrict__ src, T* __restrict__ dst, long long nvec,
+                                                          int Hs, int Ws, int C, int accumulate) {
+  const int cv = C / 8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % cv);
+    long long r = i / cv;
+    const int q = static_cast<int>(r % 4); r /= 4;
+    const int X = static_cast<int>(r % Ws); r /= Ws;
+    const int Y = static_cast<int>(r % Hs);
+    const long long n = r / Hs;
+    const long long big = (((n * 2 * Hs + 2 * Y + (q >> 1)) * 2 * Ws) + 2 * X + (q & 1)) * C + v * 8;
+    const long long small = i * 8;
+    Vec8<T> a;
+    if (TO_DEPTH) {
+      a.load(src + big);
+      a.store(dst + small);
+    } else {
+      a.load(src + small);
+      if (accumulate) {
+        Vec8<T> b;
+        b.load(dst + big);
+        float fa[8], fb[8];
+        a.get(fa); b.get(fb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+        a.set(fa);
+      }
+      a.store(dst + big);
+    }
+  }
+}
+// x [N, 2Hs, 2Ws, C] -> y [N, Hs, Ws, 4C]
+int space_to_depth(int dtype, const void* x, void* y, int N, int Hs, int Ws, int C, cudaStream_t s) {
+  PP_REQUIRE(C % 8 == 0 && C > 0, "space_to_depth: C=%d must be a multiple of 8", C);
+  const long long nvec = static_cast<long long>(N) * Hs * Ws * 4 * (C / 8);
+  PP_DISPATCH_T(dtype, (space_depth_kernel<T, true><<<grid_for(nvec, 256), 256, 0, s>>>(
+                           static_cast<const T*>(x), static_cast<T*>(y), nvec, Hs, Ws, C, 0)););
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+// y [N, Hs, Ws, 4C] -> x [N, 2Hs, 2Ws, C] (accumulate: +=)
+int depth_to_space(int dtype, const void* y, void* x, int N, int Hs, int Ws, int C, int accumulate, cudaStream_t s) {
+  PP_REQUIRE(C % 8 == 0 && C > 0, "depth_to_space: C=%d must be a multiple of 8", C);
+  const long long nvec = static_cast<long long>(N) * Hs * Ws * 4 * (C / 8);
+  PP_DISPATCH_T(dtype, (space_depth_kernel<T, false><<<grid_for(nvec, 256), 256, 0, s>>>(
+                           static_cast<const T*>(y), static_cast<T*>(x), nvec, Hs, Ws, C, accumulate)););
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+__device__ __forceinline__ int s2_k_of(int t, int sub) {   // embedded tap t, sub-row -> original ky (or -1: zero)
+  return t == 0 ? (sub == 1 ? 0 : -1) : (t == 1 ? 1 + sub : -1);
+}
+__global__ void __launch_bounds__(256) embed_s2_weight_kernel(const float* __restrict__ w, float* __restrict__ we,
+                                                              int Cout, int C) {
+  const long long total = static_cast<long long>(Cout) * 4 * C * 9;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i % 9);
+    const int cc = static_cast<int>((i / 9) % (4 * C));
+    const long long co = i / (9LL * 4 * C);
+    const int q = cc / C, c = cc % C;
+    const int ky = s2_k_of(t / 3, q >> 1), kx = s2_k_of(t % 3, q & 1);
+    we[i] = (ky >= 0 && kx >= 0) ? w[((co * C + c) * 3 + ky) * 3 + kx] : 0.f;
+  }
+}
+__global__ void __launch_bounds__(256) collapse_s2_wgrad_kernel(const float* __restrict__ dwe, float* __restrict__ dw,
+                                                                int Cout, int C) {
+  const long long total = static_cast<long long>(Cout) * C * 9;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % 9), ky = k / 3, kx = k % 3;
+    const int c = static_cast<int>((i / 9) % C);
+    const long long co = i / (9LL * C);
+    const int ty = ky == 0 ? 0 : 1, sy = ky == 0 ? 1 : ky - 1;
+    const int tx = kx == 0 ? 0 : 1, sx = kx == 0 ? 1 : kx - 1;
+    dw[i] += dwe[((co * 4 * C + (sy * 2 + sx) * C + c) * 9) + ty * 3 + tx];
+  }
+}
+int embed_s2_weight(const float* w, float* we, int Cout, int C, cudaStream_t s) {
+  embed_s2_weight_kernel<<<grid_for(static_cast<long long>(Cout) * 4 * C * 9, 256), 256, 0, s>>>(w, we, Cout, C);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+int collapse_s2_wgrad(const float* dwe, float* dw, int Cout, int C, cudaStream_t s) {
+  collapse_s2_wgrad_kernel<<<grid_for(static_cast<long long>(Cout) * C * 9, 256), 256, 0, s>>>(dwe, dw, Cout, C);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// wt: ConvTranspose2d weight [Cin][Cout][S][S]; we: [S*S*Cout][Cin][3][3]
+__global__ void __launch_bounds__(256) embed_ct_weight_kernel(const float* __restrict__ wt, float* __restrict__ we,
+                                                              int Cin, int Cout, int S) {
+  const long long total = static_cast<long long>(S) * S * Cout * Cin * 9;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i % 9);
+    const int ci = static_cast<int>((i / 9) % Cin);
+    const long long r = i / (9LL * Cin);
+    const int q = static_cast<int>(r / Cout), co = static_cast<int>(r % Cout);
+    we[i] = t == 4 ? wt[((static_cast<long long>(ci) * Cout + co) * S + q / S) * S + q % S] : 0.f;
+  }
+}
+__global__ void __launch_bounds__(256) collapse_ct_wgrad_kernel(const float* __restrict__ dwe, float* __restrict__ dwt,
+                                                                int Cin, int Cout, int S) {
+  const long long total = static_cast<long long>(Cin) * Cout * S * S;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i % (S * S));
+    const int co = static_cast<int>((i / (S * S)) % Cout);
+    const long long ci = i / (static_cast<long long>(S) * S * Cout);
+    dwt[i] += dwe[((static_cast<long long>(q) * Cout + co) * Cin + ci) * 9 + 4];
+  }
+}
+int embed_ct_weight(const float* wt, float* we, int Cin, int Cout, int S, cudaStream_t s) {
+  PP_REQUIRE(S == 1 || S == 2, "embed_ct_weight: kernel/stride %d unsupported (1 or 2)", S);
+  embed_ct_weight_kernel<<<grid_for(static_cast<long long>(S) * S * Cout * Cin * 9, 256), 256, 0, s>>>(wt, we, Cin, Cout, S);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+int collapse_ct_wgrad(const float* dwe, float* dwt, int Cin, int Cout, int S, cudaStream_t s) {
+  collapse_ct_wgrad_kernel<<<grid_for(static_cast<long long>(Cin) * Cout * S * S, 256), 256, 0, s>>>(dwe, dwt, Cin, Cout, S);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ==============================================================================================
 // Adam with L2 weight decay folded into the gradient (torch.optim.Adam semantics,
 // train_chaos.py:219), over one flat fp32 parameter buffer. step is the 1-based step count.
 // ==============================================================================================

@@ -60,6 +60,13 @@ int upsample_planes_fwd(const float* x, float* y, long long NC, int h, int w, in
 int upsample_planes_bwd(const float* gy, float* gx, long long NC, int h, int w, int H, int W, cudaStream_t s);
 int nchw_to_nhwc(int dtype, const float* src, void* dst, int N, int C, int HW, cudaStream_t s);
 int nhwc_to_nchw(int dtype, const void* src, float* dst, int N, int C, int HW, cudaStream_t s);
+// strided-conv / transposed-conv variant (unet.py:113-116,141): layout shuffles and zero-embedded kernels
+int space_to_depth(int dtype, const void* x, void* y, int N, int Hs, int Ws, int C, cudaStream_t s);
+int depth_to_space(int dtype, const void* y, void* x, int N, int Hs, int Ws, int C, int accumulate, cudaStream_t s);
+int embed_s2_weight(const float* w, float* we, int Cout, int C, cudaStream_t s);
+int collapse_s2_wgrad(const float* dwe, float* dw, int Cout, int C, cudaStream_t s);
+int embed_ct_weight(const float* wt, float* we, int Cin, int Cout, int S, cudaStream_t s);
+int collapse_ct_wgrad(const float* dwe, float* dwt, int Cin, int Cout, int S, cudaStream_t s);
 int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
               float wd, int step, float grad_scale, cudaStream_t s);
 

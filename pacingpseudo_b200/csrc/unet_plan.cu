@@ -18,12 +18,20 @@ namespace pp {
 namespace {
 
 struct Act { int C; int res; };  // channels, spatial divisor relative to the input
+// Layer kinds. KIND_S2 / KIND_CT belong to the strided-conv / transposed-conv variant (unet.py:113-116,141) and run on
+// the same stride-1 conv kernels with zero-embedded weights (ops.cu: embed_s2_weight / embed_ct_weight):
+//   KIND_S2: Conv2d(3x3, stride 2) + BN + LeakyReLU; the input activation is the space-to-depth tensor (cin0 = 4 C)
+//   KIND_CT: ConvTranspose2d(k = s = S, bias=False): a plain (no BN, no bias) conv to S*S*Cout channels (cout), then
+//            a depth-to-space op when S == 2
+enum ConvKind { KIND_CONV = 0, KIND_S2 = 1, KIND_CT = 2 };
 struct ConvL {
   int in0, in1;            // activation ids (in0 == -1: the network input, Cin = 1)
   int cin0, cin1, cout, dil, out;
   std::string name;        // module path, e.g. "enc_block1.conv_block.conv_layer1"
+  int kind = KIND_CONV;
+  int S = 1;               // KIND_CT: kernel size == stride
 };
-enum OpKind { OP_CONV = 0, OP_POOL = 1, OP_UP = 2 };
+enum OpKind { OP_CONV = 0, OP_POOL = 1, OP_UP = 2, OP_S2D = 3, OP_D2S = 4 };
 struct Op { OpKind kind; int layer; int src; int dst; };
 
 inline long long align_up(long long v) { return (v + 255) & ~255LL; }
@@ -32,6 +40,7 @@ inline long long align_up(long long v) { return (v + 255) & ~255LL; }
 
 struct UNetPlan {
   int input_ch, init_ch, max_ch, num_classes, output_stride, dtype;
+  int strided = 0;         // 1: is_stride_conv and is_trans_conv (the reference only allows both or neither, unet.py:25)
   std::vector<Act> acts;
   std::vector<ConvL> convs;
   std::vector<Op> ops;
@@ -55,14 +64,19 @@ struct UNetPlan {
 
   int new_act(int C, int res) { acts.push_back({C, res}); return int(acts.size()) - 1; }
 
-  int add_conv(const std::string& name, int in0, int in1, int cin0, int cin1, int cout, int dil, int res) {
+  int add_conv(const std::string& name, int in0, int in1, int cin0, int cin1, int cout, int dil, int res,
+               int kind = KIND_CONV, int S = 1) {
     const int out = new_act(cout, res);
-    convs.push_back({in0, in1, cin0, cin1, cout, dil, out, name});
+    ConvL c{in0, in1, cin0, cin1, cout, dil, out, name};
+    c.kind = kind;
+    c.S = S;
+    convs.push_back(c);
     ops.push_back({OP_CONV, int(convs.size()) - 1, -1, out});
     return out;
   }
-  int double_conv(const std::string& block, int in0, int in1, int cin0, int cin1, int cout, int dil, int res) {
-    const int a = add_conv(block + ".conv_block.conv_layer1", in0, in1, cin0, cin1, cout, dil, res);
+  int double_conv(const std::string& block, int in0, int in1, int cin0, int cin1, int cout, int dil, int res,
+                  int kind1 = KIND_CONV) {
+    const int a = add_conv(block + ".conv_block.conv_layer1", in0, in1, cin0, cin1, cout, dil, res, kind1);
     return add_conv(block + ".conv_block.conv_layer2", a, -1, cout, 0, cout, dil, res);
   }
 
@@ -78,13 +92,21 @@ struct UNetPlan {
     int enc[6];
     int cur = -1, cur_c = input_ch, res = 1;
     for (int k = 0; k < 6; ++k) {
-      if (pool[k]) {
+      int kind1 = KIND_CONV, cin = cur_c;
+      if (pool[k] && !strided) {
         const int p = new_act(cur_c, res * 2);
         ops.push_back({OP_POOL, -1, cur, p});
         cur = p;
         res *= 2;
+      } else if (pool[k]) {   // stride-2 first conv (unet.py:113-116) == stride-1 conv over the space-to-depth input
+        const int p = new_act(4 * cur_c, res * 2);
+        ops.push_back({OP_S2D, -1, cur, p});
+        cur = p;
+        res *= 2;
+        kind1 = KIND_S2;
+        cin = 4 * cur_c;
       }
-      cur = double_conv("enc_block" + std::to_string(k + 1), cur, -1, cur_c, 0, ch[k], dil[k], res);
+      cur = double_conv("enc_block" + std::to_string(k + 1), cur, -1, cin, 0, ch[k], dil[k], res, kind1);
       cur_c = ch[k];
       enc[k] = cur;
       named["encoder/stage" + std::to_string(k + 1)] = cur;
@@ -95,7 +117,18 @@ struct UNetPlan {
       const int stage = 5 - i;
       const int skip = enc[stage - 1];
       int low = cur;
-      if (scales[i] > 1) {
+      if (strided) {   // ConvTranspose2d(lower_ch, skip_ch, S, S, bias=False) (unet.py:141), also for S == 1
+        const int S = scales[i], skip_c = acts[skip].C;
+        low = add_conv("dec_block" + std::to_string(stage) + ".up_samp", cur, -1, cur_c, 0, S * S * skip_c, 1, res,
+                       KIND_CT, S);
+        if (S == 2) {
+          const int u = new_act(skip_c, res / 2);
+          ops.push_back({OP_D2S, -1, low, u});
+          low = u;
+          res /= 2;
+        }
+        cur_c = skip_c;
+      } else if (scales[i] > 1) {
         const int u = new_act(cur_c, res / scales[i]);
         ops.push_back({OP_UP, -1, cur, u});
         low = u;
@@ -113,6 +146,8 @@ struct UNetLayout {
   long long total = 0;
   std::vector<long long> act_data, act_grad;          // per activation
   std::vector<long long> yraw, coef, sums, wf, wd;     // per conv layer
+  std::vector<long long> wexp;                         // per conv layer: zero-embedded fp32 OIHW kernel (KIND_S2 / KIND_CT), else -1
+  long long dwe_scratch = 0;                           // embedded weight gradient of one such layer (fp32 OIHW)
   long long dy_scratch = 0, dy_stride = 0, dwp_scratch = 0, dws_scratch = 0, dws_floats = 0, bsums = 0, bcoef = 0;
   long long sums_begin = 0, sums_bytes = 0, bsums_begin = 0, bsums_bytes = 0;
   std::vector<long long> bsums_layer;
@@ -124,7 +159,7 @@ static UNetLayout make_layout(const UNetPlan& pl, int N, int H, int W, int G) {
   long long off = 0;
   auto take = [&](long long bytes) { long long o = off; off += align_up(bytes); return o; };
   auto act_bytes = [&](const Act& a) { return static_cast<long long>(N) * (H / a.res) * (W / a.res) * a.C * es; };
-  long long max_act = 0, max_w = 0;
+  long long max_act = 0, max_w = 0, max_we = 0;
   int max_c = 0;
   for (const Act& a : pl.acts) {
     L.act_data.push_back(take(act_bytes(a)));
@@ -137,6 +172,8 @@ static UNetLayout make_layout(const UNetPlan& pl, int N, int H, int W, int G) {
     const long long wn = 9LL * c.cout * (c.cin0 + c.cin1);
     L.wf.push_back(take(wn * es));
     L.wd.push_back(take(wn * es));
+    L.wexp.push_back(c.kind != KIND_CONV ? take(wn * 4) : -1);
+    if (c.kind != KIND_CONV) max_we = std::max(max_we, wn);
     max_w = std::max(max_w, wn);
     max_c = std::max(max_c, c.cout);
   }
@@ -154,6 +191,7 @@ static UNetLayout make_layout(const UNetPlan& pl, int N, int H, int W, int G) {
   L.dwp_scratch = take(max_w * 4);
   L.dws_floats = 2 * max_w;                 // split-K partial gradients of the wide layers (>= 2 splits each)
   L.dws_scratch = take(L.dws_floats * 4);
+  if (max_we > 0) L.dwe_scratch = take(max_we * 4);
   L.bsums = take(sizeof(double) * 2 * G * max_c);
   L.bcoef = take(sizeof(float) * 2 * G * max_c);
   L.total = off;
@@ -219,6 +257,14 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
     for (size_t l = 0; l < pl.convs.size(); ++l) {
       const ConvL& c = pl.convs[l];
       if (c.in0 < 0) continue;
+      if (c.kind != KIND_CONV) {   // rebuild the zero-embedded fp32 kernel from the master weights, then pack that
+        float* we = reinterpret_cast<float*>(base + L.wexp[l]);
+        const float* w = static_cast<const float*>(params[l * kParamsPerConv]);
+        rc = c.kind == KIND_S2 ? embed_s2_weight(w, we, c.cout, c.cin0 / 4, s)
+                               : embed_ct_weight(w, we, c.cin0, c.cout / (c.S * c.S), c.S, s);
+        if (rc) return rc;
+        pw.push_back(we);
+      } else
       pw.push_back(static_cast<const float*>(params[l * kParamsPerConv]));
       pf.push_back(base + L.wf[l]);
       pd.push_back(base + L.wd[l]);
@@ -263,6 +309,16 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
         const int h = H / ao.res, w = W / ao.res;
         void* yraw = act_part(L.yraw[op.layer], ao, k);
         const long long Pg = static_cast<long long>(N / G) * h * w;
+        if (c.kind == KIND_CT) {   // plain linear layer: no bias, no BatchNorm, no activation
+          const void* x0 = act_part(L.act_data[c.in0], pl.acts[c.in0], k);
+          void* y = act_part(L.act_data[c.out], ao, k);
+          const void* wf = base + L.wf[op.layer];
+          rc = dt == PP_BF16 ? conv3x3_tc(x0, c.cin0, nullptr, 0, wf, nullptr, y, c.cout, 0, nullptr, 0, 0, Np, h, w, 1, sk)
+                             : conv3x3_simt(dt, x0, c.cin0, nullptr, 0, wf, nullptr, y, c.cout, 0, nullptr, 0, 0, Np, h, w,
+                                            1, sk);
+          if (rc) return rc;
+          continue;
+        }
         bool fused_stats = false;
         if (dt == PP_BF16 && c.in0 >= 0) {
           // batch statistics ride in the conv epilogue when a pixel tile never straddles two statistics groups
@@ -308,6 +364,18 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
         const Act& as = pl.acts[op.src];
         rc = maxpool_fwd(dt, act_part(L.act_data[op.src], as, k), act_part(L.act_data[op.dst], pl.acts[op.dst], k), Np,
                          H / as.res, W / as.res, as.C, sk);
+        if (rc) return rc;
+      } else if (op.kind == OP_S2D) {
+        const Act& as = pl.acts[op.src];
+        const Act& ad = pl.acts[op.dst];
+        rc = space_to_depth(dt, act_part(L.act_data[op.src], as, k), act_part(L.act_data[op.dst], ad, k), Np, H / ad.res,
+                            W / ad.res, as.C, sk);
+        if (rc) return rc;
+      } else if (op.kind == OP_D2S) {
+        const Act& as = pl.acts[op.src];
+        const Act& ad = pl.acts[op.dst];
+        rc = depth_to_space(dt, act_part(L.act_data[op.src], as, k), act_part(L.act_data[op.dst], ad, k), Np, H / as.res,
+                            W / as.res, ad.C, 0, sk);
         if (rc) return rc;
       } else {
         const Act& as = pl.acts[op.src];
@@ -400,11 +468,15 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
       const int kb = ov ? (nbuf++ % UNetPlan::kDyBufs) : 0;
       void* dy = base + L.dy_scratch + kb * L.dy_stride;
       if (ov && buf_used[kb]) PP_CHECK_CUDA(cudaStreamWaitEvent(s, pl.buf_free[kb], 0));   // its last reader is done
-      rc = bn_bwd(dt, base + L.act_grad[c.out], base + L.yraw[op.layer],
-                  reinterpret_cast<const float*>(base + L.coef[op.layer]),
-                  reinterpret_cast<double*>(base + L.bsums_layer[op.layer]), reinterpret_cast<float*>(base + L.bcoef),
-                  gg[2], gg[3], gg[1], dy, G, Pg, c.cout, training, 0.01f, s, /*sums_zeroed=*/true);
-      if (rc) return rc;
+      if (c.kind == KIND_CT) {
+        dy = base + L.act_grad[c.out];   // plain layer: the activation gradient IS the conv-output gradient
+      } else {
+        rc = bn_bwd(dt, base + L.act_grad[c.out], base + L.yraw[op.layer],
+                    reinterpret_cast<const float*>(base + L.coef[op.layer]),
+                    reinterpret_cast<double*>(base + L.bsums_layer[op.layer]), reinterpret_cast<float*>(base + L.bcoef),
+                    gg[2], gg[3], gg[1], dy, G, Pg, c.cout, training, 0.01f, s, /*sums_zeroed=*/true);
+        if (rc) return rc;
+      }
       if (ov) {
         PP_CHECK_CUDA(cudaEventRecord(pl.dy_ready[kb], s));
         PP_CHECK_CUDA(cudaStreamWaitEvent(ws_, pl.dy_ready[kb], 0));
@@ -429,20 +501,29 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
       float* dwp = reinterpret_cast<float*>(base + L.dwp_scratch);
       const void* x0 = base + L.act_data[c.in0];
       const void* x1 = c.in1 >= 0 ? base + L.act_data[c.in1] : nullptr;
+      // embedded layers: the OIHW gradient of the zero-embedded kernel lands in a scratch, then is gathered back
+      float* g_oihw = gg[0];
+      if (c.kind != KIND_CONV) {
+        g_oihw = reinterpret_cast<float*>(base + L.dwe_scratch);
+        PP_CHECK_CUDA(cudaMemsetAsync(g_oihw, 0, sizeof(float) * 9 * c.cout * ctot, ws_));
+      }
       if (dt == PP_BF16) {
         // wide sources accumulate straight into the OIHW gradient; narrow ones go through the packed scratch
         if (conv3x3_wgrad_tc_uses_scratch(c.cout, c.cin0, c.cin1))
           PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * c.cout * ctot, ws_));
-        rc = conv3x3_wgrad_tc(dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, gg[0], N, h, w, c.dil, ws_,
+        rc = conv3x3_wgrad_tc(dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, g_oihw, N, h, w, c.dil, ws_,
                               reinterpret_cast<float*>(base + L.dws_scratch), L.dws_floats);
         if (rc) return rc;
       } else {
         PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * c.cout * ctot, ws_));
         rc = conv3x3_wgrad_simt(dt, dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, N, h, w, c.dil, ws_);
         if (rc) return rc;
-        rc = unpack_wgrad(dwp, gg[0], c.cout, ctot, 1, ws_);
+        rc = unpack_wgrad(dwp, g_oihw, c.cout, ctot, 1, ws_);
         if (rc) return rc;
       }
+      if (c.kind == KIND_S2) rc = collapse_s2_wgrad(g_oihw, gg[0], c.cout, c.cin0 / 4, ws_);
+      else if (c.kind == KIND_CT) rc = collapse_ct_wgrad(g_oihw, gg[0], c.cin0, c.cout / (c.S * c.S), c.S, ws_);
+      if (rc) return rc;
       rc = grads_ready();
       if (rc) return rc;
       // dgrad: forward kernel on the flipped/transposed pack, scattered to the two sources
@@ -466,6 +547,22 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
       }
       rc = maxpool_bwd(dt, base + L.act_data[op.src], base + L.act_grad[op.dst], base + L.act_grad[op.src], N,
                        H / as.res, W / as.res, as.C, written[op.src], s);
+      if (rc) return rc;
+      written[op.src] = 1;
+    } else if (op.kind == OP_S2D || op.kind == OP_D2S) {
+      const Act& as = pl.acts[op.src];
+      const Act& ad = pl.acts[op.dst];
+      if (!written[op.dst]) {
+        PP_CHECK_CUDA(cudaMemsetAsync(base + L.act_grad[op.dst], 0, act_bytes(ad), s));
+        written[op.dst] = 1;
+      }
+      if (op.kind == OP_S2D)   // forward gathered big -> small: the gradient scatters small -> big
+        rc = depth_to_space(dt, base + L.act_grad[op.dst], base + L.act_grad[op.src], N, H / ad.res, W / ad.res, as.C,
+                            written[op.src], s);
+      else {
+        PP_REQUIRE(!written[op.src], "unet_backward: transposed-conv output has a second consumer");
+        rc = space_to_depth(dt, base + L.act_grad[op.dst], base + L.act_grad[op.src], N, H / as.res, W / as.res, ad.C, s);
+      }
       if (rc) return rc;
       written[op.src] = 1;
     } else {
@@ -492,7 +589,8 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
   return PP_OK;
 }
 
-UNetPlan* unet_create(int input_ch, int init_ch, int max_ch, int num_classes, int output_stride, int dtype) {
+UNetPlan* unet_create(int input_ch, int init_ch, int max_ch, int num_classes, int output_stride, int dtype,
+                      int strided) {
   if (input_ch != 1) { set_error("unet: input_ch=%d unsupported (the reference data is single-channel)", input_ch); return nullptr; }
   if (init_ch % 32 != 0 || max_ch % 32 != 0 || init_ch <= 0 || max_ch < init_ch) {
     set_error("unet: init_ch=%d / max_ch=%d must be positive multiples of 32", init_ch, max_ch);
@@ -505,6 +603,7 @@ UNetPlan* unet_create(int input_ch, int init_ch, int max_ch, int num_classes, in
   UNetPlan* pl = new UNetPlan();
   pl->input_ch = input_ch; pl->init_ch = init_ch; pl->max_ch = max_ch; pl->num_classes = num_classes;
   pl->output_stride = output_stride; pl->dtype = dtype;
+  pl->strided = strided ? 1 : 0;
   pl->build();
   return pl;
 }
@@ -551,8 +650,16 @@ int unet_num_convs(const UNetPlan* pl) { return int(pl->convs.size()); }
 int unet_conv_info(const UNetPlan* pl, int layer, int* cin, int* cout, int* dil, const char** name) {
   PP_REQUIRE(layer >= 0 && layer < int(pl->convs.size()), "unet_conv_info: bad layer %d", layer);
   const ConvL& c = pl->convs[layer];
-  *cin = c.in0 < 0 ? pl->input_ch : c.cin0 + c.cin1;
-  *cout = c.cout; *dil = c.dil; *name = c.name.c_str();
+  // the PARAMETER's channels: a stride-2 layer reads 4 C space-to-depth channels, a transposed conv writes S*S*Cout
+  *cin = c.in0 < 0 ? pl->input_ch : (c.kind == KIND_S2 ? c.cin0 / 4 : c.cin0 + c.cin1);
+  *cout = c.kind == KIND_CT ? c.cout / (c.S * c.S) : c.cout;
+  *dil = c.dil; *name = c.name.c_str();
+  return PP_OK;
+}
+int unet_conv_kind(const UNetPlan* pl, int layer, int* kind, int* scale) {
+  PP_REQUIRE(layer >= 0 && layer < int(pl->convs.size()), "unet_conv_kind: bad layer %d", layer);
+  *kind = pl->convs[layer].kind;
+  *scale = pl->convs[layer].kind == KIND_S2 ? 2 : pl->convs[layer].S;
   return PP_OK;
 }
 long long unet_workspace_bytes(const UNetPlan* pl, int N, int H, int W, int G) {

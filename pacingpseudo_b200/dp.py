@@ -93,7 +93,8 @@ class GradientAllReducer:
         spans = []
         mods = unet._layer_modules()
         for i, m in enumerate(mods):
-            ps = [m.conv.weight, m.conv.bias, m.norm_op.weight, m.norm_op.bias]
+            ps = ([m.weight] if not hasattr(m, "conv") else   # ConvTranspose2d of the trans-conv variant
+                  [m.conv.weight, m.conv.bias, m.norm_op.weight, m.norm_op.bias])
             if i == len(mods) - 1:
                 ps += [unet.final_conv.weight, unet.final_conv.bias]
             locs = [where[id(p)] for p in ps]

@@ -94,18 +94,28 @@ class DoubleConv(nn.Module):
 
 
 class EncBlock(nn.Module):
+    """unet.py:100-127: max-pool + double conv, or (is_stride_conv) a stride-2 first conv, or dilated convs."""
+
     def __init__(self, in_ch, out_ch, do_subsamp=True, is_stride_conv=False, dilation=1):
         super().__init__()
         self.pooling = nn.MaxPool2d(2, 2) if (do_subsamp and not is_stride_conv) else None
-        self.conv_block = DoubleConv(in_ch, out_ch, padding1=dilation, dilation1=dilation,
+        stride1 = 2 if (do_subsamp and is_stride_conv) else 1
+        self.conv_block = DoubleConv(in_ch, out_ch, stride1=stride1, padding1=dilation, dilation1=dilation,
                                      padding2=dilation, dilation2=dilation)
 
 
 class DecBlock(nn.Module):
+    """unet.py:129-152: bilinear up-sampling, or (is_trans_conv) ConvTranspose2d(lower_ch, skip_ch, ks, stride,
+    bias=False) that also adjusts the channels, then the double conv over cat((up, skip), 1)."""
+
     def __init__(self, lower_ch, skip_ch, out_ch, trans_ks=2, trans_stride=2, is_trans_conv=False):
         super().__init__()
-        self.up_samp = nn.Upsample(scale_factor=trans_stride, mode='bilinear', align_corners=True)
-        self.conv_block = DoubleConv(lower_ch + skip_ch, skip_ch)
+        if is_trans_conv:
+            self.up_samp = nn.ConvTranspose2d(lower_ch, skip_ch, trans_ks, trans_stride, bias=False)
+            self.conv_block = DoubleConv(2 * skip_ch, out_ch)
+        else:
+            self.up_samp = nn.Upsample(scale_factor=trans_stride, mode='bilinear', align_corners=True)
+            self.conv_block = DoubleConv(lower_ch + skip_ch, skip_ch)
 
 
 class UNet(nn.Module):
@@ -116,37 +126,35 @@ class UNet(nn.Module):
         self.end_points = EndPoints()
         assert is_trans_conv == is_stride_conv, \
             "Only combo of stride_conv and trans_conv or maxpool and upsample is allowed."
-        if is_stride_conv or is_trans_conv:
-            raise NotImplementedError(
-                "pacingpseudo_b200: the strided-conv / transposed-conv UNet variant (unet.py:113-116,141) is not "
-                "built yet; every published run uses maxpool + bilinear (SURVEY.md section 2.3).")
         assert output_stride in [8, 16, 32]
+        sc, tc = is_stride_conv, is_trans_conv
         ch_ls = [min(max_ch, 2 ** k * init_ch) for k in range(6)]
-        self.enc_block1 = EncBlock(input_ch, ch_ls[0], do_subsamp=False)
-        self.enc_block2 = EncBlock(ch_ls[0], ch_ls[1], do_subsamp=True)
-        self.enc_block3 = EncBlock(ch_ls[1], ch_ls[2], do_subsamp=True)
-        self.enc_block4 = EncBlock(ch_ls[2], ch_ls[3], do_subsamp=True)
+        self.enc_block1 = EncBlock(input_ch, ch_ls[0], do_subsamp=False, is_stride_conv=sc)
+        self.enc_block2 = EncBlock(ch_ls[0], ch_ls[1], do_subsamp=True, is_stride_conv=sc)
+        self.enc_block3 = EncBlock(ch_ls[1], ch_ls[2], do_subsamp=True, is_stride_conv=sc)
+        self.enc_block4 = EncBlock(ch_ls[2], ch_ls[3], do_subsamp=True, is_stride_conv=sc)
         if output_stride == 32:
-            self.enc_block5 = EncBlock(ch_ls[3], ch_ls[4], do_subsamp=True)
-            self.enc_block6 = EncBlock(ch_ls[4], ch_ls[5], do_subsamp=True)
-            self.dec_block5 = DecBlock(ch_ls[5], ch_ls[4], ch_ls[4], 2, 2)
-            self.dec_block4 = DecBlock(ch_ls[4], ch_ls[3], ch_ls[3], 2, 2)
+            self.enc_block5 = EncBlock(ch_ls[3], ch_ls[4], do_subsamp=True, is_stride_conv=sc)
+            self.enc_block6 = EncBlock(ch_ls[4], ch_ls[5], do_subsamp=True, is_stride_conv=sc)
+            self.dec_block5 = DecBlock(ch_ls[5], ch_ls[4], ch_ls[4], 2, 2, is_trans_conv=tc)
+            self.dec_block4 = DecBlock(ch_ls[4], ch_ls[3], ch_ls[3], 2, 2, is_trans_conv=tc)
         elif output_stride == 16:
-            self.enc_block5 = EncBlock(ch_ls[3], ch_ls[4], do_subsamp=True)
-            self.enc_block6 = EncBlock(ch_ls[4], ch_ls[5], do_subsamp=False, dilation=2)
-            self.dec_block5 = DecBlock(ch_ls[5], ch_ls[4], ch_ls[4], 1, 1)
-            self.dec_block4 = DecBlock(ch_ls[4], ch_ls[3], ch_ls[3], 2, 2)
+            self.enc_block5 = EncBlock(ch_ls[3], ch_ls[4], do_subsamp=True, is_stride_conv=sc)
+            self.enc_block6 = EncBlock(ch_ls[4], ch_ls[5], do_subsamp=False, is_stride_conv=sc, dilation=2)
+            self.dec_block5 = DecBlock(ch_ls[5], ch_ls[4], ch_ls[4], 1, 1, is_trans_conv=tc)
+            self.dec_block4 = DecBlock(ch_ls[4], ch_ls[3], ch_ls[3], 2, 2, is_trans_conv=tc)
         else:
-            self.enc_block5 = EncBlock(ch_ls[3], ch_ls[4], do_subsamp=False, dilation=2)
-            self.enc_block6 = EncBlock(ch_ls[4], ch_ls[5], do_subsamp=False, dilation=4)
-            self.dec_block5 = DecBlock(ch_ls[5], ch_ls[4], ch_ls[4], 1, 1)
-            self.dec_block4 = DecBlock(ch_ls[4], ch_ls[3], ch_ls[3], 1, 1)
-        self.dec_block3 = DecBlock(ch_ls[3], ch_ls[2], ch_ls[2])
-        self.dec_block2 = DecBlock(ch_ls[2], ch_ls[1], ch_ls[1])
-        self.dec_block1 = DecBlock(ch_ls[1], ch_ls[0], ch_ls[0])
+            self.enc_block5 = EncBlock(ch_ls[3], ch_ls[4], do_subsamp=False, is_stride_conv=sc, dilation=2)
+            self.enc_block6 = EncBlock(ch_ls[4], ch_ls[5], do_subsamp=False, is_stride_conv=sc, dilation=4)
+            self.dec_block5 = DecBlock(ch_ls[5], ch_ls[4], ch_ls[4], 1, 1, is_trans_conv=tc)
+            self.dec_block4 = DecBlock(ch_ls[4], ch_ls[3], ch_ls[3], 1, 1, is_trans_conv=tc)
+        self.dec_block3 = DecBlock(ch_ls[3], ch_ls[2], ch_ls[2], is_trans_conv=tc)
+        self.dec_block2 = DecBlock(ch_ls[2], ch_ls[1], ch_ls[1], is_trans_conv=tc)
+        self.dec_block1 = DecBlock(ch_ls[1], ch_ls[0], ch_ls[0], is_trans_conv=tc)
         self.final_conv = nn.Conv2d(ch_ls[0], num_classes, 1, 1)
 
         self._cfg = (input_ch, init_ch, max_ch, num_classes, output_stride)
+        self._strided = bool(is_stride_conv)
         self._precision = precision or default_precision()
         self._engine = None
 
@@ -154,7 +162,7 @@ class UNet(nn.Module):
     @property
     def engine(self):
         if self._engine is None:
-            self._engine = UNetEngine(*self._cfg, self._precision)
+            self._engine = UNetEngine(*self._cfg, self._precision, strided=self._strided)
         return self._engine
 
     def _layer_modules(self):
@@ -170,6 +178,10 @@ class UNet(nn.Module):
         """-> (logits NCHW fp32, {name: native NHWC feature}). `groups` = BatchNorm statistics groups."""
         learnable, buffers = [], []
         for m in self._layer_modules():
+            if isinstance(m, nn.ConvTranspose2d):   # weight only (bias=False, no BatchNorm): unet.py:141
+                learnable += [m.weight, None, None, None]
+                buffers += [None, None, None]
+                continue
             learnable += [m.conv.weight, m.conv.bias, m.norm_op.weight, m.norm_op.bias]
             buffers += [m.norm_op.running_mean, m.norm_op.running_var, m.norm_op.num_batches_tracked]
         learnable += [self.final_conv.weight, self.final_conv.bias]

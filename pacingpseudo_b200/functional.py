@@ -46,23 +46,27 @@ def _view_bytes(ws, offset, shape, dtype):
 class UNetEngine:
     """C-side executor handle + layer table for one UNet configuration (models/unet.py:10-60)."""
 
-    def __init__(self, input_ch, init_ch, max_ch, num_classes, output_stride, precision):
+    def __init__(self, input_ch, init_ch, max_ch, num_classes, output_stride, precision, strided=False):
         self.lib = get_lib()
         self.code = dtype_code(precision)
         self.precision = precision
         self.num_classes = num_classes
         h = ctypes.c_void_p()
-        self.lib.call("pp_unet_create", input_ch, init_ch, max_ch, num_classes, output_stride, self.code,
-                      ctypes.byref(h))
+        self.lib.call("pp_unet_create_ex", input_ch, init_ch, max_ch, num_classes, output_stride, self.code,
+                      int(bool(strided)), ctypes.byref(h))
         self.handle = h
         self.nconv = self.lib.cdll.pp_unet_num_convs(self.handle)
         self.layers = []
+        self.kinds = []   # per layer (kind, scale): 0 conv+BN, 1 stride-2 conv+BN, 2 ConvTranspose2d (weight only)
         for i in range(self.nconv):
             cin, cout, dil = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
             name = ctypes.c_char_p()
             self.lib.call("pp_unet_conv_info", self.handle, i, ctypes.byref(cin), ctypes.byref(cout),
                           ctypes.byref(dil), ctypes.byref(name))
             self.layers.append((name.value.decode(), cin.value, cout.value, dil.value))
+            kind, scale = ctypes.c_int(), ctypes.c_int()
+            self.lib.call("pp_unet_conv_kind", self.handle, i, ctypes.byref(kind), ctypes.byref(scale))
+            self.kinds.append((kind.value, scale.value))
 
     def __del__(self):
         try:
@@ -89,6 +93,7 @@ class UNetFunction(torch.autograd.Function):
 
     `learnable` = per conv layer [weight, bias, gamma, beta] in engine order, then head [weight, bias].
     `buffers`   = per conv layer [running_mean, running_var, num_batches_tracked] (updated in place).
+    A ConvTranspose2d layer (engine.kinds[i][0] == 2) has a weight only: its other slots are None.
     """
 
     @staticmethod
@@ -108,7 +113,7 @@ class UNetFunction(torch.autograd.Function):
             params += [w, b, g, bt, rm, rv, nbt]
         params += [learnable[4 * nconv], learnable[4 * nconv + 1]]
         for t in params:
-            if not t.is_cuda or not t.is_contiguous():
+            if t is not None and (not t.is_cuda or not t.is_contiguous()):
                 raise RuntimeError("UNet parameters/buffers must be contiguous CUDA tensors")
         with torch.cuda.device(dev):
             ws = torch.empty(engine.workspace_bytes(N, H, W, groups), dtype=torch.uint8, device=dev)
@@ -149,13 +154,16 @@ class UNetFunction(torch.autograd.Function):
             # The kernels ACCUMULATE (+=) into the gradient buffers. Parameters whose .grad has been pre-attached by
             # pacingpseudo_b200.optim.FlatAdam (views of one flat buffer, marked _pp_direct_grad) are written in place
             # and reported to autograd as None: no per-parameter `grad += g` kernels, no temporary gradient copy.
-            direct = [getattr(t, "_pp_direct_grad", False) and t.grad is not None and t.grad.is_contiguous()
-                      and t.grad.dtype == torch.float32 for t in ctx.params]
-            sizes = [0 if d else t.numel() for d, t in zip(direct, ctx.params)]
+            direct = [t is not None and getattr(t, "_pp_direct_grad", False) and t.grad is not None
+                      and t.grad.is_contiguous() and t.grad.dtype == torch.float32 for t in ctx.params]
+            sizes = [0 if (d or t is None) else t.numel() for d, t in zip(direct, ctx.params)]
             flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
             grads, ret = [], []
             for d, t, g in zip(direct, ctx.params, flat.split(sizes)):
-                if d:
+                if t is None:
+                    grads.append(None)
+                    ret.append(None)
+                elif d:
                     grads.append(t.grad)
                     ret.append(None)
                 else:

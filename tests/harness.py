@@ -69,7 +69,7 @@ def run_case_oracle(name, dtype=torch.float32, quant=False):
         sd[k].requires_grad_(True)
     cfg = O.StepConfig(num_classes=C, ignored_index=C, detach_weak_cr=bool(case.get("detach")),
                        loss_cr_variants=case.get("cr", "ce_loss"), ensemble_mode=case.get("mode", "cosine_similarity"),
-                       output_stride=case["os"], quant=quant)
+                       output_stride=case["os"], quant=quant, strided=bool(case.get("strided")))
     rec = {}
     for step in range(case.get("steps", 1)):
         batch = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in case_batch(case, step).items()}
@@ -86,7 +86,7 @@ def run_case_oracle(name, dtype=torch.float32, quant=False):
             rec["s%d/memory_bank" % step] = sd["aux_path.memory_bank"].detach().double().numpy().reshape(C, 64)
         else:
             logits = O.unet_forward(sd, batch["image"], case["training"], output_stride=case["os"],
-                                    quant=quant)["segmentation/logits"]
+                                    quant=quant, strided=bool(case.get("strided")))["segmentation/logits"]
             if case["kind"] == "baseline":
                 loss = O.partial_cross_entropy(logits, batch["scribble"].argmax(1), C)
                 rec["s%d/loss_pce" % step] = np.array(loss.item())
@@ -118,13 +118,15 @@ def build_cuda_model(case, precision, device="cuda"):
     if case["kind"] == "pacing":
         model = ConsistencyRegulr(
             kwargs_unet=dict(input_ch=1, init_ch=32, max_ch=512, num_classes=C, output_stride=case["os"],
-                             is_stride_conv=False, is_trans_conv=False, elab_end_points=True, precision=precision),
+                             is_stride_conv=bool(case.get("strided")), is_trans_conv=bool(case.get("strided")),
+                             elab_end_points=True, precision=precision),
             kwargs_aux_path=dict(num_classes=C, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[512, 512],
                                  hid_ch=64, aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
                                  ensemble_mode=case.get("mode", "cosine_similarity")),
             args_parser=ref_args(case))
     else:
-        model = UNet(1, 32, 512, C, case["os"], False, False, True, precision=precision)
+        model = UNet(1, 32, 512, C, case["os"], bool(case.get("strided")), bool(case.get("strided")), True,
+                     precision=precision)
     model.load_state_dict(build_state(case), strict=True)
     return model.to(device).train(case["training"])
 

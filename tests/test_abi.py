@@ -110,8 +110,16 @@ def test_dropin_modules_mirror_reference_state_dict():
     assert len(sd) == 165
     assert sum(p.numel() for p in cr.parameters()) == 20245381
     assert sum(p.numel() for p in cr.parameters() if p.requires_grad) == 20245061
-    with pytest.raises(NotImplementedError):
-        UNet(is_stride_conv=True, is_trans_conv=True)
+    # the is_stride_conv + is_trans_conv variant (unet.py:113-116,141): stride-2 holders, ConvTranspose2d weights
+    for os_ in (8, 16, 32):
+        m = UNet(1, 32, 512, 4, os_, True, True, True)
+        sd = m.state_dict()
+        exp = O.unet_param_shapes(1, 32, 512, 4, os_, strided=True)
+        assert list(sd) == list(exp)
+        assert all(tuple(sd[k].shape) == tuple(exp[k]) for k in exp)
+        assert m.enc_block2.conv_block.conv_layer1.conv.stride == (2, 2) and m.enc_block2.pooling is None
+    with pytest.raises(AssertionError):
+        UNet(is_stride_conv=True, is_trans_conv=False)   # unet.py:25
     with pytest.raises(RuntimeError, match="CUDA"):
         UNet(1, 32, 512, 5, 8)(torch.zeros(1, 1, 16, 16))  # no CPU fallback
 

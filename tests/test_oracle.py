@@ -12,7 +12,8 @@ from oracle import pp_oracle as O
 from oracle.gen_golden import CASES
 
 FAST_CASES = ["pacing_train_bn", "pacing_eval_bn", "pacing_acdc_kl_mean", "pacing_l1_detach", "pacing_l2_nomask",
-              "baseline_pce", "upperbound_ce_dice", "unet_os16", "unet_os32"]
+              "baseline_pce", "upperbound_ce_dice", "unet_os16", "unet_os32",
+              "unet_strided_os32", "unet_strided_os16_eval", "pacing_strided_os8"]
 
 
 @pytest.mark.parametrize("name", FAST_CASES)
