@@ -39,6 +39,9 @@ def parse_args():
     ap.add_argument("--bn", default="train", choices=["train", "eval"],
                     help="BatchNorm regime: batch statistics (epoch 0) or running statistics (epochs >= 1, SURVEY T2)")
     ap.add_argument("--epoch", type=int, default=40, help="epoch used for loss ramp-up weights and bank momentum")
+    ap.add_argument("--unet-variant", default="maxpool", choices=["maxpool", "strided"],
+                    help="strided: is_stride_conv + is_trans_conv (unet.py:113-116,141); not the headline config")
+    ap.add_argument("--output-stride", type=int, default=8, choices=[8, 16, 32])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile-pass", action="store_true", help="skip the per-launch CUDA-event pass (ncu runs)")
@@ -126,7 +129,9 @@ def workload_config(args, pairs_override=None):
                         args.size, args.size, args.classes),
         "pairs_per_gpu": pairs_override if pairs_override is not None else args.batch,
         "global_pairs": (pairs_override if pairs_override is not None else args.batch) * max(1, args.gpus),
-        "unet": "init_ch 32, max_ch 512, output_stride 8, maxpool + bilinear", "bn": args.bn,
+        "unet": "init_ch 32, max_ch 512, output_stride %d, %s" % (
+            args.output_stride, "maxpool + bilinear" if args.unet_variant == "maxpool"
+            else "stride-2 conv + ConvTranspose2d (is_stride_conv, is_trans_conv)"), "bn": args.bn,
         "loss_cr_variants": "ce_loss", "optimizer": "Adam lr 1e-4 wd 3e-4", "parallelism": "dp%d" % max(1, args.gpus),
         "l2": "per-step working set (~3.4 GB of activations per GPU) >> 126 MB L2; no explicit flush",
     }
@@ -256,8 +261,9 @@ def run_ours(args):
     ns = argparse.Namespace(ignored_index=C, do_loss_ent=True, do_decoder_consistency=True, detach_weak_cr=False,
                             loss_cr_variants="ce_loss", do_aux_path=True, do_memory=True)
     model = ConsistencyRegulr(
-        kwargs_unet=dict(input_ch=1, init_ch=32, max_ch=512, num_classes=C, output_stride=8, is_stride_conv=False,
-                         is_trans_conv=False, elab_end_points=True, precision=args.precision),
+        kwargs_unet=dict(input_ch=1, init_ch=32, max_ch=512, num_classes=C, output_stride=args.output_stride,
+                         is_stride_conv=args.unet_variant == "strided", is_trans_conv=args.unet_variant == "strided",
+                         elab_end_points=True, precision=args.precision),
         kwargs_aux_path=dict(num_classes=C, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[512, 512],
                              hid_ch=64, aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
                              ensemble_mode='cosine_similarity'),
@@ -375,7 +381,7 @@ def run_ours(args):
     dom = prof["conv3x3_tc (fwd+dgrad)"]
     steps_p = max(1, args.steps)
     tf = lambda p: (p["flops"] / (p["ms"] / 1e3) / 1e12) if p["ms"] > 0 else 0.0
-    gf = GF_PER_PAIR.get((S, C))
+    gf = GF_PER_PAIR.get((S, C)) if (args.unet_variant == "maxpool" and args.output_stride == 8) else None
     traffic = load_traffic()
     line = {
         "metric": "train imgs/sec (256^2 pacingpseudo step)", "value": value, "unit": "img/s", "n_gpus": world,

@@ -144,6 +144,14 @@ int pp_bn_apply(int dtype, const void* y, const float* coef, void* a, int G, lon
 int pp_bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* bsums, float* bcoef,
               float* dgamma, float* dbeta, float* dbias, void* dy, int G, long long Pg, int C, int training,
               float slope, void* stream);
+/* nn.Dropout2d of the aux path (aux_path_memory.py:23,31), forward and backward: y[n,p,c] = x[n,p,c] *
+ * scale[n*ld + c] on NHWC tensors [N][HW][C]; scale holds 0 or 1/(1-p) per (sample, channel); y may alias x. */
+int pp_channel_scale(int dtype, const void* x, const float* scale, void* y, int N, int HW, int C, int ld,
+                     void* stream);
+/* Layout shuffles of the strided-conv / transposed-conv UNet variant (unet.py:113-116,141; see pp_unet_create_ex):
+ * x[N, 2Hs, 2Ws, C] <-> y[N, Hs, Ws, 4C] with y channel (sy*2+sx)*C + c = x[2Y+sy, 2X+sx, c]; accumulate: x += . */
+int pp_space_to_depth(int dtype, const void* x, void* y, int N, int Hs, int Ws, int C, void* stream);
+int pp_depth_to_space(int dtype, const void* y, void* x, int N, int Hs, int Ws, int C, int accumulate, void* stream);
 /* MaxPool2d(2,2) (unet.py:109) */
 int pp_maxpool_fwd(int dtype, const void* x, void* y, int N, int H, int W, int C, void* stream);
 int pp_maxpool_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int H, int W, int C, int accumulate,

@@ -34,6 +34,9 @@ CASES = {
     # is_stride_conv + is_trans_conv (unet.py:113-116,141): stride-2 first convs, ConvTranspose2d up-sampling
     "unet_strided_os32": dict(kind="baseline", N=2, C=4, H=64, W=64, os=32, training=True, strided=True),
     "unet_strided_os16_eval": dict(kind="upper", N=2, C=5, H=64, W=64, os=16, training=False, strided=True),
+    # aux_drop_prob = 0.5 with PINNED Dropout2d masks (F.dropout2d replaced by O.synth_drop_factors in call order)
+    "pacing_dropout": dict(kind="pacing", N=3, C=5, H=64, W=64, os=8, training=True, cr="ce_loss",
+                           mode="cosine_similarity", steps=2, drop_p=0.5),
     "pacing_strided_os8": dict(kind="pacing", N=2, C=5, H=64, W=64, os=8, training=True, cr="ce_loss",
                                mode="cosine_similarity", steps=2, strided=True),
 }
@@ -78,8 +81,8 @@ def run_reference(name, case):
                              is_stride_conv=bool(case.get("strided")), is_trans_conv=bool(case.get("strided")),
                              elab_end_points=True),
             kwargs_aux_path=dict(num_classes=C, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[512, 512],
-                                 hid_ch=64, aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
-                                 ensemble_mode=case["mode"]),
+                                 hid_ch=64, aux_drop_prob=float(case.get("drop_p", 0.)), do_memory=True, max_step=400,
+                                 update_momentum=0.9, ensemble_mode=case["mode"]),
             args_parser=ref_args(case))
     else:
         model = UNet(1, 32, 512, C, case["os"], bool(case.get("strided")), bool(case.get("strided")), True)
@@ -92,7 +95,19 @@ def run_reference(name, case):
             batch.pop("valid_mask")
         model.zero_grad()
         if case["kind"] == "pacing":
+            if case.get("drop_p"):   # pin the masks: the reference's nn.Dropout2d calls F.dropout2d, in this order
+                queue = list(O.synth_drop_factors(500 + step, case["N"], 1024, 64, C, case["drop_p"]))
+
+                def pinned_dropout2d(x, p=0.5, training=True, inplace=False, _q=queue):
+                    f = _q.pop(0)
+                    assert training and tuple(f.shape) == tuple(x.shape[:2]), (f.shape, x.shape)
+                    return x * f[:, :, None, None]
+                orig_dropout2d = torch.nn.functional.dropout2d
+                torch.nn.functional.dropout2d = pinned_dropout2d
             out = model({k: v for k, v in batch.items() if k != "label"}, mode="train", step=step * 37)
+            if case.get("drop_p"):
+                torch.nn.functional.dropout2d = orig_dropout2d
+                assert not queue, "the reference made fewer dropout calls than expected"
             loss = O.total_loss(out, epoch=40)
             for k in ("loss_pce", "loss_ent", "loss_cr", "loss_aux_cls", "loss_memory"):
                 rec["s%d/%s" % (step, k)] = np.array(out[k].item())

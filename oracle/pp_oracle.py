@@ -302,14 +302,24 @@ def compute_dice_np(scores, target):
     return out
 
 
+def synth_drop_factors(seed, N, cin, hid, C, p):
+    """Deterministic Dropout2d factors (0 or 1/(1-p)) for the three dropout calls of one aux-path forward, in call
+    order: input features [N, cin], bottleneck output [N, hid], memory bank [C, hid] (aux_path_memory.py:23,31,60)."""
+    g = torch.Generator().manual_seed(seed)
+    return tuple((torch.rand(shape, generator=g) >= p).float() / (1.0 - p) for shape in ((N, cin), (N, hid), (C, hid)))
+
+
 def ramp_up_mo(step, max_step, base_mo=0.9, gamma=0.9):
     """aux_path_memory.py:118-120."""
     return (1 - step / max_step) ** gamma * base_mo
 
 
-def aux_forward(sd, feats, out_hw, training, prefix='aux_path.', quant=False):
-    """aux_path_memory.py:49-52 (Dropout2d(p=0) is the identity)."""
+def aux_forward(sd, feats, out_hw, training, prefix='aux_path.', quant=False, drop=None):
+    """aux_path_memory.py:49-52. drop = None (Dropout2d(p=0) is the identity) or (s_in [N, Cin], s_hid [N, hid]):
+    the two nn.Dropout2d layers (aux_path_memory.py:23,31) as explicit per-(sample, channel) factors, 0 or 1/(1-p)."""
     x = torch.cat(feats, 1)
+    if drop is not None:
+        x = _q(x * drop[0].to(x.dtype)[:, :, None, None], quant)
     y = F.conv2d(x, _qw(sd[prefix + 'layer_bottleneck.1.weight'], quant), sd[prefix + 'layer_bottleneck.1.bias'], 1, 1)
     y = _q(y, quant)
     g, b = sd[prefix + 'layer_bottleneck.2.weight'], sd[prefix + 'layer_bottleneck.2.bias']
@@ -326,7 +336,8 @@ def aux_forward(sd, feats, out_hw, training, prefix='aux_path.', quant=False):
     z = (y - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + EPS_BN)
     z = z * g[None, :, None, None] + b[None, :, None, None]
     aux_features = _q(torch.where(z > 0, z, z * SLOPE), quant)
-    low = F.conv2d(aux_features, sd[prefix + 'fc_cls.1.weight'])
+    fc_in = aux_features if drop is None else _q(aux_features * drop[1].to(x.dtype)[:, :, None, None], quant)
+    low = F.conv2d(fc_in, sd[prefix + 'fc_cls.1.weight'])
     return upsample_bilinear_ac(low, out_hw), aux_features
 
 
@@ -371,7 +382,7 @@ class StepConfig:
         del self.__dict__['self']
 
 
-def consistency_forward(sd, batch, cfg, mode='train', step=0, training=True):
+def consistency_forward(sd, batch, cfg, mode='train', step=0, training=True, drop=None):
     """ConsistencyRegulr.forward. `sd` keys carry the `backbone.` / `aux_path.` prefixes of the reference
     state dict. `training` is the module's BatchNorm mode (train_chaos.py never re-enters .train())."""
     net = cfg
@@ -406,13 +417,18 @@ def consistency_forward(sd, batch, cfg, mode='train', step=0, training=True):
         out['segmentation/logits_strong'] = zs
     if mode == 'train' and net.do_aux_path:
         feats = [ep[s] for s in net.feat_stage]
-        za, aux_features = aux_forward(sd, feats, batch['scribble'].shape[-2:], training, quant=net.quant)
+        # drop = (s_in, s_hid, s_bank): explicit Dropout2d factors of the aux path (aux_drop_prob > 0, train mode)
+        za, aux_features = aux_forward(sd, feats, batch['scribble'].shape[-2:], training, quant=net.quant,
+                                       drop=None if drop is None else drop[:2])
         out['logits_aux_cls'] = za
         out['loss_aux_cls'] = partial_cross_entropy(za, target, net.ignored_index)
         if net.do_memory:
             memory_update(sd['aux_path.memory_bank'], aux_features.detach(), batch['scribble'], step, net.max_step,
                           net.update_momentum, net.ensemble_mode)
-            lm = F.conv2d(sd['aux_path.memory_bank'], sd['aux_path.fc_cls.1.weight'])[:, :, 0, 0]
+            bank = sd['aux_path.memory_bank']
+            if drop is not None:   # fc_cls = Dropout2d + 1x1 conv is applied to the bank as well (aux_path_memory.py:60)
+                bank = bank * drop[2].to(bank.dtype)[:, :, None, None]
+            lm = F.conv2d(bank, sd['aux_path.fc_cls.1.weight'])[:, :, 0, 0]
             out['loss_memory'] = partial_cross_entropy(lm, torch.arange(lm.shape[0]), -100)
     return out
 

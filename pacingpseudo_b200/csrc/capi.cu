@@ -158,6 +158,16 @@ int pp_bn_bwd(int dtype, const void* da, const void* y, const float* coef, doubl
               float slope, void* stream) {
   return bn_bwd(dtype, da, y, coef, bsums, bcoef, dgamma, dbeta, dbias, dy, G, Pg, C, training, slope, ST(stream));
 }
+int pp_channel_scale(int dtype, const void* x, const float* scale, void* y, int N, int HW, int C, int ld,
+                     void* stream) {
+  return channel_scale(dtype, x, scale, y, N, HW, C, ld, ST(stream));
+}
+int pp_space_to_depth(int dtype, const void* x, void* y, int N, int Hs, int Ws, int C, void* stream) {
+  return space_to_depth(dtype, x, y, N, Hs, Ws, C, ST(stream));
+}
+int pp_depth_to_space(int dtype, const void* y, void* x, int N, int Hs, int Ws, int C, int accumulate, void* stream) {
+  return depth_to_space(dtype, y, x, N, Hs, Ws, C, accumulate, ST(stream));
+}
 int pp_maxpool_fwd(int dtype, const void* x, void* y, int N, int H, int W, int C, void* stream) {
   return maxpool_fwd(dtype, x, y, N, H, W, C, ST(stream));
 }

@@ -1388,6 +1388,40 @@ int collapse_ct_wgrad(const float* dwe, float* dwt, int Cin, int Cout, int S, cu
 }
 
 // ==============================================================================================
+// nn.Dropout2d of the aux path (aux_path_memory.py:23,31): whole channels of a sample are zeroed and the rest
+// scaled by 1/(1-p). The caller supplies the per-(sample, channel) factors (0 or 1/(1-p)); the same kernel applies
+// them to the activations in the forward pass and to their gradients in the backward pass (y may alias x).
+// scale row n starts at scale + n * ld (ld >= C: the two concat sources share one [N][C0 + C1] table).
+// ==============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) channel_scale_kernel(const T* x, const float* __restrict__ scale, T* y,
+                                                            long long nvec, int HW, int C, int ld) {
+  const int cv = C / 8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % cv);
+    const long long n = i / (static_cast<long long>(cv) * HW);
+    const float* sc = scale + n * ld + v * 8;
+    Vec8<T> a;
+    a.load(x + i * 8);
+    float f[8];
+    a.get(f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] *= __ldg(sc + k);
+    a.set(f);
+    a.store(y + i * 8);
+  }
+}
+int channel_scale(int dtype, const void* x, const float* scale, void* y, int N, int HW, int C, int ld, cudaStream_t s) {
+  PP_REQUIRE(C % 8 == 0 && C > 0 && ld >= C, "channel_scale: C=%d (multiple of 8) / ld=%d", C, ld);
+  const long long nvec = static_cast<long long>(N) * HW * (C / 8);
+  PP_DISPATCH_T(dtype, (channel_scale_kernel<T><<<grid_for(nvec, 256), 256, 0, s>>>(
+                           static_cast<const T*>(x), scale, static_cast<T*>(y), nvec, HW, C, ld)););
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ==============================================================================================
 // Adam with L2 weight decay folded into the gradient (torch.optim.Adam semantics,
 // train_chaos.py:219), over one flat fp32 parameter buffer. step is the 1-based step count.
 // ==============================================================================================

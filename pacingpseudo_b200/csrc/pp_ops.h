@@ -67,6 +67,7 @@ int embed_s2_weight(const float* w, float* we, int Cout, int C, cudaStream_t s);
 int collapse_s2_wgrad(const float* dwe, float* dw, int Cout, int C, cudaStream_t s);
 int embed_ct_weight(const float* wt, float* we, int Cin, int Cout, int S, cudaStream_t s);
 int collapse_ct_wgrad(const float* dwe, float* dwt, int Cin, int Cout, int S, cudaStream_t s);
+int channel_scale(int dtype, const void* x, const float* scale, void* y, int N, int HW, int C, int ld, cudaStream_t s);
 int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
               float wd, int step, float grad_scale, cudaStream_t s);
 

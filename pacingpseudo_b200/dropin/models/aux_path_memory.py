@@ -53,23 +53,38 @@ class AuxPath(nn.Module):
     # ---- native path ---------------------------------------------------------------------------
     def run_native(self, feats, scribble, step, code):
         """feats: native NHWC tensors in feat_stage order. -> (logits_aux NCHW full-res, aux_features NHWC)."""
-        if self.training and self.aux_drop_prob > 0:
-            raise NotImplementedError("pacingpseudo_b200 AuxPath: aux_drop_prob > 0 (Dropout2d) is not built yet")
         conv, bn = self.layer_bottleneck[1], self.layer_bottleneck[2]
         fa = feats[0]
         fb = feats[1] if len(feats) > 1 else None
+        drop = None
+        self._bank_drop = None
+        if self.training and self.aux_drop_prob > 0:   # the two nn.Dropout2d layers (aux_path_memory.py:23,31)
+            n_in = fa.shape[-1] + (fb.shape[-1] if fb is not None else 0)
+            drop = (self.drop_factors(fa.shape[0], n_in, fa.device), self.drop_factors(fa.shape[0], self.hid_ch, fa.device))
+            if self.do_memory:   # fc_cls (with its Dropout2d) is also applied to the bank (aux_path_memory.py:60)
+                self._bank_drop = self.drop_factors(self.num_classes, self.hid_ch, fa.device)
         logits, aux_features = AuxPathFunction.apply(
             code, (bn.running_mean, bn.running_var, bn.num_batches_tracked), self.training,
-            tuple(scribble.shape[-2:]), fa, fb, conv.weight, conv.bias, bn.weight, bn.bias, self.fc_cls[1].weight)
+            tuple(scribble.shape[-2:]), drop, fa, fb, conv.weight, conv.bias, bn.weight, bn.bias, self.fc_cls[1].weight)
         if self.do_memory:
             self.memory_update(aux_features, scribble, step, _code=code)
             if self.bank_sync is not None:
                 self.bank_sync(self.memory_bank.data)
         return logits, aux_features
 
+    def drop_factors(self, n, channels, device):
+        """Dropout2d as per-(sample, channel) factors: 0 with probability p, else 1/(1-p). Drawn from torch's CUDA
+        generator (the reference draws from the same distribution; the streams differ, as they do between torch
+        versions). Tests replace this method to pin the masks."""
+        p = float(self.aux_drop_prob)
+        if p >= 1.0:
+            return torch.zeros((n, channels), dtype=torch.float32, device=device)
+        keep = torch.rand((n, channels), device=device) >= p
+        return keep.float() / (1.0 - p)
+
     def memory_loss(self):
         bank = self.memory_bank.data.view(self.num_classes, self.hid_ch)
-        return MemoryLossFunction.apply(bank, self.fc_cls[1].weight)
+        return MemoryLossFunction.apply(bank, self.fc_cls[1].weight, getattr(self, "_bank_drop", None))
 
     def forward(self, end_points, scribble, step):
         native = getattr(end_points, 'native', None)

@@ -185,10 +185,14 @@ class UNetFunction(torch.autograd.Function):
 # Aux path (models/aux_path_memory.py:46-66): cat -> conv3x3 -> BN -> LeakyReLU -> 1x1 -> bilinear x8
 # --------------------------------------------------------------------------------------------
 class AuxPathFunction(torch.autograd.Function):
-    """(feat_a, feat_b, conv_w, conv_b, gamma, beta, fc_w) -> (logits_aux NCHW fp32 full-res, aux_features NHWC)."""
+    """(feat_a, feat_b, conv_w, conv_b, gamma, beta, fc_w) -> (logits_aux NCHW fp32 full-res, aux_features NHWC).
+
+    drop = None, or the two nn.Dropout2d layers of aux_path_memory.py:23,31 as per-(sample, channel) factors
+    (s_in [N, Ca + Cb], s_hid [N, hid]; entries 0 or 1/(1-p)): s_in scales the concatenated input features,
+    s_hid the bottleneck output in front of the 1x1 classifier (the returned aux_features stay un-dropped)."""
 
     @staticmethod
-    def forward(ctx, code, buffers, training, out_hw, feat_a, feat_b, conv_w, conv_b, gamma, beta, fc_w):
+    def forward(ctx, code, buffers, training, out_hw, drop, feat_a, feat_b, conv_w, conv_b, gamma, beta, fc_w):
         require_cuda(feat_a, "aux features")
         lib = get_lib()
         dev = feat_a.device
@@ -207,6 +211,17 @@ class AuxPathFunction(torch.autograd.Function):
             wf = torch.empty(9 * hid * (Ca + Cb) * es, dtype=torch.uint8, device=dev)
             wd = torch.empty_like(wf)
             lib.call("pp_pack_weights", code, ptr(conv_w), ptr(wf), ptr(wd), hid, Ca + Cb, st)
+            s_in = s_hid = None
+            if drop is not None:
+                s_in, s_hid = (t.contiguous().float() for t in drop)
+                fa_d = torch.empty_like(feat_a)
+                lib.call("pp_channel_scale", code, ptr(feat_a), ptr(s_in), ptr(fa_d), N, h * w, Ca, Ca + Cb, st)
+                feat_a = fa_d
+                if feat_b is not None:
+                    fb_d = torch.empty_like(feat_b)
+                    lib.call("pp_channel_scale", code, ptr(feat_b), ctypes.c_void_p(s_in.data_ptr() + 4 * Ca), ptr(fb_d),
+                             N, h * w, Cb, Ca + Cb, st)
+                    feat_b = fb_d
             yraw = torch.empty((N, h, w, hid), dtype=adt, device=dev)
             lib.call("pp_conv3x3", code, ptr(feat_a), Ca, ptr(feat_b), Cb, ptr(wf), ptr(conv_b), ptr(yraw), hid, 0,
                      None, 0, 0, N, h, w, 1, st)
@@ -220,11 +235,15 @@ class AuxPathFunction(torch.autograd.Function):
             act = torch.empty_like(yraw)
             lib.call("pp_bn_apply", code, ptr(yraw), ptr(coef), ptr(act), 1, Pg, hid, 0.01, st)
             low = torch.empty((N, C, h, w), dtype=torch.float32, device=dev)
-            lib.call("pp_head_fwd", code, ptr(act), ptr(fc_w), None, ptr(low), Pg, h * w, hid, C, st)
+            act_in = act
+            if s_hid is not None:
+                act_in = torch.empty_like(act)
+                lib.call("pp_channel_scale", code, ptr(act), ptr(s_hid), ptr(act_in), N, h * w, hid, hid, st)
+            lib.call("pp_head_fwd", code, ptr(act_in), ptr(fc_w), None, ptr(low), Pg, h * w, hid, C, st)
             logits = torch.empty((N, C, H, W), dtype=torch.float32, device=dev)
             lib.call("pp_upsample_planes_fwd", ptr(low), ptr(logits), N * C, h, w, H, W, st)
         ctx.code, ctx.training, ctx.dims = code, int(training), (N, h, w, Ca, Cb, hid, C, H, W)
-        ctx.save_for_backward(feat_a, feat_b, wd, yraw, coef, act, fc_w)
+        ctx.save_for_backward(feat_a, feat_b, wd, yraw, coef, act_in, fc_w, s_in, s_hid)
         ctx.mark_non_differentiable(act)
         return logits, act
 
@@ -232,7 +251,7 @@ class AuxPathFunction(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g_logits, _g_act):
         lib = get_lib()
-        feat_a, feat_b, wd, yraw, coef, act, fc_w = ctx.saved_tensors
+        feat_a, feat_b, wd, yraw, coef, act, fc_w, s_in, s_hid = ctx.saved_tensors   # feat_*/act: after dropout
         code = ctx.code
         N, h, w, Ca, Cb, hid, C, H, W = ctx.dims
         dev = feat_a.device
@@ -247,6 +266,8 @@ class AuxPathFunction(torch.autograd.Function):
             d_fc = torch.zeros_like(fc_w)
             lib.call("pp_head_bwd", code, ptr(g_low), ptr(act), ptr(fc_w), ptr(d_act), ptr(d_fc), None, Pg, h * w, hid,
                      C, st)
+            if s_hid is not None:
+                lib.call("pp_channel_scale", code, ptr(d_act), ptr(s_hid), ptr(d_act), N, h * w, hid, hid, st)
             bsums = torch.empty(2 * hid, dtype=torch.float64, device=dev)
             bcoef = torch.empty(2 * hid, dtype=torch.float32, device=dev)
             d_gamma = torch.zeros(hid, dtype=torch.float32, device=dev)
@@ -263,7 +284,12 @@ class AuxPathFunction(torch.autograd.Function):
             g_b = torch.empty_like(feat_b) if feat_b is not None else None
             lib.call("pp_conv3x3", code, ptr(dy), hid, None, 0, ptr(wd), None, ptr(g_a), Ca, 0, ptr(g_b), Cb, 0, N, h, w,
                      1, st)
-        return None, None, None, None, g_a, g_b, d_w, d_bias, d_gamma, d_beta, d_fc
+            if s_in is not None:
+                lib.call("pp_channel_scale", code, ptr(g_a), ptr(s_in), ptr(g_a), N, h * w, Ca, Ca + Cb, st)
+                if g_b is not None:
+                    lib.call("pp_channel_scale", code, ptr(g_b), ctypes.c_void_p(s_in.data_ptr() + 4 * Ca), ptr(g_b), N,
+                             h * w, Cb, Ca + Cb, st)
+        return None, None, None, None, None, g_a, g_b, d_w, d_bias, d_gamma, d_beta, d_fc
 
 
 # --------------------------------------------------------------------------------------------
@@ -426,15 +452,19 @@ class DiceFunction(torch.autograd.Function):
 
 
 class MemoryLossFunction(torch.autograd.Function):
-    """cross_entropy(fc_cls(memory_bank), arange(C)); gradient flows to fc_cls.weight only."""
+    """cross_entropy(fc_cls(memory_bank), arange(C)); gradient flows to fc_cls.weight only.
+    s_bank: optional [C, hid] Dropout2d factors (fc_cls[0] also acts on the bank, aux_path_memory.py:31,60)."""
 
     @staticmethod
-    def forward(ctx, bank, fc_w):
+    def forward(ctx, bank, fc_w, s_bank=None):
         require_cuda(fc_w, "fc_cls weight")
         C, hid = bank.shape[0], bank.shape[1]
         dev = fc_w.device
         bank_c = bank.detach().contiguous().float().clone()  # the bank is mutated in place by later steps
         with torch.cuda.device(dev):
+            if s_bank is not None:
+                get_lib().call("pp_channel_scale", F32, ptr(bank_c), ptr(s_bank.contiguous().float()), ptr(bank_c), C, 1,
+                               hid, hid, current_stream(dev))
             loss = torch.zeros((), dtype=torch.float32, device=dev)
             probs = torch.empty(C * C, dtype=torch.float32, device=dev)
             get_lib().call("pp_memory_loss_fwd", ptr(bank_c), ptr(fc_w.contiguous()), ptr(loss), ptr(probs), C, hid,
@@ -452,7 +482,7 @@ class MemoryLossFunction(torch.autograd.Function):
             d = torch.zeros_like(fc_w)
             get_lib().call("pp_memory_loss_bwd", ptr(bank_c), ptr(probs), ptr(g.contiguous().float()), ptr(d), C, hid,
                            current_stream(dev))
-        return None, d
+        return None, d, None
 
 
 def memory_update(code, aux_features, scribble, bank, mode, m):

@@ -76,7 +76,11 @@ def run_case_oracle(name, dtype=torch.float32, quant=False):
         for k in learn:
             sd[k].grad = None
         if case["kind"] == "pacing":
-            out = O.consistency_forward(sd, batch, cfg, mode="train", step=step * 37, training=case["training"])
+            drop = None
+            if case.get("drop_p"):
+                drop = tuple(t.to(dtype) for t in O.synth_drop_factors(500 + step, case["N"], 1024, 64, C, case["drop_p"]))
+            out = O.consistency_forward(sd, batch, cfg, mode="train", step=step * 37, training=case["training"],
+                                        drop=drop)
             loss = O.total_loss(out, epoch=40)
             for k in ("loss_pce", "loss_ent", "loss_cr", "loss_aux_cls", "loss_memory"):
                 rec["s%d/%s" % (step, k)] = np.array(out[k].item())
@@ -121,8 +125,8 @@ def build_cuda_model(case, precision, device="cuda"):
                              is_stride_conv=bool(case.get("strided")), is_trans_conv=bool(case.get("strided")),
                              elab_end_points=True, precision=precision),
             kwargs_aux_path=dict(num_classes=C, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[512, 512],
-                                 hid_ch=64, aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
-                                 ensemble_mode=case.get("mode", "cosine_similarity")),
+                                 hid_ch=64, aux_drop_prob=float(case.get("drop_p", 0.)), do_memory=True, max_step=400,
+                                 update_momentum=0.9, ensemble_mode=case.get("mode", "cosine_similarity")),
             args_parser=ref_args(case))
     else:
         model = UNet(1, 32, 512, C, case["os"], bool(case.get("strided")), bool(case.get("strided")), True,
@@ -141,6 +145,9 @@ def run_case_cuda(name, precision, device="cuda"):
         batch = {k: v.to(device) for k, v in case_batch(case, step).items()}
         model.zero_grad(set_to_none=True)
         if case["kind"] == "pacing":
+            if case.get("drop_p"):   # pin the Dropout2d masks (call order: input features, bottleneck output, bank)
+                queue = list(O.synth_drop_factors(500 + step, case["N"], 1024, 64, C, case["drop_p"]))
+                model.aux_path.drop_factors = lambda n, ch, dev, _q=queue: _q.pop(0).to(dev)
             out = model({k: v for k, v in batch.items() if k != "label"}, mode="train", step=step * 37)
             loss = O.total_loss(out, epoch=40)
             for k in ("loss_pce", "loss_ent", "loss_cr", "loss_aux_cls", "loss_memory"):

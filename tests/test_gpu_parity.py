@@ -591,6 +591,70 @@ def test_full_size_baseline_vs_oracle(pp):
             assert me["logits"] <= 1.6 * emu["logits"] and me["grad_all"] <= 1.6 * emu["grad_all"], (me, emu)
 
 
+@pytest.mark.parametrize("max_ch,os_,strided,size", [(1024, 8, False, 64), (1024, 32, True, 64), (512, 16, True, 128),
+                                                      (512, 8, True, 112)])
+def test_unet_variants_fp32_mode_vs_oracle(pp, max_ch, os_, strided, size):
+    """train_chaos.py:71 allows max_ch 1024; unet.py:113-116,141 the stride-2 / ConvTranspose2d variant, here at larger
+    and ragged (112 = 7 * 16) sizes than the golden cases: logits, pCE and every gradient against the fp32 CPU oracle
+    in the library's fp32 mode, plus a bf16 run against the north-star bf16 tolerances on the loss."""
+    from pacingpseudo_b200.synth import make_batch
+    from pacingpseudo_b200.dropin import DROPIN_PATH
+    if DROPIN_PATH not in sys.path:
+        sys.path.insert(0, DROPIN_PATH)
+    from models.unet import UNet
+    from losses import losses as DL
+    C, N = 4, 2
+    sd = O.synth_state_dict(O.unet_param_shapes(1, 32, max_ch, C, os_, strided=strided), seed=11)
+    batch = make_batch(N, C, size, size, seed=21)
+    target = batch["scribble"].argmax(1)
+    names = [k for k in sd if sd[k].is_floating_point() and "running" not in k]
+    s_ = {k: v.clone() for k, v in sd.items()}
+    for k in names:
+        s_[k].requires_grad_(True)
+    z_ref = O.unet_forward(s_, batch["image"], True, max_ch=max_ch, output_stride=os_, strided=strided)["segmentation/logits"]
+    l_ref = O.partial_cross_entropy(z_ref, target, C)
+    l_ref.backward()
+    for precision in ("fp32", "bf16"):
+        model = UNet(1, 32, max_ch, C, os_, strided, strided, True, precision=precision)
+        model.load_state_dict(sd, strict=True)
+        model = model.cuda().train()
+        z = model(batch["image"].cuda())["segmentation/logits"]
+        loss = DL.partial_cross_entropy_loss(z, target.cuda(), C)
+        loss.backward()
+        tol = Hn.TOL[precision]
+        assert abs(loss.item() - l_ref.item()) <= tol["loss"] * abs(l_ref.item()), (precision, loss.item(), l_ref.item())
+        if precision == "fp32":
+            assert _rel(z.detach(), z_ref.detach()) < tol["logits"]
+            # conv biases in front of a batch-statistics BatchNorm have a mathematically zero gradient (noise / noise)
+            worst = max((_rel(p.grad, s_[k].grad), k) for k, p in model.named_parameters()
+                        if not k.endswith(".conv.bias"))
+            assert worst[0] < tol["grad"], worst
+        for k, p in model.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), k
+
+
+def test_space_depth_and_channel_scale_operators(pp):
+    """pp_space_to_depth / pp_depth_to_space (exact permutations, += variant) and pp_channel_scale against torch."""
+    L, _, pplib = pp
+    g = torch.Generator().manual_seed(3)
+    for dtype, code in ((torch.bfloat16, pplib.BF16), (torch.float32, pplib.F32)):
+        N, Hs, Ws, C = 2, 5, 7, 24
+        x = torch.randn(N, 2 * Hs, 2 * Ws, C, generator=g).to(dtype).cuda()
+        y = torch.empty(N, Hs, Ws, 4 * C, dtype=dtype, device="cuda")
+        L.call("pp_space_to_depth", code, _p(x), _p(y), N, Hs, Ws, C, _st())
+        ref = x.view(N, Hs, 2, Ws, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(N, Hs, Ws, 4 * C)
+        assert torch.equal(y, ref)
+        back = torch.empty_like(x)
+        L.call("pp_depth_to_space", code, _p(y), _p(back), N, Hs, Ws, C, 0, _st())
+        assert torch.equal(back, x)
+        L.call("pp_depth_to_space", code, _p(y), _p(back), N, Hs, Ws, C, 1, _st())
+        assert torch.equal(back.float(), (x.float() * 2).to(dtype).float())
+        sc = (torch.rand(N, C + 8, generator=g) > 0.5).float().cuda() * 2.0
+        out = torch.empty_like(x)
+        L.call("pp_channel_scale", code, _p(x), ctypes.c_void_p(sc.data_ptr() + 4 * 8), _p(out), N, 4 * Hs * Ws, C, C + 8, _st())
+        assert torch.equal(out.float(), (x.float() * sc[:, None, None, 8:]).to(dtype).float())
+
+
 def test_data_parallel_equivalence_emulated(pp):
     """DP(G ranks) == mean over ranks of single-GPU gradients on each rank's local batch. Emulated on one GPU
     by looping the ranks sequentially (the all-reduce itself is exercised by tests/test_dp_gloo.py on CPU)."""

@@ -13,7 +13,7 @@ from oracle.gen_golden import CASES
 
 FAST_CASES = ["pacing_train_bn", "pacing_eval_bn", "pacing_acdc_kl_mean", "pacing_l1_detach", "pacing_l2_nomask",
               "baseline_pce", "upperbound_ce_dice", "unet_os16", "unet_os32",
-              "unet_strided_os32", "unet_strided_os16_eval", "pacing_strided_os8"]
+              "unet_strided_os32", "unet_strided_os16_eval", "pacing_strided_os8", "pacing_dropout"]
 
 
 @pytest.mark.parametrize("name", FAST_CASES)
