@@ -241,7 +241,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from pacingpseudo_b200 import dp
-    from pacingpseudo_b200.data import DevicePrefetcher, LossReader
+    from pacingpseudo_b200.data import (DevicePrefetcher, LossReader, compact_batch, sample_strong_params,
+                                        strong_color_augment)
     from pacingpseudo_b200.dropin import DROPIN_PATH
     from pacingpseudo_b200.lib import get_lib
     from pacingpseudo_b200.optim import FlatAdam
@@ -285,6 +286,13 @@ def run_ours(args):
         pool_host.append({k: b[k].pin_memory() for k in keys})
     pool_dev = [{k: v.to(dev) for k, v in b.items()} for b in pool_host]
     h2d_bytes = sum(v.numel() * v.element_size() for v in pool_host[0].values())
+    # compact variant: uint8 scribble index map, no scribble_strong, image_strong made on the device
+    pool_compact = []
+    for i, b in enumerate(pool_host):
+        c = compact_batch(b, C)
+        c["strong_params"] = sample_strong_params(B, 1.0, torch.Generator().manual_seed(dp.shard_seed(99, rank, i)))
+        pool_compact.append({k: v.pin_memory() for k, v in c.items()})
+    h2d_bytes_compact = sum(v.numel() * v.element_size() for v in pool_compact[0].values())
     w_ent = loss_weight_ramp_up(args.epoch, 1.0, scale=8.0)
     w_cr = loss_weight_ramp_up(args.epoch, 1.0, scale=8.0)
 
@@ -292,6 +300,8 @@ def run_ours(args):
     prefetcher = DevicePrefetcher((), dev)
 
     def step(batch, read_back):
+        if "strong_params" in batch:   # compact host format: the strong branch's image is produced on the device
+            batch = dict(batch, image_strong=strong_color_augment(batch["image"], batch["strong_params"]))
         out = model(batch, mode='train', step=args.epoch)
         loss = out['loss_pce']
         loss_ent = out['loss_ent'] * w_ent
@@ -319,7 +329,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(nsteps, host_inputs, profile):
+    def timed(nsteps, host_inputs, profile, pool=None):
+        pool = pool_host if pool is None else pool
         barrier()
         lib.cdll.pp_profile_reset()
         lib.cdll.pp_profile_enable(1 if profile else 0)
@@ -327,7 +338,7 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         if host_inputs:   # pinned host batches, H2D on a copy stream one step ahead (pacingpseudo_b200/data.py)
-            for batch in prefetcher.reset(pool_host[i % len(pool_host)] for i in range(nsteps)):
+            for batch in prefetcher.reset(pool[i % len(pool)] for i in range(nsteps)):
                 step(batch, host_inputs)
             if host_inputs == "async":
                 assert len(loss_reader.flush()) == 5
@@ -362,12 +373,21 @@ def run_ours(args):
             step(batch, "async")
         ms_e2e, _ = timed(args.steps, host_inputs="async", profile=False)
         ms_e2e_item, _ = timed(args.steps, host_inputs="item", profile=False)
+        for batch in prefetcher.reset(pool_compact[i] for i in range(3)):   # staging buffers of the compact format
+            step(batch, "async")
+        ms_e2e_compact, _ = timed(args.steps, host_inputs="async", profile=False, pool=pool_compact)
         e2e = {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": "img/s", "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / args.steps,
                "how": "pinned host batches -> DevicePrefetcher (H2D into persistent staging buffers on a copy stream, "
                       "one step ahead) -> ConsistencyRegulr.forward / backward / FlatAdam.step -> LossReader (the five "
                       "loss scalars, non-blocking D2H to pinned memory every step, read one step later)",
-               "ms_per_step_blocking_item_reads": ms_e2e_item / args.steps}
+               "ms_per_step_blocking_item_reads": ms_e2e_item / args.steps,
+               "compact_input": {
+                   "value": B * world * args.steps / (ms_e2e_compact / 1e3), "unit": "img/s",
+                   "ms_per_step": ms_e2e_compact / args.steps, "h2d_bytes_per_step": h2d_bytes_compact,
+                   "how": "same loop from the compact host format (SURVEY 8f N3): image + uint8 scribble index map + "
+                          "valid mask + 8 augmentation draws per slice; image_strong = pp_strong_color_augment(image) "
+                          "on the device (different strong images than the reference-format leg, same work)"}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -195,6 +195,14 @@ int pp_dice_bwd(const float* z, const float* label, const float* coef, const flo
 int pp_memory_update_scratch_floats(int C, int hid);
 int pp_memory_update(int dtype, const void* feat, const float* scribble, float* bank, float* scratch, int C, int h,
                      int w, int H, int W, int hid, int cosine_mode, float m, float one_minus_m, void* stream);
+/* the same update from a COMPACT scribble: uint8 class-index map [N][H][W] (C = unlabelled) instead of the fp32 one-hot
+ * tensor ToTorchTensor builds (datasets/augmentations.py:421-446); SURVEY 8f N3: 24x less host->device traffic. */
+int pp_memory_update_idx(int dtype, const void* feat, const uint8_t* scribble_idx, float* bank, float* scratch, int C,
+                         int h, int w, int H, int W, int hid, int cosine_mode, float m, float one_minus_m, void* stream);
+/* Strong colour augmentation on the device: Brightness -> Contrast -> GammaAugmentation(retain_stats)
+ * of datasets/augmentations.py:98-166 as CHAOSTwoStream applies them (chaos_dataset.py:68-75) to each base-transformed
+ * slice. image/out: fp32 [N][HW]; params: [N][8] = {apply_brightness, b, apply_contrast, a, apply_gamma, gamma, 0, 0}. */
+int pp_strong_color_augment(const float* image, const float* params, float* out, int N, int HW, void* stream);
 /* cross_entropy_loss(fc_cls(memory_bank), arange(C)) (aux_path_memory.py:61; consistency_reglur_memory.py:94) */
 int pp_memory_loss_fwd(const float* bank, const float* wfc, float* loss, float* probs, int C, int hid,
                        void* stream);

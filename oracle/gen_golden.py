@@ -206,6 +206,73 @@ def dice_metric_vectors():
     return {"dice": np.array([compute_dice(scores[n], onehot[n]) for n in range(scores.shape[0])], dtype=np.float64)}
 
 
+def strong_augment_inputs():
+    """Seeded slices (base-transformed: mean/std normalised, zero outside a valid rectangle) and per-slice draws for
+    the strong colour chain: every apply / skip combination of the three transforms, gamma below and above 1."""
+    from pacingpseudo_b200.synth import make_batch
+    imgs = make_batch(8, 5, 48, 40, seed=77)["image"][:, 0].numpy().astype(np.float32)
+    params = np.array([
+        # apply_b, b, apply_c, a, apply_g, gamma, 0, 0
+        [1, 0.55, 1, 1.62, 1, 0.43, 0, 0],
+        [1, -0.7, 1, 0.31, 1, 1.71, 0, 0],
+        [0, 0.0, 1, 1.2, 1, 1.3, 0, 0],
+        [1, 0.2, 0, 1.0, 1, 0.8, 0, 0],
+        [1, -0.3, 1, 0.75, 0, 1.0, 0, 0],
+        [0, 0.0, 0, 1.0, 1, 0.25, 0, 0],
+        [1, 0.79, 0, 1.0, 0, 1.0, 0, 0],
+        [0, 0.0, 0, 1.0, 0, 1.0, 0, 0],
+    ], dtype=np.float32)
+    return imgs, params
+
+
+def strong_augment_vectors():
+    """The reference's own Brightness / Contrast / GammaAugmentation classes (TransformsColor(strength=1) chain) run on
+    the seeded slices with np.random.uniform replaced by the pinned draws, in the order the classes consume them."""
+    import types
+    for name in ("skimage", "skimage.transform"):      # imported by datasets/augmentations.py:8, unused by these classes
+        sys.modules.setdefault(name, types.ModuleType(name))
+    # the HuggingFace `datasets` package in site-packages shadows the reference's (namespace) `datasets` directory, so
+    # its two files are loaded by path under that name: augmentations.py, then chaos_aug_configs.py (which does
+    # `from datasets.augmentations import *`); the chain is TransformsColor(strength=1).strong_transforms itself
+    import importlib.util
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "datasets" or k.startswith("datasets.")}
+    try:
+        pkg = types.ModuleType("datasets")
+        pkg.__path__ = [os.path.join(REF, "datasets")]
+        sys.modules["datasets"] = pkg
+        for name, rel in (("datasets.augmentations", "augmentations.py"),
+                          ("datasets.chaos_aug_configs", os.path.join("chaos", "chaos_aug_configs.py"))):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(REF, "datasets", rel))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+        chain = sys.modules["datasets.chaos_aug_configs"].TransformsColor(1.0).strong_transforms
+    finally:
+        for k in [k for k in sys.modules if k == "datasets" or k.startswith("datasets.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    imgs, params = strong_augment_inputs()
+    outs = []
+    orig = np.random.uniform
+    try:
+        for img, p in zip(imgs, params):
+            ab, b, ac, a, ag, gamma = p[:6]
+            draws = [0.0 if ab else 0.99] + ([float(b)] if ab else []) + [0.0 if ac else 0.99] + ([float(a)] if ac else [])
+            if ag:   # apply draw, the branch draw (< 0.5 -> gamma from [lo, 1)), the gamma draw
+                draws += [0.0, 0.0 if gamma < 1 else 0.99, float(gamma)]
+            else:
+                draws += [0.99]
+            np.random.uniform = lambda *a_, _q=draws, **k_: _q.pop(0)
+            data = {"image": img.copy()}
+            for t in chain:
+                data = t(data)
+            assert not draws, "the reference consumed fewer draws than expected"
+            outs.append(np.asarray(data["image"], dtype=np.float32))
+    finally:
+        np.random.uniform = orig
+    return {"out": np.stack(outs), "params": params}
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference not found at %s" % REF)
@@ -219,6 +286,9 @@ def main():
         print("wrote loss_functions.npz")
         np.savez_compressed(os.path.join(out_dir, "dice_metric.npz"), **dice_metric_vectors())
         print("wrote dice_metric.npz")
+    if len(sys.argv) == 1 or "strong_augment" in sys.argv[1:]:
+        np.savez_compressed(os.path.join(out_dir, "strong_augment.npz"), **strong_augment_vectors())
+        print("wrote strong_augment.npz")
     only = [a for a in sys.argv[1:] if not a.startswith("-")]   # optional: regenerate the named cases only
     for name, case in CASES.items():
         if only and name not in only:

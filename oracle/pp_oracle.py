@@ -282,6 +282,29 @@ def dice(logits, onehot):
 
 
 # ------------------------------------------------------------------------------------------------
+# strong colour augmentation (datasets/augmentations.py:98-166 as chained by chaos_aug_configs.py:63-86)
+# ------------------------------------------------------------------------------------------------
+def strong_color_augment_np(image, params):
+    """Brightness -> Contrast -> GammaAugmentation(retain_stats=True, invert_data=False) on ONE float32 slice (H, W)
+    with explicit draws: params = [apply_brightness, b, apply_contrast, a, apply_gamma, gamma, ...]."""
+    import numpy as np
+    eps = np.float32(1e-8)
+    x = np.asarray(image, dtype=np.float32)
+    ab, b, ac, a, ag, gamma = (np.float32(v) for v in params[:6])
+    if ab:
+        x = x + b                                                  # augmentations.py:110
+    if ac:
+        mean_, max_, min_ = np.mean(x), np.max(x), np.min(x)       # :125-127
+        x = np.clip((x - mean_) * a + mean_, min_, max_)           # :128
+    if ag:
+        mean_, std_, max_, min_ = np.mean(x), np.std(x), np.max(x), np.min(x)   # :146-149
+        x = np.power((x - min_) / (max_ - min_ + eps), gamma)      # :156
+        x = (x - np.mean(x)) / (np.std(x) + eps)                   # :159
+        x = x * std_ + mean_                                       # :160
+    return x.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
 # aux path + memory bank (models/aux_path_memory.py)
 # ------------------------------------------------------------------------------------------------
 def compute_dice_np(scores, target):

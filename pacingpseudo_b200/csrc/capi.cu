@@ -233,6 +233,14 @@ int pp_memory_update(int dtype, const void* feat, const float* scribble, float* 
   return memory_update(dtype, feat, scribble, bank, scratch, C, h, w, H, W, hid, cosine_mode, m, one_minus_m,
                        ST(stream));
 }
+int pp_memory_update_idx(int dtype, const void* feat, const uint8_t* scribble_idx, float* bank, float* scratch, int C,
+                         int h, int w, int H, int W, int hid, int cosine_mode, float m, float one_minus_m, void* stream) {
+  return memory_update(dtype, feat, nullptr, bank, scratch, C, h, w, H, W, hid, cosine_mode, m, one_minus_m, ST(stream),
+                       scribble_idx);
+}
+int pp_strong_color_augment(const float* image, const float* params, float* out, int N, int HW, void* stream) {
+  return strong_color_augment(image, params, out, N, HW, ST(stream));
+}
 int pp_memory_loss_fwd(const float* bank, const float* wfc, float* loss, float* probs, int C, int hid,
                        void* stream) {
   return memory_loss_fwd(bank, wfc, loss, probs, C, hid, ST(stream));

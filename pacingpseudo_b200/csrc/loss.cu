@@ -1069,7 +1069,8 @@ constexpr int kMemSlices = 32;     // blocks per class in the gather phase
 template <typename T>
 __global__ void __launch_bounds__(256)
 memory_gather_kernel(const T* __restrict__ feat /*[N][h][w][hid], sample 0 used*/, const float* __restrict__ scribble
-                     /*[N][K][H][W], sample 0 used*/, const float* __restrict__ bank /*[C][hid]*/,
+                     /*[N][K][H][W], sample 0 used; or nullptr*/, const uint8_t* __restrict__ scribble_idx
+                     /*[N][H][W] class index map, sample 0 used*/, const float* __restrict__ bank /*[C][hid]*/,
                      float* __restrict__ scratch, int h, int w, int H, int W, int hid, float sh, float sw) {
   __shared__ float s_rhat[256];
   __shared__ float s_U[8][256], s_E[8][256];
@@ -1097,13 +1098,13 @@ memory_gather_kernel(const T* __restrict__ feat /*[N][h][w][hid], sample 0 used*
 #pragma unroll
   for (int r = 0; r < kMaxHidPerLane; ++r) { U[r] = 0.f; E[r] = 0.f; }
   float S = 0.f, cnt = 0.f;
-  const float* plane = scribble + static_cast<long long>(cls) * H * W;  // sample 0, channel cls
+  const float* plane = scribble ? scribble + static_cast<long long>(cls) * H * W : nullptr;  // sample 0, channel cls
   const int HWp = H * W;
   const int per = (HWp + kMemSlices - 1) / kMemSlices;
   const int pbeg = slice * per, pend = min(pbeg + per, HWp);
   for (int base = pbeg + warp * 32; base < pend; base += 8 * 32) {
     const int pix = base + lane;
-    const bool hit = (pix < pend) && (plane[pix] == 1.f);
+    const bool hit = (pix < pend) && (plane ? plane[pix] == 1.f : scribble_idx[pix] == cls);
     unsigned bal = __ballot_sync(0xffffffffu, hit);
     while (bal) {
       const int b = __ffs(bal) - 1;
@@ -1201,18 +1202,20 @@ __global__ void memory_apply_kernel(const float* __restrict__ scratch, float* __
 int memory_update_scratch_floats(int C, int hid) { return C * kMemSlices * (2 * hid + 2); }
 
 int memory_update(int dtype, const void* feat, const float* scribble, float* bank, float* scratch, int C, int h, int w,
-                  int H, int W, int hid, int cosine_mode, float m, float one_minus_m, cudaStream_t s) {
+                  int H, int W, int hid, int cosine_mode, float m, float one_minus_m, cudaStream_t s,
+                  const uint8_t* scribble_idx) {
   PP_REQUIRE(hid % 32 == 0 && hid <= 256, "memory_update: hid_ch=%d unsupported (multiple of 32, <= 256)", hid);
   PP_REQUIRE(scratch != nullptr, "memory_update: scratch buffer required");
+  PP_REQUIRE((scribble != nullptr) != (scribble_idx != nullptr), "memory_update: one-hot OR index-map scribble");
   const float sh = H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f;
   const float sw = W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f;
   dim3 grid(kMemSlices, C);
   if (dtype == PP_F32)
-    memory_gather_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(feat), scribble, bank, scratch, h, w, H,
-                                                     W, hid, sh, sw);
+    memory_gather_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(feat), scribble, scribble_idx, bank,
+                                                     scratch, h, w, H, W, hid, sh, sw);
   else
-    memory_gather_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(feat), scribble, bank,
-                                                             scratch, h, w, H, W, hid, sh, sw);
+    memory_gather_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(feat), scribble,
+                                                             scribble_idx, bank, scratch, h, w, H, W, hid, sh, sw);
   memory_apply_kernel<<<C, 256, 0, s>>>(scratch, bank, hid, cosine_mode, m, one_minus_m);
   PP_LAUNCH_CHECK_N(2);
   return PP_OK;

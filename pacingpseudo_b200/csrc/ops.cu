@@ -1422,6 +1422,98 @@ int channel_scale(int dtype, const void* x, const float* scale, void* y, int N, 
 }
 
 // ==============================================================================================
+// Strong colour augmentation of the two-stream dataset on the device: Brightness -> Contrast ->
+// GammaAugmentation(retain_stats) of datasets/augmentations.py:98-166, applied by CHAOSTwoStream.__getitem__
+// (chaos_dataset.py:68-75) to the base-transformed slice. Each transform needs whole-image statistics (mean / std /
+// min / max), so one 1024-thread block owns one image (<= 256 KB, L2 resident) and walks it up to four times:
+//   pass 1: stats of x1 = x + b                         (Brightness; Contrast's mean_/min_/max_)
+//   pass 2: stats of x2 = clip((x1 - mean1) a + mean1, min1, max1)       (Gamma's mean_/std_/min_/max_)
+//   pass 3: stats of x3 = ((x2 - min2) / (max2 - min2 + eps)) ^ gamma    (retain_stats: its mean / std)
+//   pass 4: out = (x3 - mean3) / (std3 + eps) * std2 + mean2
+// params per image (8 floats): [apply_brightness, b, apply_contrast, a, apply_gamma, gamma, 0, 0]; the caller draws
+// them (pacingpseudo_b200.data.sample_strong_params mirrors the reference's probabilities and ranges).
+// ==============================================================================================
+struct ImgStats { double sum, sq; float mn, mx; };
+__device__ __forceinline__ ImgStats block_stats(double sum, double sq, float mn, float mx) {
+  __shared__ double s_sum[32], s_sq[32];
+  __shared__ float s_mn[32], s_mx[32];
+  __syncthreads();   // protects the shared arrays between consecutive calls
+  sum = warp_sum_d(sum);
+  sq = warp_sum_d(sq);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { s_sum[warp] = sum; s_sq[warp] = sq; s_mn[warp] = mn; s_mx[warp] = mx; }
+  __syncthreads();
+  ImgStats r{0.0, 0.0, INFINITY, -INFINITY};
+  for (int w = 0; w < nw; ++w) {
+    r.sum += s_sum[w]; r.sq += s_sq[w];
+    r.mn = fminf(r.mn, s_mn[w]); r.mx = fmaxf(r.mx, s_mx[w]);
+  }
+  return r;
+}
+__global__ void __launch_bounds__(1024) strong_augment_kernel(const float* __restrict__ image,
+                                                              const float* __restrict__ params,
+                                                              float* __restrict__ out, int HW) {
+  const float* x = image + static_cast<size_t>(blockIdx.x) * HW;
+  float* y = out + static_cast<size_t>(blockIdx.x) * HW;
+  const float* p = params + blockIdx.x * 8;
+  const bool do_c = p[2] != 0.f, do_g = p[4] != 0.f;
+  const float b = p[0] != 0.f ? p[1] : 0.f, a = p[3], gamma = p[5];
+  const float eps = 1e-8f;
+  const double n = static_cast<double>(HW);
+  float mean1 = 0.f, min1 = 0.f, max1 = 0.f;
+  if (do_c) {
+    double s = 0.0, q = 0.0;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const float v = x[i] + b;
+      s += v; mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    const ImgStats st = block_stats(s, q, mn, mx);
+    mean1 = static_cast<float>(st.sum / n); min1 = st.mn; max1 = st.mx;
+  }
+  auto x2_of = [&](float v) {
+    v += b;
+    return do_c ? fminf(fmaxf((v - mean1) * a + mean1, min1), max1) : v;
+  };
+  if (!do_g) {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) y[i] = x2_of(x[i]);
+    return;
+  }
+  double s = 0.0, q = 0.0;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float v = x2_of(x[i]);
+    s += v; q += static_cast<double>(v) * v; mn = fminf(mn, v); mx = fmaxf(mx, v);
+  }
+  const ImgStats s2 = block_stats(s, q, mn, mx);
+  const float mean2 = static_cast<float>(s2.sum / n);
+  const float std2 = static_cast<float>(sqrt(fmax(s2.sq / n - (s2.sum / n) * (s2.sum / n), 0.0)));
+  const float min2 = s2.mn, inv_rng = 1.f / (s2.mx - s2.mn + eps);
+  auto x3_of = [&](float v) { return powf((x2_of(v) - min2) * inv_rng, gamma); };
+  s = 0.0; q = 0.0;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float v = x3_of(x[i]);
+    s += v; q += static_cast<double>(v) * v;
+  }
+  const ImgStats s3 = block_stats(s, q, 0.f, 0.f);
+  const float mean3 = static_cast<float>(s3.sum / n);
+  const float std3 = static_cast<float>(sqrt(fmax(s3.sq / n - (s3.sum / n) * (s3.sum / n), 0.0)));
+  const float k = std2 / (std3 + eps);
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) y[i] = (x3_of(x[i]) - mean3) * k + mean2;
+}
+int strong_color_augment(const float* image, const float* params, float* out, int N, int HW, cudaStream_t s) {
+  PP_REQUIRE(N >= 1 && HW >= 1, "strong_color_augment: bad shape N=%d HW=%d", N, HW);
+  strong_augment_kernel<<<N, 1024, 0, s>>>(image, params, out, HW);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+// ==============================================================================================
 // Adam with L2 weight decay folded into the gradient (torch.optim.Adam semantics,
 // train_chaos.py:219), over one flat fp32 parameter buffer. step is the 1-based step count.
 // ==============================================================================================

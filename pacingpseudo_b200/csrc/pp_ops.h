@@ -68,6 +68,7 @@ int collapse_s2_wgrad(const float* dwe, float* dw, int Cout, int C, cudaStream_t
 int embed_ct_weight(const float* wt, float* we, int Cin, int Cout, int S, cudaStream_t s);
 int collapse_ct_wgrad(const float* dwe, float* dwt, int Cin, int Cout, int S, cudaStream_t s);
 int channel_scale(int dtype, const void* x, const float* scale, void* y, int N, int HW, int C, int ld, cudaStream_t s);
+int strong_color_augment(const float* image, const float* params, float* out, int N, int HW, cudaStream_t s);
 int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
               float wd, int step, float grad_scale, cudaStream_t s);
 
@@ -89,8 +90,10 @@ int dice_fwd(const float* z, const float* label, double* sums, float* coef, floa
 int dice_bwd(const float* z, const float* label, const float* coef, const float* g, float* dz, int N, int C, int HW,
              int accumulate, cudaStream_t s);
 int memory_update_scratch_floats(int C, int hid);
+// scribble: fp32 one-hot [N][K][H][W] (reference format), or nullptr with scribble_idx: uint8 index map [N][H][W]
 int memory_update(int dtype, const void* feat, const float* scribble, float* bank, float* scratch, int C, int h, int w,
-                  int H, int W, int hid, int cosine_mode, float m, float one_minus_m, cudaStream_t s);
+                  int H, int W, int hid, int cosine_mode, float m, float one_minus_m, cudaStream_t s,
+                  const uint8_t* scribble_idx = nullptr);
 int memory_loss_fwd(const float* bank, const float* wfc, float* loss, float* probs, int C, int hid, cudaStream_t s);
 int memory_loss_bwd(const float* bank, const float* probs, const float* g, float* dwfc, int C, int hid, cudaStream_t s);
 

@@ -122,3 +122,54 @@ class LossReader:
 
     def flush(self):
         return self._collect((self.i - 1) & 1) if self.i else None
+
+
+# ------------------------------------------------------------------------------------------------
+# Compact input format + device-side strong augmentation
+# ------------------------------------------------------------------------------------------------
+def sample_strong_params(n, strength=1.0, generator=None):
+    """Per-image parameters of TransformsColor.get_strong_transforms(strength) (chaos_aug_configs.py:63-86), drawn with
+    the reference's probabilities and ranges: Brightness U(-0.8 s, 0.8 s) p=0.8; Contrast U(max(0, 1-0.8 s), 1+0.8 s)
+    p=0.8; Gamma p=0.8, with probability 1/2 from [lo, 1) when lo < 1, else from [max(1, lo), hi]
+    (augmentations.py:150-153). -> CPU fp32 tensor [n, 8] for strong_color_augment."""
+    u = lambda *shape: torch.rand(*shape, generator=generator)
+    lo, hi = max(0.0, 1 - strength * 0.8), 1 + strength * 0.8
+    p = torch.zeros(n, 8)
+    p[:, 0] = (u(n) < 0.8).float()
+    p[:, 1] = (u(n) * 2 - 1) * strength * 0.8
+    p[:, 2] = (u(n) < 0.8).float()
+    p[:, 3] = lo + u(n) * (hi - lo)
+    p[:, 4] = (u(n) < 0.8).float()
+    low_half = (u(n) < 0.5) & (lo < 1.0)
+    g_lo = lo + u(n) * (1.0 - lo)
+    g_hi = max(1.0, lo) + u(n) * (hi - max(1.0, lo))
+    p[:, 5] = torch.where(low_half, g_lo, g_hi)
+    return p
+
+
+def strong_color_augment(image, params):
+    """image_strong from the weak image ON THE DEVICE: Brightness -> Contrast -> GammaAugmentation(retain_stats)
+    (datasets/augmentations.py:98-166) with the given per-image parameters ([N, 8], see sample_strong_params).
+    image: CUDA fp32 (N, 1, H, W). One hand-written kernel (pp_strong_color_augment); no CPU path."""
+    from .lib import current_stream, get_lib, ptr, require_cuda
+    require_cuda(image, "image")
+    image = image.contiguous().float()
+    n = image.shape[0]
+    hw = image[0].numel()
+    params = params.to(device=image.device, dtype=torch.float32).contiguous()
+    if tuple(params.shape) != (n, 8):
+        raise ValueError("strong_color_augment: params must be [N, 8], got %r" % (tuple(params.shape),))
+    out = torch.empty_like(image)
+    with torch.cuda.device(image.device):
+        get_lib().call("pp_strong_color_augment", ptr(image), ptr(params), ptr(out), n, hw, current_stream(image.device))
+    return out
+
+
+def compact_batch(batch, num_classes):
+    """Host-side: the reference batch (fp32 one-hot `scribble` (N, C+1, H, W), train_chaos.py:264-269) in the compact
+    format the drop-in modules also accept: `scribble` as a uint8 class-index map (N, H, W); `image_strong` and the
+    unused `scribble_strong` dropped (the strong image is produced on the device by strong_color_augment)."""
+    out = {"image": batch["image"], "scribble": batch["scribble"].argmax(1).to(torch.uint8)}
+    if "valid_mask" in batch:
+        out["valid_mask"] = batch["valid_mask"]
+    return out

@@ -93,7 +93,8 @@ class AuxPath(nn.Module):
                                "(elab_end_points=True)")
         code = PF.BF16 if native[self.feat_stage[0]].dtype == torch.bfloat16 else PF.F32
         logits, _ = self.run_native([native[s] for s in self.feat_stage], scribble, step, code)
-        out = {'logits_aux_cls': logits, 'aux_targets': PF.onehot_argmax(scribble).long()}
+        out = {'logits_aux_cls': logits,
+               'aux_targets': (scribble if scribble.dim() == 3 else PF.onehot_argmax(scribble)).long()}
         if self.do_memory:
             # logits_memory is produced for API parity; its loss/gradient go through memory_loss()
             w = self.fc_cls[1].weight

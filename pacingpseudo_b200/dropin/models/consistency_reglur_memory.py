@@ -44,8 +44,9 @@ class ConsistencyRegulr(nn.Module):
         self.backbone.end_points._set_native(feats)
         self.backbone.end_points.update({'segmentation/logits': logits_all[n:] if do_cr else logits_weak})
 
+        # fp32 one-hot (N, C+1, H, W) as ToTorchTensor builds it, or the compact uint8 class-index map (N, H, W)
         scribble = names_to_data['scribble']
-        scb_target = PF.onehot_argmax(scribble)
+        scb_target = scribble.to(torch.uint8) if scribble.dim() == 3 else PF.onehot_argmax(scribble)
         valid_mask = names_to_data.get('valid_mask')
 
         logits_aux = None

@@ -486,13 +486,16 @@ class MemoryLossFunction(torch.autograd.Function):
 
 
 def memory_update(code, aux_features, scribble, bank, mode, m):
-    """In-place bank update from sample 0 (aux_path_memory.py:68-116). aux_features: native NHWC."""
+    """In-place bank update from sample 0 (aux_path_memory.py:68-116). aux_features: native NHWC.
+    scribble: fp32 one-hot (N, C+1, H, W) (reference format) or a uint8 class-index map (N, H, W)."""
     lib = get_lib()
     N, h, w, hid = aux_features.shape
-    _, K, H, W = scribble.shape
+    H, W = scribble.shape[-2:]
     C = bank.shape[0]
-    scribble = scribble.contiguous().float()
+    index_map = scribble.dim() == 3
+    scribble = scribble.contiguous().to(torch.uint8) if index_map else scribble.contiguous().float()
     with torch.cuda.device(bank.device):
         scratch = torch.empty(lib.cdll.pp_memory_update_scratch_floats(C, hid), dtype=torch.float32, device=bank.device)
-        lib.call("pp_memory_update", code, ptr(aux_features), ptr(scribble), ptr(bank), ptr(scratch), C, h, w, H, W, hid,
-                 1 if mode == "cosine_similarity" else 0, float(m), float(1.0 - m), current_stream(bank.device))
+        lib.call("pp_memory_update_idx" if index_map else "pp_memory_update", code, ptr(aux_features), ptr(scribble),
+                 ptr(bank), ptr(scratch), C, h, w, H, W, hid, 1 if mode == "cosine_similarity" else 0, float(m),
+                 float(1.0 - m), current_stream(bank.device))

@@ -130,3 +130,31 @@ def test_dice_metric_oracle_matches_reference_golden():
     assert np.isnan(gold[0, 4]) and gold[1, 2] == 0.0 and gold[2, 1] == 0.0
     assert np.array_equal(np.isnan(mine), np.isnan(gold))
     assert np.allclose(mine, gold, rtol=1e-12, atol=0, equal_nan=True)
+
+
+def test_strong_color_augment_oracle_matches_reference_golden():
+    """oracle.strong_color_augment_np (restating datasets/augmentations.py:98-166) against the outputs of the
+    reference's own Brightness / Contrast / GammaAugmentation chain with pinned draws (oracle/gen_golden.py)."""
+    from oracle.gen_golden import strong_augment_inputs
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "strong_augment.npz"))
+    imgs, params = strong_augment_inputs()
+    np.testing.assert_array_equal(params, gold["params"])
+    for i in range(len(imgs)):
+        got = O.strong_color_augment_np(imgs[i], params[i])
+        np.testing.assert_allclose(got, gold["out"][i], rtol=1e-6, atol=1e-6, err_msg="slice %d" % i)
+    np.testing.assert_array_equal(O.strong_color_augment_np(imgs[7], params[7]), imgs[7])   # nothing applied
+
+
+def test_sample_strong_params_ranges():
+    """Draw ranges / probabilities of TransformsColor.get_strong_transforms (chaos_aug_configs.py:63-86)."""
+    from pacingpseudo_b200.data import sample_strong_params
+    for strength in (1.0, 0.25):
+        p = sample_strong_params(4000, strength, torch.Generator().manual_seed(0))
+        lo, hi = max(0.0, 1 - 0.8 * strength), 1 + 0.8 * strength
+        assert p.shape == (4000, 8) and p.dtype == torch.float32
+        for col in (0, 2, 4):
+            assert set(p[:, col].unique().tolist()) <= {0.0, 1.0} and abs(p[:, col].mean().item() - 0.8) < 0.03
+        assert p[:, 1].abs().max() <= 0.8 * strength and p[:, 1].min() < 0 < p[:, 1].max()
+        assert lo <= p[:, 3].min() and p[:, 3].max() <= hi
+        assert lo <= p[:, 5].min() and p[:, 5].max() <= hi
+        assert abs((p[:, 5] < 1).float().mean().item() - 0.5) < 0.04   # half of the gammas below 1 (augmentations.py:150)
