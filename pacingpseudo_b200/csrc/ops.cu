@@ -6,6 +6,7 @@
 //   Adam. Reference call sites: /root/reference/models/unet.py:60,109,144,188-193,
 //   /root/reference/models/aux_path_memory.py:22-33,52 and /root/reference/train_chaos.py:219.
 #include "pp_common.cuh"
+#include <stdlib.h>
 
 namespace pp {
 
@@ -802,7 +803,8 @@ int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* 
   PP_REQUIRE(C % 8 == 0 && C / 8 <= kBnThreads && kBnThreads % (C / 8) == 0, "bn_bwd: C=%d unsupported", C);
   PP_REQUIRE_INT32(Pg * C, "bn_bwd");
   if (!sums_zeroed) PP_CHECK_CUDA(cudaMemsetAsync(bsums, 0, sizeof(double) * 2 * G * C, s));
-  int cpg = (sm_count() * 8) / G;
+  static const int red_bps = [] { const char* e = getenv("PP_BN_RED_BPS"); return e ? atoi(e) : 8; }();
+  int cpg = (sm_count() * (red_bps > 0 ? red_bps : 8)) / G;
   if (cpg < 1) cpg = 1;
   long long chunk = ceil_div_ll(Pg, cpg);
   if (chunk < 64) chunk = 64;
