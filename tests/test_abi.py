@@ -124,6 +124,75 @@ def test_dropin_modules_mirror_reference_state_dict():
         UNet(1, 32, 512, 5, 8)(torch.zeros(1, 1, 16, 16))  # no CPU fallback
 
 
+def test_checkpoint_round_trip_in_reference_format(tmp_path):
+    """a ConsistencyRegulr checkpoint written by the drop-in loads (a) back into the drop-in, (b) into a
+    plain UNet through the `backbone.` prefix stripping of inference.py:138-146, and (c) into the REFERENCE modules and
+    back when the reference is present (build container) - same keys, shapes, dtypes and values."""
+    import argparse
+    import sys
+    from collections import OrderedDict
+    import torch
+    from pacingpseudo_b200.dropin import DROPIN_PATH
+    if DROPIN_PATH not in sys.path:
+        sys.path.insert(0, DROPIN_PATH)
+    from models.unet import UNet
+    from models.consistency_reglur_memory import ConsistencyRegulr
+
+    def make(cls_cr, strided=False):
+        return cls_cr(
+            kwargs_unet=dict(input_ch=1, init_ch=32, max_ch=512, num_classes=3, output_stride=16, is_stride_conv=strided,
+                             is_trans_conv=strided, elab_end_points=True),
+            kwargs_aux_path=dict(num_classes=3, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[512, 512],
+                                 hid_ch=64, aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
+                                 ensemble_mode='cosine_similarity'),
+            args_parser=argparse.Namespace())
+
+    for strided in (False, True):
+        torch.manual_seed(3)
+        cr = make(ConsistencyRegulr, strided)
+        with torch.no_grad():
+            cr.aux_path.memory_bank.normal_()
+        path = str(tmp_path / ("ckpt_%d.pth" % strided))
+        torch.save(cr.state_dict(), path)                     # train_chaos.py:420 torch.save(model.state_dict(), ...)
+        state = torch.load(path)
+        cr2 = make(ConsistencyRegulr, strided)
+        cr2.load_state_dict(state)                            # strict
+        assert all(torch.equal(a, b) for a, b in zip(cr.state_dict().values(), cr2.state_dict().values()))
+        unet = UNet(1, 32, 512, 3, 16, strided, strided, True)
+        with pytest.raises(RuntimeError):
+            unet.load_state_dict(state)
+        stripped = OrderedDict((k.partition('.')[-1], v) for k, v in state.items() if 'backbone' in k)   # inference.py:141-145
+        unet.load_state_dict(stripped)
+        assert all(torch.equal(stripped[k], v) for k, v in unet.state_dict().items())
+
+    if not os.path.isdir("/root/reference"):
+        return
+    torch.Tensor.cuda, saved_cuda = (lambda self, *a, **k: self), torch.Tensor.cuda   # AuxPath.__init__ calls .cuda()
+    mods = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split('.')[0] in ("models", "losses")}
+    # the reference's `models` directory has no __init__.py: a regular package of that name anywhere on sys.path (the
+    # drop-in) would win over it, so the drop-in path is taken off sys.path while the reference is imported
+    sys.path.remove(DROPIN_PATH)
+    sys.path.insert(0, "/root/reference")
+    try:
+        from models.consistency_reglur_memory import ConsistencyRegulr as RefCR
+        assert "/root/reference" in sys.modules["models.consistency_reglur_memory"].__file__
+        for strided in (False, True):
+            ref = make(RefCR, strided)
+            ref.load_state_dict(torch.load(str(tmp_path / ("ckpt_%d.pth" % strided))))       # drop-in -> reference
+            back = make(ConsistencyRegulr, strided)
+            back.load_state_dict(ref.state_dict())                                             # reference -> drop-in
+            sd_ref = ref.state_dict()
+            assert list(sd_ref) == list(back.state_dict())
+            assert all(torch.equal(sd_ref[k], v) and sd_ref[k].dtype == v.dtype for k, v in back.state_dict().items())
+    finally:
+        sys.path.remove("/root/reference")
+        sys.path.insert(0, DROPIN_PATH)
+        torch.Tensor.cuda = saved_cuda
+        for k in [k for k in sys.modules if k.split('.')[0] in ("models", "losses")]:
+            del sys.modules[k]
+        sys.modules.update(mods)
+
+
 def test_graft_build_compiles_library_and_standalone_checker():
     """__graft_entry__.build() (the driver's 'does it build' check): the shared library and the standalone
     tcgen05 cross-check binary (tests/cuda/test_conv_tc.cu, linked against the kernel objects) must both build, so a
