@@ -1107,6 +1107,140 @@ __global__ void __launch_bounds__(256) upsample_nhwc_bwd_kernel(const T* __restr
   }
 }
 
+// Strip variant for the UNet's scale-2 layers: the gather above reads ~16 output-gradient vectors per input vector and
+// is bound by L1/L2 traffic (168 us for the 250 MB of the 256^2 layer). Here a block owns P consecutive INPUT rows of
+// one image and a thread owns TWO adjacent input columns x 8 channels; it streams the contributing output rows once,
+// top to bottom. Per output row Y (block-uniform lerp_src(Y) = rows i0, i1 with weights w0, w1) it loads the union
+// window of its two columns (<= kPairWin vectors, 6 at scale 2), folds it horizontally into hx0 / hx1 with the
+// per-pair tap weights from shared memory, and adds w0 * hx to the accumulators of row i0 and w1 * hx to those of
+// row i1, kept as a sliding (current, next) pair that is flushed when Y moves past a row. Loads per input vector:
+// (2P + 2) * 6 / (2P) = 6.75 at P = 8 instead of 16; fixed summation order (deterministic); a few KB of shared
+// memory and ~100 registers, so the blocks still co-reside with the conv CTAs of the weight-gradient stream.
+constexpr int kPairWin = 8;
+struct PairTaps { int lo, n; float wa[kPairWin], wb[kPairWin]; };
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_nhwc_bwd_strip_kernel(const T* __restrict__ gy, T* __restrict__ gx,
+                                                                      int h, int w, int H, int W, int C, float sh,
+                                                                      float sw, int P, int strips, int accumulate) {
+  extern __shared__ float s_raw[];
+  PairTaps* s_tp = reinterpret_cast<PairTaps*>(s_raw);
+  const int pairs = (w + 1) / 2;
+  for (int j = threadIdx.x; j < pairs; j += blockDim.x) {
+    const int xa = 2 * j, xb = 2 * j + 1;
+    PairTaps t;
+    t.lo = xa == 0 ? 0 : lerp_first_out(xa - 1, w, W, sw);
+    const int hi = lerp_first_out(min(xb, w - 1) + 1, w, W, sw);
+    t.n = hi - t.lo;
+#pragma unroll
+    for (int k = 0; k < kPairWin; ++k) {
+      const int X = t.lo + k;
+      t.wa[k] = (k < t.n) ? lerp_weight(X, xa, w, sw) : 0.f;
+      t.wb[k] = (k < t.n && xb < w) ? lerp_weight(X, xb, w, sw) : 0.f;
+    }
+    s_tp[j] = t;
+  }
+  __syncthreads();
+  const int n = blockIdx.x / strips, y0 = (blockIdx.x % strips) * P;
+  const int y1 = min(y0 + P, h);
+  const int Ybeg = y0 == 0 ? 0 : lerp_first_out(y0 - 1, h, H, sh), Yend = lerp_first_out(y1, h, H, sh);
+  const int vecs = C / 8;
+  const T* gimg = gy + static_cast<size_t>(n) * H * W * C;
+  T* ximg = gx + static_cast<size_t>(n) * h * w * C;
+  // grid.y walks the (column pair, channel vector) range in blockDim.x chunks: one pass over the strip per thread
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < pairs * vecs; t += gridDim.y * blockDim.x) {
+    const int j = t / vecs, v = t - j * vecs;
+    const PairTaps& tp = s_tp[j];
+    const int xa = 2 * j;
+    const bool has_b = xa + 1 < w;
+    float cur0[8], cur1[8], nxt0[8], nxt1[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { cur0[c] = 0.f; cur1[c] = 0.f; nxt0[c] = 0.f; nxt1[c] = 0.f; }
+    int cur_row = y0;
+    auto flush = [&]() {   // row cur_row is complete: store it, slide the window down one row
+      if (cur_row < y1) {
+        T* o = ximg + (static_cast<size_t>(cur_row) * w + xa) * C + v * 8;
+        Vec8<T> q;
+        if (accumulate) {
+          float old[8];
+          q.load(o); q.get(old);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) cur0[c] += old[c];
+          if (has_b) {
+            q.load(o + C); q.get(old);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cur1[c] += old[c];
+          }
+        }
+        q.set(cur0); q.store(o);
+        if (has_b) { q.set(cur1); q.store(o + C); }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { cur0[c] = nxt0[c]; cur1[c] = nxt1[c]; nxt0[c] = 0.f; nxt1[c] = 0.f; }
+      ++cur_row;
+    };
+    // software pipeline: the window of row Y + 1 is in flight while row Y is folded (the chain per thread is
+    // ~2P dependent rounds of memory latency otherwise)
+    Vec8<T> nx[kPairWin];
+    auto load_row = [&](int Y) {
+      const T* grow = gimg + (static_cast<size_t>(Y) * W + tp.lo) * C + v * 8;
+#pragma unroll
+      for (int k = 0; k < kPairWin; ++k)
+        if (k < tp.n) nx[k].load(grow + static_cast<size_t>(k) * C);
+    };
+    if (Ybeg < Yend) load_row(Ybeg);
+    for (int Y = Ybeg; Y < Yend; ++Y) {
+      const Lerp ly = lerp_src(Y, h, sh);
+      Vec8<T> pkr[kPairWin];
+#pragma unroll
+      for (int k = 0; k < kPairWin; ++k) pkr[k] = nx[k];
+      if (Y + 1 < Yend) load_row(Y + 1);
+      while (ly.i0 > cur_row) flush();
+      float hx0[8], hx1[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { hx0[c] = 0.f; hx1[c] = 0.f; }
+#pragma unroll
+      for (int k = 0; k < kPairWin; ++k) {
+        if (k < tp.n) {
+          float f[8];
+          pkr[k].get(f);
+          const float wa = tp.wa[k], wb = tp.wb[k];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { hx0[c] = fmaf(wa, f[c], hx0[c]); hx1[c] = fmaf(wb, f[c], hx1[c]); }
+        }
+      }
+      // lower tap -> row i0, upper tap -> row i1 (i1 == i0 on the last input row); rows above the strip are not ours
+      const float w_cur = (ly.i0 == cur_row ? ly.w0 : 0.f) + (ly.i1 == cur_row ? ly.w1 : 0.f);
+      const float w_nxt = (ly.i1 == cur_row + 1) ? ly.w1 : 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        cur0[c] = fmaf(w_cur, hx0[c], cur0[c]); cur1[c] = fmaf(w_cur, hx1[c], cur1[c]);
+        nxt0[c] = fmaf(w_nxt, hx0[c], nxt0[c]); nxt1[c] = fmaf(w_nxt, hx1[c], nxt1[c]);
+      }
+    }
+    while (cur_row < y1) flush();
+  }
+}
+// host mirror of the device tap window: widest union window of an input-column pair
+static int upsample_pair_window(int w, int W, float sw) {
+  auto first_out = [&](int i) {
+    if (i <= 0) return 0;
+    if (i >= w || sw <= 0.f) return W;
+    int a = static_cast<int>(static_cast<float>(i) / sw);
+    a = a < 0 ? 0 : (a > W ? W : a);
+    while (a > 0 && static_cast<int>(sw * static_cast<float>(a - 1)) >= i) --a;
+    while (a < W && static_cast<int>(sw * static_cast<float>(a)) < i) ++a;
+    return a;
+  };
+  int widest = 0;
+  for (int j = 0; j < (w + 1) / 2; ++j) {
+    const int xa = 2 * j, xb = 2 * j + 1;
+    const int lo = xa == 0 ? 0 : first_out(xa - 1);
+    const int hi = first_out((xb < w - 1 ? xb : w - 1) + 1);
+    widest = hi - lo > widest ? hi - lo : widest;
+  }
+  return widest;
+}
+
 int upsample_nhwc_fwd(int dtype, const void* x, void* y, int N, int h, int w, int H, int W, int C, cudaStream_t s) {
   PP_REQUIRE(C % 8 == 0, "upsample_nhwc_fwd: C=%d must be a multiple of 8", C);
   PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * C, "upsample_nhwc_fwd");
@@ -1121,6 +1255,22 @@ int upsample_nhwc_bwd(int dtype, const void* gy, void* gx, int N, int h, int w, 
                       cudaStream_t s) {
   PP_REQUIRE(C % 8 == 0, "upsample_nhwc_bwd: C=%d must be a multiple of 8", C);
   PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * C, "upsample_nhwc_bwd");
+  static const int strip_on = [] { const char* e = getenv("PP_UPSAMPLE_STRIP"); return (e && e[0] == '0') ? 0 : 1; }();
+  const size_t smem_strip = static_cast<size_t>((w + 1) / 2) * sizeof(PairTaps);
+  if (strip_on && H >= h && W > w && h > 1 && smem_strip <= 48 * 1024 &&
+      upsample_pair_window(w, W, ac_scale(w, W)) <= kPairWin) {
+    const int work = ((w + 1) / 2) * (C / 8);
+    const int threads = work >= 256 ? 256 : (work >= 128 ? 128 : 64);
+    const int ychunks = ceil_div(work, threads);
+    int P = 8;
+    while (P > 2 && static_cast<long long>(N) * ceil_div(h, P) * ychunks < 4LL * sm_count()) P >>= 1;
+    const int strips = ceil_div(h, P);
+    PP_DISPATCH_T(dtype, upsample_nhwc_bwd_strip_kernel<T><<<dim3(N * strips, ychunks), threads, smem_strip, s>>>(
+                             static_cast<const T*>(gy), static_cast<T*>(gx), h, w, H, W, C, ac_scale(h, H),
+                             ac_scale(w, W), P, strips, accumulate););
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+  }
   const int threads = w * (C / 8) >= 256 ? 256 : 128;
   const size_t smem = static_cast<size_t>(w) * (kUpWin + 2) * sizeof(float);
   PP_REQUIRE(smem <= 48 * 1024, "upsample_nhwc_bwd: input width %d too large", w);
