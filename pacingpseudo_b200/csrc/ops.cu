@@ -293,10 +293,77 @@ __global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const T* __restri
   __syncthreads();
   for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
 }
+// Run variant (W % 4 == 0): a thread owns FOUR consecutive pixels of a row for its 8 channels, so the 3 x 6 input
+// window is loaded once for the four pixels (18 instead of 36 scalar loads) and four 16-byte dy loads are in flight
+// per thread. The kernel above keeps 16 KB of dy in flight per SM and is latency-bound (86 us for 100 MB); this is the
+// last kernel of the backward pass (nothing overlaps it), so its duration is fully exposed.
+template <typename T>
+__global__ void __launch_bounds__(256) first_conv_wgrad_run4_kernel(const T* __restrict__ dy, const float* __restrict__ x,
+                                                                    float* __restrict__ dw, int N, int H, int W,
+                                                                    int Cout) {
+  extern __shared__ float sacc[];  // [Cout*9]
+  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int vecs = Cout / 8;
+  const int v = threadIdx.x % vecs;
+  const int rpb = 256 / vecs;                      // pixel runs per block iteration
+  float acc[8][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
+  const int runs = (N * H * W) >> 2;
+  const int runs_per_row = W >> 2;
+  for (int r = blockIdx.x * rpb + threadIdx.x / vecs; r < runs; r += gridDim.x * rpb) {
+    const int row = r / runs_per_row, px = (r - row * runs_per_row) << 2, py = row % H;
+    Vec8<T> g[4];
+    const T* gp = dy + (static_cast<size_t>(row) * W + px) * Cout + v * 8;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) g[u].load(gp + static_cast<size_t>(u) * Cout);
+    float xin[3][6];                               // rows py-1..py+1, columns px-1..px+4 (zero padding)
+    const float* xr = x + static_cast<size_t>(row) * W + px;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const bool rok = (py + a - 1 >= 0) && (py + a - 1 < H);
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        const bool ok = rok && (px + b - 1 >= 0) && (px + b - 1 < W);
+        xin[a][b] = ok ? __ldg(xr + (a - 1) * W + (b - 1)) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      g[u].get(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(f[j], xin[t / 3][u + t % 3], acc[j][t]);
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float a = acc[j][t];
+      for (int o = vecs; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);   // lanes with the same v
+      if (lane < vecs) atomicAdd(&sacc[(v * 8 + j) * 9 + t], a);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
+}
 int first_conv_wgrad(int dtype, const void* dy, const float* x, float* dw, int N, int H, int W, int Cout,
                      cudaStream_t s) {
   PP_REQUIRE(pow2_vecs(Cout), "first_conv_wgrad: Cout=%d unsupported (8,16,...,256)", Cout);
   PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * Cout, "first_conv_wgrad");
+  static const int run4_on = [] { const char* e = getenv("PP_FIRST_WGRAD_RUN4"); return (e && e[0] == '0') ? 0 : 1; }();
+  if (run4_on && W % 4 == 0) {
+    PP_DISPATCH_T(dtype, first_conv_wgrad_run4_kernel<T><<<sm_count() * 2, 256, Cout * 9 * sizeof(float), s>>>(
+                             static_cast<const T*>(dy), x, dw, N, H, W, Cout););
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+  }
   const int blocks = sm_count() * 2;
   PP_DISPATCH_T(dtype, first_conv_wgrad_kernel<T><<<blocks, 256, Cout * 9 * sizeof(float), s>>>(
                            static_cast<const T*>(dy), x, dw, N, H, W, Cout););
@@ -361,24 +428,30 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ a, 
 // Backward of the 1x1 head in ONE pass over dlogits and the activations:
 //   da[p][ci] = sum_c dl[c][p] * w[c][ci]            (skipped when da == nullptr)
 //   dW[c][ci] += sum_p dl[c][p] * a[p][ci];  db[c] += sum_p dl[c][p]
+// The weights of the thread's channel group are read from shared memory (two broadcast LDS.128 per class) instead of
+// 8*NC registers: with them in registers the kernel needed ~130 registers, ONE 256-thread block per SM, and kept only
+// 18 KB of loads in flight per SM (89 us for 231 MB, the first and fully exposed kernel of the backward pass). Now two
+// blocks per SM with four pixels in flight per thread.
 template <typename T, int CIN, int NC>
-__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dlogits, const T* __restrict__ a,
-                                                       const float* __restrict__ w, T* __restrict__ da,
-                                                       float* __restrict__ dw, float* __restrict__ db, int P, int HW,
-                                                       int C) {
+__global__ void __launch_bounds__(256, (NC <= 5 ? 2 : 1)) head_bwd_kernel(const float* __restrict__ dlogits, const T* __restrict__ a,
+                                                          const float* __restrict__ w, T* __restrict__ da,
+                                                          float* __restrict__ dw, float* __restrict__ db, int P, int HW,
+                                                          int C) {
   constexpr int VECS = CIN / 8, PPB = 256 / VECS;
   __shared__ float sacc[NC * CIN + NC];
+  __shared__ __align__(16) float s_w[NC * CIN];
   for (int i = threadIdx.x; i < NC * CIN + NC; i += blockDim.x) sacc[i] = 0.f;
+  for (int i = threadIdx.x; i < NC * CIN; i += blockDim.x) s_w[i] = i < C * CIN ? w[i] : 0.f;
   __syncthreads();
   const int v = threadIdx.x % VECS;
-  float wr[NC][8], accw[NC][8], accb[NC];
+  float accw[NC][8], accb[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     accb[c] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { wr[c][j] = c < C ? w[c * CIN + v * 8 + j] : 0.f; accw[c][j] = 0.f; }
+    for (int j = 0; j < 8; ++j) accw[c][j] = 0.f;
   }
-  constexpr int U = 2;
+  constexpr int U = 3;
   for (int p0 = blockIdx.x * PPB + threadIdx.x / VECS; p0 < P; p0 += gridDim.x * PPB * U) {
     Vec8<T> pk[U];
     float dl[U][NC];
@@ -406,10 +479,13 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         accb[c] += dl[u][c];
+        const float4 w0 = *reinterpret_cast<const float4*>(&s_w[c * CIN + v * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&s_w[c * CIN + v * 8 + 4]);
+        const float wr[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           accw[c][j] = fmaf(dl[u][c], f[j], accw[c][j]);
-          o[j] = fmaf(dl[u][c], wr[c][j], o[j]);
+          o[j] = fmaf(dl[u][c], wr[j], o[j]);
         }
       }
       if (da != nullptr && p < P) {
@@ -466,8 +542,8 @@ int head_bwd(int dtype, const float* dlogits, const void* a, const float* w, voi
   PP_REQUIRE(C >= 1 && C <= kMaxClasses, "head_bwd: num_classes=%d unsupported", C);
   PP_REQUIRE(Cin == 32 || Cin == 64 || Cin == 128, "head_bwd: Cin=%d unsupported (32/64/128)", Cin);
   PP_REQUIRE_INT32(P * Cin, "head_bwd");
-  int grid = sm_count() * 4;
-  const long long need = ceil_div_ll(P, 2 * (256 / (Cin / 8)));
+  int grid = sm_count() * 2;
+  const long long need = ceil_div_ll(P, 3 * (256 / (Cin / 8)));
   if (grid > need) grid = static_cast<int>(need < 1 ? 1 : need);
 #define PP_HEAD_BWD(CIN_, NC_)                                                                                     \
   head_bwd_kernel<T, CIN_, NC_><<<grid, 256, 0, s>>>(dlogits, static_cast<const T*>(a), w, static_cast<T*>(da), dw, db, \
