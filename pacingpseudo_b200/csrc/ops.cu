@@ -215,6 +215,54 @@ __global__ void __launch_bounds__(256) first_conv_fwd_kernel(const float* __rest
   }
 }
 
+// Run variant (W % 4 == 0): four consecutive pixels of a row per thread share one 3 x 6 input window (18 loads issued
+// together instead of 4 x 9 in four dependent rounds); the per-pixel kernel above is latency-bound (41 us for 50 MB).
+template <typename T>
+__global__ void __launch_bounds__(256, 2) first_conv_fwd_run4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                  const float* __restrict__ bias, T* __restrict__ y,
+                                                                  int N, int H, int W, int Cout) {
+  const int vecs = Cout / 8;
+  const int v = threadIdx.x % vecs;
+  const int rpb = 256 / vecs;                // pixel runs per block iteration
+  float wr[8][9], br[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    br[j] = bias ? bias[v * 8 + j] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[j][t] = w[(v * 8 + j) * 9 + t];
+  }
+  const int runs = (N * H * W) >> 2, runs_per_row = W >> 2;
+  for (int r = blockIdx.x * rpb + threadIdx.x / vecs; r < runs; r += gridDim.x * rpb) {
+    const int row = r / runs_per_row, px = (r - row * runs_per_row) << 2, py = row % H;
+    const float* xr = x + static_cast<size_t>(row) * W + px;
+    float xin[3][6];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const bool rok = (py + a - 1 >= 0) && (py + a - 1 < H);
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        const bool ok = rok && (px + b - 1 >= 0) && (px + b - 1 < W);
+        xin[a][b] = ok ? __ldg(xr + (a - 1) * W + (b - 1)) : 0.f;
+      }
+    }
+    T* yo = y + (static_cast<size_t>(row) * W + px) * Cout + v * 8;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = br[j];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) a = fmaf(xin[t / 3][u + t % 3], wr[j][t], a);
+        o[j] = a;
+      }
+      Vec8<T> pk;
+      pk.set(o);
+      pk.store(yo + static_cast<size_t>(u) * Cout);
+    }
+  }
+}
+
 static bool pow2_vecs(int C) { return C % 8 == 0 && C <= 256 && ((C / 8) & (C / 8 - 1)) == 0; }
 
 int first_conv_fwd(int dtype, const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
@@ -223,6 +271,13 @@ int first_conv_fwd(int dtype, const float* x, const float* w, const float* bias,
   const long long P = static_cast<long long>(N) * H * W;
   PP_REQUIRE_INT32(P * Cout, "first_conv_fwd");
   const int ppb = 256 / (Cout / 8);
+  static const int run4_on = [] { const char* e = getenv("PP_FIRST_CONV_RUN4"); return (e && e[0] == '0') ? 0 : 1; }();
+  if (run4_on && W % 4 == 0) {
+    PP_DISPATCH_T(dtype, first_conv_fwd_run4_kernel<T><<<grid_for(ceil_div_ll(P / 4, ppb) * 256, 256, 8), 256, 0, s>>>(
+                             x, w, bias, static_cast<T*>(y), N, H, W, Cout););
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+  }
   PP_DISPATCH_T(dtype, first_conv_fwd_kernel<T><<<grid_for(ceil_div_ll(P, ppb) * 256, 256, 8), 256, 0, s>>>(
                            x, w, bias, static_cast<T*>(y), N, H, W, Cout););
   PP_LAUNCH_CHECK();
@@ -392,7 +447,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ a, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) wr[c][j] = c < C ? w[c * CIN + v * 8 + j] : 0.f;
   }
-  constexpr int U = 2;
+  constexpr int U = 4;
   for (int p0 = blockIdx.x * PPB + threadIdx.x / VECS; p0 < P; p0 += gridDim.x * PPB * U) {
     Vec8<T> pk[U];
 #pragma unroll
@@ -528,7 +583,7 @@ int head_fwd(int dtype, const void* a, const float* w, const float* bias, float*
   PP_REQUIRE(C >= 1 && C <= kMaxClasses, "head_fwd: num_classes=%d unsupported (max %d)", C, kMaxClasses);
   PP_REQUIRE(Cin == 32 || Cin == 64 || Cin == 128, "head_fwd: Cin=%d unsupported (32/64/128)", Cin);
   PP_REQUIRE_INT32(P * Cin, "head_fwd");
-  const int grid = grid_for(ceil_div_ll(P, 2 * (256 / (Cin / 8))) * 256, 256, 8);
+  const int grid = grid_for(ceil_div_ll(P, 4 * (256 / (Cin / 8))) * 256, 256, 8);
 #define PP_HEAD_FWD(CIN_, NC_) \
   head_fwd_kernel<T, CIN_, NC_><<<grid, 256, 0, s>>>(static_cast<const T*>(a), w, bias, logits, int(P), HW, C)
   PP_DISPATCH_T(dtype, PP_HEAD_DISPATCH(PP_HEAD_FWD););
