@@ -148,9 +148,81 @@ class ClockSampler:
     BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
             0x80: "hw_power_brake_slowdown"}
 
+    # Poller PROCESS (no GIL contention with the launch loop, which can starve an in-process thread down to a single
+    # sample): prints "unix_time sm_mhz reasons_mask" every ~2 ms from before the warm-up; stop(t0, t1) keeps the
+    # samples that fall inside the timed region. The in-process thread below stays as a fallback.
+    POLLER = (
+        "import sys, time, pynvml\n"
+        "pynvml.nvmlInit()\n"
+        "try:\n"
+        "    h = pynvml.nvmlDeviceGetHandleByUUID(sys.argv[1])\n"
+        "except Exception:\n"
+        "    h = pynvml.nvmlDeviceGetHandleByIndex(int(sys.argv[2]))\n"
+        "print('max', pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM), flush=True)\n"
+        "while True:\n"
+        "    t = time.time()\n"
+        "    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)\n"
+        "    try:\n"
+        "        m = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)\n"
+        "    except Exception:\n"
+        "        m = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)\n"
+        "    sys.stdout.write('%.6f %d %d\\n' % (t, sm, m))\n"
+        "    sys.stdout.flush()\n"
+        "    time.sleep(0.002)\n")
+
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
         self.nvml, self.handle, self.samples, self.mask, self.stop_flag = None, None, [], 0, False
+        self.poller, self.poller_lines, self.poller_thr = None, [], None
+
+    def start_poller(self):
+        """Call BEFORE the warm-up: the process needs ~0.1-0.3 s to import pynvml."""
+        try:
+            import torch
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            self.poller = subprocess.Popen([sys.executable, "-c", self.POLLER, uuid, str(idx)], stdout=subprocess.PIPE,
+                                           stderr=subprocess.DEVNULL, text=True)
+            self.poller_thr = threading.Thread(target=self._drain, daemon=True)
+            self.poller_thr.start()
+        except Exception:
+            self.poller = None
+
+    def _drain(self):
+        try:
+            for line in self.poller.stdout:
+                self.poller_lines.append(line)
+        except Exception:
+            pass
+
+    def _poller_result(self, t0, t1):
+        if self.poller is None:
+            return None
+        time.sleep(0.01)
+        self.poller.terminate()
+        try:
+            self.poller.wait(timeout=5)
+        except Exception:
+            self.poller.kill()
+        self.poller_thr.join(timeout=2)
+        smax, sm, mask = None, [], 0
+        for ln in list(self.poller_lines):
+            f = ln.split()
+            try:
+                if f[0] == "max":
+                    smax = float(f[1])
+                elif t0 <= float(f[0]) <= t1:
+                    sm.append(float(f[1]))
+                    mask |= int(f[2])
+            except (ValueError, IndexError):
+                continue
+        if len(sm) < 3:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": smax,
+                "reasons": sorted(v for k, v in self.BITS.items() if mask & k), "samples": len(sm),
+                "source": "nvml (poller process, samples inside the timed region)"}
 
     def _nvml_handle(self):
         import pynvml
@@ -199,7 +271,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        if t0 is not None:
+            res = self._poller_result(t0, t1)
+            if res is not None:
+                if self.nvml is not None:
+                    self.stop_flag = True
+                elif self.proc is not None:
+                    self.proc.terminate()
+                return res
         if self.nvml is not None:
             self.stop_flag = True
             self.thr.join(timeout=2)
@@ -351,13 +431,16 @@ def run_ours(args):
         ms = dp.max_over_ranks(e0.elapsed_time(e1), dev)
         return ms, lib.cdll.pp_launch_count() - l0
 
-    for i in range(args.warmup):
-        step(pool_dev[i % len(pool_dev)], False)
     sampler = ClockSampler(dev.index)
     if rank == 0:
+        sampler.start_poller()
+    for i in range(args.warmup):
+        step(pool_dev[i % len(pool_dev)], False)
+    if rank == 0:
         sampler.start()
+    t_begin = time.time()
     ms, launches = timed(args.steps, host_inputs=False, profile=False)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
     # the same K steps once more with every tcgen05 conv launch bracketed by CUDA events on its stream (roofline)
     ms_prof, _ = timed(0 if args.no_profile_pass else args.steps, host_inputs=False, profile=True)
     prof = {}
