@@ -56,6 +56,11 @@ class AuxPath(nn.Module):
         conv, bn = self.layer_bottleneck[1], self.layer_bottleneck[2]
         fa = feats[0]
         fb = feats[1] if len(feats) > 1 else None
+        w_conv = conv.weight
+        true_in = list(self.feat_ch)[:len(feats)]
+        if [f.shape[-1] for f in feats] != true_in:   # zero-padded stages (max_ch = 728): matching zero weight columns
+            from models.unet import pad_in_channels
+            w_conv = pad_in_channels(w_conv, [(t, f.shape[-1]) for t, f in zip(true_in, feats)]).contiguous()
         drop = None
         self._bank_drop = None
         if self.training and self.aux_drop_prob > 0:   # the two nn.Dropout2d layers (aux_path_memory.py:23,31)
@@ -65,7 +70,7 @@ class AuxPath(nn.Module):
                 self._bank_drop = self.drop_factors(self.num_classes, self.hid_ch, fa.device)
         logits, aux_features = AuxPathFunction.apply(
             code, (bn.running_mean, bn.running_var, bn.num_batches_tracked), self.training,
-            tuple(scribble.shape[-2:]), drop, fa, fb, conv.weight, conv.bias, bn.weight, bn.bias, self.fc_cls[1].weight)
+            tuple(scribble.shape[-2:]), drop, fa, fb, w_conv, conv.bias, bn.weight, bn.bias, self.fc_cls[1].weight)
         if self.do_memory:
             self.memory_update(aux_features, scribble, step, _code=code)
             if self.bank_sync is not None:

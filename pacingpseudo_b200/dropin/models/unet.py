@@ -28,6 +28,7 @@ class EndPoints(dict):
     def __init__(self):
         super().__init__()
         self.native = {}
+        self.true_channels = {}   # stages whose native tensor carries zero padding channels (max_ch = 728)
 
     def _set_native(self, feats):
         self.native = dict(feats)
@@ -36,7 +37,9 @@ class EndPoints(dict):
 
     def _materialise(self, key):
         if not dict.__contains__(self, key) and key in self.native:
-            dict.__setitem__(self, key, self.native[key].permute(0, 3, 1, 2).float())
+            t = self.native[key]
+            c = self.true_channels.get(key, t.shape[-1])
+            dict.__setitem__(self, key, t[..., :c].permute(0, 3, 1, 2).float())
 
     def __getitem__(self, key):
         self._materialise(key)
@@ -118,6 +121,37 @@ class DecBlock(nn.Module):
             self.conv_block = DoubleConv(lower_ch + skip_ch, skip_ch)
 
 
+_KERNEL_WIDTHS = (32, 64, 128, 256, 512, 1024)   # channel counts the conv / BatchNorm kernels are built for
+
+
+def kernel_width(c):
+    """Smallest supported channel count >= c. A stage of another width (`--max_ch 728`, train_chaos.py:71) runs with
+    zero weights, zero gamma / beta / bias on the padding channels: they stay exactly 0 through conv, BatchNorm and
+    LeakyReLU and contribute nothing downstream, so the network computes what the reference computes."""
+    for w in _KERNEL_WIDTHS:
+        if c <= w:
+            return w
+    raise ValueError("pacingpseudo_b200 UNet: %d channels exceed the widest supported stage (1024)" % c)
+
+
+def pad_in_channels(w, segments):
+    """w: (Cout, sum of true widths, kh, kw); segments: [(true, internal), ...] in concat order -> zero columns are
+    inserted after each segment (differentiable: autograd slices the gradient back)."""
+    if all(t == i for t, i in segments):
+        return w
+    parts, off = [], 0
+    for t, i in segments:
+        parts.append(w[:, off:off + t])
+        if i > t:
+            parts.append(w.new_zeros((w.shape[0], i - t) + tuple(w.shape[2:])))
+        off += t
+    return torch.cat(parts, 1)
+
+
+def pad_vector(v, n, value=0.0):
+    return v if v.shape[0] == n else torch.cat((v, v.new_full((n - v.shape[0],), value)))
+
+
 class UNet(nn.Module):
     def __init__(self, input_ch=1, init_ch=32, max_ch=512, num_classes=4, output_stride=32,
                  is_stride_conv=False, is_trans_conv=False, elab_end_points=False, precision=None):
@@ -153,7 +187,17 @@ class UNet(nn.Module):
         self.dec_block1 = DecBlock(ch_ls[1], ch_ls[0], ch_ls[0], is_trans_conv=tc)
         self.final_conv = nn.Conv2d(ch_ls[0], num_classes, 1, 1)
 
-        self._cfg = (input_ch, init_ch, max_ch, num_classes, output_stride)
+        # kernel-side widths: stages that are not 32 * 2^k wide are zero-padded up to the next such width
+        self._ch_true = ch_ls
+        self._ch_int = [kernel_width(c) for c in ch_ls]
+        self._padded = self._ch_int != ch_ls
+        if self._padded and is_stride_conv:
+            raise NotImplementedError("pacingpseudo_b200 UNet: max_ch=%d with is_stride_conv/is_trans_conv" % max_ch)
+        for i, name in enumerate(_STAGES):
+            k = i if i < 6 else 10 - i           # encoder stage i+1 -> ch[i]; decoder stage s -> ch[s-1]
+            if self._ch_int[k] != ch_ls[k]:
+                self.end_points.true_channels[name] = ch_ls[k]
+        self._cfg = (input_ch, init_ch, max(self._ch_int), num_classes, output_stride)
         self._strided = bool(is_stride_conv)
         self._precision = precision or default_precision()
         self._engine = None
@@ -176,18 +220,48 @@ class UNet(nn.Module):
 
     def run_native(self, x, groups=1, feat_names=()):
         """-> (logits NCHW fp32, {name: native NHWC feature}). `groups` = BatchNorm statistics groups."""
-        learnable, buffers = [], []
-        for m in self._layer_modules():
+        learnable, buffers, copy_back = [], [], []
+        for (name, _cin, cout_i, _dil), m in zip(self.engine.layers, self._layer_modules()):
             if isinstance(m, nn.ConvTranspose2d):   # weight only (bias=False, no BatchNorm): unet.py:141
                 learnable += [m.weight, None, None, None]
                 buffers += [None, None, None]
                 continue
-            learnable += [m.conv.weight, m.conv.bias, m.norm_op.weight, m.norm_op.bias]
-            buffers += [m.norm_op.running_mean, m.norm_op.running_var, m.norm_op.num_batches_tracked]
+            w, b, g, bt = m.conv.weight, m.conv.bias, m.norm_op.weight, m.norm_op.bias
+            rm, rv = m.norm_op.running_mean, m.norm_op.running_var
+            if self._padded:
+                w = pad_in_channels(w, self._in_segments(name))
+                if w.shape[0] != cout_i:
+                    n_t = w.shape[0]
+                    w = torch.cat((w, w.new_zeros((cout_i - n_t,) + tuple(w.shape[1:]))), 0)
+                    b, g, bt = pad_vector(b, cout_i), pad_vector(g, cout_i), pad_vector(bt, cout_i)
+                    rm_p, rv_p = pad_vector(rm.detach(), cout_i), pad_vector(rv.detach(), cout_i, 1.0)
+                    copy_back.append((rm, rm_p, rv, rv_p, n_t))
+                    rm, rv = rm_p, rv_p
+                w = w.contiguous()
+            learnable += [w, b, g, bt]
+            buffers += [rm, rv, m.norm_op.num_batches_tracked]
         learnable += [self.final_conv.weight, self.final_conv.bias]
         feat_names = tuple(feat_names)
         outs = UNetFunction.apply(self.engine, buffers, groups, self.training, feat_names, x, *learnable)
+        if self.training:
+            with torch.no_grad():
+                for rm, rm_p, rv, rv_p, n_t in copy_back:   # the kernels updated the padded running statistics
+                    rm.copy_(rm_p[:n_t])
+                    rv.copy_(rv_p[:n_t])
         return outs[0], dict(zip(feat_names, outs[1:]))
+
+    def _in_segments(self, name):
+        """[(true, internal)] input-channel segments of a conv layer, in the reference's concat order (up, skip)."""
+        ct, ci = self._ch_true, self._ch_int
+        block, _, layer = name.partition('.conv_block.')
+        k = int(block[-1])
+        if block.startswith('enc'):
+            if layer == 'conv_layer2':
+                return [(ct[k - 1], ci[k - 1])]
+            return [(self._cfg[0], self._cfg[0])] if k == 1 else [(ct[k - 2], ci[k - 2])]
+        if layer == 'conv_layer2':
+            return [(ct[k - 1], ci[k - 1])]
+        return [(ct[k], ci[k]), (ct[k - 1], ci[k - 1])]   # DecBlock(lower = ch[k], skip = ch[k-1]) (unet.py:36-58)
 
     def forward(self, x):
         names = _STAGES if self.elab_end_points else ()

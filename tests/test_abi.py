@@ -120,6 +120,19 @@ def test_dropin_modules_mirror_reference_state_dict():
         assert m.enc_block2.conv_block.conv_layer1.conv.stride == (2, 2) and m.enc_block2.pooling is None
     with pytest.raises(AssertionError):
         UNet(is_stride_conv=True, is_trans_conv=False)   # unet.py:25
+    # max_ch = 728 (train_chaos.py:71): reference-shaped parameters, kernel-side stage width padded to 1024
+    from models.unet import pad_in_channels
+    m = UNet(1, 32, 728, 5, 8, False, False, True)
+    exp = O.unet_param_shapes(1, 32, 728, 5, 8)
+    assert list(m.state_dict()) == list(exp) and all(tuple(m.state_dict()[k].shape) == tuple(exp[k]) for k in exp)
+    assert m._ch_int == [32, 64, 128, 256, 512, 1024] and m._cfg[2] == 1024
+    assert m.end_points.true_channels == {"encoder/stage6": 728}
+    assert m._in_segments("dec_block5.conv_block.conv_layer1") == [(728, 1024), (512, 512)]
+    w = torch.arange(10.0).view(2, 5, 1, 1).requires_grad_()
+    p = pad_in_channels(w, [(2, 4), (3, 3)])
+    assert p.view(2, -1).tolist() == [[0, 1, 0, 0, 2, 3, 4], [5, 6, 0, 0, 7, 8, 9]]
+    p.sum().backward()
+    assert torch.equal(w.grad, torch.ones_like(w))
     with pytest.raises(RuntimeError, match="CUDA"):
         UNet(1, 32, 512, 5, 8)(torch.zeros(1, 1, 16, 16))  # no CPU fallback
 

@@ -592,7 +592,7 @@ def test_full_size_baseline_vs_oracle(pp):
 
 
 @pytest.mark.parametrize("max_ch,os_,strided,size", [(1024, 8, False, 64), (1024, 32, True, 64), (512, 16, True, 128),
-                                                      (512, 8, True, 112)])
+                                                      (512, 8, True, 112), (728, 8, False, 64), (728, 16, False, 64)])
 def test_unet_variants_fp32_mode_vs_oracle(pp, max_ch, os_, strided, size):
     """train_chaos.py:71 allows max_ch 1024; unet.py:113-116,141 the stride-2 / ConvTranspose2d variant, here at larger
     and ragged (112 = 7 * 16) sizes than the golden cases: logits, pCE and every gradient against the fp32 CPU oracle
@@ -631,6 +631,57 @@ def test_unet_variants_fp32_mode_vs_oracle(pp, max_ch, os_, strided, size):
             assert worst[0] < tol["grad"], worst
         for k, p in model.named_parameters():
             assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        if max_ch == 728:   # zero-padded stage: the end point is handed out at its true width, running stats come back
+            assert model.end_points["encoder/stage6"].shape[1] == 728
+            rm = model.enc_block6.conv_block.conv_layer2.norm_op.running_mean
+            assert rm.shape[0] == 728
+            # bf16 activations move a batch mean by ~3e-3 relative; the fp32 mode stays within 1e-3
+            assert _rel(rm, s_["enc_block6.conv_block.conv_layer2.norm_op.running_mean"]) < (1e-3 if precision == "fp32" else 2e-2)
+
+
+def test_pacing_step_max_ch_728_vs_oracle(pp):
+    """Full pacingpseudo step with `--max_ch 728` (train_chaos.py:71; aux path fed by the 728-wide stage 6): the five
+    losses, the bank and the aux-conv gradient against the fp32 oracle, fp32 mode."""
+    import argparse
+    from pacingpseudo_b200.synth import make_batch
+    from pacingpseudo_b200.dropin import DROPIN_PATH
+    if DROPIN_PATH not in sys.path:
+        sys.path.insert(0, DROPIN_PATH)
+    from models.consistency_reglur_memory import ConsistencyRegulr
+    C = 3
+    shapes = {"backbone." + k: v for k, v in O.unet_param_shapes(1, 32, 728, C, 8).items()}
+    shapes.update({"aux_path." + k: v for k, v in O.aux_param_shapes(C, (728, 512), 64).items()})
+    sd = O.synth_state_dict(shapes, seed=5)
+    batch = make_batch(2, C, 64, 64, seed=31)
+    batch.pop("label")
+    ns = argparse.Namespace(ignored_index=C, do_loss_ent=True, do_decoder_consistency=True, detach_weak_cr=False,
+                            loss_cr_variants="ce_loss", do_aux_path=True, do_memory=True)
+    model = ConsistencyRegulr(
+        kwargs_unet=dict(input_ch=1, init_ch=32, max_ch=728, num_classes=C, output_stride=8, is_stride_conv=False,
+                         is_trans_conv=False, elab_end_points=True, precision="fp32"),
+        kwargs_aux_path=dict(num_classes=C, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[728, 512],
+                             hid_ch=64, aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
+                             ensemble_mode='cosine_similarity'),
+        args_parser=ns)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    out = model({k: v.cuda() for k, v in batch.items()}, mode="train", step=5)
+    O.total_loss(out, epoch=40).backward()
+
+    s_ = {k: v.clone() for k, v in sd.items()}
+    learn = [k for k in s_ if s_[k].is_floating_point() and "running" not in k and not k.endswith("memory_bank")]
+    for k in learn:
+        s_[k].requires_grad_(True)
+    cfg = O.StepConfig(num_classes=C, ignored_index=C, max_ch=728)
+    ref = O.consistency_forward(s_, batch, cfg, mode="train", step=5, training=True)
+    O.total_loss(ref, epoch=40).backward()
+    for k in ("loss_pce", "loss_ent", "loss_cr", "loss_aux_cls", "loss_memory"):
+        assert abs(out[k].item() - ref[k].item()) <= 1e-4 * max(1.0, abs(ref[k].item())), (k, out[k].item(), ref[k].item())
+    assert _rel(model.aux_path.memory_bank.detach(), s_["aux_path.memory_bank"]) < 1e-4
+    for k in ("aux_path.layer_bottleneck.1.weight", "backbone.enc_block6.conv_block.conv_layer2.conv.weight",
+              "backbone.dec_block5.conv_block.conv_layer1.conv.weight", "backbone.enc_block1.conv_block.conv_layer1.conv.weight"):
+        g = dict(model.named_parameters())[k].grad
+        assert g.shape == s_[k].grad.shape and _rel(g, s_[k].grad) < 2e-2, (k, _rel(g, s_[k].grad))
 
 
 def test_space_depth_and_channel_scale_operators(pp):
