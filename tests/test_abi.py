@@ -137,6 +137,42 @@ def test_dropin_modules_mirror_reference_state_dict():
         UNet(1, 32, 512, 5, 8)(torch.zeros(1, 1, 16, 16))  # no CPU fallback
 
 
+def test_unet_plan_layer_table_matches_the_modules():
+    """The C-side executor's layer table (pp_unet_conv_info / pp_unet_conv_kind: host-only, no GPU needed) against the
+    drop-in modules for every output stride and both UNet variants: each layer names a module whose parameter has the
+    reported (Cout, Cin) and kind; workspace sizes and end-point shapes are consistent."""
+    import sys
+    import torch.nn as nn
+    from pacingpseudo_b200.dropin import DROPIN_PATH
+    if DROPIN_PATH not in sys.path:
+        sys.path.insert(0, DROPIN_PATH)
+    from models.unet import UNet
+    for strided in (False, True):
+        for os_ in (8, 16, 32):
+            m = UNet(1, 32, 512, 4, os_, strided, strided, True, precision="bf16")
+            eng = m.engine
+            mods = m._layer_modules()
+            assert len(mods) == eng.nconv == (22 + (5 if strided else 0))
+            n_s2 = 0
+            for (name, cin, cout, dil), (kind, scale), mod in zip(eng.layers, eng.kinds, mods):
+                if kind == 2:
+                    assert isinstance(mod, nn.ConvTranspose2d) and name.endswith(".up_samp")
+                    assert tuple(mod.weight.shape) == (cin, cout, scale, scale) and mod.bias is None
+                    continue
+                assert tuple(mod.conv.weight.shape) == (cout, cin, 3, 3), name
+                assert mod.conv.dilation == (dil, dil) and mod.conv.stride == ((2, 2) if kind == 1 else (1, 1)), name
+                n_s2 += kind == 1
+            assert n_s2 == (0 if not strided else {8: 3, 16: 4, 32: 5}[os_])
+            # every trainable parameter of the module tree is covered exactly once (plus the 1x1 head)
+            covered = sum(p.numel() for mod in mods for p in mod.parameters()) + sum(p.numel() for p in m.final_conv.parameters())
+            assert covered == sum(p.numel() for p in m.parameters())
+            assert eng.workspace_bytes(4, 64, 64, 2) > eng.workspace_bytes(2, 64, 64, 1) > 0
+            _, _, C6, h6, w6 = eng.activation("encoder/stage6", 2, 64, 64, 1)
+            assert (C6, h6, w6) == (512, 64 // os_, 64 // os_)
+            _, _, C1, h1, w1 = eng.activation("decoder/stage1", 2, 64, 64, 1)
+            assert (C1, h1, w1) == (32, 64, 64)
+
+
 def test_checkpoint_round_trip_in_reference_format(tmp_path):
     """a ConsistencyRegulr checkpoint written by the drop-in loads (a) back into the drop-in, (b) into a
     plain UNet through the `backbone.` prefix stripping of inference.py:138-146, and (c) into the REFERENCE modules and
