@@ -72,7 +72,7 @@ int pp_unet_activation(pp_unet_t u, const char* name, int N, int H, int W, int G
                        int* C, int* h, int* w);
 /* params: per conv layer [weight OIHW, bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
  * bn.num_batches_tracked(int64)] in pp_unet_conv_info order, then head [weight, bias].
- * x: fp32 [N,1,H,W]; logits out: fp32 NCHW [N,num_classes,H,W]. training=1: batch statistics +
+ * x: fp32 NCHW [N,input_ch,H,W]; logits out: fp32 NCHW [N,num_classes,H,W]. training=1: batch statistics +
  * running-stat update (unet.py:189 BatchNorm2d in train()), 0: running statistics. */
 int pp_unet_forward(pp_unet_t u, const float* x, void* const* params, void* workspace, int N, int H, int W, int G,
                     int training, float* logits, void* stream);
@@ -124,7 +124,7 @@ int pp_conv3x3_wgrad_reference(int dtype, const void* dy, int Cout, const void* 
 /* OIHW fp32 -> forward pack wf[9][Cout][Cin] and dgrad pack wd[9][Cin][Cout] (flipped taps) */
 int pp_pack_weights(int dtype, const float* w_oihw, void* wf, void* wd, int Cout, int Cin, void* stream);
 int pp_unpack_wgrad(const float* dwp, float* g_oihw, int Cout, int Cin, int accumulate, void* stream);
-/* first conv, Cin = 1 (unet.py:28) */
+/* first conv, Cin = 1 (unet.py:28); the whole-UNet executor also handles --input_ch 2..16 (NCHW fp32 input) */
 int pp_first_conv_fwd(int dtype, const float* x, const float* w, const float* bias, void* y, int N, int H, int W,
                       int Cout, void* stream);
 int pp_first_conv_wgrad(int dtype, const void* dy, const float* x, float* dw, int N, int H, int W, int Cout,

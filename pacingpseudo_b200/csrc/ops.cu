@@ -263,14 +263,111 @@ __global__ void __launch_bounds__(256, 2) first_conv_fwd_run4_kernel(const float
   }
 }
 
+// Multi-channel input (input_ch > 1, unet.py:28 with --input_ch): x is NCHW fp32 [N][Cin][H][W], w OIHW [Cout][Cin][3][3].
+// Same thread mapping as the single-channel kernels, the input channels are walked in a loop with the weights in shared
+// memory (forward) / one grid.y slice per input channel (weight gradient). Not a tuned path: every shipped dataset is
+// single-channel.
+template <typename T>
+__global__ void __launch_bounds__(256) first_conv_fwd_cin_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, T* __restrict__ y, int N,
+                                                                 int H, int W, int Cout, int Cin) {
+  extern __shared__ float s_wc[];             // [Cout][Cin][9]
+  for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) s_wc[i] = w[i];
+  __syncthreads();
+  const int vecs = Cout / 8;
+  const int v = threadIdx.x % vecs;
+  const int ppb = 256 / vecs;
+  const int P = N * H * W, HW = H * W;
+  for (int p = blockIdx.x * ppb + threadIdx.x / vecs; p < P; p += gridDim.x * ppb) {
+    const int n = p / HW, hw = p - n * HW, py = hw / W, px = hw - py * W;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = bias ? bias[v * 8 + j] : 0.f;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float* xr = x + (static_cast<size_t>(n) * Cin + ci) * HW + hw;
+      float xin[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int dy = t / 3 - 1, dx = t % 3 - 1;
+        const bool ok = (py + dy >= 0) && (py + dy < H) && (px + dx >= 0) && (px + dx < W);
+        xin[t] = ok ? __ldg(xr + dy * W + dx) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float* wj = s_wc + (static_cast<size_t>(v * 8 + j) * Cin + ci) * 9;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) o[j] = fmaf(xin[t], wj[t], o[j]);
+      }
+    }
+    Vec8<T> pk;
+    pk.set(o);
+    pk.store(y + static_cast<size_t>(p) * Cout + v * 8);
+  }
+}
+// grid.y = input channel
+template <typename T>
+__global__ void __launch_bounds__(256) first_conv_wgrad_cin_kernel(const T* __restrict__ dy, const float* __restrict__ x,
+                                                                   float* __restrict__ dw, int N, int H, int W, int Cout,
+                                                                   int Cin) {
+  extern __shared__ float sacc[];  // [Cout*9]
+  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int ci = blockIdx.y;
+  const int vecs = Cout / 8;
+  const int v = threadIdx.x % vecs;
+  const int ppb = 256 / vecs;
+  float acc[8][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
+  const int P = N * H * W, HW = H * W;
+  for (int p = blockIdx.x * ppb + threadIdx.x / vecs; p < P; p += gridDim.x * ppb) {
+    const int n = p / HW, hw = p - n * HW, py = hw / W, px = hw - py * W;
+    Vec8<T> g;
+    g.load(dy + static_cast<size_t>(p) * Cout + v * 8);
+    float f[8];
+    g.get(f);
+    const float* xr = x + (static_cast<size_t>(n) * Cin + ci) * HW + hw;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int ddy = t / 3 - 1, ddx = t % 3 - 1;
+      const bool ok = (py + ddy >= 0) && (py + ddy < H) && (px + ddx >= 0) && (px + ddx < W);
+      const float xv = ok ? __ldg(xr + ddy * W + ddx) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j][t] = fmaf(f[j], xv, acc[j][t]);
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float a = acc[j][t];
+      for (int o = vecs; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);   // lanes with the same v
+      if (lane < vecs) atomicAdd(&sacc[(v * 8 + j) * 9 + t], a);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x)
+    atomicAdd(dw + (static_cast<size_t>(i / 9) * Cin + ci) * 9 + i % 9, sacc[i]);
+}
+
 static bool pow2_vecs(int C) { return C % 8 == 0 && C <= 256 && ((C / 8) & (C / 8 - 1)) == 0; }
 
 int first_conv_fwd(int dtype, const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
-                   cudaStream_t s) {
+                   cudaStream_t s, int Cin) {
   PP_REQUIRE(pow2_vecs(Cout), "first_conv_fwd: Cout=%d unsupported (8,16,...,256)", Cout);
+  PP_REQUIRE(Cin >= 1 && Cin <= 16, "first_conv_fwd: input_ch=%d unsupported (1..16)", Cin);
   const long long P = static_cast<long long>(N) * H * W;
   PP_REQUIRE_INT32(P * Cout, "first_conv_fwd");
   const int ppb = 256 / (Cout / 8);
+  if (Cin > 1) {
+    PP_DISPATCH_T(dtype, (first_conv_fwd_cin_kernel<T><<<grid_for(ceil_div_ll(P, ppb) * 256, 256, 8), 256,
+                                                        sizeof(float) * Cout * Cin * 9, s>>>(x, w, bias, static_cast<T*>(y),
+                                                                                             N, H, W, Cout, Cin)););
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+  }
   static const int run4_on = [] { const char* e = getenv("PP_FIRST_CONV_RUN4"); return (e && e[0] == '0') ? 0 : 1; }();
   if (run4_on && W % 4 == 0) {
     PP_DISPATCH_T(dtype, first_conv_fwd_run4_kernel<T><<<grid_for(ceil_div_ll(P / 4, ppb) * 256, 256, 8), 256, 0, s>>>(
@@ -409,9 +506,16 @@ __global__ void __launch_bounds__(256) first_conv_wgrad_run4_kernel(const T* __r
   for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
 }
 int first_conv_wgrad(int dtype, const void* dy, const float* x, float* dw, int N, int H, int W, int Cout,
-                     cudaStream_t s) {
+                     cudaStream_t s, int Cin) {
   PP_REQUIRE(pow2_vecs(Cout), "first_conv_wgrad: Cout=%d unsupported (8,16,...,256)", Cout);
+  PP_REQUIRE(Cin >= 1 && Cin <= 16, "first_conv_wgrad: input_ch=%d unsupported (1..16)", Cin);
   PP_REQUIRE_INT32(static_cast<long long>(N) * H * W * Cout, "first_conv_wgrad");
+  if (Cin > 1) {
+    PP_DISPATCH_T(dtype, (first_conv_wgrad_cin_kernel<T><<<dim3(sm_count(), Cin), 256, Cout * 9 * sizeof(float), s>>>(
+                             static_cast<const T*>(dy), x, dw, N, H, W, Cout, Cin)););
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+  }
   static const int run4_on = [] { const char* e = getenv("PP_FIRST_WGRAD_RUN4"); return (e && e[0] == '0') ? 0 : 1; }();
   if (run4_on && W % 4 == 0) {
     PP_DISPATCH_T(dtype, first_conv_wgrad_run4_kernel<T><<<sm_count() * 2, 256, Cout * 9 * sizeof(float), s>>>(

@@ -33,10 +33,11 @@ int pack_weights(int dtype, const float* w, void* wf, void* wd, int Cout, int Ci
 int pack_weights_multi(int dtype, int n, const float* const* w, void* const* wf, void* const* wd, const int* cout,
                        const int* cin, cudaStream_t s);
 int unpack_wgrad(const float* dwp, float* g, int Cout, int Cin, int accumulate, cudaStream_t s);
+// Cin > 1: x is NCHW fp32 [N][Cin][H][W] (multi-channel input, --input_ch)
 int first_conv_fwd(int dtype, const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
-                   cudaStream_t s);
+                   cudaStream_t s, int Cin = 1);
 int first_conv_wgrad(int dtype, const void* dy, const float* x, float* dw, int N, int H, int W, int Cout,
-                     cudaStream_t s);
+                     cudaStream_t s, int Cin = 1);
 int head_fwd(int dtype, const void* a, const float* w, const float* bias, float* logits, long long P, int HW, int Cin,
              int C, cudaStream_t s);
 int head_bwd(int dtype, const float* dlogits, const void* a, const float* w, void* da, float* dw, float* db, long long P,

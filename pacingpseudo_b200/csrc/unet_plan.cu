@@ -333,8 +333,9 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
         double* sums = reinterpret_cast<double*>(base + L.sums[op.layer]) + static_cast<long long>(k) * Gp * reps * c.cout * 2;
         float* coef = reinterpret_cast<float*>(base + L.coef[op.layer]) + static_cast<long long>(k) * Gp * 4 * c.cout;
         if (c.in0 < 0) {
-          rc = first_conv_fwd(dt, x + static_cast<long long>(k) * Np * H * W, static_cast<const float*>(pp[0]),
-                              static_cast<const float*>(pp[1]), yraw, Np, h, w, c.cout, sk);
+          rc = first_conv_fwd(dt, x + static_cast<long long>(k) * Np * pl.input_ch * H * W,
+                              static_cast<const float*>(pp[0]), static_cast<const float*>(pp[1]), yraw, Np, h, w, c.cout,
+                              sk, pl.input_ch);
         } else {
           void* wf = base + L.wf[op.layer];
           const void* x0 = act_part(L.act_data[c.in0], pl.acts[c.in0], k);
@@ -491,7 +492,7 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
         return PP_OK;
       };
       if (c.in0 < 0) {
-        rc = first_conv_wgrad(dt, dy, x, gg[0], N, h, w, c.cout, ws_);
+        rc = first_conv_wgrad(dt, dy, x, gg[0], N, h, w, c.cout, ws_, pl.input_ch);
         if (rc) return rc;
         rc = grads_ready();
         if (rc) return rc;
@@ -591,7 +592,7 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
 
 UNetPlan* unet_create(int input_ch, int init_ch, int max_ch, int num_classes, int output_stride, int dtype,
                       int strided) {
-  if (input_ch != 1) { set_error("unet: input_ch=%d unsupported (the reference data is single-channel)", input_ch); return nullptr; }
+  if (input_ch < 1 || input_ch > 16) { set_error("unet: input_ch=%d unsupported (1..16)", input_ch); return nullptr; }
   if (init_ch % 32 != 0 || max_ch % 32 != 0 || init_ch <= 0 || max_ch < init_ch) {
     set_error("unet: init_ch=%d / max_ch=%d must be positive multiples of 32", init_ch, max_ch);
     return nullptr;

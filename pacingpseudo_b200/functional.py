@@ -51,6 +51,7 @@ class UNetEngine:
         self.code = dtype_code(precision)
         self.precision = precision
         self.num_classes = num_classes
+        self.input_ch = input_ch
         h = ctypes.c_void_p()
         self.lib.call("pp_unet_create_ex", input_ch, init_ch, max_ch, num_classes, output_stride, self.code,
                       int(bool(strided)), ctypes.byref(h))
@@ -102,8 +103,8 @@ class UNetFunction(torch.autograd.Function):
         lib = engine.lib
         x = x.contiguous().float()
         N, cin, H, W = x.shape
-        if cin != 1:
-            raise RuntimeError("pacingpseudo_b200 UNet expects single-channel input (got %d)" % cin)
+        if cin != engine.input_ch:
+            raise RuntimeError("pacingpseudo_b200 UNet built for %d input channel(s), got %d" % (engine.input_ch, cin))
         dev = x.device
         nconv = engine.nconv
         params = []

@@ -77,7 +77,7 @@ def test_unet_plan_matches_reference_layer_table(lib):
 def test_error_convention(lib):
     h = ctypes.c_void_p()
     with pytest.raises(RuntimeError, match="input_ch"):
-        lib.call("pp_unet_create", 3, 32, 512, 5, 8, pplib.BF16, ctypes.byref(h))
+        lib.call("pp_unet_create", 17, 32, 512, 5, 8, pplib.BF16, ctypes.byref(h))
     with pytest.raises(RuntimeError, match="output_stride"):
         lib.call("pp_unet_create", 1, 32, 512, 5, 4, pplib.BF16, ctypes.byref(h))
 

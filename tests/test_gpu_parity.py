@@ -684,6 +684,46 @@ def test_pacing_step_max_ch_728_vs_oracle(pp):
         assert g.shape == s_[k].grad.shape and _rel(g, s_[k].grad) < 2e-2, (k, _rel(g, s_[k].grad))
 
 
+def test_unet_multi_channel_input_vs_oracle(pp):
+    """--input_ch 3 (train_chaos.py:65): NCHW fp32 input with three channels through the generic first-conv kernels,
+    two BatchNorm statistics groups (the two parts of the batch run on two streams) against the fp32 oracle."""
+    from pacingpseudo_b200.dropin import DROPIN_PATH
+    if DROPIN_PATH not in sys.path:
+        sys.path.insert(0, DROPIN_PATH)
+    from models.unet import UNet
+    from losses import losses as DL
+    C, N, Cin = 4, 4, 3
+    sd = O.synth_state_dict(O.unet_param_shapes(Cin, 32, 512, C, 16), seed=13)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(N, Cin, 48, 64, generator=g)
+    target = torch.randint(0, C + 1, (N, 48, 64), generator=g)
+    names = [k for k in sd if sd[k].is_floating_point() and "running" not in k]
+    s_ = {k: v.clone() for k, v in sd.items()}
+    for k in names:
+        s_[k].requires_grad_(True)
+    # two statistics groups == two independent forward passes over the halves (running stats: first half, then second)
+    z_ref = torch.cat([O.unet_forward(s_, x[i:i + 2], True, output_stride=16)["segmentation/logits"] for i in (0, 2)], 0)
+    l_ref = O.partial_cross_entropy(z_ref, target, C)
+    l_ref.backward()
+    for precision in ("fp32", "bf16"):
+        model = UNet(Cin, 32, 512, C, 16, False, False, True, precision=precision)
+        model.load_state_dict(sd, strict=True)
+        model = model.cuda().train()
+        z, _ = model.run_native(x.cuda(), groups=2)
+        loss = DL.partial_cross_entropy_loss(z, target.cuda(), C)
+        loss.backward()
+        tol = Hn.TOL[precision]
+        assert abs(loss.item() - l_ref.item()) <= tol["loss"] * abs(l_ref.item()), (precision, loss.item(), l_ref.item())
+        if precision == "fp32":
+            assert _rel(z.detach(), z_ref.detach()) < tol["logits"]
+            for k in ("enc_block1.conv_block.conv_layer1.conv.weight", "enc_block1.conv_block.conv_layer2.conv.weight",
+                      "final_conv.weight"):
+                gk = dict(model.named_parameters())[k].grad
+                assert _rel(gk, s_[k].grad) < tol["grad"], (k, _rel(gk, s_[k].grad))
+    with pytest.raises(RuntimeError, match="input channel"):
+        model(torch.zeros(1, 1, 16, 16, device="cuda"))
+
+
 def test_space_depth_and_channel_scale_operators(pp):
     """pp_space_to_depth / pp_depth_to_space (exact permutations, += variant) and pp_channel_scale against torch."""
     L, _, pplib = pp
