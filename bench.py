@@ -159,7 +159,9 @@ class ClockSampler:
         "except Exception:\n"
         "    h = pynvml.nvmlDeviceGetHandleByIndex(int(sys.argv[2]))\n"
         "print('max', pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM), flush=True)\n"
-        "while True:\n"
+        "import os\n"
+        "parent, t_end = os.getppid(), time.time() + 900\n"
+        "while os.getppid() == parent and time.time() < t_end:   # never outlive the bench process\n"
         "    t = time.time()\n"
         "    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)\n"
         "    try:\n"

@@ -69,6 +69,11 @@ class GradientAllReducer:
         n = flat_grad.numel()
         self.stream = torch.cuda.Stream(flat_grad.device) if flat_grad.is_cuda else None
         self.unet = None
+        # A zero-padded UNet (max_ch = 728) hands padded temporaries to the kernels; autograd adds their sliced gradients
+        # to the flat buffer only AFTER pp_unet_backward has returned, i.e. after the per-layer events fired: such a model
+        # is reduced after the whole backward pass (no overlap) instead of racing the accumulation.
+        if unet is not None and getattr(unet, "_padded", False):
+            unet = None
         if unet is not None and optimizer is not None and flat_grad.is_cuda:
             spans = self._layer_spans(unet, optimizer)
             plan = plan_layer_buckets(spans, num_buckets)

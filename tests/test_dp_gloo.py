@@ -70,3 +70,21 @@ def test_layer_bucket_plan_follows_backward_order():
         assert lo == hi2 and lo2 < hi2
     assert all(lo == spans[fl][0] for fl, lo, _ in plan)
     assert plan_layer_buckets(spans, 1) == [(0, 0, off)]
+
+
+def test_padded_unet_is_reduced_after_backward_not_overlapped():
+    """A zero-padded UNet (max_ch=728) gets its padded layers' gradients from autograd after pp_unet_backward returned:
+    GradientAllReducer must not arm the per-layer events for it (host logic, no GPU needed)."""
+    import torch
+    from pacingpseudo_b200 import dp
+
+    class FakeUNet:
+        _padded = True
+
+        @property
+        def engine(self):
+            raise AssertionError("the executor must not be touched for a padded model")
+
+    flat = torch.zeros(1000)
+    red = dp.GradientAllReducer(flat, num_buckets=4, unet=FakeUNet(), optimizer=object())
+    assert red.unet is None and sum(b - a for a, b in red.buckets) == 1000

@@ -919,8 +919,9 @@ def test_conv3x3_wgrad_oihw_split_k_deterministic(pp, case):
                                   (1, 4, 5, 8, 32), (2, 16, 16, 1, 64), (1, 8, 8, 3, 64)])
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
 def test_upsample_nhwc_forward_backward_shapes(pp, case, precision):
-    """nn.Upsample(bilinear, align_corners=True) (unet.py:144) forward and backward at realistic sizes: the separable
-    shared-memory backward, its accumulate (+=) mode, and the gather fallback for large scale factors."""
+    """nn.Upsample(bilinear, align_corners=True) (unet.py:144) forward and backward at realistic sizes: the strip
+    backward kernel (scale 2, incl. odd widths), its accumulate (+=) mode, and the per-pixel gather kernel that other
+    scale factors (1, 3, 8) fall back to."""
     L, PF, _ = pp
     N, h, w, sc, C = case
     code = PF.dtype_code(precision)
