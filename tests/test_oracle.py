@@ -158,3 +158,40 @@ def test_sample_strong_params_ranges():
         assert lo <= p[:, 3].min() and p[:, 3].max() <= hi
         assert lo <= p[:, 5].min() and p[:, 5].max() <= hi
         assert abs((p[:, 5] < 1).float().mean().item() - 0.5) < 0.04   # half of the gammas below 1 (augmentations.py:150)
+
+
+def test_zero_padded_stage_width_is_an_identity():
+    """max_ch = 728 runs on the kernels as a 1024-wide stage with zero weights / gamma / beta / bias on the padding
+    channels (dropin/models/unet.py). On the CPU oracle: the padded 1024-wide network built with the drop-in's own
+    padding helpers reproduces the 728-wide logits, end points and running statistics, train and eval BatchNorm."""
+    from pacingpseudo_b200.dropin import DROPIN_PATH
+    if DROPIN_PATH not in sys.path:
+        sys.path.insert(0, DROPIN_PATH)
+    from models.unet import UNet, pad_in_channels, pad_vector
+    C = 3
+    sd = O.synth_state_dict(O.unet_param_shapes(1, 32, 728, C, 16), seed=21)
+    m = UNet(1, 32, 728, C, 16, False, False, True)
+    padded = {}
+    for (name, _cin, cout_i, _dil) in m.engine.layers:          # host-only executor table: no GPU needed
+        w = pad_in_channels(sd[name + ".conv.weight"], m._in_segments(name))
+        n_t = w.shape[0]
+        padded[name + ".conv.weight"] = torch.cat((w, w.new_zeros((cout_i - n_t,) + tuple(w.shape[1:]))), 0)
+        for key, fill in ((".conv.bias", 0.0), (".norm_op.weight", 0.0), (".norm_op.bias", 0.0),
+                          (".norm_op.running_mean", 0.0), (".norm_op.running_var", 1.0)):
+            padded[name + key] = pad_vector(sd[name + key], cout_i, fill)
+        padded[name + ".norm_op.num_batches_tracked"] = sd[name + ".norm_op.num_batches_tracked"].clone()
+    padded["final_conv.weight"], padded["final_conv.bias"] = sd["final_conv.weight"], sd["final_conv.bias"]
+    assert {k: tuple(v.shape) for k, v in padded.items()} == \
+        {k: tuple(v) for k, v in O.unet_param_shapes(1, 32, 1024, C, 16).items()}
+    x = torch.randn(2, 1, 32, 48, generator=torch.Generator().manual_seed(4))
+    for training in (True, False):
+        a = {k: v.clone() for k, v in sd.items()}
+        b = {k: v.clone() for k, v in padded.items()}
+        ref = O.unet_forward(a, x, training, max_ch=728, output_stride=16)
+        got = O.unet_forward(b, x, training, max_ch=1024, output_stride=16)
+        # same mathematics, different fp32 summation order inside the CPU convolutions (other channel counts)
+        np.testing.assert_allclose(got["segmentation/logits"].numpy(), ref["segmentation/logits"].numpy(), rtol=1e-4, atol=3e-5)
+        np.testing.assert_allclose(got["encoder/stage6"][:, :728].numpy(), ref["encoder/stage6"].numpy(), rtol=1e-4, atol=3e-5)
+        assert float(got["encoder/stage6"][:, 728:].abs().max()) == 0.0
+        k = "enc_block6.conv_block.conv_layer2.norm_op.running_var"
+        np.testing.assert_allclose(b[k][:728].numpy(), a[k].numpy(), rtol=1e-4)
