@@ -195,3 +195,53 @@ def test_zero_padded_stage_width_is_an_identity():
         assert float(got["encoder/stage6"][:, 728:].abs().max()) == 0.0
         k = "enc_block6.conv_block.conv_layer2.norm_op.running_var"
         np.testing.assert_allclose(b[k][:728].numpy(), a[k].numpy(), rtol=1e-4)
+
+
+def test_strided_variant_identities_on_the_cpu():
+    """the two identities that put the stride-2 conv and ConvTranspose2d(k = s) on the stride-1 conv
+    kernels, restated in torch with the index maps of csrc/ops.cu (embed_s2_weight / embed_ct_weight /
+    space_depth_kernel) and checked against F.conv2d(stride=2) / F.conv_transpose2d, incl. odd block counts."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(9)
+
+    def space_to_depth(x):      # NCHW: y[n, (sy*2+sx)*C + c, Y, X] = x[n, c, 2Y+sy, 2X+sx]
+        n, c, h, w = x.shape
+        return x.view(n, c, h // 2, 2, w // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(n, 4 * c, h // 2, w // 2)
+
+    def depth_to_space(y, S):   # inverse, channel (a*S+b)*C + c
+        n, cc, h, w = y.shape
+        c = cc // (S * S)
+        return y.view(n, S, S, c, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, c, h * S, w * S)
+
+    def k_of(t, sub):           # ops.cu s2_k_of: embedded tap, sub-row -> original tap (or None: zero)
+        return (0 if sub == 1 else None) if t == 0 else ((1 + sub) if t == 1 else None)
+
+    cout, c = 5, 3
+    w = torch.randn(cout, c, 3, 3, generator=g, dtype=torch.float64)
+    we = torch.zeros(cout, 4 * c, 3, 3, dtype=torch.float64)
+    for q in range(4):
+        for ty in range(3):
+            for tx in range(3):
+                ky, kx = k_of(ty, q >> 1), k_of(tx, q & 1)
+                if ky is not None and kx is not None:
+                    we[:, q * c:(q + 1) * c, ty, tx] = w[:, :, ky, kx]
+    assert int((we != 0).any(dim=(0, 1)).sum()) == 4            # only the taps (dy, dx) in {-1, 0}^2 carry weights
+    for h, wd in ((8, 8), (6, 10), (2, 2)):
+        x = torch.randn(2, c, h, wd, generator=g, dtype=torch.float64)
+        ref = F.conv2d(x, w, stride=2, padding=1)
+        got = F.conv2d(space_to_depth(x), we, padding=1)
+        assert torch.allclose(got, ref, atol=1e-12), (h, wd)
+
+    cin, cout = 4, 3
+    for S in (1, 2):
+        wt = torch.randn(cin, cout, S, S, generator=g, dtype=torch.float64)
+        we = torch.zeros(S * S * cout, cin, 3, 3, dtype=torch.float64)
+        for a in range(S):
+            for b in range(S):
+                q = a * S + b
+                we[q * cout:(q + 1) * cout, :, 1, 1] = wt[:, :, a, b].t()
+        x = torch.randn(2, cin, 5, 7, generator=g, dtype=torch.float64)
+        ref = F.conv_transpose2d(x, wt, stride=S)
+        got = depth_to_space(F.conv2d(x, we, padding=1), S)
+        assert torch.allclose(got, ref, atol=1e-12), S
+        assert torch.allclose(O.conv_transpose_ks(x, wt), ref, atol=1e-12)
