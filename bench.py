@@ -2,11 +2,14 @@
 """bench.py — PacingPseudo train-step throughput (BASELINE.json metric: train imgs/sec, 256x256 pacingpseudo step).
 
     python bench.py --gpus N --steps K --warmup W            # this repo (hand-written sm_100a path)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference modules on the host cores
+    python bench.py --workload {pacing,baseline,upperbound} --size 224 --classes 4 --batch 96 ...   # configs 1-5
 
-A step = one full pacingpseudo iteration (train_chaos.py:263-315): batched weak+strong UNet forward, partial CE +
-entropy + consistency + aux partial CE + memory loss, memory-bank update, backward, gradient all-reduce (N > 1),
-Adam. One "image" = one weak+strong pair, as batch_size counts them (train_chaos.py:237). Prints ONE JSON line.
+Workloads (BASELINE.json configs): `pacing` (default, configs 2/3/5) = one full pacingpseudo iteration
+(train_chaos.py:263-315): batched weak+strong UNet forward, partial CE + entropy + consistency + aux partial CE +
+memory loss, memory-bank update, backward, gradient all-reduce (N > 1), Adam; one "image" = one weak+strong pair, as
+batch_size counts them (train_chaos.py:237). `baseline` (config 1 on the GPU) = UNet + partial CE + Adam.
+`upperbound` (config 4) = UNet + CE + Dice on dense labels (upper_bound_chaos.py:157-171). Prints ONE JSON line.
 """
 import argparse
 import json
@@ -24,14 +27,23 @@ _RESULT_OUT = sys.stdout
 GF_PER_PAIR = {  # algorithmic conv FLOPs per weak+strong pair, BASELINE.md section 3 (fwd F, bwd 2F)
     (256, 5): 348.25e9, (256, 4): 348.22e9, (224, 4): 266.61e9, (224, 2): 266.57e9,
 }
+GF_PER_IMAGE = {  # baseline / upperbound step = 3 F_unet per image
+    (256, 5): 172.31e9, (256, 4): 172.30e9, (224, 4): 131.92e9, (224, 2): 131.90e9,
+}
+WORKLOADS = {
+    "pacing": "pacingpseudo full step (--do_loss_ent --do_decoder_consistency --do_aux_path --do_memory)",
+    "baseline": "baseline UNet + partial cross-entropy on scribbles",
+    "upperbound": "upperbound UNet + cross-entropy + Dice on dense labels (upper_bound_chaos.py)",
+}
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pacing", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=12, help="weak+strong pairs per GPU (train_chaos.py:93)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--classes", type=int, default=5)
@@ -45,6 +57,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile-pass", action="store_true", help="skip the per-launch CUDA-event pass (ncu runs)")
+    ap.add_argument("--no-same-box", action="store_true", help="skip the cuDNN same-box comparison (N=1 only)")
+    ap.add_argument("--ref-max-seconds", type=float, default=240.0,
+                    help="reference arm: if K+W steps at the full per-GPU batch would exceed this, each step becomes a "
+                         "bounded sample (fewer slices per step, stated in config / sample)")
     return ap.parse_args()
 
 
@@ -67,55 +83,199 @@ def load_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port of the full pacingpseudo step on the host cores
+# reference arm / cpu_baseline / same-box cuDNN: the UNMODIFIED reference modules (baseline/_ref, oracle/fetch_ref.py)
 # ------------------------------------------------------------------------------------------------
-def cpu_pacing_steps(args, steps, warmup, pairs=1):
+def gaussian_ramp_up(t, base_value, max_t=80, scale=5.0):
+    """utils/utils.py:53-65 (utils/ imports skimage, which is not installed: restated, 3 lines)."""
+    return base_value * math.exp(-scale * (1 - t / max_t)) if t < max_t else base_value
+
+
+def reference_available():
+    try:
+        from oracle.fetch_ref import fetch
+        return fetch()
+    except Exception:
+        return False
+
+
+class ReferenceStep:
+    """One training step of the reference's own modules, as train_chaos.py:263-315 / upper_bound_chaos.py:152-171
+    drive them (loss weighting with the in-place `*=` / `+=`, Adam lr 1e-4 wd 3e-4), on `device` ("cpu" or "cuda")."""
+
+    def __init__(self, args, device, autocast=None, channels_last=False):
+        import torch
+        from oracle.fetch_ref import cpu_only, import_reference
+        UNet, ConsistencyRegulr, RL = import_reference()
+        self.torch, self.RL, self.args, self.device = torch, RL, args, device
+        self.autocast, self.channels_last = autocast, channels_last
+        C = args.classes
+        torch.manual_seed(1)  # train_chaos.py:28,437
+        kw_unet = dict(input_ch=1, init_ch=32, max_ch=512, num_classes=C, output_stride=args.output_stride,
+                       is_stride_conv=args.unet_variant == "strided", is_trans_conv=args.unet_variant == "strided",
+                       elab_end_points=True)
+        if args.workload == "pacing":
+            ns = argparse.Namespace(ignored_index=C, do_loss_ent=True, do_decoder_consistency=True, detach_weak_cr=False,
+                                    loss_cr_variants="ce_loss", do_aux_path=True, do_memory=True)
+            kw_aux = dict(num_classes=C, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[512, 512], hid_ch=64,
+                          aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
+                          ensemble_mode='cosine_similarity')
+            if device == "cpu":
+                with cpu_only():
+                    model = ConsistencyRegulr(kwargs_unet=kw_unet, kwargs_aux_path=kw_aux, args_parser=ns)
+            else:
+                model = ConsistencyRegulr(kwargs_unet=kw_unet, kwargs_aux_path=kw_aux, args_parser=ns)
+        else:
+            model = UNet(**kw_unet)
+        model = model.to(device)
+        if channels_last:
+            model = model.to(memory_format=torch.channels_last)
+        model.train(args.bn == "train")
+        self.model = model
+        self.opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=3e-4)   # train_chaos.py:219
+        self.w = gaussian_ramp_up(args.epoch, 1.0, scale=8.0)
+
+    def __call__(self, batch):
+        torch, args, RL, C = self.torch, self.args, self.RL, self.args.classes
+        ctx = torch.autocast("cuda", dtype=self.autocast) if self.autocast is not None else _NullCtx()
+        with ctx:
+            if args.workload == "pacing":
+                out = self.model(batch, mode='train', step=args.epoch)
+                loss = out['loss_pce']
+                loss_ent = out['loss_ent'] * self.w
+                loss += loss_ent
+                loss_cr = out['loss_cr'] * self.w
+                loss += loss_cr
+                loss_aux = out['loss_aux_cls']
+                loss_aux *= 0.01
+                loss += loss_aux
+                loss_mem = out['loss_memory']
+                loss_mem *= 1
+                loss += loss_mem
+            elif args.workload == "baseline":
+                logits = self.model(batch['image'])['segmentation/logits']
+                loss = RL.partial_cross_entropy_loss(logits, torch.argmax(batch['scribble'], dim=1), C)
+            else:
+                logits = self.model(batch['image'])['segmentation/logits']
+                target = torch.argmax(batch['label'], dim=1).long()
+                loss = RL.partial_cross_entropy_loss(logits, target, C)
+                loss += RL.dice_loss_fn(logits, batch['label'])
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        return loss
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def workload_keys(workload):
+    """Tensors the reference training loop moves to the GPU each step (train_chaos.py:264-269 deletes the labels;
+    upper_bound_chaos.py:152-155 moves the whole batch of its single-stream dataset)."""
+    if workload == "pacing":
+        return ("image", "image_strong", "scribble", "scribble_strong", "valid_mask")
+    if workload == "baseline":
+        return ("image", "scribble", "valid_mask")
+    return ("image", "label")
+
+
+def cpu_reference_steps(args, steps, warmup, per_step, max_seconds=None):
+    """-> (times, cores, slices per step, kind). kind 'reference' = the unmodified reference modules from
+    baseline/_ref on the host cores; 'port' = the oracle restatement (only when baseline/_ref is absent)."""
     import torch
-    from oracle import pp_oracle as O
-    from oracle.gen_golden import build_state
     from pacingpseudo_b200.synth import make_batch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    case = dict(kind="pacing", C=args.classes, os=8)
-    sd = build_state(case)
-    learn = [k for k in sd if sd[k].is_floating_point() and "running" not in k and not k.endswith("memory_bank")]
-    for k in learn:
-        sd[k].requires_grad_(True)
-    cfg = O.StepConfig(num_classes=args.classes, ignored_index=args.classes)
-    state = {}
+    keys = workload_keys(args.workload)
+    if reference_available():
+        kind, stepper = "reference", ReferenceStep(args, "cpu")
+    else:
+        kind, stepper = "port", _OraclePortStep(args)
     times = []
-    for it in range(warmup + steps):
-        batch = make_batch(pairs, args.classes, args.size, args.size, seed=1234 + it)
+    it = 0
+    while it < warmup + steps:
+        b = make_batch(per_step, args.classes, args.size, args.size, seed=1234 + it)
+        batch = {k: b[k] for k in keys}
         t0 = time.perf_counter()
-        for k in learn:
-            sd[k].grad = None
-        out = O.consistency_forward(sd, batch, cfg, mode="train", step=args.epoch, training=(args.bn == "train"))
-        loss = O.total_loss(out, args.epoch)
-        loss.backward()
-        with torch.no_grad():
-            O.adam_step({k: sd[k] for k in learn}, {k: sd[k].grad for k in learn}, state, 1e-4, 3e-4, it + 1)
+        stepper(batch)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return times, cores, pairs
+        elif it == 0 and max_seconds is not None and per_step > 1 and dt * (warmup + steps) > 1.5 * max_seconds:
+            # bounded sample: the first (cold) step says the whole run would overshoot -> fewer slices per step
+            per_step = max(1, int(per_step * max_seconds / (dt * (warmup + steps))))
+        it += 1
+    return times, cores, per_step, kind
+
+
+class _OraclePortStep:
+    """Fallback when baseline/_ref is absent: the oracle restatement of the same step (kind = 'port')."""
+
+    def __init__(self, args):
+        import torch
+        from oracle import pp_oracle as O
+        from oracle.gen_golden import build_state
+        self.O, self.args, self.torch = O, args, torch
+        kind = {"pacing": "pacing", "baseline": "baseline", "upperbound": "upper"}[args.workload]
+        self.sd = build_state(dict(kind=kind, C=args.classes, os=args.output_stride))
+        self.learn = [k for k in self.sd if self.sd[k].is_floating_point() and "running" not in k
+                      and not k.endswith("memory_bank")]
+        for k in self.learn:
+            self.sd[k].requires_grad_(True)
+        self.cfg = O.StepConfig(num_classes=args.classes, ignored_index=args.classes, output_stride=args.output_stride)
+        self.state, self.it = {}, 0
+
+    def __call__(self, batch):
+        O, args, sd, torch = self.O, self.args, self.sd, self.torch
+        for k in self.learn:
+            sd[k].grad = None
+        training = args.bn == "train"
+        if args.workload == "pacing":
+            out = O.consistency_forward(sd, batch, self.cfg, mode="train", step=args.epoch, training=training)
+            loss = O.total_loss(out, args.epoch)
+        else:
+            z = O.unet_forward(sd, batch["image"], training, output_stride=args.output_stride)["segmentation/logits"]
+            if args.workload == "baseline":
+                loss = O.partial_cross_entropy(z, batch["scribble"].argmax(1), args.classes)
+            else:
+                loss = O.partial_cross_entropy(z, batch["label"].argmax(1), args.classes) + O.dice(z, batch["label"])
+        loss.backward()
+        self.it += 1
+        with torch.no_grad():
+            O.adam_step({k: sd[k] for k in self.learn}, {k: sd[k].grad for k in self.learn}, self.state, 1e-4, 3e-4, self.it)
+        return loss
+
+
+def metric_name(args):
+    return "train imgs/sec (%d^2 %s step)" % (args.size, {"pacing": "pacingpseudo", "baseline": "baseline UNet+pCE",
+                                                          "upperbound": "upperbound CE+Dice"}[args.workload])
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
     t_all = time.perf_counter()
-    times, cores, pairs = cpu_pacing_steps(args, args.steps, args.warmup, pairs=1)
+    times, cores, per_step, kind = cpu_reference_steps(args, args.steps, args.warmup, args.batch, args.ref_max_seconds)
     total = sum(times)
-    value = pairs * len(times) / total
-    sample = ("oracle port (oracle/pp_oracle.py, torch %s CPU fp32) of the full pacingpseudo step on %d weak+strong pair(s) "
-              "of %dx%d per step, %d timed steps" % (__import__("torch").__version__, pairs, args.size, args.size, len(times)))
+    value = per_step * len(times) / total
+    what = ("the UNMODIFIED reference modules (models/unet.py, consistency_reglur_memory.py, aux_path_memory.py, "
+            "losses/losses.py from baseline/_ref) + torch.optim.Adam" if kind == "reference"
+            else "oracle port (oracle/pp_oracle.py; baseline/_ref absent)")
+    sample = "%s, torch %s CPU fp32, %d threads, %d slice(s) of %dx%d per step%s, %d timed steps (%.1f s)" % (
+        what, torch.__version__, cores, per_step, args.size, args.size,
+        "" if per_step == args.batch else " (bounded sample of the %d-slice batch)" % args.batch, len(times), total)
     line = {
-        "impl": "reference", "metric": "train imgs/sec (256^2 pacingpseudo step)", "value": value, "unit": "img/s",
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": "img/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, pairs_override=pairs),
-        "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, pairs_override=per_step),
+        "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
     }
@@ -123,18 +283,67 @@ def run_reference(args):
 
 
 def workload_config(args, pairs_override=None):
+    unit = "pairs" if args.workload == "pacing" else "slices"
+    per = pairs_override if pairs_override is not None else args.batch
     return {
-        "workload": "pacingpseudo full step (--do_loss_ent --do_decoder_consistency --do_aux_path --do_memory), "
-                    "CHAOS-shaped synthetic %dx%d 1-ch slices, %d classes (BASELINE.json configs[1])" % (
-                        args.size, args.size, args.classes),
-        "pairs_per_gpu": pairs_override if pairs_override is not None else args.batch,
-        "global_pairs": (pairs_override if pairs_override is not None else args.batch) * max(1, args.gpus),
+        "workload": "%s, %s-shaped synthetic %dx%d 1-ch slices, %d classes (BASELINE.json configs[%s])" % (
+            WORKLOADS[args.workload], {5: "CHAOS", 4: "ACDC", 2: "LVSC"}.get(args.classes, "CHAOS"), args.size,
+            args.size, args.classes,
+            {"pacing": {5: "1", 4: "2", 2: "4"}.get(args.classes, "1"), "baseline": "0", "upperbound": "3"}[args.workload]),
+        "%s_per_gpu" % unit: per, "global_%s" % unit: per * max(1, args.gpus),
+        "pairs_per_gpu": per, "global_pairs": per * max(1, args.gpus),
         "unet": "init_ch 32, max_ch 512, output_stride %d, %s" % (
             args.output_stride, "maxpool + bilinear" if args.unet_variant == "maxpool"
             else "stride-2 conv + ConvTranspose2d (is_stride_conv, is_trans_conv)"), "bn": args.bn,
-        "loss_cr_variants": "ce_loss", "optimizer": "Adam lr 1e-4 wd 3e-4", "parallelism": "dp%d" % max(1, args.gpus),
+        "loss_cr_variants": "ce_loss" if args.workload == "pacing" else None,
+        "optimizer": "Adam lr 1e-4 wd 3e-4", "parallelism": "dp%d" % max(1, args.gpus),
         "l2": "per-step working set (~3.4 GB of activations per GPU) >> 126 MB L2; no explicit flush",
     }
+
+
+def same_box_cudnn(args, dev, steps=5, warmup=2):
+    """SURVEY 8(d) / BASELINE.md section 4 "same box, stronger competitor": the unmodified reference modules under stock
+    torch eager + cuDNN on this B200 (fp32 without TF32, TF32, bf16 autocast + channels_last), same workload and batch,
+    CUDA-event timed. Reported next to the result; not on the product path."""
+    import torch
+    from pacingpseudo_b200.synth import make_batch
+    if not reference_available():
+        return {"unavailable": "baseline/_ref absent (run oracle/fetch_ref.py where /root/reference exists)"}
+    keys = workload_keys(args.workload)
+    batches = [{k: v.to(dev) for k, v in make_batch(args.batch, args.classes, args.size, args.size, seed=4321 + i).items()
+                if k in keys} for i in range(2)]
+    out = {"how": "unmodified reference modules (baseline/_ref), stock torch %s eager + cuDNN %s on this GPU, %d slices "
+                  "per step, %d timed steps after %d warm-up, CUDA events" % (
+                      torch.__version__, torch.backends.cudnn.version(), args.batch, steps, warmup)}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name, tf32, ac, cl in (("fp32", False, None, False), ("tf32", True, None, False),
+                                   ("bf16_autocast_channels_last", True, torch.bfloat16, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            try:
+                stepper = ReferenceStep(args, dev, autocast=ac, channels_last=cl)
+                bs = [{k: (v.contiguous(memory_format=torch.channels_last) if (cl and v.dim() == 4) else v)
+                       for k, v in b.items()} for b in batches]
+                for i in range(warmup):
+                    stepper(bs[i % 2])
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(steps):
+                    stepper(bs[i % 2])
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1) / steps
+                out[name] = {"ms_per_step": ms, "value": args.batch / (ms / 1e3), "unit": "img/s"}
+                del stepper
+            except Exception as exc:   # a competitor that fails to run is reported, never fatal to the bench
+                out[name] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -323,6 +532,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from pacingpseudo_b200 import dp
+    from pacingpseudo_b200 import functional as PF
     from pacingpseudo_b200.data import (DevicePrefetcher, LossReader, compact_batch, sample_strong_params,
                                         strong_color_augment)
     from pacingpseudo_b200.dropin import DROPIN_PATH
@@ -341,27 +551,34 @@ def run_ours(args):
     C, S, B = args.classes, args.size, args.batch
 
     torch.manual_seed(1)  # train_chaos.py:28,437
-    ns = argparse.Namespace(ignored_index=C, do_loss_ent=True, do_decoder_consistency=True, detach_weak_cr=False,
-                            loss_cr_variants="ce_loss", do_aux_path=True, do_memory=True)
-    model = ConsistencyRegulr(
-        kwargs_unet=dict(input_ch=1, init_ch=32, max_ch=512, num_classes=C, output_stride=args.output_stride,
-                         is_stride_conv=args.unet_variant == "strided", is_trans_conv=args.unet_variant == "strided",
-                         elab_end_points=True, precision=args.precision),
-        kwargs_aux_path=dict(num_classes=C, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[512, 512],
-                             hid_ch=64, aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
-                             ensemble_mode='cosine_similarity'),
-        args_parser=ns).to(dev)
+    pacing = args.workload == "pacing"
+    kw_unet = dict(input_ch=1, init_ch=32, max_ch=512, num_classes=C, output_stride=args.output_stride,
+                   is_stride_conv=args.unet_variant == "strided", is_trans_conv=args.unet_variant == "strided",
+                   elab_end_points=True, precision=args.precision)
+    if pacing:
+        ns = argparse.Namespace(ignored_index=C, do_loss_ent=True, do_decoder_consistency=True, detach_weak_cr=False,
+                                loss_cr_variants="ce_loss", do_aux_path=True, do_memory=True)
+        model = ConsistencyRegulr(
+            kwargs_unet=kw_unet,
+            kwargs_aux_path=dict(num_classes=C, feat_stage=['encoder/stage6', 'encoder/stage5'], feat_ch=[512, 512],
+                                 hid_ch=64, aux_drop_prob=0., do_memory=True, max_step=400, update_momentum=0.9,
+                                 ensemble_mode='cosine_similarity'),
+            args_parser=ns).to(dev)
+        backbone = model.backbone
+    else:
+        from models.unet import UNet
+        from losses import losses as DL
+        model = UNet(**kw_unet).to(dev)
+        backbone = model
     model.train(args.bn == "train")
     opt = FlatAdam(model.parameters(), lr=1e-4, weight_decay=3e-4)
-    reducer = dp.GradientAllReducer(opt.flat_grad, num_buckets=4, unet=model.backbone, optimizer=opt)
+    reducer = dp.GradientAllReducer(opt.flat_grad, num_buckets=4, unet=backbone, optimizer=opt)
     opt.grad_scale = 1.0 / world
-    if world > 1:
+    if world > 1 and pacing:
         model.aux_path.bank_sync = dp.make_bank_sync(0)
-        for p in opt.params:  # identical start on all ranks (same seed) — assert rather than broadcast
-            pass
 
     # a small pool of distinct per-rank batches; host copies pinned for the end-to-end leg
-    keys = ("image", "image_strong", "scribble", "scribble_strong", "valid_mask")  # what train_chaos.py:264-269 moves
+    keys = workload_keys(args.workload)  # what the reference training loop moves to the GPU each step
     pool_host = []
     for i in range(4):
         b = make_batch(B, C, S, S, seed=dp.shard_seed(1234, rank, i))
@@ -370,11 +587,13 @@ def run_ours(args):
     h2d_bytes = sum(v.numel() * v.element_size() for v in pool_host[0].values())
     # compact variant: uint8 scribble index map, no scribble_strong, image_strong made on the device
     pool_compact = []
-    for i, b in enumerate(pool_host):
-        c = compact_batch(b, C)
-        c["strong_params"] = sample_strong_params(B, 1.0, torch.Generator().manual_seed(dp.shard_seed(99, rank, i)))
-        pool_compact.append({k: v.pin_memory() for k, v in c.items()})
-    h2d_bytes_compact = sum(v.numel() * v.element_size() for v in pool_compact[0].values())
+    h2d_bytes_compact = None
+    if pacing:
+        for i, b in enumerate(pool_host):
+            c = compact_batch(b, C)
+            c["strong_params"] = sample_strong_params(B, 1.0, torch.Generator().manual_seed(dp.shard_seed(99, rank, i)))
+            pool_compact.append({k: v.pin_memory() for k, v in c.items()})
+        h2d_bytes_compact = sum(v.numel() * v.element_size() for v in pool_compact[0].values())
     w_ent = loss_weight_ramp_up(args.epoch, 1.0, scale=8.0)
     w_cr = loss_weight_ramp_up(args.epoch, 1.0, scale=8.0)
 
@@ -382,28 +601,41 @@ def run_ours(args):
     prefetcher = DevicePrefetcher((), dev)
 
     def step(batch, read_back):
-        if "strong_params" in batch:   # compact host format: the strong branch's image is produced on the device
-            batch = dict(batch, image_strong=strong_color_augment(batch["image"], batch["strong_params"]))
-        out = model(batch, mode='train', step=args.epoch)
-        loss = out['loss_pce']
-        loss_ent = out['loss_ent'] * w_ent
-        loss += loss_ent
-        loss_cr = out['loss_cr'] * w_cr
-        loss += loss_cr
-        loss_aux = out['loss_aux_cls']
-        loss_aux *= 0.01
-        loss += loss_aux
-        loss_mem = out['loss_memory']
-        loss_mem *= 1
-        loss += loss_mem
+        if pacing:
+            if "strong_params" in batch:   # compact host format: the strong branch's image is produced on the device
+                batch = dict(batch, image_strong=strong_color_augment(batch["image"], batch["strong_params"]))
+            out = model(batch, mode='train', step=args.epoch)
+            loss = out['loss_pce']
+            loss_ent = out['loss_ent'] * w_ent
+            loss += loss_ent
+            loss_cr = out['loss_cr'] * w_cr
+            loss += loss_cr
+            loss_aux = out['loss_aux_cls']
+            loss_aux *= 0.01
+            loss += loss_aux
+            loss_mem = out['loss_memory']
+            loss_mem *= 1
+            loss += loss_mem
+            scalars = [out['loss_pce'], loss_ent, loss_cr, loss_aux, loss_mem]
+        elif args.workload == "baseline":   # config 1 on the GPU: UNet + partial CE on the scribbles
+            logits = model(batch['image'])['segmentation/logits']
+            loss = DL.partial_cross_entropy_loss(logits, PF.onehot_argmax(batch['scribble']), C)
+            scalars = [loss]
+        else:   # upper_bound_chaos.py:157-165: CE on argmax(label) + Dice on the one-hot label
+            logits = model(batch['image'])['segmentation/logits']
+            loss_ce = DL.partial_cross_entropy_loss(logits, PF.onehot_argmax(batch['label']), C)
+            loss_dice = DL.dice_loss_fn(logits, batch['label'])
+            scalars = [loss_ce.detach().clone(), loss_dice]
+            loss = loss_ce
+            loss += loss_dice
         opt.zero_grad()
         loss.backward()
         reducer.allreduce()
         opt.step()
-        if read_back == "item":   # the five blocking .item() reads of train_chaos.py:275-310
-            return [t.item() for t in (out['loss_pce'], loss_ent, loss_cr, loss_aux, loss_mem)]
-        if read_back == "async":  # same five scalars, non-blocking D2H, handed back one step later
-            return loss_reader.push([out['loss_pce'], loss_ent, loss_cr, loss_aux, loss_mem])
+        if read_back == "item":   # the blocking .item() reads of train_chaos.py:275-310
+            return [t.item() for t in scalars]
+        if read_back == "async":  # same scalars, non-blocking D2H, handed back one step later
+            return loss_reader.push(scalars)
         return None
 
     def barrier():
@@ -411,27 +643,39 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(nsteps, host_inputs, profile, pool=None):
+    n_scalars = {"pacing": 5, "baseline": 1, "upperbound": 2}[args.workload]
+    step_ms = {}   # leg name -> per-step durations (CUDA events between consecutive steps), this rank
+
+    def timed(nsteps, host_inputs, profile, pool=None, leg=None):
         pool = pool_host if pool is None else pool
         barrier()
         lib.cdll.pp_profile_reset()
         lib.cdll.pp_profile_enable(1 if profile else 0)
         l0 = lib.cdll.pp_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps + 1)]
+        marks[0].record()
         if host_inputs:   # pinned host batches, H2D on a copy stream one step ahead (pacingpseudo_b200/data.py)
-            for batch in prefetcher.reset(pool[i % len(pool)] for i in range(nsteps)):
+            for i, batch in enumerate(prefetcher.reset(pool[i % len(pool)] for i in range(nsteps))):
                 step(batch, host_inputs)
+                marks[i + 1].record()
             if host_inputs == "async":
-                assert len(loss_reader.flush()) == 5
+                assert len(loss_reader.flush()) == n_scalars
         else:
             for i in range(nsteps):
                 step(pool_dev[i % len(pool_dev)], False)
+                marks[i + 1].record()
+        e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
         barrier()
         lib.cdll.pp_profile_enable(0)
-        ms = dp.max_over_ranks(e0.elapsed_time(e1), dev)
+        ms = dp.max_over_ranks(marks[0].elapsed_time(e1), dev)
+        if leg is not None and nsteps > 0:
+            step_ms[leg] = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(nsteps))
         return ms, lib.cdll.pp_launch_count() - l0
+
+    def median(leg):
+        v = step_ms.get(leg)
+        return dp.max_over_ranks(v[len(v) // 2], dev) if v else None
 
     sampler = ClockSampler(dev.index)
     if rank == 0:
@@ -441,7 +685,8 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     t_begin = time.time()
-    ms, launches = timed(args.steps, host_inputs=False, profile=False)
+    ms, launches = timed(args.steps, host_inputs=False, profile=False, leg="device")
+    ms_median = median("device")
     clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
     # the same K steps once more with every tcgen05 conv launch bracketed by CUDA events on its stream (roofline)
     ms_prof, _ = timed(0 if args.no_profile_pass else args.steps, host_inputs=False, profile=True)
@@ -456,23 +701,26 @@ def run_ours(args):
     if not args.no_e2e:
         for batch in prefetcher.reset(pool_host[i] for i in range(3)):   # allocates the staging buffers
             step(batch, "async")
-        ms_e2e, _ = timed(args.steps, host_inputs="async", profile=False)
+        ms_e2e, _ = timed(args.steps, host_inputs="async", profile=False, leg="e2e")
+        ms_e2e_median = median("e2e")
         ms_e2e_item, _ = timed(args.steps, host_inputs="item", profile=False)
-        for batch in prefetcher.reset(pool_compact[i] for i in range(3)):   # staging buffers of the compact format
-            step(batch, "async")
-        ms_e2e_compact, _ = timed(args.steps, host_inputs="async", profile=False, pool=pool_compact)
         e2e = {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": "img/s", "h2d_bytes_per_step": h2d_bytes,
-               "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / args.steps,
+               "d2h_bytes_per_step": 4 * n_scalars, "ms_per_step": ms_e2e / args.steps,
+               "ms_per_step_median": ms_e2e_median,
                "how": "pinned host batches -> DevicePrefetcher (H2D into persistent staging buffers on a copy stream, "
-                      "one step ahead) -> ConsistencyRegulr.forward / backward / FlatAdam.step -> LossReader (the five "
-                      "loss scalars, non-blocking D2H to pinned memory every step, read one step later)",
-               "ms_per_step_blocking_item_reads": ms_e2e_item / args.steps,
-               "compact_input": {
-                   "value": B * world * args.steps / (ms_e2e_compact / 1e3), "unit": "img/s",
-                   "ms_per_step": ms_e2e_compact / args.steps, "h2d_bytes_per_step": h2d_bytes_compact,
-                   "how": "same loop from the compact host format (SURVEY 8f N3): image + uint8 scribble index map + "
-                          "valid mask + 8 augmentation draws per slice; image_strong = pp_strong_color_augment(image) "
-                          "on the device (different strong images than the reference-format leg, same work)"}}
+                      "one step ahead) -> module forward / backward / FlatAdam.step -> LossReader (the step's loss "
+                      "scalars, non-blocking D2H to pinned memory every step, read one step later)",
+               "ms_per_step_blocking_item_reads": ms_e2e_item / args.steps}
+        if pacing:
+            for batch in prefetcher.reset(pool_compact[i] for i in range(3)):   # staging buffers of the compact format
+                step(batch, "async")
+            ms_e2e_compact, _ = timed(args.steps, host_inputs="async", profile=False, pool=pool_compact)
+            e2e["compact_input"] = {
+                "value": B * world * args.steps / (ms_e2e_compact / 1e3), "unit": "img/s",
+                "ms_per_step": ms_e2e_compact / args.steps, "h2d_bytes_per_step": h2d_bytes_compact,
+                "how": "same loop from the compact host format (SURVEY 8f N3): image + uint8 scribble index map + "
+                       "valid mask + 8 augmentation draws per slice; image_strong = pp_strong_color_augment(image) "
+                       "on the device (different strong images than the reference-format leg, same work)"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -486,11 +734,13 @@ def run_ours(args):
     dom = prof["conv3x3_tc (fwd+dgrad)"]
     steps_p = max(1, args.steps)
     tf = lambda p: (p["flops"] / (p["ms"] / 1e3) / 1e12) if p["ms"] > 0 else 0.0
-    gf = GF_PER_PAIR.get((S, C)) if (args.unet_variant == "maxpool" and args.output_stride == 8) else None
+    gf = (GF_PER_PAIR if pacing else GF_PER_IMAGE).get((S, C)) if (
+        args.unet_variant == "maxpool" and args.output_stride == 8) else None
     traffic = load_traffic()
     line = {
-        "metric": "train imgs/sec (256^2 pacingpseudo step)", "value": value, "unit": "img/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "metric": metric_name(args), "value": value, "unit": "img/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_per_step_median": ms_median,
+        "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
         "e2e": e2e,
@@ -522,12 +772,18 @@ def run_ours(args):
         },
     }
     if world == 1 and not args.no_cpu_baseline:
-        times, cores, pairs = cpu_pacing_steps(args, steps=12, warmup=1, pairs=2)   # ~10-15 s of host work
-        v = pairs * len(times) / sum(times)
+        # ~10-30 s of host work: the unmodified reference modules on this box's cores, one warm-up + 3 timed steps
+        del pool_dev, pool_host, pool_compact
+        torch.cuda.empty_cache()
+        times, cores, per_step, kind = cpu_reference_steps(args, steps=3, warmup=1, per_step=B, max_seconds=30.0)
+        v = per_step * len(times) / sum(times)
         line["cpu_baseline"] = {
-            "value": v, "unit": "img/s", "cores": cores, "kind": "port",
-            "sample": "oracle port of the same pacingpseudo step, %d pair(s) of %dx%d per step, %d timed steps (%.1f s)" % (
-                pairs, S, S, len(times), sum(times))}
+            "value": v, "unit": "img/s", "cores": cores, "kind": kind,
+            "sample": "%s on the host cores (%d threads): the same %s step, %d slice(s) of %dx%d per step, %d timed "
+                      "steps (%.1f s)" % ("unmodified reference modules (baseline/_ref)" if kind == "reference" else
+                                          "oracle port", cores, args.workload, per_step, S, S, len(times), sum(times))}
+    if world == 1 and not args.no_same_box:
+        line["extra"] = {"cudnn_same_box": same_box_cudnn(args, dev)}
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -137,7 +137,10 @@ def _q(x, quant):
 
 
 def _qw(w, quant):
-    return w.bfloat16().to(w.dtype) + (w - w.detach()) if quant else w
+    # straight-through: forward value bf16(w), gradient exactly 1 w.r.t. w. (The dtype casts are differentiable in
+    # autograd, so the rounding residue must be detached as a whole — `w.bfloat16().to() + (w - w.detach())` would
+    # count the gradient twice; round 1 shipped that and its emulated weight gradients were 2x too large.)
+    return w + (w.bfloat16().to(w.dtype) - w).detach() if quant else w
 
 
 # ------------------------------------------------------------------------------------------------

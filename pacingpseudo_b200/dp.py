@@ -147,6 +147,27 @@ def make_bank_sync(src=0, group=None):
     return sync
 
 
+def sync_bn_buffers(model, src=0, group=None):
+    """Call before validation / checkpointing under data parallelism: BatchNorm statistics are per rank during
+    training (each rank is exactly a reference single-GPU step), so running_mean / running_var /
+    num_batches_tracked are taken from rank `src` — eval-mode forward passes and checkpoints then agree on every rank.
+    One broadcast over a flat copy of all floating-point buffers plus one for the integer counters."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    bufs = [b for b in model.buffers()]
+    for kind in (True, False):
+        sel = [b for b in bufs if b.is_floating_point() == kind]
+        if not sel:
+            continue
+        flat = torch.cat([b.detach().reshape(-1).to(torch.float32 if kind else torch.int64) for b in sel])
+        dist.broadcast(flat, src=src, group=group)
+        off = 0
+        for b in sel:
+            n = b.numel()
+            b.data.copy_(flat[off:off + n].view_as(b).to(b.dtype))
+            off += n
+
+
 def shard_seed(base_seed, rank, step):
     """Seed of rank `rank`'s local batch at `step` (1234 + 1000*rank + step)."""
     return base_seed + 1000 * rank + step

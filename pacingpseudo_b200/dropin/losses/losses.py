@@ -23,9 +23,9 @@ def entropy_minimization_loss(input, valid_mask=None):
 
 
 def cross_entropy_loss(input, target):
-    """losses.py:26-33."""
+    """losses.py:26-33: F.cross_entropy with its default ignore_index (-100)."""
     input, target = _as_4d(input, target)
-    return PF.scribble_losses(input, target, -1)['loss_pce']
+    return PF.scribble_losses(input, target, -100)['loss_pce']
 
 
 def partial_cross_entropy_loss(input, target, ignore_index):

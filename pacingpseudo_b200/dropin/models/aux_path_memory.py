@@ -102,15 +102,23 @@ class AuxPath(nn.Module):
                'aux_targets': (scribble if scribble.dim() == 3 else PF.onehot_argmax(scribble)).long()}
         if self.do_memory:
             # logits_memory is produced for API parity; its loss/gradient go through memory_loss()
-            w = self.fc_cls[1].weight
-            out['logits_memory'] = torch.nn.functional.conv2d(self.memory_bank, w)
+            out['logits_memory'] = PF.bank_logits(self.memory_bank.data, self.fc_cls[1].weight)
             out['memory_target'] = self.memory_target
         return out
 
     @torch.no_grad()
-    def memory_update(self, aux_features, scribble, step, _code=None):
-        """aux_path_memory.py:68-116. aux_features: native NHWC tensor (or reference NCHW fp32)."""
-        if aux_features.dim() == 4 and aux_features.shape[-1] != self.hid_ch:  # reference layout NCHW
+    def memory_update(self, aux_features, scribble, step, _code=None, layout=None):
+        """aux_path_memory.py:68-116. aux_features: (N, hid, h, w) in the reference's NCHW layout (the public
+        signature; layout=None or 'nchw') or the native NHWC tensor (layout='nhwc', what run_native passes with
+        _code). The layout is never guessed from the shape: a 64-wide NCHW map with hid_ch = 64 is ambiguous."""
+        if layout is None:
+            layout = 'nhwc' if _code is not None else 'nchw'
+        if layout not in ('nchw', 'nhwc'):
+            raise ValueError("memory_update: layout must be 'nchw' or 'nhwc'")
+        if aux_features.dim() != 4 or aux_features.shape[1 if layout == 'nchw' else 3] != self.hid_ch:
+            raise RuntimeError("memory_update: expected %s features with %d channels, got shape %s" % (
+                layout.upper(), self.hid_ch, tuple(aux_features.shape)))
+        if layout == 'nchw':
             aux_features = aux_features.permute(0, 2, 3, 1).contiguous()
         code = _code if _code is not None else (PF.BF16 if aux_features.dtype == torch.bfloat16 else PF.F32)
         m = _ramp_up_mo(step, self.max_step, self.momentum)

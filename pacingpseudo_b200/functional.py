@@ -326,12 +326,24 @@ class ScribbleLossFunction(torch.autograd.Function):
         zs = zs.contiguous().float() if zs is not None else None
         za = za.contiguous().float() if za is not None else None
         mask = mask.contiguous().float() if mask is not None else None
+        Nall, C, H, W = zw.shape
+        bad_any = None
         if target is not None:
             target = target.contiguous()
             if target.dtype != torch.uint8:
-                # int64 targets of the reference API; ignore_index values outside [0, 255] never equal a class id
-                target = target.clamp(0, 255).to(torch.uint8)
-        Nall, C, H, W = zw.shape
+                # int64 targets of the reference API (F.cross_entropy semantics): the ignore label may be any integer
+                # (torch's default is -100). It is mapped to the sentinel 255 BEFORE the narrowing cast, so a negative
+                # or > 255 ignore label can never alias a class id. Labels outside [0, C) that are not the ignore
+                # label are a device-side assert in torch; here they poison the loss with NaN (no host sync on the
+                # training path, but never a silently skipped pixel).
+                if C >= 255:
+                    raise RuntimeError("scribble loss: at most 254 classes (255 is the ignore sentinel)")
+                ign = target == ignore_index
+                bad_any = (((target < 0) | (target >= C)) & ~ign).any()
+                target = torch.where(ign, torch.full_like(target, 255), target).clamp(0, 255).to(torch.uint8)
+                ignore_index = 255
+            elif not 0 <= ignore_index <= 255:
+                ignore_index = 255   # a uint8 map cannot hold this label: nothing is ignored unless it says 255
         N = Nall // 2 if siamese else Nall
         zw_p = zw.data_ptr()
         zs_p = (zw_p + N * C * H * W * 4) if siamese else (zs.data_ptr() if zs is not None else None)
@@ -343,6 +355,9 @@ class ScribbleLossFunction(torch.autograd.Function):
             lib.call("pp_scribble_loss_fwd", ctypes.c_void_p(zw_p), ctypes.c_void_p(zs_p) if zs_p else None, ptr(za),
                      ptr(target), ptr(mask), ptr(acc), ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), N, C,
                      H * W, ignore_index, int(do_ent), cr_variant, current_stream(dev))
+            if bad_any is not None:
+                outs[0].masked_fill_(bad_any, float("nan"))
+        cfg = (ignore_index, do_ent, cr_variant, detach_weak, siamese)   # the (possibly remapped) ignore label
         ctx.cfg, ctx.dims = cfg, (N, C, H, W)
         ctx.has = (zs is not None, za is not None, mask is not None)
         ctx.save_for_backward(zw, zs, za, target, mask, acc)
@@ -484,6 +499,21 @@ class MemoryLossFunction(torch.autograd.Function):
             get_lib().call("pp_memory_loss_bwd", ptr(bank_c), ptr(probs), ptr(g.contiguous().float()), ptr(d), C, hid,
                            current_stream(dev))
         return None, d, None
+
+
+def bank_logits(bank, fc_w):
+    """fc_cls applied to the memory bank (aux_path_memory.py:60): (C, hid, 1, 1) x (K, hid, 1, 1) -> (C, K, 1, 1),
+    through the 1x1 head kernel (the bank rows are C "pixels" of hid channels). No gradient: the bank loss and its
+    gradient go through MemoryLossFunction."""
+    require_cuda(fc_w, "fc_cls weight")
+    C, hid = bank.shape[0], bank.shape[1]
+    K = fc_w.shape[0]
+    dev = fc_w.device
+    with torch.cuda.device(dev):
+        out = torch.empty((C, K, 1, 1), dtype=torch.float32, device=dev)
+        get_lib().call("pp_head_fwd", F32, ptr(bank.detach().contiguous().float().view(C, hid)),
+                       ptr(fc_w.detach().contiguous().float()), None, ptr(out), C, 1, hid, K, current_stream(dev))
+    return out
 
 
 def memory_update(code, aux_features, scribble, bank, mode, m):

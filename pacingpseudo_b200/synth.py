@@ -10,7 +10,11 @@ import math
 import torch
 
 
-def make_batch(n, num_classes, height, width, seed, absent_class_in_sample0=None):
+def make_batch(n, num_classes, height, width, seed, absent_class_in_sample0=None, class_contrast=False):
+    """class_contrast=True: the k-th foreground class gets its own intensity band (amp = 0.35 + 0.45 k with 10 %
+    jitter, sharper edges) so that class identity is learnable from appearance — used by the trained-state parity
+    tests, where near-tied logits between visually identical classes would make the argmax comparison meaningless.
+    The default (False) draws every amplitude from the same range and is what the golden fixtures were made with."""
     g = torch.Generator().manual_seed(int(seed))
     C = num_classes
     yy, xx = torch.meshgrid(torch.arange(height, dtype=torch.float32), torch.arange(width, dtype=torch.float32),
@@ -30,6 +34,8 @@ def make_batch(n, num_classes, height, width, seed, absent_class_in_sample0=None
             b = (0.06 + 0.10 * torch.rand((), generator=g).item()) * height
             th = math.pi * torch.rand((), generator=g).item()
             amp = 0.5 + torch.rand((), generator=g).item()
+            if class_contrast:
+                amp = (0.35 + 0.45 * k) * (0.95 + 0.1 * (amp - 0.5))
             geo.append((cx, cy, a, b, th, amp))
         for k, (cx, cy, a, b, th, amp) in enumerate(geo, start=1):
             if i == 0 and absent_class_in_sample0 == k:

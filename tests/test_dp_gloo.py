@@ -35,6 +35,16 @@ def _worker(rank, world, port, q):
     dp.make_bank_sync(0)(bank)
     ok_bank = bool((bank == 1.0).all())
     t = dp.max_over_ranks(float(rank), dev)
+    # BatchNorm buffers are per rank during training; before validation / checkpoints rank 0's win
+    bn = torch.nn.Sequential(torch.nn.BatchNorm2d(4), torch.nn.BatchNorm2d(3))
+    for m in bn:
+        m.running_mean.fill_(float(rank + 1))
+        m.running_var.fill_(10.0 * (rank + 1))
+        m.num_batches_tracked.fill_(7 * (rank + 1))
+    dp.sync_bn_buffers(bn, src=0)
+    ok_bn = all(bool((m.running_mean == 1.0).all()) and bool((m.running_var == 10.0).all())
+                and int(m.num_batches_tracked) == 7 and m.num_batches_tracked.dtype == torch.int64 for m in bn)
+    ok_bank = ok_bank and ok_bn
     q.put((rank, ok_sum, ok_bank, t, dp.shard_seed(1234, rank, 7)))
     dist.destroy_process_group()
 

@@ -113,6 +113,77 @@ def test_conv3x3_forward_dgrad_wgrad_vs_oracle(pp, case, precision):
         assert _rel(y.float(), y2.float()) < 2e-3
 
 
+# The layer shapes bench.py actually runs (24 slices = 12 weak + 12 strong, or one 12-slice branch): full tile counts,
+# so the MT = 2 / 4 multi-tile CTAs, the 256-row deterministic split-K weight gradient at full K, the halo kernels'
+# long row rings and the row variant of the narrow weight gradient are all checked at their real grid sizes
+# (operator tests only covered M <= 4096 pixels).
+FULL_TILE_CASES = [
+    # N, H, W, C0, C1, Cout, dil
+    (24, 32, 32, 512, 0, 512, 4),     # enc_block6: M = 24*1024, 512 -> 512, dilation 4
+    (24, 32, 32, 512, 512, 512, 1),   # dec_block5 conv1: concat 1024 -> 512
+    (12, 32, 32, 512, 256, 256, 1),   # dec_block4 conv1 (one branch): 768 -> 256 (BLOCK_N 192 dgrad)
+    (12, 64, 64, 256, 128, 128, 1),   # dec_block3 conv1
+    (12, 128, 128, 128, 64, 64, 1),   # dec_block2 conv1 (BLOCK_N 64, MT 2)
+    (24, 256, 256, 32, 0, 32, 1),     # enc_block1 conv2 / dec_block1 conv2: M = 24*65536, halo kernel + row wgrad
+    (12, 256, 256, 64, 32, 32, 1),    # dec_block1 conv1: concat 96 -> 32 at full resolution
+    (12, 28, 28, 512, 0, 512, 2),     # ACDC / LVSC 224^2 bottleneck: ragged 28 x 28 tiles, dilation 2
+]
+
+
+@pytest.mark.parametrize("case", FULL_TILE_CASES)
+def test_conv3x3_full_tile_counts_vs_torch(pp, case):
+    """tcgen05 forward / dgrad / wgrad at the bench's real launch shapes against torch CPU autograd on the same
+    bf16-rounded operands. Tolerances: forward / dgrad 3e-3 rel-L2 (one bf16 rounding of the fp32 accumulator is
+    ~1.2e-3), weight gradient 5e-4 (fp32 output; only the summation order differs)."""
+    L, PF, pplib = pp
+    N, H, W, C0, C1, Co, dil = case
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, C0 + C1, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(Co, C0 + C1, 3, 3, generator=g) / (3 * (C0 + C1) ** 0.5)).bfloat16().float()
+    b = torch.randn(Co, generator=g)
+    gy = torch.randn(N, Co, H, W, generator=g).bfloat16().float()
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    y_ref = F.conv2d(xr, wr, b, 1, dil, dil)
+    y_ref.backward(gy)
+    code, adt = PF.BF16, torch.bfloat16
+    wf = torch.empty(9 * Co * (C0 + C1) * 2, dtype=torch.uint8, device="cuda")
+    wd = torch.empty_like(wf)
+    w_d, b_d = w.cuda(), b.cuda()
+    L.call("pp_pack_weights", code, _p(w_d), _p(wf), _p(wd), Co, C0 + C1, _st())
+    x0 = _nhwc(x[:, :C0], adt)
+    x1 = _nhwc(x[:, C0:], adt) if C1 else None
+    y = torch.empty(N, H, W, Co, dtype=adt, device="cuda")
+    L.call("pp_conv3x3", code, _p(x0), C0, _p(x1), C1, _p(wf), _p(b_d), _p(y), Co, 0, None, 0, 0, N, H, W, dil, _st())
+    e_fwd = _rel(y.float().permute(0, 3, 1, 2), y_ref.detach())
+    dy = _nhwc(gy, adt)
+    g0 = torch.empty(N, H, W, C0, dtype=adt, device="cuda")
+    g1 = torch.empty(N, H, W, C1, dtype=adt, device="cuda") if C1 else None
+    L.call("pp_conv3x3", code, _p(dy), Co, None, 0, _p(wd), None, _p(g0), C0, 0, _p(g1), C1, 0, N, H, W, dil, _st())
+    gx = xr.grad
+    e_d0 = _rel(g0.float().permute(0, 3, 1, 2), gx[:, :C0])
+    e_d1 = _rel(g1.float().permute(0, 3, 1, 2), gx[:, C0:]) if C1 else 0.0
+    # the training path: OIHW gradient accumulated in place, deterministic split-K scratch for the wide sources
+    gw = torch.zeros(Co, C0 + C1, 3, 3, device="cuda")
+    dwp = torch.empty(9 * Co * (C0 + C1), dtype=torch.float32, device="cuda")
+    wss = torch.empty(2 * 9 * Co * (C0 + C1), dtype=torch.float32, device="cuda")
+    L.call("pp_conv3x3_wgrad_oihw", _p(dy), Co, _p(x0), C0, _p(x1), C1, _p(dwp), _p(gw), _p(wss), wss.numel(), N, H, W,
+           dil, _st())
+    e_w = _rel(gw, wr.grad)
+    # the forward variant the training step launches: BatchNorm batch statistics in the epilogue, two groups
+    reps = L.cdll.pp_stat_replicas()
+    G = 2
+    stats = torch.zeros(reps * G * Co * 2, dtype=torch.float64, device="cuda")
+    y2 = torch.empty_like(y)
+    L.call("pp_conv3x3_bn_stats", _p(x0), C0, _p(x1), C1, _p(wf), _p(b_d), _p(y2), Co, _p(stats), G, N, H, W, dil, _st())
+    assert torch.equal(y2, y)
+    st = stats.view(reps, G, Co, 2).sum(0).cpu()
+    yq = y.float().cpu().view(G, -1, Co).double()
+    e_s = max(_rel(st[:, :, 0], yq.sum(1)), _rel(st[:, :, 1], (yq * yq).sum(1)))
+    print("full-tile case %s: fwd %.2e dgrad %.2e / %.2e wgrad %.2e stats %.2e" % (case, e_fwd, e_d0, e_d1, e_w, e_s))
+    assert e_fwd < 3e-3 and e_d0 < 3e-3 and e_d1 < 3e-3 and e_w < 5e-4 and e_s < 1e-5, (case, e_fwd, e_d0, e_d1, e_w, e_s)
+
+
 @pytest.mark.parametrize("case", [(2, 16, 16, 64, 0, 128, 1), (1, 16, 128, 32, 0, 32, 1), (1, 8, 256, 64, 32, 32, 1)])
 def test_conv3x3_bias_pointer_alignment(pp, case):
     """The C ABI accepts any 4-byte aligned bias pointer (parameters re-homed as views of a flat buffer need not be
