@@ -144,6 +144,21 @@ int pp_bn_apply(int dtype, const void* y, const float* coef, void* a, int G, lon
 int pp_bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* bsums, float* bcoef,
               float* dgamma, float* dbeta, float* dbias, void* dy, int G, long long Pg, int C, int training,
               float slope, void* stream);
+/* Eval-mode BatchNorm (running statistics; the reference's steady state: train_chaos.py:370 calls model.eval() for
+ * validation and never model.train() again) folded into the bf16 convolution (unet.py:188-190):
+ *   pp_bn_eval_coef:     coef[4*C] = scale | shift | beta | 1/gamma, scale = gamma / sqrt(running_var + eps),
+ *                        shift = beta + (conv_bias - running_mean) * scale  (conv_bias may be NULL)
+ *   pp_conv3x3_bn_eval:  a = LeakyReLU(conv3x3(x0 ++ x1, wpack) * scale + shift) written as the bf16 NHWC activation —
+ *                        no pre-BatchNorm tensor, no separate normalisation pass (coef must be 16-byte aligned)
+ *   pp_bn_bwd_eval:      backward of BatchNorm + LeakyReLU from the saved ACTIVATION in one pass:
+ *                        dy = da * lrelu'(a) * scale; dgamma += sum dz * xhat, dbeta += sum dz, dbias += scale * sum dz
+ *                        with xhat = (lrelu^-1(a) - beta) / gamma. sums: 2*C doubles + 16 bytes, zeroed by the caller. */
+int pp_bn_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                    const float* conv_bias, float* coef, int C, float eps, void* stream);
+int pp_conv3x3_bn_eval(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* coef, void* a,
+                       int Cout, float slope, int N, int H, int W, int dil, void* stream);
+int pp_bn_bwd_eval(int dtype, const void* da, const void* a, const float* coef, double* sums, float* dgamma,
+                   float* dbeta, float* dbias, void* dy, long long P, int C, float slope, void* stream);
 /* nn.Dropout2d of the aux path (aux_path_memory.py:23,31), forward and backward: y[n,p,c] = x[n,p,c] *
  * scale[n*ld + c] on NHWC tensors [N][HW][C]; scale holds 0 or 1/(1-p) per (sample, channel); y may alias x. */
 int pp_channel_scale(int dtype, const void* x, const float* scale, void* y, int N, int HW, int C, int ld,

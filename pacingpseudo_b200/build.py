@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_obj")
 LIB_PATH = os.path.join(HERE, "libpacingpseudo_b200.so")
-SOURCES = ["common.cu", "conv_tc.cu", "conv_halo.cu", "conv_simt.cu", "ops.cu", "loss.cu", "unet_plan.cu", "capi.cu"]
+SOURCES = ["common.cu", "conv_tc.cu", "conv_halo.cu", "conv_rows.cu", "conv_simt.cu", "ops.cu", "loss.cu", "unet_plan.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -158,6 +158,20 @@ int pp_bn_bwd(int dtype, const void* da, const void* y, const float* coef, doubl
               float slope, void* stream) {
   return bn_bwd(dtype, da, y, coef, bsums, bcoef, dgamma, dbeta, dbias, dy, G, Pg, C, training, slope, ST(stream));
 }
+int pp_bn_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                    const float* conv_bias, float* coef, int C, float eps, void* stream) {
+  return bn_eval_coef_multi(1, &gamma, &beta, &running_mean, &running_var, &conv_bias, &coef, &C, eps, ST(stream));
+}
+int pp_conv3x3_bn_eval(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* coef, void* a,
+                       int Cout, float slope, int N, int H, int W, int dil, void* stream) {
+  PP_REQUIRE(coef != nullptr, "pp_conv3x3_bn_eval: null coefficients");
+  const ConvAffine af{coef, coef + Cout, slope};
+  return conv3x3_tc(x0, C0, x1, C1, wpack, nullptr, a, Cout, 0, nullptr, 0, 0, N, H, W, dil, ST(stream), nullptr, 1, &af);
+}
+int pp_bn_bwd_eval(int dtype, const void* da, const void* a, const float* coef, double* sums, float* dgamma,
+                   float* dbeta, float* dbias, void* dy, long long P, int C, float slope, void* stream) {
+  return bn_bwd_eval(dtype, da, a, coef, sums, dgamma, dbeta, dbias, dy, P, C, slope, ST(stream));
+}
 int pp_channel_scale(int dtype, const void* x, const float* scale, void* y, int N, int HW, int C, int ld,
                      void* stream) {
   return channel_scale(dtype, x, scale, y, N, HW, C, ld, ST(stream));

@@ -17,6 +17,7 @@
 // Same semantics as conv3x3_tc (two concat sources, two dgrad destinations with accumulate flags, bias, fused
 // BatchNorm statistics). Reference call site: nn.Conv2d in /root/reference/models/unet.py:188.
 #include "pp_common.cuh"
+#include "pp_ops.h"
 
 namespace pp {
 
@@ -38,6 +39,9 @@ struct HaloParams {
   int imgs_per_group, groups;
   int chunk_bytes;             // bytes of one ring chunk (kBoxW rows, rounded up to 1 KB)
   int ring;                    // ring slots in use (4..kMaxRing)
+  const float* ep_scale;       // optional eval-mode BatchNorm + LeakyReLU epilogue: out = lrelu(acc * scale + shift)
+  const float* ep_shift;
+  float ep_slope;
 };
 
 template <int BLOCK_N, int BK>
@@ -213,6 +217,18 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
             for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + c + j);
           }
         }
+        if (p.ep_scale != nullptr) {   // eval-mode BatchNorm + LeakyReLU on the fp32 accumulator
+          const float4* s4 = reinterpret_cast<const float4*>(p.ep_scale + c);
+          const float4* h4 = reinterpret_cast<const float4*>(p.ep_shift + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 sv = __ldg(s4 + j), hv = __ldg(h4 + j);
+            f[4 * j] = lrelu(fmaf(f[4 * j], sv.x, hv.x), p.ep_slope);
+            f[4 * j + 1] = lrelu(fmaf(f[4 * j + 1], sv.y, hv.y), p.ep_slope);
+            f[4 * j + 2] = lrelu(fmaf(f[4 * j + 2], sv.z, hv.z), p.ep_slope);
+            f[4 * j + 3] = lrelu(fmaf(f[4 * j + 3], sv.w, hv.w), p.ep_slope);
+          }
+        }
         if (col_ok) {
           __nv_bfloat16* o = dst + pix * dstc + ch;
 #pragma unroll
@@ -337,7 +353,7 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
 
 int conv3x3_halo_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
                     int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, cudaStream_t stream,
-                    double* stats, int groups) {
+                    double* stats, int groups, const ConvAffine* affine) {
   const int cout = outc0 + outc1, ctot = C0 + C1;
   const int bk = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
   HaloParams p{};
@@ -358,6 +374,7 @@ int conv3x3_halo_tc(const void* x0, int C0, const void* x1, int C1, const void* 
   p.out0 = static_cast<__nv_bfloat16*>(out0); p.out1 = static_cast<__nv_bfloat16*>(out1);
   p.outc0 = outc0; p.outc1 = outc1; p.acc0 = acc0; p.acc1 = acc1; p.bias = bias;
   p.stats = stats;
+  if (affine != nullptr) { p.ep_scale = affine->scale; p.ep_shift = affine->shift; p.ep_slope = affine->slope; }
   p.groups = groups > 0 ? groups : 1;
   p.imgs_per_group = N / p.groups;
   p.chunk_bytes = halo_chunk_bytes(bk);

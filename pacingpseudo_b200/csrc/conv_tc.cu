@@ -22,6 +22,7 @@
 //       66-pixel row boxes per K block and realises the horizontal taps as descriptor row offsets.
 //
 #include "pp_common.cuh"
+#include "pp_ops.h"
 
 namespace pp {
 
@@ -47,6 +48,9 @@ struct ConvTcParams {
   const float* bias;           // [outc0 + outc1] or null
   double* stats;               // optional [kStatReplicas][groups][cout][2] (sum, sum of squares) of the rounded output
   int imgs_per_group, groups;  // images per BatchNorm statistics group / number of groups (stats != null)
+  const float* ep_scale;       // optional eval-mode BatchNorm + LeakyReLU epilogue: out = lrelu(acc * scale + shift)
+  const float* ep_shift;
+  float ep_slope;
 };
 
 // MT = consecutive 128-pixel M tiles per CTA (1, 2 or 4), each with its own TMEM accumulator; they share every weight
@@ -208,6 +212,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col + j);
           }
         }
+        if (p.ep_scale != nullptr) {   // eval-mode BatchNorm + LeakyReLU on the fp32 accumulator (16-byte aligned arrays)
+          const float4* s4 = reinterpret_cast<const float4*>(p.ep_scale + col);
+          const float4* h4 = reinterpret_cast<const float4*>(p.ep_shift + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sv = __ldg(s4 + j), hv = __ldg(h4 + j);
+            f[4 * j] = lrelu(fmaf(f[4 * j], sv.x, hv.x), p.ep_slope);
+            f[4 * j + 1] = lrelu(fmaf(f[4 * j + 1], sv.y, hv.y), p.ep_slope);
+            f[4 * j + 2] = lrelu(fmaf(f[4 * j + 2], sv.z, hv.z), p.ep_slope);
+            f[4 * j + 3] = lrelu(fmaf(f[4 * j + 3], sv.w, hv.w), p.ep_slope);
+          }
+        }
         if (valid) {
           __nv_bfloat16* o = dst + pix * dstc + ch;
 #pragma unroll
@@ -278,7 +294,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 bool conv3x3_halo_applicable(int C0, int C1, int cout, int outc0, int outc1, int H, int W, int dil);
 int conv3x3_halo_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
                     int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, cudaStream_t stream,
-                    double* stats, int groups);
+                    double* stats, int groups, const ConvAffine* affine);
+
+bool conv3x3_rows_applicable(int C0, int C1, int cout, int N, int H, int W, int dil);
+int conv3x3_rows_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
+                    int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil,
+                    cudaStream_t stream, double* stats, int groups, const ConvAffine* affine);
 
 // ----------------------------------------------------------------------------------------------
 // wgrad
@@ -864,8 +885,15 @@ static void conv_tc_pick_tile(int cout, int ktot, int bk, int m_tiles, int* bloc
 // x0:[N,H,W,C0] x1:[N,H,W,C1] (or null), wpack:[9][outc0+outc1][C0+C1] bf16.
 int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
                int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil,
-               cudaStream_t stream, double* stats, int groups) {
+               cudaStream_t stream, double* stats, int groups, const ConvAffine* affine) {
   const int cout = outc0 + outc1;
+  if (affine != nullptr && affine->scale == nullptr) affine = nullptr;
+  if (affine != nullptr)
+    PP_REQUIRE(affine->shift != nullptr && bias == nullptr && stats == nullptr && outc1 == 0 && acc0 == 0 &&
+                   (reinterpret_cast<uintptr_t>(affine->scale) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(affine->shift) & 15) == 0,
+               "conv3x3_tc: the affine epilogue needs 16-byte aligned scale/shift, one destination, no bias / "
+               "statistics / accumulation");
   const int ctot = C0 + C1;
   PP_REQUIRE(N > 0 && H > 0 && W > 0 && dil >= 1, "conv3x3_tc: bad shape N=%d H=%d W=%d dil=%d", N, H, W, dil);
   PP_REQUIRE(C0 % 32 == 0 && C1 % 32 == 0 && C0 > 0, "conv3x3_tc: input channels must be multiples of 32 (C0=%d C1=%d)",
@@ -874,9 +902,13 @@ int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack
   PP_REQUIRE((out1 == nullptr) == (outc1 == 0), "conv3x3_tc: out1/outc1 mismatch");
   PP_REQUIRE(outc0 % 32 == 0 && outc1 % 32 == 0, "conv3x3_tc: output channels must be multiples of 32 (outc0=%d outc1=%d)",
              outc0, outc1);
+  if (!conv3x3_halo_applicable(C0, C1, cout, outc0, outc1, H, W, dil) &&
+      conv3x3_rows_applicable(C0, C1, cout, N, H, W, dil))                // wide layers: smem-resident im2col (conv_rows.cu)
+    return conv3x3_rows_tc(x0, C0, x1, C1, wpack, bias, out0, outc0, acc0, out1, outc1, acc1, N, H, W, dil, stream, stats,
+                           groups, affine);
   if (conv3x3_halo_applicable(C0, C1, cout, outc0, outc1, H, W, dil))   // narrow high-resolution layers
     return conv3x3_halo_tc(x0, C0, x1, C1, wpack, bias, out0, outc0, acc0, out1, outc1, acc1, N, H, W, stream, stats,
-                           groups);
+                           groups, affine);
   const int bk = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
   ConvTcParams p{};
   p.N = N; p.H = H; p.W = W; p.dil = dil;
@@ -899,6 +931,7 @@ int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack
   p.kc0 = C0 / bk; p.kc1 = C1 / bk; p.ctot = ctot; p.c0 = C0;
   p.out0 = static_cast<__nv_bfloat16*>(out0); p.out1 = static_cast<__nv_bfloat16*>(out1);
   p.outc0 = outc0; p.outc1 = outc1; p.acc0 = acc0; p.acc1 = acc1; p.bias = bias;
+  if (affine != nullptr) { p.ep_scale = affine->scale; p.ep_shift = affine->shift; p.ep_slope = affine->slope; }
 
   CUtensorMap a0, a1, b;
   int rc = encode_tmap_nhwc(&a0, x0, N, H, W, C0, bk, p.bw, p.bh, p.bn, bk == 64);

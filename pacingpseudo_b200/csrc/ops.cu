@@ -6,6 +6,7 @@
 //   Adam. Reference call sites: /root/reference/models/unet.py:60,109,144,188-193,
 //   /root/reference/models/aux_path_memory.py:22-33,52 and /root/reference/train_chaos.py:219.
 #include "pp_common.cuh"
+#include "pp_ops.h"
 #include <stdlib.h>
 
 namespace pp {
@@ -179,16 +180,17 @@ int unpack_wgrad(const float* dwp, float* g, int Cout, int Cin, int accumulate, 
 template <typename T>
 __global__ void __launch_bounds__(256) first_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, T* __restrict__ y, int N,
-                                                             int H, int W, int Cout) {
+                                                             int H, int W, int Cout, const ConvAffine af) {
   const int vecs = Cout / 8;                 // power of two, <= 32 (checked by the launcher)
   const int v = threadIdx.x % vecs;
   const int ppb = 256 / vecs;                // pixels per block iteration
   float wr[8][9], br[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    br[j] = bias ? bias[v * 8 + j] : 0.f;
+  for (int j = 0; j < 8; ++j) {   // eval-mode BatchNorm folded in: the per-channel scale goes into the weights
+    const float sc = af.scale ? af.scale[v * 8 + j] : 1.f;
+    br[j] = af.scale ? af.shift[v * 8 + j] : (bias ? bias[v * 8 + j] : 0.f);
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wr[j][t] = w[(v * 8 + j) * 9 + t];
+    for (int t = 0; t < 9; ++t) wr[j][t] = w[(v * 8 + j) * 9 + t] * sc;
   }
   const int P = N * H * W;
   for (int p = blockIdx.x * ppb + threadIdx.x / vecs; p < P; p += gridDim.x * ppb) {
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(256) first_conv_fwd_kernel(const float* __rest
       float a = br[j];
 #pragma unroll
       for (int t = 0; t < 9; ++t) a = fmaf(xin[t], wr[j][t], a);
-      o[j] = a;
+      o[j] = af.scale ? lrelu(a, af.slope) : a;
     }
     Vec8<T> pk;
     pk.set(o);
@@ -220,16 +222,17 @@ __global__ void __launch_bounds__(256) first_conv_fwd_kernel(const float* __rest
 template <typename T>
 __global__ void __launch_bounds__(256, 2) first_conv_fwd_run4_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                   const float* __restrict__ bias, T* __restrict__ y,
-                                                                  int N, int H, int W, int Cout) {
+                                                                  int N, int H, int W, int Cout, const ConvAffine af) {
   const int vecs = Cout / 8;
   const int v = threadIdx.x % vecs;
   const int rpb = 256 / vecs;                // pixel runs per block iteration
   float wr[8][9], br[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    br[j] = bias ? bias[v * 8 + j] : 0.f;
+    const float sc = af.scale ? af.scale[v * 8 + j] : 1.f;
+    br[j] = af.scale ? af.shift[v * 8 + j] : (bias ? bias[v * 8 + j] : 0.f);
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wr[j][t] = w[(v * 8 + j) * 9 + t];
+    for (int t = 0; t < 9; ++t) wr[j][t] = w[(v * 8 + j) * 9 + t] * sc;
   }
   const int runs = (N * H * W) >> 2, runs_per_row = W >> 2;
   for (int r = blockIdx.x * rpb + threadIdx.x / vecs; r < runs; r += gridDim.x * rpb) {
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(256, 2) first_conv_fwd_run4_kernel(const float
         float a = br[j];
 #pragma unroll
         for (int t = 0; t < 9; ++t) a = fmaf(xin[t / 3][u + t % 3], wr[j][t], a);
-        o[j] = a;
+        o[j] = af.scale ? lrelu(a, af.slope) : a;
       }
       Vec8<T> pk;
       pk.set(o);
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(256, 2) first_conv_fwd_run4_kernel(const float
 template <typename T>
 __global__ void __launch_bounds__(256) first_conv_fwd_cin_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                  const float* __restrict__ bias, T* __restrict__ y, int N,
-                                                                 int H, int W, int Cout, int Cin) {
+                                                                 int H, int W, int Cout, int Cin, const ConvAffine af) {
   extern __shared__ float s_wc[];             // [Cout][Cin][9]
   for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) s_wc[i] = w[i];
   __syncthreads();
@@ -298,6 +301,10 @@ __global__ void __launch_bounds__(256) first_conv_fwd_cin_kernel(const float* __
 #pragma unroll
         for (int t = 0; t < 9; ++t) o[j] = fmaf(xin[t], wj[t], o[j]);
       }
+    }
+    if (af.scale) {   // shift already holds bias * scale (bias is null in this mode)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = lrelu(fmaf(o[j], af.scale[v * 8 + j], af.shift[v * 8 + j]), af.slope);
     }
     Vec8<T> pk;
     pk.set(o);
@@ -355,8 +362,13 @@ __global__ void __launch_bounds__(256) first_conv_wgrad_cin_kernel(const T* __re
 static bool pow2_vecs(int C) { return C % 8 == 0 && C <= 256 && ((C / 8) & (C / 8 - 1)) == 0; }
 
 int first_conv_fwd(int dtype, const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
-                   cudaStream_t s, int Cin) {
+                   cudaStream_t s, int Cin, const ConvAffine* affine) {
   PP_REQUIRE(pow2_vecs(Cout), "first_conv_fwd: Cout=%d unsupported (8,16,...,256)", Cout);
+  ConvAffine af{nullptr, nullptr, 0.f};
+  if (affine != nullptr && affine->scale != nullptr) {
+    PP_REQUIRE(affine->shift != nullptr && bias == nullptr, "first_conv_fwd: affine epilogue needs shift and no bias");
+    af = *affine;
+  }
   PP_REQUIRE(Cin >= 1 && Cin <= 16, "first_conv_fwd: input_ch=%d unsupported (1..16)", Cin);
   const long long P = static_cast<long long>(N) * H * W;
   PP_REQUIRE_INT32(P * Cout, "first_conv_fwd");
@@ -364,19 +376,19 @@ int first_conv_fwd(int dtype, const float* x, const float* w, const float* bias,
   if (Cin > 1) {
     PP_DISPATCH_T(dtype, (first_conv_fwd_cin_kernel<T><<<grid_for(ceil_div_ll(P, ppb) * 256, 256, 8), 256,
                                                         sizeof(float) * Cout * Cin * 9, s>>>(x, w, bias, static_cast<T*>(y),
-                                                                                             N, H, W, Cout, Cin)););
+                                                                                             N, H, W, Cout, Cin, af)););
     PP_LAUNCH_CHECK();
     return PP_OK;
   }
   static const int run4_on = [] { const char* e = getenv("PP_FIRST_CONV_RUN4"); return (e && e[0] == '0') ? 0 : 1; }();
   if (run4_on && W % 4 == 0) {
     PP_DISPATCH_T(dtype, first_conv_fwd_run4_kernel<T><<<grid_for(ceil_div_ll(P / 4, ppb) * 256, 256, 8), 256, 0, s>>>(
-                             x, w, bias, static_cast<T*>(y), N, H, W, Cout););
+                             x, w, bias, static_cast<T*>(y), N, H, W, Cout, af););
     PP_LAUNCH_CHECK();
     return PP_OK;
   }
   PP_DISPATCH_T(dtype, first_conv_fwd_kernel<T><<<grid_for(ceil_div_ll(P, ppb) * 256, 256, 8), 256, 0, s>>>(
-                           x, w, bias, static_cast<T*>(y), N, H, W, Cout););
+                           x, w, bias, static_cast<T*>(y), N, H, W, Cout, af););
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -1053,6 +1065,150 @@ int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* 
                                                                 coef, bsums, static_cast<T*>(dy), dgamma, dbeta, dbias,
                                                                 G, int(Pg), C, achunk, acpg, training, slope););
   PP_LAUNCH_CHECK_N(2);
+  return PP_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Eval-mode BatchNorm folded into the convolutions (bf16 path; the reference's steady state: train_chaos.py:370 puts the
+// model in .eval() for validation and never leaves it). Forward: the conv epilogues apply
+// lrelu(acc * scale + shift) and write the activation directly (no pre-BN tensor, no finalize / apply pass).
+// ----------------------------------------------------------------------------------------------
+struct EvalCoefTable {
+  static constexpr int kMax = 48;
+  const float* gamma[kMax];
+  const float* beta[kMax];
+  const float* rmean[kMax];
+  const float* rvar[kMax];
+  const float* bias[kMax];
+  float* coef[kMax];
+  int C[kMax];
+  int n;
+};
+// coef = [scale | shift | beta | 1/gamma], C floats each; grid.x = layer
+__global__ void __launch_bounds__(256) bn_eval_coef_multi_kernel(const __grid_constant__ EvalCoefTable tb, float eps) {
+  const int l = blockIdx.x;
+  const int C = tb.C[l];
+  float* cf = tb.coef[l];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = tb.gamma[l][c], b = tb.beta[l][c];
+    const float sc = g * (1.f / sqrtf(tb.rvar[l][c] + eps));
+    const float bias = tb.bias[l] != nullptr ? tb.bias[l][c] : 0.f;
+    cf[c] = sc;
+    cf[C + c] = b + (bias - tb.rmean[l][c]) * sc;
+    cf[2 * C + c] = b;
+    cf[3 * C + c] = g != 0.f ? 1.f / g : 0.f;   // gamma == 0: xhat is not recoverable from the activation (dgamma term 0)
+  }
+}
+int bn_eval_coef_multi(int n, const float* const* gamma, const float* const* beta, const float* const* rmean,
+                       const float* const* rvar, const float* const* bias, float* const* coef, const int* C, float eps,
+                       cudaStream_t s) {
+  for (int i0 = 0; i0 < n; i0 += EvalCoefTable::kMax) {
+    EvalCoefTable tb{};
+    tb.n = n - i0 < EvalCoefTable::kMax ? n - i0 : EvalCoefTable::kMax;
+    for (int i = 0; i < tb.n; ++i) {
+      tb.gamma[i] = gamma[i0 + i]; tb.beta[i] = beta[i0 + i]; tb.rmean[i] = rmean[i0 + i]; tb.rvar[i] = rvar[i0 + i];
+      tb.bias[i] = bias[i0 + i]; tb.coef[i] = coef[i0 + i]; tb.C[i] = C[i0 + i];
+    }
+    bn_eval_coef_multi_kernel<<<tb.n, 256, 0, s>>>(tb, eps);
+    PP_LAUNCH_CHECK();
+  }
+  return PP_OK;
+}
+
+// Backward of conv -> eval BatchNorm -> LeakyReLU from the saved ACTIVATION: one pass.
+//   dz = da * (a > 0 ? 1 : slope);  dy = dz * scale;  z = a > 0 ? a : a / slope;  xhat = (z - beta) / gamma
+//   sums[c] += (sum dz, sum dz * xhat); the last block to finish adds dgamma / dbeta / dbias (ticket counter).
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_eval_kernel(const T* __restrict__ da, const T* __restrict__ a,
+                                                                 const float* __restrict__ coef, double* sums,
+                                                                 T* __restrict__ dy, float* __restrict__ dgamma,
+                                                                 float* __restrict__ dbeta, float* __restrict__ dbias,
+                                                                 int P, int C, int chunk, float slope, float inv_slope) {
+  __shared__ float red[kBnThreads][17];
+  __shared__ unsigned int s_last;
+  constexpr int U = 4;
+  const int vecs = C / 8;
+  const int pl = kBnThreads / vecs;
+  const int v = threadIdx.x % vecs, l = threadIdx.x / vecs;
+  const int p0 = blockIdx.x * chunk;
+  const int p1 = min(p0 + chunk, P);
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+  if (l < pl) {
+    float sc[8], bt[8], ig[8];
+    const float* cf = coef + v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = cf[j]; bt[j] = cf[2 * C + j]; ig[j] = cf[3 * C + j]; }
+    const size_t base = static_cast<size_t>(v) * 8;
+    for (int pb = p0 + l; pb < p1; pb += pl * U) {
+      Vec8<T> pa[U], py[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (pb + u * pl < p1) {
+          const size_t o = base + static_cast<size_t>(pb + u * pl) * C;
+          pa[u].load(da + o);
+          py[u].load(a + o);
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pb + u * pl >= p1) break;
+        float fa[8], fy[8], o[8];
+        pa[u].get(fa);
+        py[u].get(fy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool pos = fy[j] > 0.f;
+          const float dz = pos ? fa[j] : fa[j] * slope;
+          const float z = pos ? fy[j] : fy[j] * inv_slope;
+          s[j] += dz;
+          ss[j] = fmaf(dz, (z - bt[j]) * ig[j], ss[j]);
+          o[j] = dz * sc[j];
+        }
+        pa[u].set(o);
+        pa[u].store(dy + base + static_cast<size_t>(pb + u * pl) * C);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s[j]; red[threadIdx.x][8 + j] = ss[j]; }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 2 * C; t += kBnThreads) {
+    const int c = t % C, st = t / C;
+    double acc = 0.0;
+    for (int k = 0; k < pl; ++k) acc += static_cast<double>(red[k * vecs + c / 8][st * 8 + c % 8]);
+    atomicAdd(sums + static_cast<size_t>(c) * 2 + st, acc);
+  }
+  // last block: parameter gradients from the complete sums
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(sums + 2 * static_cast<size_t>(C));
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int c = threadIdx.x; c < C; c += kBnThreads) {
+      const double sdz = __ldcg(sums + static_cast<size_t>(c) * 2), sdx = __ldcg(sums + static_cast<size_t>(c) * 2 + 1);
+      dbeta[c] += static_cast<float>(sdz);
+      dgamma[c] += static_cast<float>(sdx);
+      if (dbias != nullptr) dbias[c] += static_cast<float>(sdz * static_cast<double>(coef[c]));
+    }
+  }
+}
+
+int bn_bwd_eval(int dtype, const void* da, const void* a, const float* coef, double* sums, float* dgamma, float* dbeta,
+                float* dbias, void* dy, long long P, int C, float slope, cudaStream_t s) {
+  PP_REQUIRE(C % 8 == 0 && C / 8 <= kBnThreads && kBnThreads % (C / 8) == 0, "bn_bwd_eval: C=%d unsupported", C);
+  PP_REQUIRE(slope != 0.f, "bn_bwd_eval: a zero slope is not invertible");
+  PP_REQUIRE_INT32(P * C, "bn_bwd_eval");
+  int chunk, blocks;
+  bn_chunks(1, P, 16, &chunk, &blocks);
+  PP_DISPATCH_T(dtype, bn_bwd_eval_kernel<T><<<blocks, kBnThreads, 0, s>>>(
+                           static_cast<const T*>(da), static_cast<const T*>(a), coef, sums, static_cast<T*>(dy), dgamma,
+                           dbeta, dbias, int(P), C, chunk, slope, 1.f / slope););
+  PP_LAUNCH_CHECK();
   return PP_OK;
 }
 

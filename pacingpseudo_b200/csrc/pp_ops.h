@@ -10,10 +10,18 @@ int init_device(int device);
 const char* last_error();
 
 // ---- convolutions -------------------------------------------------------------------------------
+// Optional epilogue of the forward convolutions: eval-mode BatchNorm + LeakyReLU folded into the conv (unet.py:188-190
+// with running statistics): out = lrelu(acc * scale[c] + shift[c]); `shift` already contains bias * scale, so the
+// conv is called WITHOUT a bias. Both arrays hold Cout floats and must be 16-byte aligned.
+struct ConvAffine {
+  const float* scale;
+  const float* shift;
+  float slope;
+};
 // stats/groups (optional): fused BatchNorm partial sums [groups][cout][2] of the rounded output (caller zeroes)
 int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
                int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil, cudaStream_t s,
-               double* stats = nullptr, int groups = 1);
+               double* stats = nullptr, int groups = 1, const ConvAffine* affine = nullptr);
 // g_oihw == nullptr: packed dwp[9][Cout][C0+C1] += ; else the OIHW gradient is accumulated in place (dwp is scratch
 // for narrow sources, zeroed by the caller when conv3x3_wgrad_tc_uses_scratch())
 int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dwp,
@@ -35,7 +43,7 @@ int pack_weights_multi(int dtype, int n, const float* const* w, void* const* wf,
 int unpack_wgrad(const float* dwp, float* g, int Cout, int Cin, int accumulate, cudaStream_t s);
 // Cin > 1: x is NCHW fp32 [N][Cin][H][W] (multi-channel input, --input_ch)
 int first_conv_fwd(int dtype, const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
-                   cudaStream_t s, int Cin = 1);
+                   cudaStream_t s, int Cin = 1, const ConvAffine* affine = nullptr);
 int first_conv_wgrad(int dtype, const void* dy, const float* x, float* dw, int N, int H, int W, int Cout,
                      cudaStream_t s, int Cin = 1);
 int head_fwd(int dtype, const void* a, const float* w, const float* bias, float* logits, long long P, int HW, int Cin,
@@ -51,6 +59,17 @@ int bn_apply(int dtype, const void* y, const float* coef, void* a, int G, long l
 int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* bsums, float* bcoef, float* dgamma,
            float* dbeta, float* dbias, void* dy, int G, long long Pg, int C, int training, float slope, cudaStream_t s,
            bool sums_zeroed = false);
+// Eval-mode BatchNorm folded into the convolutions (bf16 path). coef[l] = [scale | shift | beta | 1/gamma] (4*C floats):
+//   scale = gamma / sqrt(running_var + eps), shift = beta + (bias - running_mean) * scale  (one launch for all layers)
+int bn_eval_coef_multi(int n, const float* const* gamma, const float* const* beta, const float* const* rmean,
+                       const float* const* rvar, const float* const* bias, float* const* coef, const int* C, float eps,
+                       cudaStream_t s);
+// Backward of conv -> eval-BN -> LeakyReLU given only the saved ACTIVATION a (no pre-BN tensor exists in this mode):
+//   dz = da * (a > 0 ? 1 : slope), dy = dz * scale; z = a > 0 ? a : a / slope, xhat = (z - beta) / gamma;
+//   dgamma += sum dz * xhat, dbeta += sum dz, dbias += scale * sum dz   (ONE pass; the last block folds the sums).
+// sums: 2*C doubles + one unsigned ticket (placed after them), zeroed by the caller.
+int bn_bwd_eval(int dtype, const void* da, const void* a, const float* coef, double* sums, float* dgamma, float* dbeta,
+                float* dbias, void* dy, long long P, int C, float slope, cudaStream_t s);
 int maxpool_fwd(int dtype, const void* x, void* y, int N, int H, int W, int C, cudaStream_t s);
 int maxpool_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int H, int W, int C, int accumulate,
                 cudaStream_t s);

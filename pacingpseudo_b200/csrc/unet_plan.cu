@@ -183,7 +183,8 @@ static UNetLayout make_layout(const UNetPlan& pl, int N, int H, int W, int G) {
   for (const ConvL& c : pl.convs) L.sums.push_back(take(sizeof(double) * 2 * G * c.cout * kStatReplicas));
   L.sums_bytes = off - L.sums_begin;
   L.bsums_begin = off;
-  for (const ConvL& c : pl.convs) L.bsums_layer.push_back(take(sizeof(double) * 2 * G * c.cout));
+  // (+16 bytes: the ticket counter of the one-pass eval-mode BatchNorm backward sits behind a layer's sums)
+  for (const ConvL& c : pl.convs) L.bsums_layer.push_back(take(sizeof(double) * 2 * G * c.cout + 16));
   L.bsums_bytes = off - L.bsums_begin;
   L.dy_scratch = take(max_act);
   L.dy_stride = align_up(max_act);
@@ -211,6 +212,15 @@ static int check_shape(const UNetPlan& pl, int N, int H, int W, int G) {
   PP_REQUIRE(H % div == 0 && W % div == 0 && H >= div && W >= div,
              "unet: H=%d W=%d must be multiples of %d (maxpool stages)", H, W, div);
   return PP_OK;
+}
+
+// Eval-mode BatchNorm (running statistics) on the bf16 path is folded into the convolutions: the conv epilogue writes
+// lrelu(acc * scale + shift) directly, there is no pre-BN tensor, no finalize / apply pass, and the backward pass is
+// one pass per layer from the saved activation (ops.cu: bn_eval_coef_multi, bn_bwd_eval). PP_NO_EVAL_FUSION=1 keeps the
+// unfused kernels (A/B experiments); the fp32 precision mode always uses them.
+static bool eval_fusion(const UNetPlan& pl, int training) {
+  static const int off = [] { const char* e = getenv("PP_NO_EVAL_FUSION"); return (e && e[0] == '1') ? 1 : 0; }();
+  return !training && pl.dtype == PP_BF16 && !off;
 }
 
 // internal streams / events of the overlap machinery (see UNetPlan), created on first use on the current device
@@ -275,6 +285,27 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
     if (rc) return rc;
     if (training) PP_CHECK_CUDA(cudaMemsetAsync(base + L.sums_begin, 0, L.sums_bytes, s));   // all layers' statistics
   }
+  const bool fuse_eval = eval_fusion(pl, training);
+  if (fuse_eval) {   // scale / shift of every BatchNorm layer from the running statistics, one launch
+    std::vector<const float*> g, b, rm, rv, bias;
+    std::vector<float*> cf;
+    std::vector<int> cc;
+    for (size_t l = 0; l < pl.convs.size(); ++l) {
+      const ConvL& c = pl.convs[l];
+      if (c.kind == KIND_CT) continue;
+      void* const* pp = params + l * kParamsPerConv;
+      bias.push_back(static_cast<const float*>(pp[1]));
+      g.push_back(static_cast<const float*>(pp[2]));
+      b.push_back(static_cast<const float*>(pp[3]));
+      rm.push_back(static_cast<const float*>(pp[4]));
+      rv.push_back(static_cast<const float*>(pp[5]));
+      cf.push_back(reinterpret_cast<float*>(base + L.coef[l]));
+      cc.push_back(c.cout);
+    }
+    rc = bn_eval_coef_multi(int(cc.size()), g.data(), b.data(), rm.data(), rv.data(), bias.data(), cf.data(), cc.data(),
+                            1e-5f, s);
+    if (rc) return rc;
+  }
   // Statistics groups (the weak and the strong branch of the siamese step) are independent until the losses, so
   // with overlap enabled every group runs on its own stream: the HBM-bound BatchNorm / pool / upsample kernels of one
   // branch overlap the tensor-core kernels of the other. Only the running-statistics update is ordered (weak, then
@@ -316,6 +347,22 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
           rc = dt == PP_BF16 ? conv3x3_tc(x0, c.cin0, nullptr, 0, wf, nullptr, y, c.cout, 0, nullptr, 0, 0, Np, h, w, 1, sk)
                              : conv3x3_simt(dt, x0, c.cin0, nullptr, 0, wf, nullptr, y, c.cout, 0, nullptr, 0, 0, Np, h, w,
                                             1, sk);
+          if (rc) return rc;
+          continue;
+        }
+        if (fuse_eval) {   // conv + running-statistics BatchNorm + LeakyReLU in one kernel: writes the activation
+          const float* cf = reinterpret_cast<const float*>(base + L.coef[op.layer]);
+          const ConvAffine af{cf, cf + c.cout, 0.01f};
+          void* a_out = act_part(L.act_data[c.out], ao, k);
+          if (c.in0 < 0) {
+            rc = first_conv_fwd(dt, x + static_cast<long long>(k) * Np * pl.input_ch * H * W,
+                                static_cast<const float*>(pp[0]), nullptr, a_out, Np, h, w, c.cout, sk, pl.input_ch, &af);
+          } else {
+            const void* x0 = act_part(L.act_data[c.in0], pl.acts[c.in0], k);
+            const void* x1 = c.in1 >= 0 ? act_part(L.act_data[c.in1], pl.acts[c.in1], k) : nullptr;
+            rc = conv3x3_tc(x0, c.cin0, x1, c.cin1, base + L.wf[op.layer], nullptr, a_out, c.cout, 0, nullptr, 0, 0, Np,
+                            h, w, c.dil, sk, nullptr, Gp, &af);
+          }
           if (rc) return rc;
           continue;
         }
@@ -449,6 +496,7 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
   }
 
   const bool ov = pl.overlap == 1;
+  const bool fuse_eval = eval_fusion(pl, training);
   cudaStream_t ws_ = ov ? pl.side : s;       // stream of the weight-gradient kernels
   PP_CHECK_CUDA(cudaMemsetAsync(base + L.bsums_begin, 0, L.bsums_bytes, s));   // BatchNorm-backward sums of all layers
   bool buf_used[UNetPlan::kDyBufs] = {false, false, false};
@@ -471,6 +519,12 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
       if (ov && buf_used[kb]) PP_CHECK_CUDA(cudaStreamWaitEvent(s, pl.buf_free[kb], 0));   // its last reader is done
       if (c.kind == KIND_CT) {
         dy = base + L.act_grad[c.out];   // plain layer: the activation gradient IS the conv-output gradient
+      } else if (fuse_eval) {   // one pass from the saved activation (no pre-BN tensor exists in this mode)
+        rc = bn_bwd_eval(dt, base + L.act_grad[c.out], base + L.act_data[c.out],
+                         reinterpret_cast<const float*>(base + L.coef[op.layer]),
+                         reinterpret_cast<double*>(base + L.bsums_layer[op.layer]), gg[2], gg[3], gg[1], dy,
+                         static_cast<long long>(N) * h * w, c.cout, 0.01f, s);
+        if (rc) return rc;
       } else {
         rc = bn_bwd(dt, base + L.act_grad[c.out], base + L.yraw[op.layer],
                     reinterpret_cast<const float*>(base + L.coef[op.layer]),

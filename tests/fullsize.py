@@ -207,10 +207,20 @@ def distances(rec, ref, bn_training):
         if k in ref:
             short = {"segmentation/logits": "weak", "segmentation/logits_strong": "strong", "logits_aux_cls": "aux"}[k]
             m["logits_" + short] = rel(rec[k], ref[k])
-            m["argmax_" + short] = float((rec[k].argmax(1).cpu() == ref[k].argmax(1).cpu()).float().mean())
+            same = rec[k].argmax(1).cpu() == ref[k].argmax(1).cpu()
+            m["argmax_" + short] = float(same.float().mean())
+            # pixels whose REFERENCE decision is not inside the logit tolerance band: top-2 margin > 2e-2 * max |z|
+            # (a flip inside the band is what the logit tolerance itself permits; object boundaries always hold a few
+            # 1e-4 of the pixels there, and 8x more for the aux logits, which are a bilinear x8 up-sampling)
+            top2 = ref[k].float().topk(2, dim=1).values
+            decided = (top2[:, 0] - top2[:, 1]) > 2e-2 * ref[k].abs().max()
+            m["argmax_%s_decided" % short] = float(same[decided].float().mean()) if bool(decided.any()) else 1.0
+            m["decided_frac_" + short] = float(decided.float().mean())
     for k in LOSS_KEYS + ("loss_ce", "loss_dice", "total"):
         if k in ref:
-            m[k] = abs(float(rec[k]) - float(ref[k])) / max(abs(float(ref[k])), 1e-12)
+            # relative, with the same 1e-2 floor on the loss magnitude as tests/harness.py: a trained pCE of ~1e-3
+            # carries ~1e-7 of fp32 summation noise, which is 1e-4 RELATIVE without saying anything about parity
+            m[k] = abs(float(rec[k]) - float(ref[k])) / max(abs(float(ref[k])), 1e-2)
     if "bank" in ref:
         m["bank"] = rel(rec["bank"], ref["bank"])
     g, g0 = rec["grads"], ref["grads"]

@@ -184,6 +184,54 @@ def test_conv3x3_full_tile_counts_vs_torch(pp, case):
     assert e_fwd < 3e-3 and e_d0 < 3e-3 and e_d1 < 3e-3 and e_w < 5e-4 and e_s < 1e-5, (case, e_fwd, e_d0, e_d1, e_w, e_s)
 
 
+@pytest.mark.parametrize("case", [(2, 32, 32, 64, 0, 128, 1), (2, 16, 16, 256, 256, 256, 2), (1, 8, 256, 64, 32, 32, 1),
+                                  (2, 16, 128, 32, 0, 64, 1), (3, 28, 28, 128, 0, 512, 4)])
+def test_conv_bn_eval_fused_forward_backward_vs_torch(pp, case):
+    """Eval-mode BatchNorm + LeakyReLU folded into the conv epilogue (unet.py:188-190 with running statistics), and its
+    one-pass backward from the saved activation, against torch CPU autograd of conv2d -> batch_norm(eval) ->
+    leaky_relu on the same bf16-rounded operands (generic and halo kernels, concat sources, dilation)."""
+    L, PF, pplib = pp
+    N, H, W, C0, C1, Co, dil = case
+    g = torch.Generator().manual_seed(sum(case) + 5)
+    x = torch.randn(N, C0 + C1, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(Co, C0 + C1, 3, 3, generator=g) / (3 * (C0 + C1) ** 0.5)).bfloat16().float()
+    b = 0.1 * torch.randn(Co, generator=g)
+    gamma = 1.0 + 0.3 * torch.randn(Co, generator=g)
+    beta = 0.2 * torch.randn(Co, generator=g)
+    rm = 0.1 * torch.randn(Co, generator=g)
+    rv = 0.5 + torch.rand(Co, generator=g)
+    ga = torch.randn(N, Co, H, W, generator=g).bfloat16().float()
+    gam_r, bet_r, b_r = gamma.clone().requires_grad_(), beta.clone().requires_grad_(), b.clone().requires_grad_()
+    y = F.conv2d(x, w, b_r, 1, dil, dil)
+    a_ref = F.leaky_relu(F.batch_norm(y, rm, rv, gam_r, bet_r, False, 0.1, 1e-5), 0.01)
+    y.retain_grad()
+    a_ref.backward(ga)
+    code, adt = PF.BF16, torch.bfloat16
+    wf = torch.empty(9 * Co * (C0 + C1) * 2, dtype=torch.uint8, device="cuda")
+    wd = torch.empty_like(wf)
+    w_d = w.cuda()
+    L.call("pp_pack_weights", code, _p(w_d), _p(wf), _p(wd), Co, C0 + C1, _st())
+    coef = torch.empty(4 * Co, device="cuda")
+    g_d, be_d, rm_d, rv_d, b_d = gamma.cuda(), beta.cuda(), rm.cuda(), rv.cuda(), b.cuda()   # keep the buffers alive
+    L.call("pp_bn_eval_coef", _p(g_d), _p(be_d), _p(rm_d), _p(rv_d), _p(b_d), _p(coef), Co, 1e-5, _st())
+    x0 = _nhwc(x[:, :C0], adt)
+    x1 = _nhwc(x[:, C0:], adt) if C1 else None
+    a = torch.empty(N, H, W, Co, dtype=adt, device="cuda")
+    L.call("pp_conv3x3_bn_eval", _p(x0), C0, _p(x1), C1, _p(wf), _p(coef), _p(a), Co, 0.01, N, H, W, dil, _st())
+    assert _rel(a.float().permute(0, 3, 1, 2), a_ref.detach()) < 3e-3
+    # backward from the activation the oracle produced (rounded to bf16), so both sides see the same LeakyReLU mask
+    a_in = _nhwc(a_ref.detach(), adt)
+    da = _nhwc(ga, adt)
+    sums = torch.zeros(2 * Co + 2, dtype=torch.float64, device="cuda")
+    dgam, dbet, dbias = (torch.zeros(Co, device="cuda") for _ in range(3))
+    dy = torch.empty_like(da)
+    L.call("pp_bn_bwd_eval", code, _p(da), _p(a_in), _p(coef), _p(sums), _p(dgam), _p(dbet), _p(dbias), _p(dy),
+           N * H * W, Co, 0.01, _st())
+    assert _rel(dy.float().permute(0, 3, 1, 2), y.grad) < 3e-3
+    assert _rel(dbet, bet_r.grad) < 1e-4 and _rel(dbias, b_r.grad) < 1e-4
+    assert _rel(dgam, gam_r.grad) < 5e-3    # xhat is recovered from the bf16 activation
+
+
 @pytest.mark.parametrize("case", [(2, 16, 16, 64, 0, 128, 1), (1, 16, 128, 32, 0, 32, 1), (1, 8, 256, 64, 32, 32, 1)])
 def test_conv3x3_bias_pointer_alignment(pp, case):
     """The C ABI accepts any 4-byte aligned bias pointer (parameters re-homed as views of a flat buffer need not be
