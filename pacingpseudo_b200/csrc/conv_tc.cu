@@ -21,6 +21,10 @@
 //   wgrad (32/64-channel sources) :  taps packed into the MMA M dimension; the row variant fetches X as three
 //       66-pixel row boxes per K block and realises the horizontal taps as descriptor row offsets.
 //
+#include <array>
+#include <map>
+#include <mutex>
+
 #include "pp_common.cuh"
 #include "pp_ops.h"
 
@@ -295,11 +299,6 @@ bool conv3x3_halo_applicable(int C0, int C1, int cout, int outc0, int outc1, int
 int conv3x3_halo_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
                     int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, cudaStream_t stream,
                     double* stats, int groups, const ConvAffine* affine);
-
-bool conv3x3_rows_applicable(int C0, int C1, int cout, int N, int H, int W, int dil);
-int conv3x3_rows_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
-                    int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil,
-                    cudaStream_t stream, double* stats, int groups, const ConvAffine* affine);
 
 // ----------------------------------------------------------------------------------------------
 // wgrad
@@ -882,6 +881,123 @@ static void conv_tc_pick_tile(int cout, int ktot, int bk, int m_tiles, int* bloc
   }
 }
 
+static int conv3x3_generic(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias,
+                           void* out0, int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil,
+                           cudaStream_t stream, double* stats, int groups, const ConvAffine* affine);
+
+// ----------------------------------------------------------------------------------------------
+// Kernel choice for the wide layers. Candidates: the generic per-tap TMA kernel above (its own (BLOCK_N, MT) model)
+// and the best few tilings of the shared-memory-resident kernel (conv_rows.cu: single CTA / CTA pair, BLOCK_N, MT).
+// No closed-form model ranks them reliably across the UNet's shapes (wave quantisation against 148 SMs, pad-column
+// waste, shared-memory operand bandwidth and L2 traffic all move with the shape), so the FIRST call with a new shape
+// measures them — cuDNN's "benchmark" mode: each candidate runs the real convolution into the caller's buffers (same
+// result every time, BatchNorm statistics switched off for the trial runs), timed with CUDA events on the caller's
+// stream, ONE stream synchronisation per new shape (documented exception to "never syncs", like pp_init). The winner is
+// cached per (shape, epilogue kind). Launches that ACCUMULATE into their destination cannot be repeated and launches
+// inside a CUDA-graph capture cannot be timed: they use the cached winner of the same shape if there is one, else the
+// cost models. PP_CONV_AUTOTUNE=0 uses the models only; PP_CONV_TUNE_DEBUG=1 prints the trials.
+// ----------------------------------------------------------------------------------------------
+struct ConvChoice {
+  bool rows = false;
+  RowsPlan plan{};
+};
+
+static double generic_model_cost(int N, int H, int W, int C0, int C1, int cout) {
+  int bw, bh, bn;
+  pixel_box(W, H, 128, &bw, &bh, &bn);
+  const int m_tiles = ceil_div(W, bw) * ceil_div(H, bh) * ceil_div(N, bn);
+  const int ktot = C0 + C1, bk = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
+  int block_n, mt;
+  conv_tc_pick_tile(cout, ktot, bk, m_tiles, &block_n, &mt);
+  const double ctas = static_cast<double>(ceil_div(m_tiles, mt)) * (cout / block_n);
+  const int per_sm = (block_n <= 96 && mt == 1) ? 2 : 1;
+  const double waves = ceil(ctas / (sm_count() * per_sm));
+  const double n_mma = static_cast<double>(mt) * 9.0 * ktot / 16.0;
+  const double mma = n_mma * block_n / 2.0;
+  const double tma_bytes = 9.0 * ktot * 2.0 * (128.0 * mt + block_n);
+  const double smem_cyc = (n_mma * (4096.0 + 32.0 * block_n) + tma_bytes) / 120.0;
+  const double l2 = tma_bytes / 40.0;
+  double body = mma > smem_cyc ? mma : smem_cyc;
+  if (l2 > body) body = l2;
+  return waves * (body * per_sm + 6000.0 + mt * ((block_n + 63) / 64) * 450.0 * per_sm);
+}
+
+static int conv_choose(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
+                       int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil,
+                       cudaStream_t stream, double* stats, int groups, const ConvAffine* affine, ConvChoice* choice) {
+  static std::mutex mu;
+  static std::map<std::array<int, 9>, ConvChoice> cache;
+  static const int autotune = [] { const char* e = getenv("PP_CONV_AUTOTUNE"); return (e && e[0] == '0') ? 0 : 1; }();
+  static const int debug = [] { const char* e = getenv("PP_CONV_TUNE_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
+  const int cout = outc0 + outc1;
+  const std::array<int, 9> key = {N, H, W, C0, C1, outc0, outc1, dil,
+                                  (bias != nullptr ? 1 : 0) | (stats != nullptr ? 2 : 0) | (affine != nullptr ? 4 : 0)};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *choice = it->second; return PP_OK; }
+  }
+  RowsPlan plans[6];
+  const int np = conv3x3_rows_plans(N, H, W, dil, C0, C1, cout, plans, 6);
+  ConvChoice best;
+  if (np == 0) { *choice = best; return PP_OK; }
+  static const int force = [] {   // PP_CONV_FORCE=rows | generic: profiling / A-B runs
+    const char* e = getenv("PP_CONV_FORCE");
+    return e == nullptr ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'g' ? 2 : 0));
+  }();
+  if (force) {
+    if (force == 1) { best.rows = true; best.plan = plans[0]; }
+    *choice = best;
+    return PP_OK;
+  }
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &cap);
+  const bool can_time = autotune && acc0 == 0 && acc1 == 0 && cap == cudaStreamCaptureStatusNone;
+  if (!can_time) {   // cost models only; not cached, a later repeatable launch of the same shape may still measure
+    if (plans[0].cost < generic_model_cost(N, H, W, C0, C1, cout)) { best.rows = true; best.plan = plans[0]; }
+    *choice = best;
+    return PP_OK;
+  }
+  cudaEvent_t e0, e1;
+  PP_CHECK_CUDA(cudaEventCreate(&e0));
+  PP_CHECK_CUDA(cudaEventCreate(&e1));
+  float best_ms = 1e30f;
+  for (int c = -1; c < np; ++c) {   // -1: the generic kernel
+    int rc = PP_OK;
+    for (int it = 0; it < 4 && rc == PP_OK; ++it) {   // one warm-up + three timed launches
+      if (it == 1) cudaEventRecord(e0, stream);
+      rc = c < 0 ? conv3x3_generic(x0, C0, x1, C1, wpack, bias, out0, outc0, 0, out1, outc1, 0, N, H, W, dil, stream, nullptr,
+                                   groups, affine)
+                 : conv3x3_rows_tc(x0, C0, x1, C1, wpack, bias, out0, outc0, 0, out1, outc1, 0, N, H, W, dil, stream, nullptr,
+                                   groups, affine, &plans[c]);
+    }
+    if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    cudaEventRecord(e1, stream);
+    PP_CHECK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (debug) {
+      if (c < 0) fprintf(stderr, "conv tune N=%d %dx%d C=%d+%d->%d+%d dil=%d: generic %.1f us\n", N, H, W, C0, C1, outc0, outc1,
+                         dil, ms / 3 * 1e3);
+      else fprintf(stderr, "   rows BLOCK_N=%d BK=%d MT=%d PAIR=%d R=%d: %.1f us (model %.0f)\n", plans[c].block_n, plans[c].bk,
+                   plans[c].mt, plans[c].pair, plans[c].R, ms / 3 * 1e3, plans[c].cost);
+    }
+    if (ms < best_ms) {
+      best_ms = ms;
+      best.rows = c >= 0;
+      if (c >= 0) best.plan = plans[c];
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    cache[key] = best;
+  }
+  *choice = best;
+  return PP_OK;
+}
+
 // x0:[N,H,W,C0] x1:[N,H,W,C1] (or null), wpack:[9][outc0+outc1][C0+C1] bf16.
 int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
                int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil,
@@ -902,13 +1018,26 @@ int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack
   PP_REQUIRE((out1 == nullptr) == (outc1 == 0), "conv3x3_tc: out1/outc1 mismatch");
   PP_REQUIRE(outc0 % 32 == 0 && outc1 % 32 == 0, "conv3x3_tc: output channels must be multiples of 32 (outc0=%d outc1=%d)",
              outc0, outc1);
-  if (!conv3x3_halo_applicable(C0, C1, cout, outc0, outc1, H, W, dil) &&
-      conv3x3_rows_applicable(C0, C1, cout, N, H, W, dil))                // wide layers: smem-resident im2col (conv_rows.cu)
-    return conv3x3_rows_tc(x0, C0, x1, C1, wpack, bias, out0, outc0, acc0, out1, outc1, acc1, N, H, W, dil, stream, stats,
-                           groups, affine);
   if (conv3x3_halo_applicable(C0, C1, cout, outc0, outc1, H, W, dil))   // narrow high-resolution layers
     return conv3x3_halo_tc(x0, C0, x1, C1, wpack, bias, out0, outc0, acc0, out1, outc1, acc1, N, H, W, stream, stats,
                            groups, affine);
+  if (conv3x3_rows_applicable(C0, C1, cout, N, H, W, dil)) {            // wide layers: generic kernel or conv_rows.cu
+    ConvChoice ch;
+    int rc = conv_choose(x0, C0, x1, C1, wpack, bias, out0, outc0, acc0, out1, outc1, acc1, N, H, W, dil, stream, stats,
+                         groups, affine, &ch);
+    if (rc) return rc;
+    if (ch.rows)
+      return conv3x3_rows_tc(x0, C0, x1, C1, wpack, bias, out0, outc0, acc0, out1, outc1, acc1, N, H, W, dil, stream,
+                             stats, groups, affine, &ch.plan);
+  }
+  return conv3x3_generic(x0, C0, x1, C1, wpack, bias, out0, outc0, acc0, out1, outc1, acc1, N, H, W, dil, stream, stats,
+                         groups, affine);
+}
+
+static int conv3x3_generic(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias,
+                           void* out0, int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil,
+                           cudaStream_t stream, double* stats, int groups, const ConvAffine* affine) {
+  const int cout = outc0 + outc1, ctot = C0 + C1;
   const int bk = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
   ConvTcParams p{};
   p.N = N; p.H = H; p.W = W; p.dil = dil;

@@ -22,6 +22,16 @@ struct ConvAffine {
 int conv3x3_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
                int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil, cudaStream_t s,
                double* stats = nullptr, int groups = 1, const ConvAffine* affine = nullptr);
+// conv_rows.cu (wide layers, shared-memory-resident im2col, optional CTA pairs): candidate tilings and the launcher
+struct RowsPlan {
+  int block_n, bk, mt, pair, R, rbox, a_bytes, nb, smem;
+  double cost;
+};
+int conv3x3_rows_plans(int N, int H, int W, int dil, int C0, int C1, int cout, RowsPlan* out, int max_out);
+bool conv3x3_rows_applicable(int C0, int C1, int cout, int N, int H, int W, int dil);
+int conv3x3_rows_tc(const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias, void* out0,
+                    int outc0, int acc0, void* out1, int outc1, int acc1, int N, int H, int W, int dil, cudaStream_t s,
+                    double* stats, int groups, const ConvAffine* affine, const RowsPlan* plan = nullptr);
 // g_oihw == nullptr: packed dwp[9][Cout][C0+C1] += ; else the OIHW gradient is accumulated in place (dwp is scratch
 // for narrow sources, zeroed by the caller when conv3x3_wgrad_tc_uses_scratch())
 int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dwp,
