@@ -854,23 +854,29 @@ int bn_finalize(const double* sums, const float* gamma, const float* beta, float
 
 // a = lrelu(y * scale + shift). Blocks own (group, pixel chunk); a thread keeps one 8-channel vector's
 // coefficients in registers and streams pixels with four independent 16-byte loads in flight.
+// Wide layers are split into channel SLABS of at most kBnSlabVecs 8-channel vectors (grid.y): with C = 512 one block row
+// of 64 vectors would leave only 2 pixel lanes per 128-thread block and a few hundred threads per SM — these kernels sit
+// on the critical chain between the convolutions, so their latency at the 32 x 32 stages matters as much as bandwidth.
+static constexpr int kBnSlabVecs = 16;
+static inline int bn_slab_vecs(int C) { return C / 8 < kBnSlabVecs ? C / 8 : kBnSlabVecs; }
+
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ coef,
                                                        T* __restrict__ a, int Pg, int C, int chunk,
-                                                       int chunks_per_group, float slope) {
+                                                       int chunks_per_group, float slope, int vecs) {
   constexpr int U = 4;
-  const int vecs = C / 8;
   const int pl = kBnThreads / vecs;
   const int v = threadIdx.x % vecs, l = threadIdx.x / vecs;
+  const int c0 = blockIdx.y * vecs * 8 + v * 8;   // first channel of this thread
   const int g = blockIdx.x / chunks_per_group;
   const int p0 = (blockIdx.x % chunks_per_group) * chunk;
   const int p1 = min(p0 + chunk, Pg);
   if (l >= pl) return;
   float sc[8], sh[8];
-  const float* cf = coef + static_cast<size_t>(g) * 4 * C + v * 8;
+  const float* cf = coef + static_cast<size_t>(g) * 4 * C + c0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = cf[j]; sh[j] = cf[C + j]; }
-  const size_t base = static_cast<size_t>(g) * Pg * C + v * 8;
+  const size_t base = static_cast<size_t>(g) * Pg * C + c0;
   for (int pb = p0 + l; pb < p1; pb += pl * U) {
     Vec8<T> pk[U];
 #pragma unroll
@@ -889,8 +895,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
   }
 }
 
-static void bn_chunks(int G, long long Pg, int blocks_per_sm, int* chunk, int* cpg) {
-  int c = (sm_count() * blocks_per_sm) / G;
+static void bn_chunks(int G, long long Pg, int blocks_per_sm, int* chunk, int* cpg, int slabs = 1) {
+  int c = (sm_count() * blocks_per_sm) / (G * slabs);
   if (c < 1) c = 1;
   long long ch = ceil_div_ll(Pg, c);
   if (ch < 64) ch = 64;
@@ -903,9 +909,11 @@ int bn_apply(int dtype, const void* y, const float* coef, void* a, int G, long l
   PP_REQUIRE(C % 8 == 0 && C / 8 <= kBnThreads && kBnThreads % (C / 8) == 0, "bn_apply: C=%d unsupported", C);
   PP_REQUIRE_INT32(Pg * C, "bn_apply");
   int chunk, cpg;
-  bn_chunks(G, Pg, 16, &chunk, &cpg);
-  PP_DISPATCH_T(dtype, bn_apply_kernel<T><<<G * cpg, kBnThreads, 0, s>>>(static_cast<const T*>(y), coef, static_cast<T*>(a),
-                                                                  int(Pg), C, chunk, cpg, slope););
+  const int vecs = bn_slab_vecs(C), slabs = (C / 8) / vecs;
+  PP_REQUIRE((C / 8) % vecs == 0, "bn_apply: C=%d does not split into channel slabs", C);
+  bn_chunks(G, Pg, 16, &chunk, &cpg, slabs);
+  PP_DISPATCH_T(dtype, bn_apply_kernel<T><<<dim3(G * cpg, slabs), kBnThreads, 0, s>>>(
+                           static_cast<const T*>(y), coef, static_cast<T*>(a), int(Pg), C, chunk, cpg, slope, vecs););
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -916,16 +924,17 @@ template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y,
                                                             const float* __restrict__ coef, double* __restrict__ bsums,
                                                             long long Pg, int C, long long chunk, int chunks_per_group,
-                                                            float slope) {
+                                                            float slope, int vecs) {
   __shared__ float red[kBnThreads][17];
-  const int vecs = C / 8;
   const int pl = kBnThreads / vecs;
   const int v = threadIdx.x % vecs, l = threadIdx.x / vecs;
+  const int cs = blockIdx.y * vecs * 8;          // first channel of this block's slab
+  const int c0 = cs + v * 8;
   const int g = blockIdx.x / chunks_per_group;
   const long long p0 = static_cast<long long>(blockIdx.x % chunks_per_group) * chunk;
   const long long p1 = (p0 + chunk < Pg) ? p0 + chunk : Pg;
   float s[8], ss[8], sc[8], sh[8], mu[8], rs[8];
-  const float* cf = coef + static_cast<long long>(g) * 4 * C + v * 8;
+  const float* cf = coef + static_cast<long long>(g) * 4 * C + c0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     s[j] = 0.f; ss[j] = 0.f;
@@ -933,7 +942,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __re
   }
   if (l < pl) {
     constexpr int U = 8;
-    const long long base = (static_cast<long long>(g) * Pg) * C + v * 8;
+    const long long base = (static_cast<long long>(g) * Pg) * C + c0;
     for (long long pb = p0 + l; pb < p1; pb += static_cast<long long>(pl) * U) {
       Vec8<T> pa[U], py[U];
 #pragma unroll
@@ -961,11 +970,12 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __re
 #pragma unroll
   for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s[j]; red[threadIdx.x][8 + j] = ss[j]; }
   __syncthreads();
-  for (int t = threadIdx.x; t < 2 * C; t += kBnThreads) {
-    const int c = t % C, st = t / C;
+  const int cb = vecs * 8;                       // channels of this slab
+  for (int t = threadIdx.x; t < 2 * cb; t += kBnThreads) {
+    const int c = t % cb, st = t / cb;
     double acc = 0.0;
     for (int k = 0; k < pl; ++k) acc += static_cast<double>(red[k * vecs + c / 8][st * 8 + c % 8]);
-    atomicAdd(bsums + (static_cast<long long>(g) * C + c) * 2 + st, acc);
+    atomicAdd(bsums + (static_cast<long long>(g) * C + cs + c) * 2 + st, acc);
   }
 }
 
@@ -979,11 +989,11 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
                                                            const double* __restrict__ bsums, T* __restrict__ dy,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            float* __restrict__ dbias, int G, int Pg, int C, int chunk,
-                                                           int chunks_per_group, int training, float slope) {
+                                                           int chunks_per_group, int training, float slope, int vecs) {
   constexpr int U = 4;
-  const int vecs = C / 8;
   const int pl = kBnThreads / vecs;
   const int v = threadIdx.x % vecs, l = threadIdx.x / vecs;
+  const int c0 = blockIdx.y * vecs * 8 + v * 8;   // first channel of this thread (channel slab = blockIdx.y)
   const int g = blockIdx.x / chunks_per_group;
   const int p0 = (blockIdx.x % chunks_per_group) * chunk;
   const int p1 = min(p0 + chunk, Pg);
@@ -991,7 +1001,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
   if (blockIdx.x == 0 && l == 0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = v * 8 + j;
+      const int c = c0 + j;
       double dg = 0.0, dbt = 0.0, dbs = 0.0;
       for (int gg = 0; gg < G; ++gg) {
         const double sdz = bsums[(static_cast<size_t>(gg) * C + c) * 2];
@@ -1005,8 +1015,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
     }
   }
   float sc[8], sh[8], mu[8], rs[8], k1[8], k2[8];
-  const float* cf = coef + static_cast<size_t>(g) * 4 * C + v * 8;
-  const double* bs = bsums + (static_cast<size_t>(g) * C + v * 8) * 2;
+  const float* cf = coef + static_cast<size_t>(g) * 4 * C + c0;
+  const double* bs = bsums + (static_cast<size_t>(g) * C + c0) * 2;
   const double inv = 1.0 / static_cast<double>(Pg);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -1014,7 +1024,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
     k1[j] = training ? static_cast<float>(bs[2 * j] * inv) : 0.f;
     k2[j] = training ? static_cast<float>(bs[2 * j + 1] * inv) : 0.f;
   }
-  const size_t base = static_cast<size_t>(g) * Pg * C + v * 8;
+  const size_t base = static_cast<size_t>(g) * Pg * C + c0;
   for (int pb = p0 + l; pb < p1; pb += pl * U) {
     Vec8<T> pa[U], py[U];
 #pragma unroll
@@ -1050,20 +1060,22 @@ int bn_bwd(int dtype, const void* da, const void* y, const float* coef, double* 
   PP_REQUIRE(C % 8 == 0 && C / 8 <= kBnThreads && kBnThreads % (C / 8) == 0, "bn_bwd: C=%d unsupported", C);
   PP_REQUIRE_INT32(Pg * C, "bn_bwd");
   if (!sums_zeroed) PP_CHECK_CUDA(cudaMemsetAsync(bsums, 0, sizeof(double) * 2 * G * C, s));
-  static const int red_bps = [] { const char* e = getenv("PP_BN_RED_BPS"); return e ? atoi(e) : 8; }();
-  int cpg = (sm_count() * (red_bps > 0 ? red_bps : 8)) / G;
+  static const int red_bps = [] { const char* e = getenv("PP_BN_RED_BPS"); return e ? atoi(e) : 4; }();
+  const int vecs = bn_slab_vecs(C), slabs = (C / 8) / vecs;
+  PP_REQUIRE((C / 8) % vecs == 0, "bn_bwd: C=%d does not split into channel slabs", C);
+  int cpg = (sm_count() * (red_bps > 0 ? red_bps : 4)) / (G * slabs);
   if (cpg < 1) cpg = 1;
   long long chunk = ceil_div_ll(Pg, cpg);
   if (chunk < 64) chunk = 64;
   cpg = static_cast<int>(ceil_div_ll(Pg, chunk));
   int achunk, acpg;
-  bn_chunks(G, Pg, 16, &achunk, &acpg);
+  bn_chunks(G, Pg, 16, &achunk, &acpg, slabs);
   PP_DISPATCH_T(dtype,
-                bn_bwd_reduce_kernel<T><<<G * cpg, kBnThreads, 0, s>>>(static_cast<const T*>(da), static_cast<const T*>(y),
-                                                                coef, bsums, Pg, C, chunk, cpg, slope);
-                bn_bwd_apply_kernel<T><<<G * acpg, kBnThreads, 0, s>>>(static_cast<const T*>(da), static_cast<const T*>(y),
-                                                                coef, bsums, static_cast<T*>(dy), dgamma, dbeta, dbias,
-                                                                G, int(Pg), C, achunk, acpg, training, slope););
+                bn_bwd_reduce_kernel<T><<<dim3(G * cpg, slabs), kBnThreads, 0, s>>>(
+                    static_cast<const T*>(da), static_cast<const T*>(y), coef, bsums, Pg, C, chunk, cpg, slope, vecs);
+                bn_bwd_apply_kernel<T><<<dim3(G * acpg, slabs), kBnThreads, 0, s>>>(
+                    static_cast<const T*>(da), static_cast<const T*>(y), coef, bsums, static_cast<T*>(dy), dgamma, dbeta,
+                    dbias, G, int(Pg), C, achunk, acpg, training, slope, vecs););
   PP_LAUNCH_CHECK_N(2);
   return PP_OK;
 }
@@ -1123,13 +1135,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_eval_kernel(const T* __rest
                                                                  const float* __restrict__ coef, double* sums,
                                                                  T* __restrict__ dy, float* __restrict__ dgamma,
                                                                  float* __restrict__ dbeta, float* __restrict__ dbias,
-                                                                 int P, int C, int chunk, float slope, float inv_slope) {
+                                                                 int P, int C, int chunk, float slope, float inv_slope,
+                                                                 int vecs) {
   __shared__ float red[kBnThreads][17];
   __shared__ unsigned int s_last;
   constexpr int U = 4;
-  const int vecs = C / 8;
   const int pl = kBnThreads / vecs;
   const int v = threadIdx.x % vecs, l = threadIdx.x / vecs;
+  const int cs = blockIdx.y * vecs * 8;          // channel slab of this block
   const int p0 = blockIdx.x * chunk;
   const int p1 = min(p0 + chunk, P);
   float s[8], ss[8];
@@ -1137,10 +1150,10 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_eval_kernel(const T* __rest
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
   if (l < pl) {
     float sc[8], bt[8], ig[8];
-    const float* cf = coef + v * 8;
+    const float* cf = coef + cs + v * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = cf[j]; bt[j] = cf[2 * C + j]; ig[j] = cf[3 * C + j]; }
-    const size_t base = static_cast<size_t>(v) * 8;
+    const size_t base = static_cast<size_t>(cs) + static_cast<size_t>(v) * 8;
     for (int pb = p0 + l; pb < p1; pb += pl * U) {
       Vec8<T> pa[U], py[U];
 #pragma unroll
@@ -1173,18 +1186,19 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_eval_kernel(const T* __rest
 #pragma unroll
   for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s[j]; red[threadIdx.x][8 + j] = ss[j]; }
   __syncthreads();
-  for (int t = threadIdx.x; t < 2 * C; t += kBnThreads) {
-    const int c = t % C, st = t / C;
+  const int cb = vecs * 8;
+  for (int t = threadIdx.x; t < 2 * cb; t += kBnThreads) {
+    const int c = t % cb, st = t / cb;
     double acc = 0.0;
     for (int k = 0; k < pl; ++k) acc += static_cast<double>(red[k * vecs + c / 8][st * 8 + c % 8]);
-    atomicAdd(sums + static_cast<size_t>(c) * 2 + st, acc);
+    atomicAdd(sums + static_cast<size_t>(cs + c) * 2 + st, acc);
   }
-  // last block: parameter gradients from the complete sums
+  // last block (of all slabs): parameter gradients from the complete sums
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int* ticket = reinterpret_cast<unsigned int*>(sums + 2 * static_cast<size_t>(C));
-    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1u : 0u;
   }
   __syncthreads();
   if (s_last) {
@@ -1204,10 +1218,15 @@ int bn_bwd_eval(int dtype, const void* da, const void* a, const float* coef, dou
   PP_REQUIRE(slope != 0.f, "bn_bwd_eval: a zero slope is not invertible");
   PP_REQUIRE_INT32(P * C, "bn_bwd_eval");
   int chunk, blocks;
-  bn_chunks(1, P, 16, &chunk, &blocks);
-  PP_DISPATCH_T(dtype, bn_bwd_eval_kernel<T><<<blocks, kBnThreads, 0, s>>>(
+  const int vecs = bn_slab_vecs(C), slabs = (C / 8) / vecs;
+  PP_REQUIRE((C / 8) % vecs == 0, "bn_bwd_eval: C=%d does not split into channel slabs", C);
+  // fewer, fatter blocks than the pure streaming kernels: every block ends with 2 * (slab channels) double atomics on a
+  // handful of cache lines, and ~2400 blocks of them cost more than the pass itself (88 us instead of ~30 us at 128^2)
+  static const int bps = [] { const char* e = getenv("PP_BN_EVAL_BPS"); return e ? atoi(e) : 6; }();
+  bn_chunks(1, P, bps > 0 ? bps : 6, &chunk, &blocks, slabs);
+  PP_DISPATCH_T(dtype, bn_bwd_eval_kernel<T><<<dim3(blocks, slabs), kBnThreads, 0, s>>>(
                            static_cast<const T*>(da), static_cast<const T*>(a), coef, sums, static_cast<T*>(dy), dgamma,
-                           dbeta, dbias, int(P), C, chunk, slope, 1.f / slope););
+                           dbeta, dbias, int(P), C, chunk, slope, 1.f / slope, vecs););
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
