@@ -66,12 +66,14 @@ def parse_args():
 
 
 def load_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/r01_conv_traffic.json)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
-            return json.load(f)
-    except Exception:
-        return {}
+    """DRAM bytes per launch of the dominant kernel family from the committed ncu pass (profiles/r0N_conv_traffic.json)."""
+    for name in ("r02_conv_traffic.json", "r01_conv_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f)
+        except Exception:
+            continue
+    return {}
 
 
 def load_peaks():
@@ -759,7 +761,8 @@ def run_ours(args):
         "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
         "e2e": e2e,
         "roofline": {
-            "bound": "tensor", "kernel": "conv3x3_tc_kernel: tcgen05 implicit-GEMM 3x3 conv, forward + dgrad launches",
+            "bound": "tensor", "kernel": "tcgen05 implicit-GEMM 3x3 conv, forward + dgrad launches (conv3x3_rows_tc_kernel / conv3x3_tc_kernel / "
+                                   "conv3x3_halo_tc_kernel, chosen per shape)",
             "achieved": tf(dom), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
             "frac": tf(dom) / peaks["tf_sustained"], "peak_source": peaks["src"] + " bf16 sustained",
             "traffic": traffic.get("conv3x3_tc_bytes_per_launch"), "traffic_source": traffic.get("source"),

@@ -60,6 +60,11 @@ int pp_unet_create_ex(int input_ch, int init_ch, int max_ch, int num_classes, in
                       int strided, pp_unet_t* out);
 void pp_unet_destroy(pp_unet_t u);
 int pp_unet_num_convs(pp_unet_t u);
+/* Whole-pass CUDA-graph replay: pp_unet_forward / pp_unet_backward called again with the SAME pointers, shapes and
+ * flags are captured once (on an internal stream; the ~200-260 launches over the plan's internal streams become one
+ * graph) and replayed with one cudaGraphLaunch on the caller's stream. PP_GRAPHS=0 disables it; passes that record
+ * data-parallel gradient events (pp_unet_set_grad_events) always run eagerly. Number of replays so far: */
+long long pp_graph_replays(void);
 /* layer -> Cin, Cout, dilation and module path ("enc_block1.conv_block.conv_layer1", ...) */
 int pp_unet_conv_info(pp_unet_t u, int layer, int* cin, int* cout, int* dil, const char** name);
 /* kind 0: Conv2d 3x3 stride 1 + BN + LeakyReLU; 1: the same with stride 2 (scale = 2); 2: ConvTranspose2d with

@@ -14,6 +14,7 @@ void unet_destroy(UNetPlan* pl);
 int unet_set_grad_events(UNetPlan* pl, int n, const int* layers);
 int unet_wait_grad_event(const UNetPlan* pl, int i, cudaStream_t s);
 int unet_num_convs(const UNetPlan* pl);
+long long unet_graph_replays();
 int unet_conv_info(const UNetPlan* pl, int layer, int* cin, int* cout, int* dil, const char** name);
 long long unet_workspace_bytes(const UNetPlan* pl, int N, int H, int W, int G);
 int unet_activation(const UNetPlan* pl, const char* name, int N, int H, int W, int G, int* act_id, long long* offset,
@@ -62,6 +63,7 @@ int pp_unet_wait_grad_event(pp_unet_t u, int i, void* stream) {
   return unet_wait_grad_event(reinterpret_cast<pp::UNetPlan*>(u), i, static_cast<cudaStream_t>(stream));
 }
 int pp_unet_num_convs(pp_unet_t u) { return unet_num_convs(reinterpret_cast<pp::UNetPlan*>(u)); }
+long long pp_graph_replays(void) { return unet_graph_replays(); }
 int pp_unet_conv_info(pp_unet_t u, int layer, int* cin, int* cout, int* dil, const char** name) {
   return unet_conv_info(reinterpret_cast<pp::UNetPlan*>(u), layer, cin, cout, dil, name);
 }

@@ -41,6 +41,7 @@ static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mu;
 
 void prof_enable(int on) { g_prof_on.store(on); }
+bool prof_enabled() { return g_prof_on.load() != 0; }
 int prof_begin(int family, double flops, cudaStream_t s) {
   if (!g_prof_on.load()) return -1;
   std::lock_guard<std::mutex> lk(g_prof_mu);

@@ -50,6 +50,7 @@ void count_launches(int n);
 long long launch_count();
 enum : int { PROF_CONV = 0, PROF_WGRAD = 1, PROF_LOSS = 2, PROF_FAMILIES = 3 };  // PROF_LOSS counts BYTES, not FLOPs
 void prof_enable(int on);
+bool prof_enabled();
 int prof_begin(int family, double flops, cudaStream_t s);   // -> slot or -1 when profiling is off
 void prof_end(int slot, cudaStream_t s);
 int prof_collect(int family, double* ms, double* flops, long long* launches);  // synchronises the events

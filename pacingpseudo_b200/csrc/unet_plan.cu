@@ -5,8 +5,10 @@
 // carved from ONE caller-owned workspace. One C call launches the ~200 kernels of a pass, so the
 // Python side pays no per-layer overhead. The channel concat of the decoder is never materialised
 // (two-source K loop in the conv kernels); scale-1 "upsampling" (output_stride 8) is a no-op alias.
+#include <atomic>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -61,6 +63,23 @@ struct UNetPlan {
   mutable cudaStream_t part_stream[kMaxParts] = {};
   mutable cudaEvent_t fork = nullptr, stat_order[kMaxParts] = {}, part_done[kMaxParts] = {};
   mutable int overlap = -1;   // -1: not initialised, 0: off, 1: on
+  // CUDA-graph replay of a whole pass (PP_GRAPHS=0 turns it off). A pass is ~200-260 launches over up to four internal
+  // streams; when the SAME call (same pointers, shapes, flags) has been seen once eagerly, the next one is captured
+  // (the internal fork / join events become graph edges) and later identical calls are ONE cudaGraphLaunch: no per-launch
+  // host cost, shorter gaps between dependent kernels. PyTorch's caching allocator hands the same blocks back every
+  // step, so in steady state every step hits; a call whose pointers differ simply runs eagerly (or gets its own graph).
+  struct GraphEntry {
+    std::vector<unsigned long long> key;
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;
+    int seen = 0;
+    unsigned long long last_use = 0;
+  };
+  mutable std::vector<GraphEntry> graphs;
+  mutable std::mutex graph_mu;
+  mutable cudaStream_t cap_stream = nullptr;   // passes are captured on this stream (the caller's may be the legacy
+                                               // default stream, which cannot capture) and replayed on the caller's
+  mutable unsigned long long graph_clock = 0;
 
   int new_act(int C, int res) { acts.push_back({C, res}); return int(acts.size()) - 1; }
 
@@ -253,8 +272,8 @@ static int overlap_init(const UNetPlan& pl) {
   return PP_OK;
 }
 
-int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* ws, int N, int H, int W, int G,
-                 int training, float* logits, cudaStream_t s) {
+static int unet_forward_eager(const UNetPlan& pl, const float* x, void* const* params, void* ws, int N, int H, int W,
+                              int G, int training, float* logits, cudaStream_t s) {
   int rc = check_shape(pl, N, H, W, G);
   if (rc) return rc;
   const UNetLayout L = make_layout(pl, N, H, W, G);
@@ -452,9 +471,9 @@ int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* 
 
 // dfeat: optional external gradients w.r.t. named activations (NHWC, activation dtype), e.g. the
 // aux path's gradient into encoder/stage5 and encoder/stage6. dfeat_act[i] = activation id.
-int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void* ws, int N, int H, int W, int G,
-                  int training, const float* dlogits, int n_dfeat, const int* dfeat_act, const void* const* dfeat,
-                  float* const* grads, cudaStream_t user_stream) {
+static int unet_backward_eager(const UNetPlan& pl, const float* x, void* const* params, void* ws, int N, int H, int W,
+                               int G, int training, const float* dlogits, int n_dfeat, const int* dfeat_act,
+                               const void* const* dfeat, float* const* grads, cudaStream_t user_stream) {
   int rc = check_shape(pl, N, H, W, G);
   if (rc) return rc;
   rc = overlap_init(pl);
@@ -538,7 +557,7 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
       }
       auto grads_ready = [&]() -> int {   // all parameter gradients of layers >= op.layer are enqueued
         for (size_t e = 0; e < pl.ev_layer.size(); ++e)
-          if (pl.ev_layer[e] == op.layer) PP_CHECK_CUDA(cudaEventRecord(pl.ev[e], ws_));
+          if (pl.ev_layer[e] == op.layer) PP_CHECK_CUDA(cudaEventRecord(pl.ev[e], ws_));   // (never inside a capture)
         if (ov) {
           PP_CHECK_CUDA(cudaEventRecord(pl.buf_free[kb], ws_));
           buf_used[kb] = true;
@@ -644,6 +663,139 @@ int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void*
   return PP_OK;
 }
 
+// ---- CUDA-graph replay of whole passes (see UNetPlan::GraphEntry) ---------------------------------------------------
+static std::atomic<long long> g_graph_replays{0};
+long long unet_graph_replays() { return g_graph_replays.load(); }
+
+static bool graphs_enabled() {
+  static const int on = [] { const char* e = getenv("PP_GRAPHS"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+
+template <typename Fn>
+static int run_with_graph(const UNetPlan& pl, std::vector<unsigned long long>&& key, cudaStream_t s, Fn&& eager) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (!graphs_enabled() || prof_enabled() || cudaStreamIsCapturing(s, &cap) != cudaSuccess ||
+      cap != cudaStreamCaptureStatusNone)
+    return eager(s);
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+  bool capture = false;
+  {
+    std::lock_guard<std::mutex> lk(pl.graph_mu);
+    UNetPlan::GraphEntry* hit = nullptr;
+    for (auto& g : pl.graphs)
+      if (g.key == key) { hit = &g; break; }
+    if (hit == nullptr) {
+      if (pl.graphs.size() >= 12) {   // evict the least recently used entry
+        size_t lru = 0;
+        for (size_t i = 1; i < pl.graphs.size(); ++i)
+          if (pl.graphs[i].last_use < pl.graphs[lru].last_use) lru = i;
+        if (pl.graphs[lru].exec != nullptr) cudaGraphExecDestroy(pl.graphs[lru].exec);
+        pl.graphs.erase(pl.graphs.begin() + lru);
+      }
+      UNetPlan::GraphEntry g;
+      g.key = key;
+      g.seen = 1;
+      g.last_use = ++pl.graph_clock;
+      pl.graphs.push_back(std::move(g));
+    } else {
+      hit->last_use = ++pl.graph_clock;
+      if (hit->exec != nullptr) { exec = hit->exec; launches = hit->launches; }
+      else if (hit->seen >= 1) capture = true;   // seen once eagerly (kernel choices are measured by now): capture this one
+      ++hit->seen;
+    }
+  }
+  static const int debug = [] { const char* e = getenv("PP_GRAPHS_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
+  if (debug) fprintf(stderr, "pp graph pass %llu: %s\n", key[0], exec != nullptr ? "replay" : (capture ? "capture" : "eager"));
+  if (exec != nullptr) {
+    PP_CHECK_CUDA(cudaGraphLaunch(exec, s));
+    count_launches(static_cast<int>(launches));
+    g_graph_replays.fetch_add(1);
+    return PP_OK;
+  }
+  if (!capture) return eager(s);
+  const long long l0 = launch_count();
+  {
+    std::lock_guard<std::mutex> lk(pl.graph_mu);
+    if (pl.cap_stream == nullptr) PP_CHECK_CUDA(cudaStreamCreateWithFlags(&pl.cap_stream, cudaStreamNonBlocking));
+  }
+  if (cudaStreamBeginCapture(pl.cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return eager(s);
+  }
+  const int rc = eager(pl.cap_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(pl.cap_stream, &graph);
+  if (rc != PP_OK || ce != cudaSuccess || graph == nullptr) {
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    if (rc != PP_OK) return rc;
+    cudaGetLastError();
+    return eager(s);   // not capturable here: run it the ordinary way
+  }
+  cudaGraphExec_t ex = nullptr;
+  if (cudaGraphInstantiate(&ex, graph, 0) != cudaSuccess || ex == nullptr) {
+    cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return eager(s);
+  }
+  cudaGraphDestroy(graph);
+  launches = launch_count() - l0;
+  {
+    std::lock_guard<std::mutex> lk(pl.graph_mu);
+    bool stored = false;
+    for (auto& g : pl.graphs)
+      if (g.key == key && g.exec == nullptr) { g.exec = ex; g.launches = launches; stored = true; break; }
+    if (!stored) { cudaGraphExecDestroy(ex); return eager(s); }
+  }
+  PP_CHECK_CUDA(cudaGraphLaunch(ex, s));   // the captured launches were recorded, not run
+  return PP_OK;
+}
+
+static void key_push_ptrs(std::vector<unsigned long long>* key, void* const* p, size_t n) {
+  unsigned long long h = 1469598103934665603ULL;   // FNV-1a over the pointer table
+  for (size_t i = 0; i < n; ++i) {
+    h ^= reinterpret_cast<unsigned long long>(p[i]);
+    h *= 1099511628211ULL;
+  }
+  key->push_back(h);
+  key->push_back(n);
+}
+
+int unet_forward(const UNetPlan& pl, const float* x, void* const* params, void* ws, int N, int H, int W, int G,
+                 int training, float* logits, cudaStream_t s) {
+  std::vector<unsigned long long> key = {1ULL, reinterpret_cast<unsigned long long>(x), reinterpret_cast<unsigned long long>(ws),
+                                         reinterpret_cast<unsigned long long>(logits), static_cast<unsigned long long>(N),
+                                         static_cast<unsigned long long>(H), static_cast<unsigned long long>(W),
+                                         static_cast<unsigned long long>(G), static_cast<unsigned long long>(training)};
+  key_push_ptrs(&key, params, pl.convs.size() * kParamsPerConv + 2);
+  return run_with_graph(pl, std::move(key), s, [&](cudaStream_t st) {
+    return unet_forward_eager(pl, x, params, ws, N, H, W, G, training, logits, st);
+  });
+}
+
+int unet_backward(const UNetPlan& pl, const float* x, void* const* params, void* ws, int N, int H, int W, int G,
+                  int training, const float* dlogits, int n_dfeat, const int* dfeat_act, const void* const* dfeat,
+                  float* const* grads, cudaStream_t user_stream) {
+  auto eager = [&](cudaStream_t st) {
+    return unet_backward_eager(pl, x, params, ws, N, H, W, G, training, dlogits, n_dfeat, dfeat_act, dfeat, grads, st);
+  };
+  // the data-parallel gradient events are recorded for streams OUTSIDE this call: keep such passes out of graphs
+  if (!pl.ev.empty()) return eager(user_stream);
+  std::vector<unsigned long long> key = {2ULL, reinterpret_cast<unsigned long long>(x), reinterpret_cast<unsigned long long>(ws),
+                                         reinterpret_cast<unsigned long long>(dlogits), static_cast<unsigned long long>(N),
+                                         static_cast<unsigned long long>(H), static_cast<unsigned long long>(W),
+                                         static_cast<unsigned long long>(G), static_cast<unsigned long long>(training),
+                                         static_cast<unsigned long long>(n_dfeat)};
+  for (int i = 0; i < n_dfeat; ++i) {
+    key.push_back(static_cast<unsigned long long>(dfeat_act[i]));
+    key.push_back(reinterpret_cast<unsigned long long>(dfeat[i]));
+  }
+  key_push_ptrs(&key, params, pl.convs.size() * kParamsPerConv + 2);
+  key_push_ptrs(&key, reinterpret_cast<void* const*>(grads), pl.convs.size() * kGradsPerConv + 2);
+  return run_with_graph(pl, std::move(key), user_stream, eager);
+}
+
 UNetPlan* unet_create(int input_ch, int init_ch, int max_ch, int num_classes, int output_stride, int dtype,
                       int strided) {
   if (input_ch < 1 || input_ch > 16) { set_error("unet: input_ch=%d unsupported (1..16)", input_ch); return nullptr; }
@@ -664,6 +816,9 @@ UNetPlan* unet_create(int input_ch, int init_ch, int max_ch, int num_classes, in
 }
 void unet_destroy(UNetPlan* pl) {
   if (pl) {
+    for (auto& g : pl->graphs)
+      if (g.exec != nullptr) cudaGraphExecDestroy(g.exec);
+    if (pl->cap_stream) cudaStreamDestroy(pl->cap_stream);
     for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
     for (int k = 0; k < UNetPlan::kDyBufs; ++k) {
       if (pl->dy_ready[k]) cudaEventDestroy(pl->dy_ready[k]);

@@ -74,7 +74,8 @@ class GradientAllReducer:
         # is reduced after the whole backward pass (no overlap) instead of racing the accumulation.
         if unet is not None and getattr(unet, "_padded", False):
             unet = None
-        if unet is not None and optimizer is not None and flat_grad.is_cuda:
+        if unet is not None and optimizer is not None and flat_grad.is_cuda and self.world > 1:
+            # (a single process needs no events: pp_unet_backward then stays eligible for CUDA-graph replay)
             spans = self._layer_spans(unet, optimizer)
             plan = plan_layer_buckets(spans, num_buckets)
             self.overlapped = plan[:-1]                        # [(first_layer, lo, hi)] each with its own event

@@ -22,11 +22,16 @@ for (_, name), m in per.items():
     f[3] += m.get("gpu__time_duration.sum", 0.0)
 out = {k: {"launches": f[0], "dram_read_bytes_per_launch": f[1] / f[0], "dram_write_bytes_per_launch": f[2] / f[0],
            "avg_us": f[3] / f[0]} for k, f in fam.items()}
-d = out["conv3x3_tc_kernel"]
+# the roofline's dominant kernel family = every forward / dgrad tcgen05 conv launch (bench.py's PROF_CONV family):
+# the generic per-tap kernel, the shared-memory-resident rows kernel (round 2) and the narrow-layer halo kernel
+dom = [k for k in out if re.fullmatch(r"conv3x3_(tc|rows_tc|halo_tc)_kernel", k)]
+n_dom = sum(out[k]["launches"] for k in dom)
+b_dom = sum(out[k]["launches"] * (out[k]["dram_read_bytes_per_launch"] + out[k]["dram_write_bytes_per_launch"]) for k in dom)
+raw = sys.argv[3] if len(sys.argv) > 3 else src
 res = {"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-                 "(tests/run_ncu_round.sh; raw: profiles/r01_ncu_traffic.csv), mean over the %d conv3x3_tc_kernel "
-                 "launches of one warm-up + two steps" % d["launches"],
-       "conv3x3_tc_bytes_per_launch": d["dram_read_bytes_per_launch"] + d["dram_write_bytes_per_launch"],
+                 "(raw: %s), mean over the %d forward/dgrad conv launches (%s) of the profiled steps" % (
+                     raw, n_dom, ", ".join(sorted(dom))),
+       "conv3x3_tc_bytes_per_launch": b_dom / max(1, n_dom),
        "per_kernel": out}
 json.dump(res, open(dst, "w"), indent=1)
 for k, v in out.items():

@@ -569,6 +569,42 @@ def test_memory_update_vs_oracle(pp, mode):
 GOLDEN_CASES = list(CASES)
 
 
+def test_cuda_graph_replay_of_whole_passes_is_identical_to_eager(pp):
+    """pp_unet_forward / pp_unet_backward are replayed as CUDA graphs once the same call (pointers, shapes) recurs: the
+    eager first pass, the captured second one and the replays must agree (forward: bit-identical logits in eval mode;
+    backward into FlatAdam's flat gradient buffer: identical up to the fp32 atomics of the narrow weight gradients)."""
+    L, PF, _ = pp
+    from pacingpseudo_b200.optim import FlatAdam
+    from pacingpseudo_b200.synth import make_batch
+    case = dict(kind="baseline", C=5, os=8, training=False)
+    model = Hn.build_cuda_model(case, "bf16").eval()
+    opt = FlatAdam(model.parameters(), lr=0.0)
+    batch = make_batch(4, 5, 128, 128, seed=31)
+    x = batch["image"].cuda()
+    target = batch["scribble"].argmax(1).to(torch.uint8).cuda()
+    from losses import losses as DL
+    r0 = L.cdll.pp_graph_replays()
+    # results go into storage allocated up front: the caching allocator then hands the SAME blocks (workspace, logits,
+    # loss gradient) to every iteration, which is what a steady-state training loop looks like and what replay keys on
+    logits = torch.empty(6, 4, 5, 128, 128, device="cuda")
+    grads = torch.empty(6, opt.flat_grad.numel(), device="cuda")
+    for it in range(6):
+        opt.zero_grad()
+        z = model(x)["segmentation/logits"]
+        loss = DL.partial_cross_entropy_loss(z, target, 5)
+        loss.backward()
+        logits[it].copy_(z.detach())
+        grads[it].copy_(opt.flat_grad)
+        del z, loss
+    torch.cuda.synchronize()
+    if os.environ.get("PP_GRAPHS", "1") != "0":
+        assert L.cdll.pp_graph_replays() - r0 >= 4, "the repeated passes were not replayed as graphs"
+    for z in logits[1:]:
+        assert torch.equal(z, logits[0])
+    for g in grads[1:]:
+        assert torch.isfinite(g).all() and _rel(g, grads[0]) < 1e-4
+
+
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_dropin_modules_fp32_mode_vs_reference_golden(pp, name):
     rec = Hn.run_case_cuda(name, "fp32")
