@@ -8,9 +8,9 @@ timeout 600 $TR tests/run_dp_check.py > gpurun_out/r02_dp_check_${N}gpu.log 2>&1
 timeout 600 $TR bench.py --gpus $N $S > gpurun_out/r02_bench_${N}gpu.json 2> gpurun_out/r02_bench_${N}gpu.err; echo "config2 exit $?"
 timeout 600 $TR bench.py --gpus $N $S --classes 4 > gpurun_out/r02_bench_${N}gpu_config3_acdc256.json 2> /dev/null; echo "config3 (256) exit $?"
 if [ "$2" != "quick" ]; then
-timeout 600 $TR bench.py --gpus $N $S --classes 4 --size 224 --no-e2e --no-other-bn > gpurun_out/r02_bench_${N}gpu_config3_acdc224.json 2> /dev/null; echo "config3 (224) exit $?"
+
 timeout 600 $TR bench.py --gpus $N $S --workload upperbound > gpurun_out/r02_bench_${N}gpu_config4_upperbound.json 2> /dev/null; echo "config4 exit $?"
-for B in 12 48 192; do
+for B in 12 96; do
 timeout 600 $TR bench.py --gpus $N --steps 15 --warmup 4 --no-cpu-baseline --no-same-box --no-e2e --no-other-bn --classes 2 --size 224 --batch $B > gpurun_out/r02_bench_${N}gpu_config5_lvsc224_b$B.json 2> /dev/null; echo "config5 b=$B exit $?"
 done
 fi
