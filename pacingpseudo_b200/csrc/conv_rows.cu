@@ -452,7 +452,7 @@ bool conv3x3_rows_applicable(int C0, int C1, int cout, int N, int H, int W, int 
   static const int on = [] { const char* e = getenv("PP_CONV_ROWS"); return (e && e[0] == '0') ? 0 : 1; }();
   if (!on) return false;
   if (H * (W + dil) < 256) return false;   // tiny maps: the generic kernel packs several images into one 128-pixel tile
-  if (W > 96) return false;                // full-resolution rows: the halo / generic kernels
+  if (W > 96) return false;                // full-resolution rows: the halo / generic kernels (128-wide: no gain measured)
   RowsPlan pl;
   return conv3x3_rows_plans(N, H, W, dil, C0, C1, cout, &pl, 1) > 0;
 }

@@ -969,7 +969,8 @@ static int conv_choose(const void* x0, int C0, const void* x1, int C1, const voi
     return e == nullptr ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'g' ? 2 : 0));
   }();
   if (force) {
-    if (force == 1) { best.rows = true; best.plan = plans[0]; }
+    static const int force_plan = [] { const char* e = getenv("PP_CONV_FORCE_PLAN"); return e ? atoi(e) : 0; }();
+    if (force == 1) { best.rows = true; best.plan = plans[force_plan < np ? force_plan : np - 1]; }
     *choice = best;
     return PP_OK;
   }

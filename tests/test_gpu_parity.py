@@ -176,9 +176,11 @@ def test_conv3x3_full_tile_counts_vs_torch(pp, case):
     stats = torch.zeros(reps * G * Co * 2, dtype=torch.float64, device="cuda")
     y2 = torch.empty_like(y)
     L.call("pp_conv3x3_bn_stats", _p(x0), C0, _p(x1), C1, _p(wf), _p(b_d), _p(y2), Co, _p(stats), G, N, H, W, dil, _st())
-    assert torch.equal(y2, y)
+    # (the two calls are tuned separately and may run different kernels: same values up to the fp32 summation order,
+    # i.e. a bf16 ulp on a few elements; the statistics must match the output of THEIR launch)
+    assert _rel(y2.float(), y.float()) < 1e-3
     st = stats.view(reps, G, Co, 2).sum(0).cpu()
-    yq = y.float().cpu().view(G, -1, Co).double()
+    yq = y2.float().cpu().view(G, -1, Co).double()
     e_s = max(_rel(st[:, :, 0], yq.sum(1)), _rel(st[:, :, 1], (yq * yq).sum(1)))
     print("full-tile case %s: fwd %.2e dgrad %.2e / %.2e wgrad %.2e stats %.2e" % (case, e_fwd, e_d0, e_d1, e_w, e_s))
     assert e_fwd < 3e-3 and e_d0 < 3e-3 and e_d1 < 3e-3 and e_w < 5e-4 and e_s < 1e-5, (case, e_fwd, e_d0, e_d1, e_w, e_s)
