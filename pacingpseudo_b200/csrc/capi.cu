@@ -227,6 +227,23 @@ int pp_scribble_loss_bwd(const float* zw, const float* zs, const float* za, cons
   return scribble_loss_bwd(zw, zs, za, target, mask, acc, g_pce, g_ent, g_cr, g_aux, dzw, dzs, dza, N, C, HW,
                            ignore_index, do_ent, cr_variant, detach_weak, ST(stream));
 }
+int pp_scribble_loss_lowaux_fwd(const float* zw, const float* zs, const float* za_low, int aux_h, int aux_w,
+                                const uint8_t* target, const float* mask, double* acc, float* loss_pce,
+                                float* loss_ent, float* loss_cr, float* loss_aux, int N, int C, int H, int W,
+                                int ignore_index, int do_ent, int cr_variant, void* stream) {
+  PP_REQUIRE(za_low != nullptr && aux_h > 0 && aux_w > 0 && H > 0 && W > 0, "pp_scribble_loss_lowaux_fwd: bad aux tensor");
+  return scribble_loss_fwd(zw, zs, za_low, target, mask, acc, loss_pce, loss_ent, loss_cr, loss_aux, N, C, H * W,
+                           ignore_index, do_ent, cr_variant, ST(stream), aux_h, aux_w, W);
+}
+int pp_scribble_loss_lowaux_bwd(const float* zw, const float* zs, const float* za_low, int aux_h, int aux_w,
+                                const uint8_t* target, const float* mask, const double* acc, const float* g_pce,
+                                const float* g_ent, const float* g_cr, const float* g_aux, float* dzw, float* dzs,
+                                float* dza_low, int N, int C, int H, int W, int ignore_index, int do_ent,
+                                int cr_variant, int detach_weak, void* stream) {
+  PP_REQUIRE(za_low != nullptr && aux_h > 0 && aux_w > 0 && H > 0 && W > 0, "pp_scribble_loss_lowaux_bwd: bad aux tensor");
+  return scribble_loss_bwd(zw, zs, za_low, target, mask, acc, g_pce, g_ent, g_cr, g_aux, dzw, dzs, dza_low, N, C, H * W,
+                           ignore_index, do_ent, cr_variant, detach_weak, ST(stream), aux_h, aux_w, W);
+}
 int pp_pair_loss_fwd(const float* a, const float* b, const float* mask, double* pacc, float* loss, int N, int C,
                      int HW, int variant, void* stream) {
   return pair_loss_fwd(a, b, mask, pacc, loss, N, C, HW, variant, ST(stream));

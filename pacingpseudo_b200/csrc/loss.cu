@@ -161,27 +161,73 @@ __device__ __forceinline__ void block_accumulate(float (&v)[6], double* __restri
   }
 }
 
+// Aux logits. The reference up-samples fc_cls's [N][C][h][w] output to the label size (F.interpolate, bilinear,
+// align_corners=True: aux_path_memory.py:52) and takes the partial CE of that tensor. Only LABELLED pixels (~1 % of a
+// scribble map) ever read it, so with AuxLow.h > 0 the kernels take the small tensor itself and interpolate the C logits
+// of a labelled pixel in place (4 taps per class out of L1/L2, same expression as upsample_planes_fwd), and the backward
+// pass scatters the pixel's gradient to the same 4 taps with fp32 atomics into the pre-zeroed [N][C][h][w] gradient.
+// No full-resolution aux tensor or gradient is written or read. AuxLow.h == 0: za / dza are full-resolution planes.
+struct AuxLow { int h, w, W; float sh, sw; };
+template <int NC>
+__device__ __forceinline__ void aux_logits_at(const float* __restrict__ za, const AuxLow& al, int n, int hw, int HW, int C,
+                                              float (&v)[NC]) {
+  if (al.h == 0) {
+    const float* z = za + static_cast<size_t>(n) * C * HW + hw;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) v[c] = (c < C) ? __ldg(z + static_cast<size_t>(c) * HW) : 0.f;
+  } else {
+    const int Y = hw / al.W, X = hw - Y * al.W;
+    const Lerp ly = lerp_src(Y, al.h, al.sh), lx = lerp_src(X, al.w, al.sw);
+    const float* z = za + static_cast<size_t>(n) * C * al.h * al.w;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (c < C) {
+        const float* r0 = z + (static_cast<size_t>(c) * al.h + ly.i0) * al.w;
+        const float* r1 = z + (static_cast<size_t>(c) * al.h + ly.i1) * al.w;
+        v[c] = ly.w0 * (lx.w0 * __ldg(r0 + lx.i0) + lx.w1 * __ldg(r0 + lx.i1)) +
+               ly.w1 * (lx.w0 * __ldg(r1 + lx.i0) + lx.w1 * __ldg(r1 + lx.i1));
+      } else {
+        v[c] = 0.f;
+      }
+    }
+  }
+}
+template <int NC>
+__device__ __forceinline__ void aux_grad_scatter(float* __restrict__ dza, const AuxLow& al, int n, int hw, int C,
+                                                 const float (&g)[NC]) {
+  const int Y = hw / al.W, X = hw - Y * al.W;
+  const Lerp ly = lerp_src(Y, al.h, al.sh), lx = lerp_src(X, al.w, al.sw);
+  float* z = dza + static_cast<size_t>(n) * C * al.h * al.w;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c < C) {
+      float* r0 = z + (static_cast<size_t>(c) * al.h + ly.i0) * al.w;
+      float* r1 = z + (static_cast<size_t>(c) * al.h + ly.i1) * al.w;
+      atomicAdd(r0 + lx.i0, ly.w0 * lx.w0 * g[c]);
+      atomicAdd(r0 + lx.i1, ly.w0 * lx.w1 * g[c]);
+      atomicAdd(r1 + lx.i0, ly.w1 * lx.w0 * g[c]);
+      atomicAdd(r1 + lx.i1, ly.w1 * lx.w1 * g[c]);
+    }
+  }
+}
+
 template <int V, int NC>
 __global__ void __launch_bounds__(256)
 scribble_loss_fwd_kernel(const float* __restrict__ zw, const float* __restrict__ zs, const float* __restrict__ za,
                          const uint8_t* __restrict__ target, const float* __restrict__ mask, double* __restrict__ acc,
-                         int P, int HW, int C, int ignore_index, int do_ent, int cr_variant) {
+                         int P, int HW, int C, int ignore_index, int do_ent, int cr_variant, const AuxLow al) {
   float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int groups = P / V;
   for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
     const int p = gi * V;
     const int n = p / HW, hw = p - n * HW;
     const size_t off = static_cast<size_t>(n) * C * HW + hw;
-    float vw[V][NC], vs[V][NC], va[V][NC];
+    float vw[V][NC], vs[V][NC];
     int tv[V];
     float mv[V];
     load_planes<V, NC>(zw + off, HW, C, vw);
     if (cr_variant != CR_NONE) load_planes<V, NC>(zs + off, HW, C, vs);
     load_target_mask<V>(target, mask, p, ignore_index, tv, mv);
-    bool any_lab = false;
-#pragma unroll
-    for (int j = 0; j < V; ++j) any_lab |= (target != nullptr) && (tv[j] != ignore_index) && (tv[j] < C);
-    if (za != nullptr && any_lab) load_planes<V, NC>(za + off, HW, C, va);   // aux logits matter on labelled pixels only
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       SoftmaxT<NC> w;
@@ -209,9 +255,11 @@ scribble_loss_fwd_kernel(const float* __restrict__ zw, const float* __restrict__
         softmax_of(vs[j], C, sx);
         part[ACC_CR] += m * cr_pixel(cr_variant, C, w, sx);
       }
-      if (za != nullptr && lab) {
+      if (za != nullptr && lab) {   // aux logits matter on labelled pixels only
+        float va[NC];
+        aux_logits_at<NC>(za, al, n, hw + j, HW, C, va);
         SoftmaxT<NC> a;
-        softmax_of(va[j], C, a);
+        softmax_of(va, C, a);
         float lpt = 0.f;
 #pragma unroll
         for (int c = 0; c < NC; ++c) lpt = (c == t) ? a.lp[c] : lpt;
@@ -350,7 +398,7 @@ template <int C, int CR, int V>
 __global__ void __launch_bounds__(256, 3)
 scribble_loss_fwd_lean_kernel(const float* __restrict__ zw, const float* __restrict__ zs, const float* __restrict__ za,
                               const uint8_t* __restrict__ target, const float* __restrict__ mask,
-                              double* __restrict__ acc, int P, int HW, int ignore_index, int do_ent) {
+                              double* __restrict__ acc, int P, int HW, int ignore_index, int do_ent, const AuxLow al) {
   float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int gi, g_end;
   lean_span<V>(P / V, gi, g_end);
@@ -393,14 +441,14 @@ scribble_loss_fwd_lean_kernel(const float* __restrict__ zw, const float* __restr
       }
     }
     if (za != nullptr && any_lab) {                    // aux logits matter on labelled pixels only
-      float va[V][C];
-      load_planes4<C, V>(za + off, HW, va);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         const int t = tv[j];
         if ((t != ignore_index) && (t < C)) {
+          float va[C];
+          aux_logits_at<C>(za, al, n, hw + j, HW, C, va);
           LeanSoftmax<C> a;
-          a.of(va[j]);
+          a.of(va);
           part[ACC_AUX] += a.lS - pick<C>(a.d, t);
         }
       }
@@ -416,7 +464,8 @@ scribble_loss_bwd_lean_kernel(const float* __restrict__ zw, const float* __restr
                               const double* __restrict__ acc, const float* __restrict__ g_pce,
                               const float* __restrict__ g_ent, const float* __restrict__ g_cr,
                               const float* __restrict__ g_aux, float* __restrict__ dzw, float* __restrict__ dzs,
-                              float* __restrict__ dza, int P, int HW, int ignore_index, int do_ent, int detach_weak) {
+                              float* __restrict__ dza, int P, int HW, int ignore_index, int do_ent, int detach_weak,
+                              const AuxLow al) {
   const float gp = g_pce ? *g_pce : 0.f, ge = (do_ent && g_ent) ? *g_ent : 0.f;
   const float gc = (CR != CR_NONE && g_cr) ? *g_cr : 0.f, ga = (za && g_aux) ? *g_aux : 0.f;
   const int has_mask = mask != nullptr;
@@ -509,7 +558,23 @@ scribble_loss_bwd_lean_kernel(const float* __restrict__ zw, const float* __restr
       if (dzs != nullptr) store_planes4<C, V>(dzs + off, HW, vs);
     }
     if (dzw != nullptr) store_planes4<C, V>(dzw + off, HW, vw);
-    if (do_aux) {
+    if (do_aux && al.h > 0) {                          // low-resolution aux logits: labelled pixels scatter to 4 taps
+      if (any_lab) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const int t = tv[j];
+          if ((t != ignore_index) && (t < C)) {
+            float va[C];
+            aux_logits_at<C>(za, al, n, hw + j, HW, C, va);
+            LeanSoftmax<C> a;
+            a.of(va);
+#pragma unroll
+            for (int c = 0; c < C; ++c) va[c] = k_aux * (a.p(c) - (c == t ? 1.f : 0.f));
+            aux_grad_scatter<C>(dza, al, n, hw + j, C, va);
+          }
+        }
+      }
+    } else if (do_aux) {
       float va[V][C];
       if (any_lab) {
         load_planes4<C, V>(za + off, HW, va);
@@ -560,23 +625,32 @@ static bool loss_vec4_ok(int HW, const void* a, const void* b, const void* c, co
 
 int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const uint8_t* target, const float* mask,
                       double* acc, float* loss_pce, float* loss_ent, float* loss_cr, float* loss_aux, int N, int C,
-                      int HW, int ignore_index, int do_ent, int cr_variant, cudaStream_t s) {
+                      int HW, int ignore_index, int do_ent, int cr_variant, cudaStream_t s, int aux_h, int aux_w,
+                      int W) {
   PP_REQUIRE(C >= 1 && C <= kMaxC, "scribble_loss: num_classes=%d unsupported (max %d)", C, kMaxC);
+  AuxLow al{0, 0, 0, 0.f, 0.f};
+  if (za != nullptr && aux_h > 0) {   // za is the low-resolution tensor [N][C][aux_h][aux_w]
+    PP_REQUIRE(aux_w > 0 && W > 0 && HW % W == 0, "scribble_loss: bad aux / image size (%d x %d, W=%d, HW=%d)", aux_h, aux_w, W, HW);
+    al = AuxLow{aux_h, aux_w, W, ac_scale(aux_h, HW / W), ac_scale(aux_w, W)};
+  }
+  const bool aux_full = za != nullptr && al.h == 0;
   PP_REQUIRE(cr_variant >= CR_NONE && cr_variant <= CR_KL, "scribble_loss: bad consistency variant %d", cr_variant);
   PP_REQUIRE((cr_variant == CR_NONE) == (zs == nullptr), "scribble_loss: strong logits / variant mismatch");
   const long long P = static_cast<long long>(N) * HW;
   PP_REQUIRE(P * C < (1LL << 31), "scribble_loss: %lld logits exceed the 32-bit index range", P * C);
   PP_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ACC_SLOTS, s));
   // algorithmic bytes: every logits tensor read once, u8 target + fp32 mask read once
-  const double bytes = static_cast<double>(P) * ((1 + (zs != nullptr) + (za != nullptr)) * 4.0 * C + (target != nullptr) +
-                                                 4.0 * (mask != nullptr));
+  // (a low-resolution aux tensor adds N*C*h*w*4 bytes: 0.2 MB for 12 x 5 x 32 x 32)
+  const double bytes = static_cast<double>(P) * ((1 + (zs != nullptr) + aux_full) * 4.0 * C + (target != nullptr) +
+                                                 4.0 * (mask != nullptr)) +
+                       (al.h > 0 ? 4.0 * N * C * al.h * al.w : 0.0);
   const int slot = prof_begin(PROF_LOSS, bytes, s);
 #define PP_LOSS_FWD(V_, NC_, P_)                                                                              \
   scribble_loss_fwd_kernel<V_, NC_><<<grid_for_px(P_, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW, C, \
-                                                                         ignore_index, do_ent, cr_variant)
+                                                                         ignore_index, do_ent, cr_variant, al)
 #define PP_LEAN_FWD(C_, CR_)                                                                                       \
   scribble_loss_fwd_lean_kernel<C_, CR_, 4><<<lean_grid(P / 4), 256, 0, s>>>(zw, zs, za, target, mask, acc, int(P), HW, \
-                                                                            ignore_index, do_ent)
+                                                                            ignore_index, do_ent, al)
 #define PP_LEAN_FWD_C(C_)                                                                                           \
   switch (cr_variant) {                                                                                             \
     case CR_NONE: PP_LEAN_FWD(C_, CR_NONE); break;                                                                  \
@@ -585,7 +659,7 @@ int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const u
     case CR_L2: PP_LEAN_FWD(C_, CR_L2); break;                                                                      \
     default: PP_LEAN_FWD(C_, CR_KL); break;                                                                         \
   }
-  const bool vec4 = loss_vec4_ok(HW, zw, zs, za, target, mask);
+  const bool vec4 = loss_vec4_ok(HW, zw, zs, nullptr, target, mask);   // (the aux logits are read with scalar loads)
   if (vec4 && target != nullptr && lean_classes(C) && !generic_loss_forced()) {
     if (C == 2) { PP_LEAN_FWD_C(2); } else if (C == 3) { PP_LEAN_FWD_C(3); }
     else if (C == 4) { PP_LEAN_FWD_C(4); } else { PP_LEAN_FWD_C(5); }
@@ -614,7 +688,7 @@ scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__
                          const float* __restrict__ g_ent, const float* __restrict__ g_cr,
                          const float* __restrict__ g_aux, float* __restrict__ dzw, float* __restrict__ dzs,
                          float* __restrict__ dza, int P, int HW, int C, int ignore_index, int do_ent,
-                         int cr_variant, int detach_weak) {
+                         int cr_variant, int detach_weak, const AuxLow al) {
   const float gp = g_pce ? *g_pce : 0.f, ge = (do_ent && g_ent) ? *g_ent : 0.f;
   const float gc = (cr_variant != CR_NONE && g_cr) ? *g_cr : 0.f, ga = (za && g_aux) ? *g_aux : 0.f;
   const int has_mask = mask != nullptr;
@@ -640,7 +714,8 @@ scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__
 #pragma unroll
     for (int j = 0; j < V; ++j) any_lab |= (target != nullptr) && (tv[j] != ignore_index) && (tv[j] < C);
     const bool do_aux = za != nullptr && dza != nullptr;
-    if (do_aux && any_lab) load_planes<V, NC>(za + off, HW, C, va);
+    const bool aux_low = al.h > 0;
+    if (do_aux && any_lab && !aux_low) load_planes<V, NC>(za + off, HW, C, va);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       SoftmaxT<NC> w;
@@ -695,7 +770,17 @@ scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__
       }
 #pragma unroll
       for (int c = 0; c < NC; ++c) vw[j][c] = d[c];
-      if (do_aux) {
+      if (do_aux && aux_low) {
+        if (lab) {   // labelled pixels scatter their gradient to the 4 taps of the low-resolution tensor
+          float g[NC];
+          aux_logits_at<NC>(za, al, n, hw + j, HW, C, g);
+          SoftmaxT<NC> a;
+          softmax_of(g, C, a);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) g[c] = ga * inv_lab * (a.p[c] - (c == t ? 1.f : 0.f));
+          aux_grad_scatter<NC>(dza, al, n, hw + j, C, g);
+        }
+      } else if (do_aux) {
         if (lab) {
           SoftmaxT<NC> a;
           softmax_of(va[j], C, a);
@@ -709,30 +794,38 @@ scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__
     }
     if (cr_variant != CR_NONE && dzs != nullptr) store_planes<V, NC>(dzs + off, HW, C, vs);
     if (dzw != nullptr) store_planes<V, NC>(dzw + off, HW, C, vw);
-    if (do_aux) store_planes<V, NC>(dza + off, HW, C, va);
+    if (do_aux && !aux_low) store_planes<V, NC>(dza + off, HW, C, va);
   }
 }
 
 int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const uint8_t* target, const float* mask,
                       const double* acc, const float* g_pce, const float* g_ent, const float* g_cr, const float* g_aux,
                       float* dzw, float* dzs, float* dza, int N, int C, int HW, int ignore_index, int do_ent,
-                      int cr_variant, int detach_weak, cudaStream_t s) {
+                      int cr_variant, int detach_weak, cudaStream_t s, int aux_h, int aux_w, int W) {
   PP_REQUIRE(C >= 1 && C <= kMaxC, "scribble_loss_bwd: num_classes=%d unsupported", C);
+  AuxLow al{0, 0, 0, 0.f, 0.f};
+  if (za != nullptr && aux_h > 0) {   // za / dza are the low-resolution tensors [N][C][aux_h][aux_w]
+    PP_REQUIRE(aux_w > 0 && W > 0 && HW % W == 0, "scribble_loss_bwd: bad aux / image size (%d x %d, W=%d, HW=%d)", aux_h, aux_w, W, HW);
+    al = AuxLow{aux_h, aux_w, W, ac_scale(aux_h, HW / W), ac_scale(aux_w, W)};
+    if (dza != nullptr) PP_CHECK_CUDA(cudaMemsetAsync(dza, 0, sizeof(float) * N * C * aux_h * aux_w, s));
+  }
+  const bool aux_full = za != nullptr && al.h == 0;
   const long long P = static_cast<long long>(N) * HW;
   PP_REQUIRE(P * C < (1LL << 31), "scribble_loss_bwd: %lld logits exceed the 32-bit index range", P * C);
   // algorithmic bytes: forward reads + one write per gradient tensor
-  const double bytes = static_cast<double>(P) * ((1 + (zs != nullptr) + (za != nullptr)) * 4.0 * C + (target != nullptr) +
+  const double bytes = static_cast<double>(P) * ((1 + (zs != nullptr) + aux_full) * 4.0 * C + (target != nullptr) +
                                                  4.0 * (mask != nullptr) +
-                                                 ((dzw != nullptr) + (dzs != nullptr) + (dza != nullptr)) * 4.0 * C);
+                                                 ((dzw != nullptr) + (dzs != nullptr) + (aux_full && dza != nullptr)) * 4.0 * C) +
+                       (al.h > 0 ? 8.0 * N * C * al.h * al.w : 0.0);
   const int slot = prof_begin(PROF_LOSS, bytes, s);
 #define PP_LOSS_BWD(V_, NC_, P_)                                                                                    \
   scribble_loss_bwd_kernel<V_, NC_><<<grid_for_px(P_, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent, g_cr, \
                                                                          g_aux, dzw, dzs, dza, int(P), HW, C,          \
-                                                                         ignore_index, do_ent, cr_variant, detach_weak)
+                                                                         ignore_index, do_ent, cr_variant, detach_weak, al)
 #define PP_LEAN_BWD(C_, CR_)                                                                                       \
   scribble_loss_bwd_lean_kernel<C_, CR_, 4><<<lean_grid(P / 4), 256, 0, s>>>(                                        \
       zw, zs, za, target, mask, acc, g_pce, g_ent, g_cr, g_aux, dzw, dzs, dza, int(P), HW, ignore_index, do_ent,     \
-      detach_weak)
+      detach_weak, al)
 #define PP_LEAN_BWD_C(C_)                                                                                           \
   switch (cr_variant) {                                                                                             \
     case CR_NONE: PP_LEAN_BWD(C_, CR_NONE); break;                                                                  \
@@ -741,7 +834,7 @@ int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const u
     case CR_L2: PP_LEAN_BWD(C_, CR_L2); break;                                                                      \
     default: PP_LEAN_BWD(C_, CR_KL); break;                                                                         \
   }
-  const bool vec4 = loss_vec4_ok(HW, zw, zs, za, target, mask, dzw, dzs, dza);
+  const bool vec4 = loss_vec4_ok(HW, zw, zs, aux_full ? za : nullptr, target, mask, dzw, dzs, aux_full ? dza : nullptr);
   if (vec4 && target != nullptr && lean_classes(C) && !generic_loss_forced()) {
     if (C == 2) { PP_LEAN_BWD_C(2); } else if (C == 3) { PP_LEAN_BWD_C(3); }
     else if (C == 4) { PP_LEAN_BWD_C(4); } else { PP_LEAN_BWD_C(5); }

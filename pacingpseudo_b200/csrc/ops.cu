@@ -859,6 +859,17 @@ int bn_finalize(const double* sums, const float* gamma, const float* beta, float
 // on the critical chain between the convolutions, so their latency at the 32 x 32 stages matters as much as bandwidth.
 static constexpr int kBnSlabVecs = 16;
 static inline int bn_slab_vecs(int C) { return C / 8 < kBnSlabVecs ? C / 8 : kBnSlabVecs; }
+// Replicas of the one-pass eval backward's accumulators (bn_bwd_eval): its ~890 blocks all end in 2 * (slab channels)
+// double atomics, and same-cache-line atomics serialise in L2. The atomics per line scale with 1 / (channel slabs), so the
+// narrow layers get the most replicas: 8 for C <= 128, 4 at 256, 2 at 512. PP_BN_REPLICAS=n forces a count (1 = none).
+int bn_bwd_replicas(int C) {
+  static const int forced = [] { const char* e = getenv("PP_BN_REPLICAS"); return e ? atoi(e) : 0; }();
+  if (forced > 0) return forced < kBnBwdReplicas ? forced : kBnBwdReplicas;
+  if (C % 8 != 0) return 1;
+  const int slabs = (C / 8) / bn_slab_vecs(C);
+  const int r = kBnBwdReplicas / (slabs > 0 ? slabs : 1);
+  return r < 1 ? 1 : r;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ coef,
@@ -1136,7 +1147,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_eval_kernel(const T* __rest
                                                                  T* __restrict__ dy, float* __restrict__ dgamma,
                                                                  float* __restrict__ dbeta, float* __restrict__ dbias,
                                                                  int P, int C, int chunk, float slope, float inv_slope,
-                                                                 int vecs) {
+                                                                 int vecs, int reps) {
   __shared__ float red[kBnThreads][17];
   __shared__ unsigned int s_last;
   constexpr int U = 4;
@@ -1191,20 +1202,28 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_eval_kernel(const T* __rest
     const int c = t % cb, st = t / cb;
     double acc = 0.0;
     for (int k = 0; k < pl; ++k) acc += static_cast<double>(red[k * vecs + c / 8][st * 8 + c % 8]);
-    atomicAdd(sums + static_cast<size_t>(cs + c) * 2 + st, acc);
+    // [replica][C][2]: the blocks go round-robin over the replicas (see bn_bwd_replicas)
+    atomicAdd(sums + (static_cast<size_t>((blockIdx.x + blockIdx.y) % reps) * C + cs + c) * 2 + st, acc);
   }
   // last block (of all slabs): parameter gradients from the complete sums
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(sums + 2 * static_cast<size_t>(C));
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(sums + 2 * static_cast<size_t>(C) * reps);
     s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1u : 0u;
   }
   __syncthreads();
   if (s_last) {
     __threadfence();
     for (int c = threadIdx.x; c < C; c += kBnThreads) {
-      const double sdz = __ldcg(sums + static_cast<size_t>(c) * 2), sdx = __ldcg(sums + static_cast<size_t>(c) * 2 + 1);
+      double2 part[kBnBwdReplicas];   // all replica loads in flight before the first add
+#pragma unroll
+      for (int r = 0; r < kBnBwdReplicas; ++r)
+        part[r] = r < reps ? __ldcg(reinterpret_cast<const double2*>(sums + (static_cast<size_t>(r) * C + c) * 2))
+                           : make_double2(0.0, 0.0);
+      double sdz = 0.0, sdx = 0.0;
+#pragma unroll
+      for (int r = 0; r < kBnBwdReplicas; ++r) { sdz += part[r].x; sdx += part[r].y; }
       dbeta[c] += static_cast<float>(sdz);
       dgamma[c] += static_cast<float>(sdx);
       if (dbias != nullptr) dbias[c] += static_cast<float>(sdz * static_cast<double>(coef[c]));
@@ -1213,8 +1232,10 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_eval_kernel(const T* __rest
 }
 
 int bn_bwd_eval(int dtype, const void* da, const void* a, const float* coef, double* sums, float* dgamma, float* dbeta,
-                float* dbias, void* dy, long long P, int C, float slope, cudaStream_t s) {
+                float* dbias, void* dy, long long P, int C, float slope, cudaStream_t s, int reps) {
   PP_REQUIRE(C % 8 == 0 && C / 8 <= kBnThreads && kBnThreads % (C / 8) == 0, "bn_bwd_eval: C=%d unsupported", C);
+  if (reps < 1) reps = 1;
+  if (reps > kBnBwdReplicas) reps = kBnBwdReplicas;
   PP_REQUIRE(slope != 0.f, "bn_bwd_eval: a zero slope is not invertible");
   PP_REQUIRE_INT32(P * C, "bn_bwd_eval");
   int chunk, blocks;
@@ -1226,7 +1247,7 @@ int bn_bwd_eval(int dtype, const void* da, const void* a, const float* coef, dou
   bn_chunks(1, P, bps > 0 ? bps : 6, &chunk, &blocks, slabs);
   PP_DISPATCH_T(dtype, bn_bwd_eval_kernel<T><<<dim3(blocks, slabs), kBnThreads, 0, s>>>(
                            static_cast<const T*>(da), static_cast<const T*>(a), coef, sums, static_cast<T*>(dy), dgamma,
-                           dbeta, dbias, int(P), C, chunk, slope, 1.f / slope, vecs););
+                           dbeta, dbias, int(P), C, chunk, slope, 1.f / slope, vecs, reps););
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -1334,19 +1355,7 @@ int maxpool_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int H
 // Bilinear upsampling, align_corners=True (unet.py:144 nn.Upsample; aux_path_memory.py:52
 // F.interpolate). Source index arithmetic follows ATen: src = dst * (in-1)/(out-1) in fp32.
 // ==============================================================================================
-struct Lerp { int i0, i1; float w0, w1; };
-__device__ __forceinline__ Lerp lerp_src(int dst, int in_size, float scale) {
-  const float r = scale * static_cast<float>(dst);
-  Lerp l;
-  l.i0 = static_cast<int>(r);
-  l.i1 = l.i0 + ((l.i0 < in_size - 1) ? 1 : 0);
-  l.w1 = r - static_cast<float>(l.i0);
-  l.w0 = 1.f - l.w1;
-  return l;
-}
-static inline float ac_scale(int in_size, int out_size) {
-  return out_size > 1 ? static_cast<float>(in_size - 1) / static_cast<float>(out_size - 1) : 0.f;
-}
+// (Lerp / lerp_src / ac_scale live in pp_common.cuh: the fused scribble loss samples the aux logits with them too.)
 // weight with which output index `dst` reads input index `i`
 __device__ __forceinline__ float lerp_weight(int dst, int i, int in_size, float scale) {
   const Lerp l = lerp_src(dst, in_size, scale);

@@ -88,6 +88,23 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
+// Bilinear interpolation with align_corners=True (nn.Upsample in unet.py:144, F.interpolate in aux_path_memory.py:52):
+// source index arithmetic as in ATen, src = dst * (in - 1) / (out - 1) in fp32; at the last input index the upper tap
+// folds onto the lower one.
+struct Lerp { int i0, i1; float w0, w1; };
+__device__ __forceinline__ Lerp lerp_src(int dst, int in_size, float scale) {
+  const float r = scale * static_cast<float>(dst);
+  Lerp l;
+  l.i0 = static_cast<int>(r);
+  l.i1 = l.i0 + ((l.i0 < in_size - 1) ? 1 : 0);
+  l.w1 = r - static_cast<float>(l.i0);
+  l.w0 = 1.f - l.w1;
+  return l;
+}
+static inline float ac_scale(int in_size, int out_size) {
+  return out_size > 1 ? static_cast<float>(in_size - 1) / static_cast<float>(out_size - 1) : 0.f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -77,9 +77,12 @@ int bn_eval_coef_multi(int n, const float* const* gamma, const float* const* bet
 // Backward of conv -> eval-BN -> LeakyReLU given only the saved ACTIVATION a (no pre-BN tensor exists in this mode):
 //   dz = da * (a > 0 ? 1 : slope), dy = dz * scale; z = a > 0 ? a : a / slope, xhat = (z - beta) / gamma;
 //   dgamma += sum dz * xhat, dbeta += sum dz, dbias += scale * sum dz   (ONE pass; the last block folds the sums).
-// sums: 2*C doubles + one unsigned ticket (placed after them), zeroed by the caller.
+// sums: reps * 2*C doubles ([replica][C][2]: the blocks spread their atomics over the replicas) + one unsigned ticket
+// placed after them, zeroed by the caller. bn_bwd_replicas(C) is the count the UNet plan uses (<= kBnBwdReplicas).
+constexpr int kBnBwdReplicas = 8;
+int bn_bwd_replicas(int C);
 int bn_bwd_eval(int dtype, const void* da, const void* a, const float* coef, double* sums, float* dgamma, float* dbeta,
-                float* dbias, void* dy, long long P, int C, float slope, cudaStream_t s);
+                float* dbias, void* dy, long long P, int C, float slope, cudaStream_t s, int reps = 1);
 int maxpool_fwd(int dtype, const void* x, void* y, int N, int H, int W, int C, cudaStream_t s);
 int maxpool_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int H, int W, int C, int accumulate,
                 cudaStream_t s);
@@ -104,13 +107,17 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float l
 
 // ---- loss.cu --------------------------------------------------------------------------------------
 int onehot_argmax(const float* x, uint8_t* out, int N, int K, int HW, cudaStream_t s);
+// aux_h > 0: za (and dza) are the LOW-resolution aux logits [N][C][aux_h][aux_w]; the kernels interpolate them at the
+// labelled pixels of the W-wide label map (bilinear, align_corners=True) instead of reading an up-sampled tensor, and
+// the backward pass zeroes dza and scatters into it with atomics. aux_h == 0: full-resolution planes [N][C][HW].
 int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const uint8_t* target, const float* mask,
                       double* acc, float* loss_pce, float* loss_ent, float* loss_cr, float* loss_aux, int N, int C,
-                      int HW, int ignore_index, int do_ent, int cr_variant, cudaStream_t s);
+                      int HW, int ignore_index, int do_ent, int cr_variant, cudaStream_t s, int aux_h = 0,
+                      int aux_w = 0, int W = 0);
 int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const uint8_t* target, const float* mask,
                       const double* acc, const float* g_pce, const float* g_ent, const float* g_cr, const float* g_aux,
                       float* dzw, float* dzs, float* dza, int N, int C, int HW, int ignore_index, int do_ent,
-                      int cr_variant, int detach_weak, cudaStream_t s);
+                      int cr_variant, int detach_weak, cudaStream_t s, int aux_h = 0, int aux_w = 0, int W = 0);
 int pair_loss_fwd(const float* a, const float* b, const float* mask, double* pacc, float* loss, int N, int C, int HW,
                   int variant, cudaStream_t s);
 int pair_loss_bwd(const float* a, const float* b, const float* mask, const double* pacc, const float* g, float* da,

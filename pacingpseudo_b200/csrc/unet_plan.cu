@@ -202,8 +202,9 @@ static UNetLayout make_layout(const UNetPlan& pl, int N, int H, int W, int G) {
   for (const ConvL& c : pl.convs) L.sums.push_back(take(sizeof(double) * 2 * G * c.cout * kStatReplicas));
   L.sums_bytes = off - L.sums_begin;
   L.bsums_begin = off;
-  // (+16 bytes: the ticket counter of the one-pass eval-mode BatchNorm backward sits behind a layer's sums)
-  for (const ConvL& c : pl.convs) L.bsums_layer.push_back(take(sizeof(double) * 2 * G * c.cout + 16));
+  // (eval mode: up to kBnBwdReplicas replicas of [C][2] and, behind them, the 16-byte ticket of the one-pass backward)
+  for (const ConvL& c : pl.convs)
+    L.bsums_layer.push_back(take(sizeof(double) * 2 * c.cout * std::max(G, kBnBwdReplicas) + 16));
   L.bsums_bytes = off - L.bsums_begin;
   L.dy_scratch = take(max_act);
   L.dy_stride = align_up(max_act);
@@ -542,7 +543,7 @@ static int unet_backward_eager(const UNetPlan& pl, const float* x, void* const* 
         rc = bn_bwd_eval(dt, base + L.act_grad[c.out], base + L.act_data[c.out],
                          reinterpret_cast<const float*>(base + L.coef[op.layer]),
                          reinterpret_cast<double*>(base + L.bsums_layer[op.layer]), gg[2], gg[3], gg[1], dy,
-                         static_cast<long long>(N) * h * w, c.cout, 0.01f, s);
+                         static_cast<long long>(N) * h * w, c.cout, 0.01f, s, bn_bwd_replicas(c.cout));
         if (rc) return rc;
       } else {
         rc = bn_bwd(dt, base + L.act_grad[c.out], base + L.yraw[op.layer],

@@ -52,7 +52,9 @@ class AuxPath(nn.Module):
 
     # ---- native path ---------------------------------------------------------------------------
     def run_native(self, feats, scribble, step, code):
-        """feats: native NHWC tensors in feat_stage order. -> (logits_aux NCHW full-res, aux_features NHWC)."""
+        """feats: native NHWC tensors in feat_stage order. -> (logits_aux_low NCHW fp32 (N, C, h, w), aux_features NHWC).
+        The logits are NOT up-sampled here (aux_path_memory.py:52): PF.upsample_planes(logits, scribble.shape[-2:])
+        gives the reference's tensor, and the fused scribble loss interpolates at the labelled pixels itself."""
         conv, bn = self.layer_bottleneck[1], self.layer_bottleneck[2]
         fa = feats[0]
         fb = feats[1] if len(feats) > 1 else None
@@ -70,7 +72,7 @@ class AuxPath(nn.Module):
                 self._bank_drop = self.drop_factors(self.num_classes, self.hid_ch, fa.device)
         logits, aux_features = AuxPathFunction.apply(
             code, (bn.running_mean, bn.running_var, bn.num_batches_tracked), self.training,
-            tuple(scribble.shape[-2:]), drop, fa, fb, w_conv, conv.bias, bn.weight, bn.bias, self.fc_cls[1].weight)
+            drop, fa, fb, w_conv, conv.bias, bn.weight, bn.bias, self.fc_cls[1].weight)
         if self.do_memory:
             self.memory_update(aux_features, scribble, step, _code=code)
             if self.bank_sync is not None:
@@ -97,8 +99,8 @@ class AuxPath(nn.Module):
             raise RuntimeError("pacingpseudo_b200 AuxPath needs the end points of the pacingpseudo_b200 UNet "
                                "(elab_end_points=True)")
         code = PF.BF16 if native[self.feat_stage[0]].dtype == torch.bfloat16 else PF.F32
-        logits, _ = self.run_native([native[s] for s in self.feat_stage], scribble, step, code)
-        out = {'logits_aux_cls': logits,
+        logits_low, _ = self.run_native([native[s] for s in self.feat_stage], scribble, step, code)
+        out = {'logits_aux_cls': PF.upsample_planes(logits_low, scribble.shape[-2:]),   # aux_path_memory.py:52
                'aux_targets': (scribble if scribble.dim() == 3 else PF.onehot_argmax(scribble)).long()}
         if self.do_memory:
             # logits_memory is produced for API parity; its loss/gradient go through memory_loss()

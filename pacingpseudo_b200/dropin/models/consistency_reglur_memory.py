@@ -16,6 +16,58 @@ from .aux_path_memory import *  # noqa: F401,F403
 from .aux_path_memory import AuxPath
 
 
+class _Pending(object):
+    __slots__ = ("make",)
+
+    def __init__(self, make):
+        self.make = make
+
+
+class NetOutputs(dict):
+    """The reference's output dict (consistency_reglur_memory.py:84-100) with values that are produced on first
+    access. `logits_aux_cls` is the only one: the training step never reads it (train_chaos.py:355 looks at it for
+    the TensorBoard images only; the loss kernels interpolate the low-resolution aux logits at the labelled pixels
+    themselves), so its F.interpolate (aux_path_memory.py:52) runs when somebody asks for the key. Every read path
+    (`[]`, get, items, values, pop, iteration-based copies such as dict(out) / other.update(out)) resolves it."""
+
+    def set_lazy(self, key, make):
+        dict.__setitem__(self, key, _Pending(make))
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if isinstance(v, _Pending):
+            v = v.make()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def __iter__(self):   # (an overridden __iter__ also keeps dict(out) / d.update(out) off CPython's raw-value fast path)
+        return iter(list(dict.keys(self)))
+
+    def keys(self):
+        return list(dict.keys(self))
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def pop(self, key, *default):
+        if key in self:
+            v = self[key]
+            dict.__delitem__(self, key)
+            return v
+        if default:
+            return default[0]
+        raise KeyError(key)
+
+    def copy(self):
+        return dict(self.items())
+
+
 class ConsistencyRegulr(nn.Module):
     def __init__(self, kwargs_unet, kwargs_aux_path=None, args_parser=None):
         super(ConsistencyRegulr, self).__init__()
@@ -28,7 +80,7 @@ class ConsistencyRegulr(nn.Module):
     def forward(self, names_to_data, mode=None, step=None):
         assert mode in ['train', 'val', None]
         args = self.args
-        net_outputs = {}
+        net_outputs = NetOutputs()
         image = names_to_data['image']
         n = image.shape[0]
         train = mode == 'train'
@@ -49,7 +101,7 @@ class ConsistencyRegulr(nn.Module):
         scb_target = scribble.to(torch.uint8) if scribble.dim() == 3 else PF.onehot_argmax(scribble)
         valid_mask = names_to_data.get('valid_mask')
 
-        logits_aux = None
+        logits_aux = None   # low resolution (N, C, h, w): the loss kernels interpolate at the labelled pixels
         if do_aux:
             # the reference hands the aux path the LAST end_points written, i.e. the strong branch's
             # features whenever the consistency branch ran (unet.py:23 instance-owned dict)
@@ -72,7 +124,9 @@ class ConsistencyRegulr(nn.Module):
         if do_cr:
             net_outputs.update({'loss_cr': losses['loss_cr'], 'segmentation/logits_strong': logits_all[n:]})
         if do_aux:
-            net_outputs.update({'logits_aux_cls': logits_aux, 'loss_aux_cls': losses['loss_aux']})
+            out_hw = tuple(scribble.shape[-2:])
+            net_outputs.set_lazy('logits_aux_cls', lambda: PF.upsample_planes(logits_aux, out_hw))   # aux_path_memory.py:52
+            net_outputs.update({'loss_aux_cls': losses['loss_aux']})
             if args.do_memory:
                 net_outputs.update({'loss_memory': self.aux_path.memory_loss()})
         return net_outputs

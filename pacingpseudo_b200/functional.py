@@ -185,15 +185,50 @@ class UNetFunction(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------
 # Aux path (models/aux_path_memory.py:46-66): cat -> conv3x3 -> BN -> LeakyReLU -> 1x1 -> bilinear x8
 # --------------------------------------------------------------------------------------------
+class UpsamplePlanesFunction(torch.autograd.Function):
+    """F.interpolate(x, size, mode='bilinear', align_corners=True) of fp32 NCHW planes (aux_path_memory.py:52)."""
+
+    @staticmethod
+    def forward(ctx, x, out_hw):
+        require_cuda(x, "planes")
+        x = x.contiguous().float()
+        N, C, h, w = x.shape
+        H, W = out_hw
+        y = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            get_lib().call("pp_upsample_planes_fwd", ptr(x), ptr(y), N * C, h, w, H, W, current_stream(x.device))
+        ctx.dims = (N, C, h, w, H, W)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        N, C, h, w, H, W = ctx.dims
+        g = g.contiguous().float()
+        gx = torch.empty((N, C, h, w), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            get_lib().call("pp_upsample_planes_bwd", ptr(g), ptr(gx), N * C, h, w, H, W, current_stream(g.device))
+        return gx, None
+
+
+def upsample_planes(x, out_hw):
+    return UpsamplePlanesFunction.apply(x, tuple(int(v) for v in out_hw))
+
+
 class AuxPathFunction(torch.autograd.Function):
-    """(feat_a, feat_b, conv_w, conv_b, gamma, beta, fc_w) -> (logits_aux NCHW fp32 full-res, aux_features NHWC).
+    """(feat_a, feat_b, conv_w, conv_b, gamma, beta, fc_w) -> (logits_aux_low NCHW fp32 [N, C, h, w], aux_features NHWC).
+
+    The logits are returned at the resolution fc_cls produces them (aux_path_memory.py:51). The reference's
+    F.interpolate to the label size (aux_path_memory.py:52) is either folded into the fused scribble loss, which
+    interpolates at the labelled pixels only (pp_scribble_loss_lowaux_*), or done by upsample_planes() when a caller
+    asks for the full-resolution tensor.
 
     drop = None, or the two nn.Dropout2d layers of aux_path_memory.py:23,31 as per-(sample, channel) factors
     (s_in [N, Ca + Cb], s_hid [N, hid]; entries 0 or 1/(1-p)): s_in scales the concatenated input features,
     s_hid the bottleneck output in front of the 1x1 classifier (the returned aux_features stay un-dropped)."""
 
     @staticmethod
-    def forward(ctx, code, buffers, training, out_hw, drop, feat_a, feat_b, conv_w, conv_b, gamma, beta, fc_w):
+    def forward(ctx, code, buffers, training, drop, feat_a, feat_b, conv_w, conv_b, gamma, beta, fc_w):
         require_cuda(feat_a, "aux features")
         lib = get_lib()
         dev = feat_a.device
@@ -204,7 +239,6 @@ class AuxPathFunction(torch.autograd.Function):
         Cb = feat_b.shape[3] if feat_b is not None else 0
         hid = conv_w.shape[0]
         C = fc_w.shape[0]
-        H, W = out_hw
         rm, rv, nbt = buffers
         es = 2 if code == BF16 else 4
         with torch.cuda.device(dev):
@@ -241,28 +275,24 @@ class AuxPathFunction(torch.autograd.Function):
                 act_in = torch.empty_like(act)
                 lib.call("pp_channel_scale", code, ptr(act), ptr(s_hid), ptr(act_in), N, h * w, hid, hid, st)
             lib.call("pp_head_fwd", code, ptr(act_in), ptr(fc_w), None, ptr(low), Pg, h * w, hid, C, st)
-            logits = torch.empty((N, C, H, W), dtype=torch.float32, device=dev)
-            lib.call("pp_upsample_planes_fwd", ptr(low), ptr(logits), N * C, h, w, H, W, st)
-        ctx.code, ctx.training, ctx.dims = code, int(training), (N, h, w, Ca, Cb, hid, C, H, W)
+        ctx.code, ctx.training, ctx.dims = code, int(training), (N, h, w, Ca, Cb, hid, C)
         ctx.save_for_backward(feat_a, feat_b, wd, yraw, coef, act_in, fc_w, s_in, s_hid)
         ctx.mark_non_differentiable(act)
-        return logits, act
+        return low, act
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, g_logits, _g_act):
+    def backward(ctx, g_low, _g_act):
         lib = get_lib()
         feat_a, feat_b, wd, yraw, coef, act, fc_w, s_in, s_hid = ctx.saved_tensors   # feat_*/act: after dropout
         code = ctx.code
-        N, h, w, Ca, Cb, hid, C, H, W = ctx.dims
+        N, h, w, Ca, Cb, hid, C = ctx.dims
         dev = feat_a.device
         adt = act_dtype(code)
         Pg = N * h * w
         with torch.cuda.device(dev):
             st = current_stream(dev)
-            g_logits = g_logits.contiguous().float()
-            g_low = torch.empty((N, C, h, w), dtype=torch.float32, device=dev)
-            lib.call("pp_upsample_planes_bwd", ptr(g_logits), ptr(g_low), N * C, h, w, H, W, st)
+            g_low = g_low.contiguous().float()
             d_act = torch.empty((N, h, w, hid), dtype=adt, device=dev)
             d_fc = torch.zeros_like(fc_w)
             lib.call("pp_head_bwd", code, ptr(g_low), ptr(act), ptr(fc_w), ptr(d_act), ptr(d_fc), None, Pg, h * w, hid,
@@ -290,7 +320,7 @@ class AuxPathFunction(torch.autograd.Function):
                 if g_b is not None:
                     lib.call("pp_channel_scale", code, ptr(g_b), ctypes.c_void_p(s_in.data_ptr() + 4 * Ca), ptr(g_b), N,
                              h * w, Cb, Ca + Cb, st)
-        return None, None, None, None, None, g_a, g_b, d_w, d_bias, d_gamma, d_beta, d_fc
+        return None, None, None, None, g_a, g_b, d_w, d_bias, d_gamma, d_beta, d_fc
 
 
 # --------------------------------------------------------------------------------------------
@@ -313,7 +343,10 @@ class ScribbleLossFunction(torch.autograd.Function):
     forward(cfg, zw, zs, za, target_u8, mask) -> (loss_pce, loss_ent, loss_cr, loss_aux), each an
     independent 0-dim fp32 tensor (the caller mutates them in place, train_chaos.py:274-309).
     cfg = (ignore_index, do_ent, cr_variant, detach_weak). If `zs` is None and cr_variant != none the
-    strong logits are the second half of `zw` (batched siamese tensor).
+    strong logits are the second half of `zw` (batched siamese tensor). `za` is either the full-resolution aux
+    logits (N, C, H, W) or, when its spatial size differs from the label map's, the low-resolution tensor
+    (N, C, h, w) of aux_path_memory.py:51: the kernels then interpolate it at the labelled pixels themselves
+    (bilinear, align_corners=True, aux_path_memory.py:52) and the gradient comes back at (N, C, h, w).
     """
 
     @staticmethod
@@ -349,17 +382,28 @@ class ScribbleLossFunction(torch.autograd.Function):
         zs_p = (zw_p + N * C * H * W * 4) if siamese else (zs.data_ptr() if zs is not None else None)
         if target is not None and target.shape[0] != N:
             raise RuntimeError("scribble loss: target batch %d != logits batch %d" % (target.shape[0], N))
+        aux_low = za is not None and tuple(za.shape[-2:]) != (H, W)
+        if za is not None and (za.dim() != 4 or za.shape[0] != N or za.shape[1] != C):
+            raise RuntimeError("scribble loss: aux logits %s do not match %d samples of %d classes" % (
+                tuple(za.shape), N, C))
         with torch.cuda.device(dev):
             acc = torch.empty(8, dtype=torch.float64, device=dev)
             outs = [torch.zeros((), dtype=torch.float32, device=dev) for _ in range(4)]
-            lib.call("pp_scribble_loss_fwd", ctypes.c_void_p(zw_p), ctypes.c_void_p(zs_p) if zs_p else None, ptr(za),
-                     ptr(target), ptr(mask), ptr(acc), ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), N, C,
-                     H * W, ignore_index, int(do_ent), cr_variant, current_stream(dev))
+            if aux_low:
+                lib.call("pp_scribble_loss_lowaux_fwd", ctypes.c_void_p(zw_p), ctypes.c_void_p(zs_p) if zs_p else None,
+                         ptr(za), za.shape[2], za.shape[3], ptr(target), ptr(mask), ptr(acc), ptr(outs[0]), ptr(outs[1]),
+                         ptr(outs[2]), ptr(outs[3]), N, C, H, W, ignore_index, int(do_ent), cr_variant,
+                         current_stream(dev))
+            else:
+                lib.call("pp_scribble_loss_fwd", ctypes.c_void_p(zw_p), ctypes.c_void_p(zs_p) if zs_p else None, ptr(za),
+                         ptr(target), ptr(mask), ptr(acc), ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), N, C,
+                         H * W, ignore_index, int(do_ent), cr_variant, current_stream(dev))
             if bad_any is not None:
                 outs[0].masked_fill_(bad_any, float("nan"))
         cfg = (ignore_index, do_ent, cr_variant, detach_weak, siamese)   # the (possibly remapped) ignore label
         ctx.cfg, ctx.dims = cfg, (N, C, H, W)
         ctx.has = (zs is not None, za is not None, mask is not None)
+        ctx.aux_low = aux_low
         ctx.save_for_backward(zw, zs, za, target, mask, acc)
         return tuple(outs)
 
@@ -382,10 +426,17 @@ class ScribbleLossFunction(torch.autograd.Function):
             half = N * C * H * W * 4
             zs_p = (zw_p + half) if siamese else (zs.data_ptr() if zs is not None else None)
             dzs_p = (dzw.data_ptr() + half) if siamese else (dzs.data_ptr() if dzs is not None else None)
-            lib.call("pp_scribble_loss_bwd", ctypes.c_void_p(zw_p), ctypes.c_void_p(zs_p) if zs_p else None, ptr(za),
-                     ptr(target), ptr(mask), ptr(acc), ptr(g_pce), ptr(g_ent), ptr(g_cr), ptr(g_aux),
-                     ctypes.c_void_p(dzw.data_ptr()), ctypes.c_void_p(dzs_p) if dzs_p else None, ptr(dza), N, C, H * W,
-                     ignore_index, int(do_ent), cr_variant, int(detach_weak), current_stream(dev))
+            if ctx.aux_low:   # dza is zeroed by the library and accumulated with atomics
+                lib.call("pp_scribble_loss_lowaux_bwd", ctypes.c_void_p(zw_p), ctypes.c_void_p(zs_p) if zs_p else None,
+                         ptr(za), za.shape[2], za.shape[3], ptr(target), ptr(mask), ptr(acc), ptr(g_pce), ptr(g_ent),
+                         ptr(g_cr), ptr(g_aux), ctypes.c_void_p(dzw.data_ptr()), ctypes.c_void_p(dzs_p) if dzs_p else None,
+                         ptr(dza), N, C, H, W, ignore_index, int(do_ent), cr_variant, int(detach_weak),
+                         current_stream(dev))
+            else:
+                lib.call("pp_scribble_loss_bwd", ctypes.c_void_p(zw_p), ctypes.c_void_p(zs_p) if zs_p else None, ptr(za),
+                         ptr(target), ptr(mask), ptr(acc), ptr(g_pce), ptr(g_ent), ptr(g_cr), ptr(g_aux),
+                         ctypes.c_void_p(dzw.data_ptr()), ctypes.c_void_p(dzs_p) if dzs_p else None, ptr(dza), N, C,
+                         H * W, ignore_index, int(do_ent), cr_variant, int(detach_weak), current_stream(dev))
         return None, dzw, dzs, dza, None, None
 
 

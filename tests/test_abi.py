@@ -272,3 +272,35 @@ def test_loss_weight_ramp_up_matches_the_oracle_schedule():
     from pacingpseudo_b200.schedules import loss_weight_ramp_up
     for t in (0, 1, 40, 79, 80, 200):
         assert loss_weight_ramp_up(t, 1.0, scale=8.0) == gaussian_ramp_up(t, 1.0, scale=8.0)
+
+
+def test_net_outputs_resolves_lazy_values_on_every_read_path():
+    """The drop-in ConsistencyRegulr returns the reference's dict; `logits_aux_cls` is produced on first access
+    (dropin/models/consistency_reglur_memory.py: NetOutputs). Every way a caller can read a dict must see the value."""
+    import sys
+    from pacingpseudo_b200.dropin import DROPIN_PATH
+    if DROPIN_PATH not in sys.path:
+        sys.path.insert(0, DROPIN_PATH)
+    from models.consistency_reglur_memory import NetOutputs
+
+    def fresh():
+        made = []
+        o = NetOutputs()
+        o["loss_pce"] = 1.0
+        o.set_lazy("logits_aux_cls", lambda: (made.append(1), "tensor")[1])
+        o.update({"loss_aux_cls": 2.0})
+        return o, made
+
+    o, made = fresh()
+    assert isinstance(o, dict) and "logits_aux_cls" in o and len(o) == 3 and not made     # nothing produced yet
+    assert list(o) == list(o.keys()) == ["loss_pce", "logits_aux_cls", "loss_aux_cls"] and not made
+    assert o["logits_aux_cls"] == "tensor" and o["logits_aux_cls"] == "tensor" and made == [1]   # produced once
+    for read in (lambda d: d.get("logits_aux_cls"), lambda d: dict(d)["logits_aux_cls"], lambda d: {**d}["logits_aux_cls"],
+                 lambda d: dict(d.items())["logits_aux_cls"], lambda d: d.values()[1], lambda d: d.copy()["logits_aux_cls"],
+                 lambda d: d.pop("logits_aux_cls"), lambda d: (lambda t: (t.update(d), t)[1])({})["logits_aux_cls"]):
+        o, made = fresh()
+        assert read(o) == "tensor" and made == [1]
+    o, _ = fresh()
+    assert o.get("missing", 5) == 5 and o.pop("missing", 6) == 6
+    with pytest.raises(KeyError):
+        o.pop("missing")

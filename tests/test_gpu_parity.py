@@ -541,6 +541,54 @@ def test_fused_scribble_loss_all_terms_vs_oracle(pp, variant, C, shape, use_mask
         assert _rel(a, b) < 1e-5
 
 
+@pytest.mark.parametrize("C,shape,low", [(5, (3, 32, 48), (4, 6)), (2, (2, 24, 24), (3, 3)), (4, (2, 28, 28), (7, 7)),
+                                         (7, (2, 16, 24), (2, 3)), (5, (2, 9, 7), (3, 2)), (5, (1, 16, 16), (16, 16))])
+def test_fused_scribble_loss_low_resolution_aux_logits(pp, C, shape, low):
+    """The aux logits handed over at fc_cls's resolution (aux_path_memory.py:51): the loss kernels interpolate them at
+    the labelled pixels (pp_scribble_loss_lowaux_*). Checked against F.interpolate(bilinear, align_corners=True) +
+    the fp64 oracle losses (value of every term, gradient w.r.t. the LOW-resolution tensor), against the library's own
+    full-resolution path (PF.upsample_planes + pp_scribble_loss_*), for the lean and the generic kernels."""
+    L, PF, _ = pp
+    N, H, W = shape
+    g = torch.Generator().manual_seed(7 * C + H + low[0])
+    zw0, zs0 = (3.0 * torch.randn(N, C, H, W, generator=g, dtype=torch.float64) for _ in range(2))
+    za0 = 3.0 * torch.randn(N, C, low[0], low[1], generator=g, dtype=torch.float64)
+    target = torch.randint(0, C + 1, (N, H, W), generator=g)
+    target[torch.rand(N, H, W, generator=g) < 0.8] = C
+    target[0, 0, :4] = torch.tensor([0, C, 1, C])
+    target[-1, -1, -1] = C - 1                               # the last pixel reads the last taps
+    mask = (torch.rand(N, 1, H, W, generator=g) < 0.7).double()
+    wts = (1.0, 0.37, 0.81, 0.01)
+
+    ref_in = [t.clone().requires_grad_() for t in (zw0, zs0, za0)]
+    za_full = F.interpolate(ref_in[2], size=(H, W), mode="bilinear", align_corners=True)
+    ref_terms = _oracle_fused_losses(ref_in[0], ref_in[1], za_full, target, mask, C, "ce_loss", False)
+    sum(w * t for w, t in zip(wts, ref_terms)).backward()
+
+    grads = {}
+    for how in ("low", "low-generic", "full"):
+        os.environ["PP_LOSS_GENERIC"] = "1" if how == "low-generic" else "0"
+        try:
+            dev_in = [t.float().cuda().requires_grad_() for t in (zw0, zs0, za0)]
+            za = dev_in[2] if how != "full" else PF.upsample_planes(dev_in[2], (H, W))
+            out = PF.scribble_losses(dev_in[0], target.cuda(), C, zs=dev_in[1], za=za, mask=mask.float().cuda(),
+                                     do_ent=True, cr_variant="ce_loss")
+            terms = [out["loss_pce"], out["loss_ent"], out["loss_cr"], out["loss_aux"]]
+            sum(w * t for w, t in zip(wts, terms)).backward()
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("PP_LOSS_GENERIC", None)
+        for name, t, r in zip(("pce", "ent", "cr", "aux"), terms, ref_terms):
+            assert abs(t.item() - r.item()) <= 1e-4 * max(1.0, abs(r.item())), (how, name, t.item(), r.item())
+        assert tuple(dev_in[2].grad.shape) == (N, C) + tuple(low)
+        for name, t, r in zip(("dzw", "dzs", "dza_low"), dev_in, ref_in):
+            assert _rel(t.grad, r.grad) < 1e-4, (how, name, _rel(t.grad, r.grad))
+        grads[how] = [t.grad.clone() for t in dev_in]
+    for how in ("low-generic", "full"):
+        for a, b in zip(grads["low"], grads[how]):
+            assert _rel(a, b) < 1e-5, how
+
+
 @pytest.mark.parametrize("mode", ["cosine_similarity", "mean"])
 def test_memory_update_vs_oracle(pp, mode):
     """aux_path_memory.py:68-116 incl. sample-0-only, first-touch mean, absent classes, in-place normalisation."""
