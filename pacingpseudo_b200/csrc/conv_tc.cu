@@ -803,6 +803,148 @@ conv3x3_wgrad_rows_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __gr
 }
 
 // ----------------------------------------------------------------------------------------------
+// Row variant with the horizontal taps packed into the MMA N dimension. The kernel above issues one M = 128, N = Cout
+// (32 / 64) MMA per (kx, 16 pixels): 4 KB of X and 1-2 KB of dY read from shared memory for 16-32 tensor cycles, i.e.
+// 130-320 B/cycle against the SM's 128 B/cycle — the operand reads, not HBM, pace it (measured 2.5-2.9 TB/s of
+// algorithmic traffic). Here a K block is 64 pixels of one INPUT-aligned window: X arrives as three UNhaloed 64-pixel
+// boxes (rows y-1, y, y+1: the M chunks, as above) and dY as ONE 66-pixel box starting one pixel to the left. The three
+// horizontal taps are three N chunks of the dY operand whose leading byte offset is ONE PIXEL ROW (64 / 128 B): chunk c
+// reads dY shifted by c pixels, which is tap kx = 2 - c,
+//     D[(ky, ci), (c, co)] += sum_k X[y + ky - 1, x0 + k, ci] * dY[y, x0 - 1 + k + c, co].
+// One M = 128, N = 3 * Cout MMA per 16 pixels (two for CI = 64) instead of three (six): 2.1x fewer operand bytes per
+// FLOP. Out-of-image X / dY pixels arrive as zeros (TMA), which is the convolution's padding on both sides.
+// ----------------------------------------------------------------------------------------------
+template <int CI, int NCOUT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3x3_wgrad_rowsn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                              const WgradNarrowParams p) {
+  static_assert(NCOUT <= 64, "one dY box");
+  constexpr int PIXK = 64, YROWS = PIXK + 2;
+  constexpr int ROW_A = CI * 2, ROW_B = NCOUT * 2;
+  constexpr uint32_t SWZ_A = CI == 64 ? SWZ_128B : SWZ_64B;
+  constexpr uint32_t SWZ_B = NCOUT == 64 ? SWZ_128B : SWZ_64B;
+  constexpr int XBOX = PIXK * ROW_A;                            // 4 / 8 KB: 1 KB aligned
+  constexpr int YBOX = (YROWS * ROW_B + 1023) / 1024 * 1024;
+  constexpr int STAGE_BYTES = 3 * XBOX + YBOX;
+  constexpr int NG = CI == 32 ? 1 : 2;                          // MMA groups: ky {0,1,2,-} or {0,1} + {2,-}
+  constexpr int NN = 3 * NCOUT;                                 // MMA N: (kx chunk, co)
+  constexpr int TMEM_NEED = NG * NN;
+  constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+  static_assert(TMEM_NEED <= 512, "accumulators do not fit TMEM");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 8 KB spare after the last stage: the unused M chunk of the last stage's MMAs reads up to one X box past its dY box
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * STAGE_BYTES + 8192);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kb_begin = blockIdx.x * p.kb_per_cta;
+  const int kb_end = min(kb_begin + p.kb_per_cta, p.tiles_total);
+  const int num_k = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
+
+  if (num_k > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          const int tw = kb % p.tiles_w;
+          const int y = (kb / p.tiles_w) % p.H;
+          const int n = kb / (p.tiles_w * p.H);
+          const int x0 = tw * PIXK;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sx = smem + stage * STAGE_BYTES;
+          uint8_t* sy = sx + 3 * XBOX;
+          mbar_arrive_expect_tx(&full_bar[stage], 3 * XBOX + YROWS * ROW_B);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)   // out-of-range rows / columns arrive as zeros: the conv's padding
+            tma_load_4d(sx + ky * XBOX, &tmX, &full_bar[stage], 0, x0, y + ky - 1, n);
+          tma_load_4d(sy, &tmDY, &full_bar[stage], 0, x0 - 1, y, n);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, NN, 1, 1);  // both operands MN-major
+        constexpr uint32_t ahi = smem_desc_hi(8 * ROW_A, SWZ_A), bhi = smem_desc_hi(8 * ROW_B, SWZ_B);
+        const uint32_t base_a = smem_desc_lo(smem_u32(smem), XBOX);                // M chunks: one X box (ky) apart
+        const uint32_t base_b = smem_desc_lo(smem_u32(smem) + 3 * XBOX, ROW_B);    // N chunks: ONE pixel row apart
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t soff = 0;
+        for (int it = 0; it < num_k; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            const uint32_t a_lo = base_a + soff + g * 2 * (XBOX >> 4), b_lo = base_b + soff;
+#pragma unroll
+            for (int k = 0; k < PIXK / 16; ++k)
+              umma_bf16_lohi(tmem_base + g * NN, a_lo + k * ROW_A, ahi, b_lo + k * ROW_B, bhi, idesc,
+                             (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          soff += STAGE_BYTES >> 4;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; soff = 0; }
+        }
+        umma_commit(tmem_full_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int r = q * 32 + lane;          // accumulator row = chunk * CI + ci
+      const int ci = r % CI, chunk = r / CI;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < NG; ++g) {
+        const int ky = g * 2 + chunk;        // CI = 32: chunk 0..3 (3 unused); CI = 64: group 0 = {0,1}, group 1 = {2,-}
+        const bool row_ok = (ky < 3) && (ci < p.Csrc);
+#pragma unroll 1
+        for (int c = 0; c < NN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(g * NN + c), v);
+          tmem_wait_ld();
+          if (row_ok) {
+            const int kx = 2 - c / NCOUT, co0 = c % NCOUT;   // N chunk c / NCOUT reads dY shifted by that many pixels
+            float* o = p.dw + (static_cast<long long>(ky * 3 + kx) * p.Cout + co0) * p.ctot + p.cbase + ci;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (co0 + j < p.Cout) atomicAdd(o + static_cast<long long>(j) * p.ctot, __uint_as_float(v[j]));
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncwarp();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // Host launchers
 // ----------------------------------------------------------------------------------------------
 static int pow2_ceil(int v) {
@@ -1245,14 +1387,59 @@ static int launch_wgrad_rows(const void* dy, int Cout, const void* x, int Csrc, 
   return PP_OK;
 }
 
+template <int CI, int NCOUT>
+static int launch_wgrad_rowsn(const void* dy, int Cout, const void* x, int Csrc, int ctot, int cbase, float* dw, int N,
+                              int H, int W, cudaStream_t stream) {
+  WgradNarrowParams p{};
+  p.N = N; p.H = H; p.W = W; p.dil = 1;
+  constexpr int ROW_A = CI * 2, ROW_B = NCOUT * 2;
+  constexpr int XBOX = 64 * ROW_A, YBOX = (66 * ROW_B + 1023) / 1024 * 1024;
+  constexpr int STAGE_BYTES = 3 * XBOX + YBOX;
+  p.pixk = 64;
+  p.bw = 64; p.bh = 1; p.bn = 1;
+  p.tiles_w = ceil_div(W, 64);
+  p.tiles_h = H;
+  p.tiles_total = p.tiles_w * H * N;
+  p.Cout = Cout; p.Csrc = Csrc; p.ctot = ctot; p.cbase = cbase; p.dw = dw;
+  p.stages = (200 * 1024 - 8192) / STAGE_BYTES;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  int ctas = sm_count() < p.tiles_total ? sm_count() : p.tiles_total;
+  p.kb_per_cta = ceil_div(p.tiles_total, ctas);
+  ctas = ceil_div(p.tiles_total, p.kb_per_cta);
+  CUtensorMap tx, tdy;
+  int rc = encode_tmap_nhwc(&tx, x, N, H, W, Csrc, CI, 64, 1, 1, CI == 64);
+  if (rc) return rc;
+  rc = encode_tmap_nhwc(&tdy, dy, N, H, W, Cout, NCOUT, 66, 1, 1, NCOUT == 64);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_rowsn_tc_kernel<CI, NCOUT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024 + 256));
+    attr_set = true;
+  }
+  const int smem = p.stages * STAGE_BYTES + 8192 + 1024 + 256;
+  const double flops = 2.0 * N * H * W * 9.0 * Csrc * Cout;
+  const int slot = prof_begin(PROF_WGRAD, flops, stream);
+  conv3x3_wgrad_rowsn_tc_kernel<CI, NCOUT><<<ctas, kTcThreads, smem, stream>>>(tx, tdy, p);
+  prof_end(slot, stream);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
 static bool narrow_ok(int Csrc, int Cout) { return (Csrc == 32 || Csrc == 64) && (Cout == 32 || Cout == 64); }
 
 static int wgrad_narrow(const void* dy, int Cout, const void* x, int Csrc, int ctot, int cbase, float* dw, int N, int H,
                         int W, int dil, cudaStream_t stream) {
-  static int rows_on = -1;
+  static int rows_on = -1;   // PP_WGRAD_ROWS: 0 = nine-box kernel, 1 = row kernel (kx as A offsets), 2 = kx packed into N
   if (rows_on < 0) {
     const char* e = getenv("PP_WGRAD_ROWS");
-    rows_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    rows_on = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+  }
+  if (rows_on == 2 && dil == 1 && W >= 64) {
+    if (Csrc == 32 && Cout == 32) return launch_wgrad_rowsn<32, 32>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, stream);
+    if (Csrc == 32 && Cout == 64) return launch_wgrad_rowsn<32, 64>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, stream);
+    if (Csrc == 64 && Cout == 32) return launch_wgrad_rowsn<64, 32>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, stream);
+    return launch_wgrad_rowsn<64, 64>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, stream);
   }
   if (rows_on && dil == 1 && W >= 64) {   // row variant: X fetched 3x instead of 9x (a ragged last 64-pixel block
                                           // is zero-filled by TMA and contributes nothing)
