@@ -107,7 +107,7 @@ int pp_conv3x3_wgrad_oihw(const void* dy, int Cout, const void* x0, int C0, cons
                           float* g_oihw, float* ws_split, long long ws_floats, int N, int H, int W, int dil,
                           void* stream) {
   PP_REQUIRE(g_oihw != nullptr && dwp != nullptr, "pp_conv3x3_wgrad_oihw: null gradient / scratch pointer");
-  if (conv3x3_wgrad_tc_uses_scratch(Cout, C0, C1))
+  if (conv3x3_wgrad_tc_uses_scratch(Cout, C0, C1, W, dil))
     PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * Cout * (C0 + C1), ST(stream)));
   return conv3x3_wgrad_tc(dy, Cout, x0, C0, x1, C1, dwp, g_oihw, N, H, W, dil, ST(stream), ws_split, ws_floats);
 }

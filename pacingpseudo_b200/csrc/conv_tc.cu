@@ -525,6 +525,7 @@ struct WgradNarrowParams {
   int Cout, Csrc, ctot, cbase;
   int kb_per_cta, stages, pixk;
   float* dw;
+  int ci0;                   // first channel of the source tensor this launch covers (kx-in-N row kernel; else 0)
 };
 
 template <int CI, int NCOUT>
@@ -878,7 +879,7 @@ conv3x3_wgrad_rowsn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __g
           mbar_arrive_expect_tx(&full_bar[stage], 3 * XBOX + YROWS * ROW_B);
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)   // out-of-range rows / columns arrive as zeros: the conv's padding
-            tma_load_4d(sx + ky * XBOX, &tmX, &full_bar[stage], 0, x0, y + ky - 1, n);
+            tma_load_4d(sx + ky * XBOX, &tmX, &full_bar[stage], p.ci0, x0, y + ky - 1, n);
           tma_load_4d(sy, &tmDY, &full_bar[stage], 0, x0 - 1, y, n);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -1387,10 +1388,14 @@ static int launch_wgrad_rows(const void* dy, int Cout, const void* x, int Csrc, 
   return PP_OK;
 }
 
+// x holds Cx channels per pixel; the launch covers its channels [ci0, ci0 + Csrc) (Csrc <= CI), written to the dw columns
+// [cbase, cbase + Csrc)
 template <int CI, int NCOUT>
 static int launch_wgrad_rowsn(const void* dy, int Cout, const void* x, int Csrc, int ctot, int cbase, float* dw, int N,
-                              int H, int W, cudaStream_t stream) {
+                              int H, int W, cudaStream_t stream, int Cx = 0, int ci0 = 0) {
+  if (Cx == 0) Cx = Csrc;
   WgradNarrowParams p{};
+  p.ci0 = ci0;
   p.N = N; p.H = H; p.W = W; p.dil = 1;
   constexpr int ROW_A = CI * 2, ROW_B = NCOUT * 2;
   constexpr int XBOX = 64 * ROW_A, YBOX = (66 * ROW_B + 1023) / 1024 * 1024;
@@ -1407,7 +1412,7 @@ static int launch_wgrad_rowsn(const void* dy, int Cout, const void* x, int Csrc,
   p.kb_per_cta = ceil_div(p.tiles_total, ctas);
   ctas = ceil_div(p.tiles_total, p.kb_per_cta);
   CUtensorMap tx, tdy;
-  int rc = encode_tmap_nhwc(&tx, x, N, H, W, Csrc, CI, 64, 1, 1, CI == 64);
+  int rc = encode_tmap_nhwc(&tx, x, N, H, W, Cx, CI, 64, 1, 1, CI == 64);
   if (rc) return rc;
   rc = encode_tmap_nhwc(&tdy, dy, N, H, W, Cout, NCOUT, 66, 1, 1, NCOUT == 64);
   if (rc) return rc;
@@ -1426,14 +1431,32 @@ static int launch_wgrad_rowsn(const void* dy, int Cout, const void* x, int Csrc,
   return PP_OK;
 }
 
-static bool narrow_ok(int Csrc, int Cout) { return (Csrc == 32 || Csrc == 64) && (Cout == 32 || Cout == 64); }
+static int wgrad_rows_mode() {   // PP_WGRAD_ROWS: 0 = nine-box kernel, 1 = row kernel (kx as A offsets), 2 = kx packed into N
+  static const int mode = [] {
+    const char* e = getenv("PP_WGRAD_ROWS");
+    return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+  }();
+  return mode;
+}
+// Sources that take the narrow (pixel-range per CTA, all taps) kernels: 32 / 64 channels into 32 / 64; with the
+// kx-in-N row kernel also 128 ... 256 channels as 64-channel column groups (the 192 -> 64 layer at 128^2: its 128-channel
+// source went through the generic kernel with a half-empty M = 128 tile and nine passes over X and dY, 131 us).
+static bool narrow_ok(int Csrc, int Cout, int W, int dil) {
+  if (Cout != 32 && Cout != 64) return false;
+  if (Csrc == 32 || Csrc == 64) return true;
+  return wgrad_rows_mode() == 2 && dil == 1 && W >= 64 && Csrc % 64 == 0 && Csrc <= 256;
+}
 
 static int wgrad_narrow(const void* dy, int Cout, const void* x, int Csrc, int ctot, int cbase, float* dw, int N, int H,
                         int W, int dil, cudaStream_t stream) {
-  static int rows_on = -1;   // PP_WGRAD_ROWS: 0 = nine-box kernel, 1 = row kernel (kx as A offsets), 2 = kx packed into N
-  if (rows_on < 0) {
-    const char* e = getenv("PP_WGRAD_ROWS");
-    rows_on = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+  const int rows_on = wgrad_rows_mode();
+  if (Csrc > 64) {   // 64-channel column groups of a wider source (narrow_ok() admits them for the kx-in-N kernel only)
+    for (int c0 = 0; c0 < Csrc; c0 += 64) {
+      const int rc = Cout == 32 ? launch_wgrad_rowsn<64, 32>(dy, Cout, x, 64, ctot, cbase + c0, dw, N, H, W, stream, Csrc, c0)
+                                : launch_wgrad_rowsn<64, 64>(dy, Cout, x, 64, ctot, cbase + c0, dw, N, H, W, stream, Csrc, c0);
+      if (rc) return rc;
+    }
+    return PP_OK;
   }
   if (rows_on == 2 && dil == 1 && W >= 64) {
     if (Csrc == 32 && Cout == 32) return launch_wgrad_rowsn<32, 32>(dy, Cout, x, Csrc, ctot, cbase, dw, N, H, W, stream);
@@ -1542,8 +1565,8 @@ static int wgrad_wide(const void* dy, int Cout, const void* x0, int C0, const vo
 int unpack_wgrad_range(const float* dwp, float* g, int Cout, int Cin, int ci_begin, int ci_count, int accumulate,
                        cudaStream_t s);
 
-bool conv3x3_wgrad_tc_uses_scratch(int Cout, int C0, int C1) {
-  return narrow_ok(C0, Cout) || (C1 > 0 && narrow_ok(C1, Cout));
+bool conv3x3_wgrad_tc_uses_scratch(int Cout, int C0, int C1, int W, int dil) {
+  return narrow_ok(C0, Cout, W, dil) || (C1 > 0 && narrow_ok(C1, Cout, W, dil));
 }
 
 // dy:[N,H,W,Cout] bf16, x0/x1 as in forward.
@@ -1559,7 +1582,7 @@ int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const voi
   PP_REQUIRE(Cout % 8 == 0 && C0 % 8 == 0 && C1 % 8 == 0 && C0 > 0, "conv3x3_wgrad_tc: channels must be multiples of 8");
   PP_REQUIRE((x1 == nullptr) == (C1 == 0), "conv3x3_wgrad_tc: x1/C1 mismatch");
   const int ctot = C0 + C1;
-  const bool n0 = narrow_ok(C0, Cout), n1 = C1 > 0 && narrow_ok(C1, Cout);
+  const bool n0 = narrow_ok(C0, Cout, W, dil), n1 = C1 > 0 && narrow_ok(C1, Cout, W, dil);
   const int oihw = g_oihw != nullptr;
   float* wide_dst = oihw ? g_oihw : dwp;
   int rc = PP_OK;

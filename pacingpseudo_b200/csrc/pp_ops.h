@@ -37,7 +37,7 @@ int conv3x3_rows_tc(const void* x0, int C0, const void* x1, int C1, const void* 
 int conv3x3_wgrad_tc(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dwp,
                      float* g_oihw, int N, int H, int W, int dil, cudaStream_t s, float* ws_split = nullptr,
                      long long ws_floats = 0);
-bool conv3x3_wgrad_tc_uses_scratch(int Cout, int C0, int C1);
+bool conv3x3_wgrad_tc_uses_scratch(int Cout, int C0, int C1, int W, int dil);
 int unpack_wgrad_range(const float* dwp, float* g, int Cout, int Cin, int ci_begin, int ci_count, int accumulate,
                        cudaStream_t s);
 int conv3x3_simt(int dtype, const void* x0, int C0, const void* x1, int C1, const void* wpack, const float* bias,

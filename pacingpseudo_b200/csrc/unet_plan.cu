@@ -584,7 +584,7 @@ static int unet_backward_eager(const UNetPlan& pl, const float* x, void* const* 
       }
       if (dt == PP_BF16) {
         // wide sources accumulate straight into the OIHW gradient; narrow ones go through the packed scratch
-        if (conv3x3_wgrad_tc_uses_scratch(c.cout, c.cin0, c.cin1))
+        if (conv3x3_wgrad_tc_uses_scratch(c.cout, c.cin0, c.cin1, w, c.dil))
           PP_CHECK_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 9 * c.cout * ctot, ws_));
         rc = conv3x3_wgrad_tc(dy, c.cout, x0, c.cin0, x1, c.cin1, dwp, g_oihw, N, h, w, c.dil, ws_,
                               reinterpret_cast<float*>(base + L.dws_scratch), L.dws_floats);
