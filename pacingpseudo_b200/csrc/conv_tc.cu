@@ -807,14 +807,19 @@ conv3x3_wgrad_rows_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __gr
 // Row variant with the horizontal taps packed into the MMA N dimension. The kernel above issues one M = 128, N = Cout
 // (32 / 64) MMA per (kx, 16 pixels): 4 KB of X and 1-2 KB of dY read from shared memory for 16-32 tensor cycles, i.e.
 // 130-320 B/cycle against the SM's 128 B/cycle — the operand reads, not HBM, pace it (measured 2.5-2.9 TB/s of
-// algorithmic traffic). Here a K block is 64 pixels of one INPUT-aligned window: X arrives as three UNhaloed 64-pixel
-// boxes (rows y-1, y, y+1: the M chunks, as above) and dY as ONE 66-pixel box starting one pixel to the left. The three
+// algorithmic traffic). Here a K block is a strip of R image rows x 64 pixels: X arrives as R + 2 UNhaloed 64-pixel
+// boxes (rows y0-1 ... y0+R; output row r uses boxes r, r+1, r+2 as its M chunks, so X crosses L2 -> shared memory
+// (R + 2) / R times instead of 3 times) and every dY row as ONE 66-pixel box starting one pixel to the left. The three
 // horizontal taps are three N chunks of the dY operand whose leading byte offset is ONE PIXEL ROW (64 / 128 B): chunk c
 // reads dY shifted by c pixels, which is tap kx = 2 - c,
 //     D[(ky, ci), (c, co)] += sum_k X[y + ky - 1, x0 + k, ci] * dY[y, x0 - 1 + k + c, co].
 // One M = 128, N = 3 * Cout MMA per 16 pixels (two for CI = 64) instead of three (six): 2.1x fewer operand bytes per
 // FLOP. Out-of-image X / dY pixels arrive as zeros (TMA), which is the convolution's padding on both sides.
 // ----------------------------------------------------------------------------------------------
+// image rows per K block of the kx-in-N row kernel: a strip of R rows needs R + 2 X rows, so X crosses L2 -> shared
+// memory (R + 2) / R times instead of 3 times; R is what still leaves >= 3 pipeline stages in ~190 KB
+__host__ __device__ constexpr int wgrad_rowsn_rows(int ci, int ncout) { return (ci == 32 && ncout == 32) ? 4 : 2; }
+
 template <int CI, int NCOUT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3x3_wgrad_rowsn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
@@ -824,9 +829,10 @@ conv3x3_wgrad_rowsn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __g
   constexpr int ROW_A = CI * 2, ROW_B = NCOUT * 2;
   constexpr uint32_t SWZ_A = CI == 64 ? SWZ_128B : SWZ_64B;
   constexpr uint32_t SWZ_B = NCOUT == 64 ? SWZ_128B : SWZ_64B;
+  constexpr int R = wgrad_rowsn_rows(CI, NCOUT);                // image rows per K block
   constexpr int XBOX = PIXK * ROW_A;                            // 4 / 8 KB: 1 KB aligned
   constexpr int YBOX = (YROWS * ROW_B + 1023) / 1024 * 1024;
-  constexpr int STAGE_BYTES = 3 * XBOX + YBOX;
+  constexpr int STAGE_BYTES = (R + 2) * XBOX + R * YBOX;        // [X rows y0-1 .. y0+R] [dY rows y0 .. y0+R-1]
   constexpr int NG = CI == 32 ? 1 : 2;                          // MMA groups: ky {0,1,2,-} or {0,1} + {2,-}
   constexpr int NN = 3 * NCOUT;                                 // MMA N: (kx chunk, co)
   constexpr int TMEM_NEED = NG * NN;
@@ -835,7 +841,8 @@ conv3x3_wgrad_rowsn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __g
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // 8 KB spare after the last stage: the unused M chunk of the last stage's MMAs reads up to one X box past its dY box
+  // 8 KB spare after the last stage: the unused M chunk of the strip's last rows reads one X box past the X boxes (into
+  // the dY boxes, and for the last stage possibly past them); its accumulator rows are never stored
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * STAGE_BYTES + 8192);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
@@ -870,17 +877,18 @@ conv3x3_wgrad_rowsn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __g
         uint32_t phase = 0;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           const int tw = kb % p.tiles_w;
-          const int y = (kb / p.tiles_w) % p.H;
-          const int n = kb / (p.tiles_w * p.H);
+          const int y0 = ((kb / p.tiles_w) % p.tiles_h) * R;
+          const int n = kb / (p.tiles_w * p.tiles_h);
           const int x0 = tw * PIXK;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sx = smem + stage * STAGE_BYTES;
-          uint8_t* sy = sx + 3 * XBOX;
-          mbar_arrive_expect_tx(&full_bar[stage], 3 * XBOX + YROWS * ROW_B);
+          uint8_t* sy = sx + (R + 2) * XBOX;
+          mbar_arrive_expect_tx(&full_bar[stage], (R + 2) * XBOX + R * YROWS * ROW_B);
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)   // out-of-range rows / columns arrive as zeros: the conv's padding
-            tma_load_4d(sx + ky * XBOX, &tmX, &full_bar[stage], p.ci0, x0, y + ky - 1, n);
-          tma_load_4d(sy, &tmDY, &full_bar[stage], 0, x0 - 1, y, n);
+          for (int j = 0; j < R + 2; ++j)   // out-of-range rows / columns arrive as zeros: the conv's padding
+            tma_load_4d(sx + j * XBOX, &tmX, &full_bar[stage], p.ci0, x0, y0 + j - 1, n);
+#pragma unroll
+          for (int j = 0; j < R; ++j) tma_load_4d(sy + j * YBOX, &tmDY, &full_bar[stage], 0, x0 - 1, y0 + j, n);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -889,7 +897,7 @@ conv3x3_wgrad_rowsn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __g
         constexpr uint32_t idesc = make_idesc_bf16(128, NN, 1, 1);  // both operands MN-major
         constexpr uint32_t ahi = smem_desc_hi(8 * ROW_A, SWZ_A), bhi = smem_desc_hi(8 * ROW_B, SWZ_B);
         const uint32_t base_a = smem_desc_lo(smem_u32(smem), XBOX);                // M chunks: one X box (ky) apart
-        const uint32_t base_b = smem_desc_lo(smem_u32(smem) + 3 * XBOX, ROW_B);    // N chunks: ONE pixel row apart
+        const uint32_t base_b = smem_desc_lo(smem_u32(smem) + (R + 2) * XBOX, ROW_B);   // N chunks: ONE pixel row apart
         int stage = 0;
         uint32_t phase = 0;
         uint32_t soff = 0;
@@ -897,12 +905,15 @@ conv3x3_wgrad_rowsn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __g
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
 #pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            const uint32_t a_lo = base_a + soff + g * 2 * (XBOX >> 4), b_lo = base_b + soff;
+          for (int r = 0; r < R; ++r) {      // output row y0 + r: X rows r, r+1, r+2 of the strip, dY row r
 #pragma unroll
-            for (int k = 0; k < PIXK / 16; ++k)
-              umma_bf16_lohi(tmem_base + g * NN, a_lo + k * ROW_A, ahi, b_lo + k * ROW_B, bhi, idesc,
-                             (it | k) != 0 ? 1u : 0u);
+            for (int g = 0; g < NG; ++g) {
+              const uint32_t a_lo = base_a + soff + (r + g * 2) * (XBOX >> 4), b_lo = base_b + soff + r * (YBOX >> 4);
+#pragma unroll
+              for (int k = 0; k < PIXK / 16; ++k)
+                umma_bf16_lohi(tmem_base + g * NN, a_lo + k * ROW_A, ahi, b_lo + k * ROW_B, bhi, idesc,
+                               (it | r | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           soff += STAGE_BYTES >> 4;
@@ -1398,13 +1409,14 @@ static int launch_wgrad_rowsn(const void* dy, int Cout, const void* x, int Csrc,
   p.ci0 = ci0;
   p.N = N; p.H = H; p.W = W; p.dil = 1;
   constexpr int ROW_A = CI * 2, ROW_B = NCOUT * 2;
+  constexpr int R = wgrad_rowsn_rows(CI, NCOUT);
   constexpr int XBOX = 64 * ROW_A, YBOX = (66 * ROW_B + 1023) / 1024 * 1024;
-  constexpr int STAGE_BYTES = 3 * XBOX + YBOX;
+  constexpr int STAGE_BYTES = (R + 2) * XBOX + R * YBOX;
   p.pixk = 64;
-  p.bw = 64; p.bh = 1; p.bn = 1;
+  p.bw = 64; p.bh = R; p.bn = 1;
   p.tiles_w = ceil_div(W, 64);
-  p.tiles_h = H;
-  p.tiles_total = p.tiles_w * H * N;
+  p.tiles_h = ceil_div(H, R);
+  p.tiles_total = p.tiles_w * p.tiles_h * N;
   p.Cout = Cout; p.Csrc = Csrc; p.ctot = ctot; p.cbase = cbase; p.dw = dw;
   p.stages = (200 * 1024 - 8192) / STAGE_BYTES;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
