@@ -1310,7 +1310,21 @@ __global__ void __launch_bounds__(256) wgrad_reduce_unpack_kernel(const float* _
   float acc[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) acc[t] = 0.f;
-  for (int sp = 0; sp < splits; ++sp) {
+  // These launches are latency-bound (a few thousand threads, `splits` dependent-looking round trips to L2 of 9 loads
+  // each: ~15 us whatever the layer): four splits' loads are issued together, the sums keep their fixed order.
+  int sp = 0;
+  for (; sp + 4 <= splits; sp += 4) {
+    float v[4][9];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) v[u][t] = __ldg(src + (sp + u) * split_stride + t * tap_stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[t] += v[u][t];
+  }
+  for (; sp < splits; ++sp) {
     float v[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) v[t] = __ldg(src + sp * split_stride + t * tap_stride);
