@@ -202,8 +202,10 @@ int pp_scribble_loss_bwd(const float* zw, const float* zs, const float* za, cons
 /* The same pass with the aux logits taken at the resolution fc_cls produces them, za_low [N][C][aux_h][aux_w]
  * (aux_path_memory.py:51), instead of the F.interpolate(bilinear, align_corners=True) output of aux_path_memory.py:52:
  * only labelled pixels read the aux logits, so the kernels interpolate them there (same arithmetic as
- * pp_upsample_planes_fwd) and no full-resolution aux tensor is written or read. The backward pass zeroes dza_low
- * [N][C][aux_h][aux_w] and accumulates the interpolation's transpose into it (fp32 atomics). */
+ * pp_upsample_planes_fwd) and no full-resolution aux tensor is written or read. The backward pass accumulates the
+ * interpolation's transpose in dza_scratch (N*C*aux_h*aux_w int64, 2^-44 fixed point, integer atomics: the sum does
+ * not depend on the order the blocks arrive in, so the gradient is bit-reproducible) and writes dza_low
+ * [N][C][aux_h][aux_w] from it. */
 int pp_scribble_loss_lowaux_fwd(const float* zw, const float* zs, const float* za_low, int aux_h, int aux_w,
                                 const uint8_t* target, const float* mask, double* acc, float* loss_pce,
                                 float* loss_ent, float* loss_cr, float* loss_aux, int N, int C, int H, int W,
@@ -211,8 +213,8 @@ int pp_scribble_loss_lowaux_fwd(const float* zw, const float* zs, const float* z
 int pp_scribble_loss_lowaux_bwd(const float* zw, const float* zs, const float* za_low, int aux_h, int aux_w,
                                 const uint8_t* target, const float* mask, const double* acc, const float* g_pce,
                                 const float* g_ent, const float* g_cr, const float* g_aux, float* dzw, float* dzs,
-                                float* dza_low, int N, int C, int H, int W, int ignore_index, int do_ent,
-                                int cr_variant, int detach_weak, void* stream);
+                                float* dza_low, long long* dza_scratch, int N, int C, int H, int W, int ignore_index,
+                                int do_ent, int cr_variant, int detach_weak, void* stream);
 /* stand-alone soft_label_cross_entropy_loss (a = logits, b = probabilities; losses.py:45-62), l1_loss and
  * l2_loss (a, b = probabilities; losses.py:64-96); variant = PP_CR_CE / PP_CR_L1 / PP_CR_L2. pacc: 8 doubles. */
 int pp_pair_loss_fwd(const float* a, const float* b, const float* mask, double* pacc, float* loss, int N, int C,

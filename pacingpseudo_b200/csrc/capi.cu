@@ -238,11 +238,12 @@ int pp_scribble_loss_lowaux_fwd(const float* zw, const float* zs, const float* z
 int pp_scribble_loss_lowaux_bwd(const float* zw, const float* zs, const float* za_low, int aux_h, int aux_w,
                                 const uint8_t* target, const float* mask, const double* acc, const float* g_pce,
                                 const float* g_ent, const float* g_cr, const float* g_aux, float* dzw, float* dzs,
-                                float* dza_low, int N, int C, int H, int W, int ignore_index, int do_ent,
-                                int cr_variant, int detach_weak, void* stream) {
+                                float* dza_low, long long* dza_scratch, int N, int C, int H, int W, int ignore_index,
+                                int do_ent, int cr_variant, int detach_weak, void* stream) {
   PP_REQUIRE(za_low != nullptr && aux_h > 0 && aux_w > 0 && H > 0 && W > 0, "pp_scribble_loss_lowaux_bwd: bad aux tensor");
+  PP_REQUIRE((dza_low == nullptr) == (dza_scratch == nullptr), "pp_scribble_loss_lowaux_bwd: dza_low and dza_scratch go together");
   return scribble_loss_bwd(zw, zs, za_low, target, mask, acc, g_pce, g_ent, g_cr, g_aux, dzw, dzs, dza_low, N, C, H * W,
-                           ignore_index, do_ent, cr_variant, detach_weak, ST(stream), aux_h, aux_w, W);
+                           ignore_index, do_ent, cr_variant, detach_weak, ST(stream), aux_h, aux_w, W, dza_scratch);
 }
 int pp_pair_loss_fwd(const float* a, const float* b, const float* mask, double* pacc, float* loss, int N, int C,
                      int HW, int variant, void* stream) {

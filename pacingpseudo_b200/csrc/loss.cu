@@ -192,23 +192,37 @@ __device__ __forceinline__ void aux_logits_at(const float* __restrict__ za, cons
     }
   }
 }
+// The scatter accumulates in 2^-44 fixed point with INTEGER atomics: integer addition is associative, so the low-resolution
+// gradient is bit-reproducible whatever order the blocks arrive in. (fp32 atomics here would be the only order-dependent
+// sum on the DATA-gradient path: their 1e-7 noise flips bf16 roundings further down the backward chain and two passes over
+// the same batch then differ by 1e-4 in the early layers' gradients - tests/run_dp_check.py relies on repeatability.)
+// Resolution 5.7e-14, range +-5.2e5 per element.
+constexpr double kAuxFixScale = 17592186044416.0;   // 2^44
+__device__ __forceinline__ void aux_fix_add(unsigned long long* p, float v) {
+  atomicAdd(p, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v) * kAuxFixScale)));
+}
 template <int NC>
-__device__ __forceinline__ void aux_grad_scatter(float* __restrict__ dza, const AuxLow& al, int n, int hw, int C,
-                                                 const float (&g)[NC]) {
+__device__ __forceinline__ void aux_grad_scatter(unsigned long long* __restrict__ dzq, const AuxLow& al, int n, int hw,
+                                                 int C, const float (&g)[NC]) {
   const int Y = hw / al.W, X = hw - Y * al.W;
   const Lerp ly = lerp_src(Y, al.h, al.sh), lx = lerp_src(X, al.w, al.sw);
-  float* z = dza + static_cast<size_t>(n) * C * al.h * al.w;
+  unsigned long long* z = dzq + static_cast<size_t>(n) * C * al.h * al.w;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     if (c < C) {
-      float* r0 = z + (static_cast<size_t>(c) * al.h + ly.i0) * al.w;
-      float* r1 = z + (static_cast<size_t>(c) * al.h + ly.i1) * al.w;
-      atomicAdd(r0 + lx.i0, ly.w0 * lx.w0 * g[c]);
-      atomicAdd(r0 + lx.i1, ly.w0 * lx.w1 * g[c]);
-      atomicAdd(r1 + lx.i0, ly.w1 * lx.w0 * g[c]);
-      atomicAdd(r1 + lx.i1, ly.w1 * lx.w1 * g[c]);
+      unsigned long long* r0 = z + (static_cast<size_t>(c) * al.h + ly.i0) * al.w;
+      unsigned long long* r1 = z + (static_cast<size_t>(c) * al.h + ly.i1) * al.w;
+      aux_fix_add(r0 + lx.i0, ly.w0 * lx.w0 * g[c]);
+      aux_fix_add(r0 + lx.i1, ly.w0 * lx.w1 * g[c]);
+      aux_fix_add(r1 + lx.i0, ly.w1 * lx.w0 * g[c]);
+      aux_fix_add(r1 + lx.i1, ly.w1 * lx.w1 * g[c]);
     }
   }
+}
+__global__ void __launch_bounds__(256) aux_fix_to_float_kernel(const long long* __restrict__ q, float* __restrict__ out,
+                                                               int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<float>(static_cast<double>(q[i]) * (1.0 / kAuxFixScale));
 }
 
 template <int V, int NC>
@@ -465,7 +479,7 @@ scribble_loss_bwd_lean_kernel(const float* __restrict__ zw, const float* __restr
                               const float* __restrict__ g_ent, const float* __restrict__ g_cr,
                               const float* __restrict__ g_aux, float* __restrict__ dzw, float* __restrict__ dzs,
                               float* __restrict__ dza, int P, int HW, int ignore_index, int do_ent, int detach_weak,
-                              const AuxLow al) {
+                              const AuxLow al, unsigned long long* __restrict__ dzq) {
   const float gp = g_pce ? *g_pce : 0.f, ge = (do_ent && g_ent) ? *g_ent : 0.f;
   const float gc = (CR != CR_NONE && g_cr) ? *g_cr : 0.f, ga = (za && g_aux) ? *g_aux : 0.f;
   const int has_mask = mask != nullptr;
@@ -476,7 +490,7 @@ scribble_loss_bwd_lean_kernel(const float* __restrict__ zw, const float* __restr
   const float k_cr = gc * static_cast<float>(1.0 / masked_denom(acc, has_mask, ne));
   const float k_pce = gp * inv_lab, k_aux = ga * inv_lab;
   const bool weak_gets_cr = (CR == CR_KL) || !detach_weak;
-  const bool do_aux = za != nullptr && dza != nullptr;
+  const bool do_aux = za != nullptr && (al.h > 0 ? dzq != nullptr : dza != nullptr);
 
   int gi, g_end;
   lean_span<V>(P / V, gi, g_end);
@@ -570,7 +584,7 @@ scribble_loss_bwd_lean_kernel(const float* __restrict__ zw, const float* __restr
             a.of(va);
 #pragma unroll
             for (int c = 0; c < C; ++c) va[c] = k_aux * (a.p(c) - (c == t ? 1.f : 0.f));
-            aux_grad_scatter<C>(dza, al, n, hw + j, C, va);
+            aux_grad_scatter<C>(dzq, al, n, hw + j, C, va);
           }
         }
       }
@@ -688,7 +702,7 @@ scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__
                          const float* __restrict__ g_ent, const float* __restrict__ g_cr,
                          const float* __restrict__ g_aux, float* __restrict__ dzw, float* __restrict__ dzs,
                          float* __restrict__ dza, int P, int HW, int C, int ignore_index, int do_ent,
-                         int cr_variant, int detach_weak, const AuxLow al) {
+                         int cr_variant, int detach_weak, const AuxLow al, unsigned long long* __restrict__ dzq) {
   const float gp = g_pce ? *g_pce : 0.f, ge = (do_ent && g_ent) ? *g_ent : 0.f;
   const float gc = (cr_variant != CR_NONE && g_cr) ? *g_cr : 0.f, ga = (za && g_aux) ? *g_aux : 0.f;
   const int has_mask = mask != nullptr;
@@ -713,8 +727,8 @@ scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__
     bool any_lab = false;
 #pragma unroll
     for (int j = 0; j < V; ++j) any_lab |= (target != nullptr) && (tv[j] != ignore_index) && (tv[j] < C);
-    const bool do_aux = za != nullptr && dza != nullptr;
     const bool aux_low = al.h > 0;
+    const bool do_aux = za != nullptr && (aux_low ? dzq != nullptr : dza != nullptr);
     if (do_aux && any_lab && !aux_low) load_planes<V, NC>(za + off, HW, C, va);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -778,7 +792,7 @@ scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__
           softmax_of(g, C, a);
 #pragma unroll
           for (int c = 0; c < NC; ++c) g[c] = ga * inv_lab * (a.p[c] - (c == t ? 1.f : 0.f));
-          aux_grad_scatter<NC>(dza, al, n, hw + j, C, g);
+          aux_grad_scatter<NC>(dzq, al, n, hw + j, C, g);
         }
       } else if (do_aux) {
         if (lab) {
@@ -801,13 +815,20 @@ scribble_loss_bwd_kernel(const float* __restrict__ zw, const float* __restrict__
 int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const uint8_t* target, const float* mask,
                       const double* acc, const float* g_pce, const float* g_ent, const float* g_cr, const float* g_aux,
                       float* dzw, float* dzs, float* dza, int N, int C, int HW, int ignore_index, int do_ent,
-                      int cr_variant, int detach_weak, cudaStream_t s, int aux_h, int aux_w, int W) {
+                      int cr_variant, int detach_weak, cudaStream_t s, int aux_h, int aux_w, int W,
+                      long long* aux_scratch) {
   PP_REQUIRE(C >= 1 && C <= kMaxC, "scribble_loss_bwd: num_classes=%d unsupported", C);
   AuxLow al{0, 0, 0, 0.f, 0.f};
+  unsigned long long* dzq = nullptr;
+  const int n_low = N * C * aux_h * aux_w;
   if (za != nullptr && aux_h > 0) {   // za / dza are the low-resolution tensors [N][C][aux_h][aux_w]
     PP_REQUIRE(aux_w > 0 && W > 0 && HW % W == 0, "scribble_loss_bwd: bad aux / image size (%d x %d, W=%d, HW=%d)", aux_h, aux_w, W, HW);
     al = AuxLow{aux_h, aux_w, W, ac_scale(aux_h, HW / W), ac_scale(aux_w, W)};
-    if (dza != nullptr) PP_CHECK_CUDA(cudaMemsetAsync(dza, 0, sizeof(float) * N * C * aux_h * aux_w, s));
+    if (dza != nullptr) {
+      PP_REQUIRE(aux_scratch != nullptr, "scribble_loss_bwd: the low-resolution aux gradient needs its fixed-point scratch");
+      dzq = reinterpret_cast<unsigned long long*>(aux_scratch);
+      PP_CHECK_CUDA(cudaMemsetAsync(dzq, 0, sizeof(long long) * n_low, s));
+    }
   }
   const bool aux_full = za != nullptr && al.h == 0;
   const long long P = static_cast<long long>(N) * HW;
@@ -821,11 +842,12 @@ int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const u
 #define PP_LOSS_BWD(V_, NC_, P_)                                                                                    \
   scribble_loss_bwd_kernel<V_, NC_><<<grid_for_px(P_, 256), 256, 0, s>>>(zw, zs, za, target, mask, acc, g_pce, g_ent, g_cr, \
                                                                          g_aux, dzw, dzs, dza, int(P), HW, C,          \
-                                                                         ignore_index, do_ent, cr_variant, detach_weak, al)
+                                                                         ignore_index, do_ent, cr_variant, detach_weak, al, \
+                                                                         dzq)
 #define PP_LEAN_BWD(C_, CR_)                                                                                       \
   scribble_loss_bwd_lean_kernel<C_, CR_, 4><<<lean_grid(P / 4), 256, 0, s>>>(                                        \
       zw, zs, za, target, mask, acc, g_pce, g_ent, g_cr, g_aux, dzw, dzs, dza, int(P), HW, ignore_index, do_ent,     \
-      detach_weak, al)
+      detach_weak, al, dzq)
 #define PP_LEAN_BWD_C(C_)                                                                                           \
   switch (cr_variant) {                                                                                             \
     case CR_NONE: PP_LEAN_BWD(C_, CR_NONE); break;                                                                  \
@@ -849,6 +871,10 @@ int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const u
 #undef PP_LEAN_BWD
   prof_end(slot, s);
   PP_LAUNCH_CHECK();
+  if (dzq != nullptr) {
+    aux_fix_to_float_kernel<<<ceil_div(n_low, 256), 256, 0, s>>>(reinterpret_cast<const long long*>(dzq), dza, n_low);
+    PP_LAUNCH_CHECK();
+  }
   return PP_OK;
 }
 

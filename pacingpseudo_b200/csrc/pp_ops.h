@@ -109,7 +109,8 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float l
 int onehot_argmax(const float* x, uint8_t* out, int N, int K, int HW, cudaStream_t s);
 // aux_h > 0: za (and dza) are the LOW-resolution aux logits [N][C][aux_h][aux_w]; the kernels interpolate them at the
 // labelled pixels of the W-wide label map (bilinear, align_corners=True) instead of reading an up-sampled tensor, and
-// the backward pass zeroes dza and scatters into it with atomics. aux_h == 0: full-resolution planes [N][C][HW].
+// the backward pass scatters into a zeroed fixed-point scratch with integer atomics (order-independent) and converts it
+// to dza. aux_h == 0: full-resolution planes [N][C][HW].
 int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const uint8_t* target, const float* mask,
                       double* acc, float* loss_pce, float* loss_ent, float* loss_cr, float* loss_aux, int N, int C,
                       int HW, int ignore_index, int do_ent, int cr_variant, cudaStream_t s, int aux_h = 0,
@@ -117,7 +118,8 @@ int scribble_loss_fwd(const float* zw, const float* zs, const float* za, const u
 int scribble_loss_bwd(const float* zw, const float* zs, const float* za, const uint8_t* target, const float* mask,
                       const double* acc, const float* g_pce, const float* g_ent, const float* g_cr, const float* g_aux,
                       float* dzw, float* dzs, float* dza, int N, int C, int HW, int ignore_index, int do_ent,
-                      int cr_variant, int detach_weak, cudaStream_t s, int aux_h = 0, int aux_w = 0, int W = 0);
+                      int cr_variant, int detach_weak, cudaStream_t s, int aux_h = 0, int aux_w = 0, int W = 0,
+                      long long* aux_scratch = nullptr);   // aux_h > 0: N*C*aux_h*aux_w int64 (fixed-point accumulators)
 int pair_loss_fwd(const float* a, const float* b, const float* mask, double* pacc, float* loss, int N, int C, int HW,
                   int variant, cudaStream_t s);
 int pair_loss_bwd(const float* a, const float* b, const float* mask, const double* pacc, const float* g, float* da,

@@ -426,11 +426,12 @@ class ScribbleLossFunction(torch.autograd.Function):
             half = N * C * H * W * 4
             zs_p = (zw_p + half) if siamese else (zs.data_ptr() if zs is not None else None)
             dzs_p = (dzw.data_ptr() + half) if siamese else (dzs.data_ptr() if dzs is not None else None)
-            if ctx.aux_low:   # dza is zeroed by the library and accumulated with atomics
+            if ctx.aux_low:   # accumulated in a fixed-point scratch with integer atomics (order-independent), then -> dza
+                scratch = torch.empty(za.numel(), dtype=torch.int64, device=dev)
                 lib.call("pp_scribble_loss_lowaux_bwd", ctypes.c_void_p(zw_p), ctypes.c_void_p(zs_p) if zs_p else None,
                          ptr(za), za.shape[2], za.shape[3], ptr(target), ptr(mask), ptr(acc), ptr(g_pce), ptr(g_ent),
                          ptr(g_cr), ptr(g_aux), ctypes.c_void_p(dzw.data_ptr()), ctypes.c_void_p(dzs_p) if dzs_p else None,
-                         ptr(dza), N, C, H, W, ignore_index, int(do_ent), cr_variant, int(detach_weak),
+                         ptr(dza), ptr(scratch), N, C, H, W, ignore_index, int(do_ent), cr_variant, int(detach_weak),
                          current_stream(dev))
             else:
                 lib.call("pp_scribble_loss_bwd", ctypes.c_void_p(zw_p), ctypes.c_void_p(zs_p) if zs_p else None, ptr(za),

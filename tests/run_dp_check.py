@@ -40,6 +40,12 @@ def main():
     reducer = dp.GradientAllReducer(opt.flat_grad, num_buckets=4, unet=model.backbone, optimizer=opt)
     model.aux_path.bank_sync = dp.make_bank_sync(0)
     ok = True
+    names = {}
+    for n_, p_ in model.named_parameters():
+        for q, off in zip(opt.params, opt.offsets):
+            if q is p_:
+                names[n_] = (off, off + p_.numel())
+    diag = os.environ.get("PP_DP_DIAG", "0") == "1"   # also split the error into repeatability and exchange parts
     for it in range(3):
         batch = {k: v.to(dev) for k, v in make_batch(B, C, S, S, seed=dp.shard_seed(1234, rank, it)).items()}
         def fwd_bwd():
@@ -57,6 +63,10 @@ def main():
         model.load_state_dict(state)
         # pass 2: backward with the bucketed all-reduce overlapping it
         fwd_bwd()
+        local2 = None
+        if diag:   # (synchronises: the exchange then no longer overlaps the backward pass)
+            torch.cuda.synchronize(dev)
+            local2 = opt.flat_grad.clone()
         reducer.allreduce()
         torch.cuda.synchronize(dev)
         gathered = [torch.empty_like(local) for _ in range(world)]
@@ -69,6 +79,17 @@ def main():
         dist.all_gather(banks, model.aux_path.memory_bank.data)
         same_bank = all(torch.equal(banks[0], b) for b in banks[1:])
         nz = float(local.abs().max())
+        if rank == 0 and (diag or err >= 1e-5):
+            d = (opt.flat_grad.double() - ref).abs()
+            worst = max(names.items(), key=lambda kv: float(d[kv[1][0]:kv[1][1]].max()))
+            lo, hi = worst[1]
+            print("    worst parameter %s: |diff| max %.3e, |ref| max %.3e" % (worst[0], float(d[lo:hi].max()),
+                                                                            float(ref[lo:hi].abs().max())), flush=True)
+        if local2 is not None:
+            rep = (local2.double() - local.double()).abs()
+            worst = max(names.items(), key=lambda kv: float(rep[kv[1][0]:kv[1][1]].max()))
+            print("    rank %d pass 2 vs pass 1 (no exchange): max |diff| %.3e / |g|max %.3e, worst %s" % (
+                rank, float(rep.max()), nz, worst[0]), flush=True)
         if rank == 0:
             print("step %d: buckets %s max rel err %.3e, |g|max %.3e, bank identical %s" % (
                 it, [(fl, hi - lo) for fl, lo, hi in reducer.overlapped] + reducer.tail, err, nz, same_bank), flush=True)
