@@ -221,6 +221,9 @@ def distances(rec, ref, bn_training):
             # relative, with the same 1e-2 floor on the loss magnitude as tests/harness.py: a trained pCE of ~1e-3
             # carries ~1e-7 of fp32 summation noise, which is 1e-4 RELATIVE without saying anything about parity
             m[k] = abs(float(rec[k]) - float(ref[k])) / max(abs(float(ref[k])), 1e-2)
+            m["abs_" + k] = abs(float(rec[k]) - float(ref[k]))   # reported; trained terms are also held absolutely
+    if "total" in ref:
+        m["ref_total"] = abs(float(ref["total"]))
     if "bank" in ref:
         m["bank"] = rel(rec["bank"], ref["bank"])
     g, g0 = rec["grads"], ref["grads"]
