@@ -19,7 +19,9 @@
 //       boxes, consumed as MN-major UMMA operands. Split-K over pixel ranges: either fp32 red.global accumulation,
 //       or (training step) per-split scratch slabs + a fixed-order reduction (deterministic). 192 threads.
 //   wgrad (32/64-channel sources) :  taps packed into the MMA M dimension; the row variant fetches X as three
-//       66-pixel row boxes per K block and realises the horizontal taps as descriptor row offsets.
+//       66-pixel row boxes per K block and realises the horizontal taps as descriptor row offsets; the default
+//       (conv3x3_wgrad_rowsn_tc_kernel) packs the vertical taps into M and the horizontal taps into N (dY operand chunks
+//       one pixel row apart) and walks strips of R image rows.
 //
 #include <array>
 #include <map>
