@@ -113,7 +113,7 @@ def _check_bf16_trained(m, m_emu, where):
         elif k.startswith("loss_") or k == "total":
             assert le(v, TOL16["loss"], m_emu[k]) or m["abs_" + k] <= small_abs, (where, k, v, m["abs_" + k], m_emu[k])
         elif k.startswith("argmax_") and k.endswith("_decided"):
-            assert ge(v, 0.9999, m_emu[k], 1e-4), (where, k, v, m_emu[k])
+            assert ge(v, 0.9999, m_emu[k], 2e-4), (where, k, v, m_emu[k])   # (>= 99.98 % when the emulation has no flip at all)
         elif k.startswith("argmax_"):
             # measured 99.85 ... 99.99 % (weak / strong) and 99.75 ... 99.95 % (aux: a bilinear x8 up-sampling of 32 x 32
             # logits has 8x wider near-tie bands along every boundary); the literal >= 99.9 % verdict goes to the report
